@@ -128,8 +128,8 @@ def ba_window(n_kf: int, n_lm: int, seed: int = 42, obs_per_lm: int = 6, layout:
               outlier_frac: float = 0.05, noise: bool = True) -> BAProblem:
     """Synthetic local-BA window of SURVEY.md section 8(d).
 
-    circle layout: poses on a 5 m circle, heading tangent, 0.25 m spacing; 'lawn' layout: lawn-mower
-    sweep over a square for the large scale test.  Each landmark is placed inside the frustum of a
+    circle layout: poses on a 5 m circle, heading tangent, 0.25 m spacing; 'zigzag' layout: long
+    zig-zag sweep for the large scale test.  Each landmark is placed inside the frustum of a
     'home' keyframe and observed by up to obs_per_lm consecutive keyframes that actually see it.
     """
     rng = np.random.default_rng(seed)
@@ -140,18 +140,21 @@ def ba_window(n_kf: int, n_lm: int, seed: int = 42, obs_per_lm: int = 6, layout:
 
     gt = np.zeros((n_kf, 3))
     if layout == "circle":
+        # 5 m circle, 0.25 m spacing, heading tangent; headings centred on 0 so that they stay well
+        # inside (-pi, pi) (PreEdgeSE2 does not normalise its angle error, EdgeSE2XYZ.h:80)
         R = 5.0
         dth = 0.25 / R
         for i in range(n_kf):
-            a = i * dth
-            gt[i] = (R * math.cos(a), R * math.sin(a), a + math.pi / 2)
-    elif layout == "lawn":
-        side = 60.0
-        per_row = int(side / 0.25)
+            hd = (i - n_kf / 2) * dth
+            a = hd - math.pi / 2
+            gt[i] = (R * math.cos(a), R * math.sin(a), hd)
+    elif layout == "zigzag":
+        # large-scale test: 0.25 m steps, heading +-0.7 rad alternating every 240 KFs, drifting along +x
+        x = y = 0.0
         for i in range(n_kf):
-            r, c = divmod(i, per_row)
-            xx = c * 0.25 if r % 2 == 0 else side - c * 0.25
-            gt[i] = (xx, r * 1.0, 0.0 if r % 2 == 0 else math.pi)
+            hd = 0.7 if (i // 240) % 2 == 0 else -0.7
+            gt[i] = (x, y, hd)
+            x += 0.25 * math.cos(hd); y += 0.25 * math.sin(hd)
     else:
         raise ValueError(layout)
 
@@ -243,7 +246,7 @@ BA_CONFIGS = {
     "C1": dict(n_kf=2, n_lm=200, obs_per_lm=2),
     "C3": dict(n_kf=20, n_lm=2000),
     "C4": dict(n_kf=50, n_lm=5000),
-    "C5": dict(n_kf=2000, n_lm=50000, layout="lawn"),
+    "C5": dict(n_kf=2000, n_lm=50000, layout="zigzag"),
 }
 
 
