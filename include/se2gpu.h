@@ -1,0 +1,196 @@
+/* se2gpu — C ABI of the B200-native hot paths of se2lam (ORB front-end, SE(2)-XYZ local BA).
+ *
+ * Plain C, plain pointers and sizes, int status codes, no exceptions across the boundary.
+ * The reference (izhengfan/se2lam) has no FFI layer of its own: the seam is the C++ symbols
+ * listed below, which the header shims in include/se2lam/ forward to these entry points
+ * (INTEGRATION.md shows the binding).  Every function is implemented by hand-written sm_100a
+ * CUDA in se2lam_b200/csrc; there is no CPU fallback — a call without a usable CUDA device
+ * returns SE2GPU_ERR_NO_DEVICE.
+ *
+ *   entry point                      replaces (reference file:line)
+ *   -------------------------------  -------------------------------------------------------------
+ *   se2gpu_orb_create                se2lam::ORBextractor::ORBextractor       src/ORBextractor.cpp:463-520
+ *   se2gpu_orb_extract[_device]      se2lam::ORBextractor::operator()         src/ORBextractor.cpp:727-788
+ *                                    (ComputePyramid :790-831, ComputeKeyPoints :531-716,
+ *                                     IC_Angle :130-157, computeOrbDescriptor :160-200)
+ *   se2gpu_hamming_distance          se2lam::ORBmatcher::DescriptorDistance   src/ORBmatcher.cpp:110-126
+ *   se2gpu_match_by_window           se2lam::ORBmatcher::MatchByWindow        src/ORBmatcher.cpp:278-381
+ *                                    (+ Frame grid / GetFeaturesInArea        src/Frame.cpp:64-77, 209-286)
+ *   se2gpu_match_by_projection       se2lam::ORBmatcher::MatchByProjection    src/ORBmatcher.cpp:383-454
+ *   se2gpu_search_by_bow             se2lam::ORBmatcher::SearchByBoW          src/ORBmatcher.cpp:128-276
+ *   se2gpu_ba_set_problem            Map::loadLocalGraph -> addVertexSE2 / addEdgeSE2 / addVertexSBAXYZ /
+ *                                    addEdgeSE2XYZ / addCamPara               src/Map.cpp:891-1053, src/optimizer.cpp:17-62,207-215,316-324
+ *                                    + SparseOptimizer::initializeOptimization(0)   src/LocalMapper.cpp:259
+ *   se2gpu_ba_optimize               SlamOptimizer::optimize(Config::LOCAL_ITER)    src/LocalMapper.cpp:260
+ *                                    (EdgeSE2XYZ::computeError/linearizeOplus src/EdgeSE2XYZ.cpp:61-106,
+ *                                     PreEdgeSE2 include/se2lam/EdgeSE2XYZ.h:62-102, g2o LM/Schur/Cholesky/Huber [upstream])
+ *   se2gpu_ba_get                    estimateVertexSE2 / estimateVertexSBAXYZ src/optimizer.cpp:45-50, 549-554
+ */
+#ifndef SE2GPU_H
+#define SE2GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE2GPU_OK 0
+#define SE2GPU_ERR_NO_DEVICE -1
+#define SE2GPU_ERR_CUDA -2
+#define SE2GPU_ERR_INVALID -3
+#define SE2GPU_ERR_CAPACITY -4
+
+/* ------------------------------------------------------------------------------------------ common */
+int se2gpu_device_count(void);
+/* last error message of the calling thread ("" if none) */
+const char* se2gpu_last_error(void);
+/* number of kernel launches issued by this library in this process so far (bench.py's gpu_launches) */
+unsigned long long se2gpu_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ ORB */
+typedef struct se2gpu_orb se2gpu_orb;
+
+/* bit-identical to cv::KeyPoint (28 bytes) so results can be copied straight into a
+ * std::vector<cv::KeyPoint> */
+typedef struct se2gpu_keypoint {
+    float x, y;      /* pt, in level-0 pixel coordinates */
+    float size;      /* PATCH_SIZE * scale(level), truncated to int */
+    float angle;     /* degrees, [0,360) */
+    float response;  /* FAST score */
+    int octave;      /* pyramid level */
+    int class_id;    /* -1 */
+} se2gpu_keypoint;
+
+/* ORBextractor(nfeatures, scaleFactor, nlevels, FAST_SCORE, fastTh) for frames up to max_w x max_h,
+ * batches of up to max_batch frames, on CUDA device `device`. Returns NULL on failure. */
+se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, int fast_th, int max_w, int max_h,
+                              int max_batch, int device);
+void se2gpu_orb_destroy(se2gpu_orb* h);
+
+/* operator() over a batch of n frames held in HOST memory (CV_8UC1, row stride `stride` bytes, frame i at
+ * imgs + i*frame_stride). Synchronous: copies frames in, runs the extractor, copies results out.
+ *   kps    [n * nfeatures]      frame i's keypoints start at kps + i*nfeatures
+ *   desc   [n * nfeatures * 32] 256-bit rBRIEF, row i*nfeatures + k belongs to kps[i*nfeatures + k]
+ *   counts [n]                  number of keypoints of each frame (<= nfeatures)
+ * An empty image (w<=0 || h<=0 || imgs==NULL) returns SE2GPU_OK with all counts 0 (the reference returns
+ * silently, ORBextractor.cpp:730-731). */
+int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+                       se2gpu_keypoint* kps, uint8_t* desc, int* counts);
+
+/* Same with DEVICE buffers (frames already resident in HBM, results left in HBM); asynchronous on
+ * `stream` (a cudaStream_t passed as void*; NULL = the default stream). */
+int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int stride,
+                              size_t frame_stride, se2gpu_keypoint* d_kps, uint8_t* d_desc, int* d_counts, void* stream);
+
+/* parity/debug: geometry and contents of pyramid level `level` of frame `frame` from the last extract.
+ * out must hold (h+32)*pitch bytes where pitch/h come from se2gpu_orb_level_dims. blurred!=0 returns the
+ * Gaussian-blurred plane the descriptors were sampled from. */
+int se2gpu_orb_level_dims(se2gpu_orb* h, int level, int* w, int* hgt, int* pitch);
+int se2gpu_orb_get_level(se2gpu_orb* h, int frame, int level, int blurred, uint8_t* out);
+
+/* ------------------------------------------------------------------------------------------ matcher */
+/* DescriptorDistance for n pairs of 32-byte descriptors in HOST memory: out[i] = popcount(a_i ^ b_i) */
+int se2gpu_hamming_distance(const uint8_t* a, const uint8_t* b, int n, int* out, int device);
+
+/* Keypoint grid of Frame (64 x 48 cells over [minX,maxX) x [minY,maxY)): inv_w = 64/(maxX-minX) etc. */
+typedef struct se2gpu_grid_params {
+    float min_x, min_y, inv_w, inv_h;
+} se2gpu_grid_params;
+
+/* MatchByWindow(frame1, frame2, vbPrevMatched, winSize, vnMatches12, levelOffset, minLevel, maxLevel)
+ * with nnratio = ORBmatcher::mfNNratio. prev [n1*2] is vbPrevMatched, updated in place. matches12 [n1].
+ * Returns the number of matches (>=0) or a negative error. HOST buffers. */
+int se2gpu_match_by_window(const se2gpu_keypoint* kp1, const uint8_t* desc1, int n1, const se2gpu_keypoint* kp2,
+                           const uint8_t* desc2, int n2, float* prev, se2gpu_grid_params grid, int win_size,
+                           int level_offset, int min_level, int max_level, float nnratio, int* matches12, int device);
+
+/* MatchByProjection(pNewKF, localMPs, winSize, levelOffset, vMatchesIdxMP), object graph flattened:
+ *   mp_valid[i]  = !isNull && isGoodPrl && !pNewKF->hasObservation(pMP) && inImgBound(predictUV)
+ *   mp_uv[i]     = predictUV;  mp_octave[i] = mMainOctave;  mp_desc = mMainDescriptor
+ *   kf_observed[k] = pNewKF->hasObservation(k)
+ * matches_idx_mp [n_kf]. Returns the number of matches. HOST buffers. */
+int se2gpu_match_by_projection(const se2gpu_keypoint* kf_kp, const uint8_t* kf_desc, int n_kf,
+                               const uint8_t* kf_observed, const uint8_t* mp_valid, const float* mp_uv, int n_mp,
+                               const int* mp_octave, const uint8_t* mp_desc, se2gpu_grid_params grid, int win_size,
+                               int level_offset, float nnratio, int* matches_idx_mp, int device);
+
+/* SearchByBoW(pKF1, pKF2, mapMatches12, bIfMPOnly); each DBoW2::FeatureVector flattened to ascending node
+ * ids + CSR feature lists (ptr has n_node+1 entries). matches12 [n1], -1 = unmatched. HOST buffers. */
+typedef struct se2gpu_bow_kf {
+    const float* angle;     /* keyPointsUn[i].angle */
+    const uint8_t* desc;    /* [n*32] */
+    const uint8_t* has_mp;  /* GetMapPointMatches()[i] && !isNull */
+    int n;
+    const int* node;        /* ascending node ids */
+    int n_node;
+    const int* ptr;         /* [n_node+1] */
+    const int* feat;        /* feature indices */
+} se2gpu_bow_kf;
+int se2gpu_search_by_bow(const se2gpu_bow_kf* kf1, const se2gpu_bow_kf* kf2, int mp_only, float nnratio,
+                         int check_orientation, int* matches12, int device);
+
+/* ------------------------------------------------------------------------------------------ local BA */
+typedef struct se2gpu_ba se2gpu_ba;
+
+/* one entry per completed LM iteration (OptimizationAlgorithmLevenberg::solve call) */
+typedef struct se2gpu_ba_iter_stats {
+    double chi2_before; /* activeRobustChi2 at the start of the iteration */
+    double chi2_after;  /* after the last accepted trial (== chi2_before if none) */
+    double lambda;      /* damping after the iteration */
+    double rho;         /* gain ratio of the last trial */
+    int trials;         /* lambda trials used (1..10) */
+    int accepted;       /* 1 if a trial was accepted */
+    int terminate;      /* 1 if LM returned Terminate (10 failed trials or rho==0) */
+    int pad;
+} se2gpu_ba_iter_stats;
+
+/* capacity-sized solver context on CUDA device `device` */
+se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int max_odo, int device);
+void se2gpu_ba_destroy(se2gpu_ba* h);
+
+/* Loads one local-BA window (what Map::loadLocalGraph + initializeOptimization(0) build):
+ *   poses   [P*3]  VertexSE2 estimates (x,y,theta) of Twb; vertex id = index
+ *   fixed   [P]    setFixed flags
+ *   points  [L*3]  VertexSBAPointXYZ estimates (marginalised); landmarks without edges stay untouched
+ *   edge_pose/edge_point [E], uv [E*2], info [E*3] (xx,xy,yy of the symmetric 2x2 information),
+ *   odo_i/odo_j [O] PreEdgeSE2 vertices (error = Ri^T(rj-ri)-m), odo_meas [O*3], odo_info [O*6] (00,01,02,11,12,22)
+ *   fx,cx,cy       CamPara (single focal length), Tcb [12] = row-major Rcb then tcb (SE3 of setExtParameter, inverted)
+ *   huber_delta    RobustKernelHuber delta of every EdgeSE2XYZ
+ * All HOST pointers; copies and re-indexes synchronously. */
+int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double* poses, const uint8_t* fixed,
+                          const double* points, const int* edge_pose, const int* edge_point, const double* uv,
+                          const double* info, const int* odo_i, const int* odo_j, const double* odo_meas,
+                          const double* odo_info, double fx, double cx, double cy, const double* Tcb,
+                          double huber_delta);
+
+/* optimize(max_iters): returns the number of LM iterations performed (like SparseOptimizer::optimize) or a
+ * negative error. stop_flag (may be NULL) is polled between trials (setForceStopFlag). stats (may be NULL)
+ * receives one entry per iteration. trace_poses [max_iters*P*3] / trace_points [max_iters*L*3] (may be NULL)
+ * receive the estimates after each iteration (parity tests). */
+int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char* stop_flag,
+                       se2gpu_ba_iter_stats* stats, double* trace_poses, double* trace_points);
+
+/* current estimates -> host (poses [P*3], points [L*3]) */
+int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points);
+
+/* Multi-GPU: this context owns the landmarks j with j % world == rank (call before set_problem); the reduced
+ * pose system [S | b | chi2 | scale] is summed over ranks once per LM trial through `allreduce`, which must
+ * sum (op 0) or max (op 1) `count` doubles at device pointer `buf` in place across ranks, ordered on `stream`. */
+typedef int (*se2gpu_allreduce_fn)(void* user, double* buf, size_t count, int op, void* stream);
+int se2gpu_ba_set_shard(se2gpu_ba* h, int rank, int world, se2gpu_allreduce_fn allreduce, void* user);
+/* stream all BA work is enqueued on (cudaStream_t as void*); NULL = default stream */
+int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream);
+
+/* parity/debug: linearise at the current estimate, Schur-reduce with damping `lambda`, solve; copy out whatever
+ * is non-NULL. Hpp, S: [n*n] row-major (lower triangle valid), n = 3*#free poses; bp, bs, dx_p: [n];
+ * Hll [L*9], bl [L*3], dx_l [L*3]; Hpl [E*9] (3x3 per edge, rows = pose, cols = point; original edge order).
+ * Returns n (>=0) or a negative error. Does not change the estimates. */
+int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hpp, double* bp, double* Hll, double* bl,
+                           double* Hpl, double* S, double* bs, double* dx_p, double* dx_l);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE2GPU_H */

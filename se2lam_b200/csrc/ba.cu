@@ -1,0 +1,1027 @@
+// SE(2)-XYZ local bundle adjustment on sm_100a — kernels + C ABI (include/se2gpu.h).
+//
+// Replaces, for graphs made of VertexSE2 / VertexSBAPointXYZ / EdgeSE2XYZ / PreEdgeSE2, the work done
+// inside SlamOptimizer::optimize (reference src/LocalMapper.cpp:259-260): per-edge error and analytic
+// Jacobians (src/EdgeSE2XYZ.cpp:61-106, include/se2lam/EdgeSE2XYZ.h:62-102), Huber-weighted quadratic
+// forms, Schur complement onto the pose block, the reduced solve, landmark back-substitution, the
+// additive oplus update and g2o's Levenberg-Marquardt control (restated in SURVEY.md section 8a B6-B10).
+//
+// Design (DESIGN.md section "BA"): every accumulation is a GATHER with a fixed summation order, so a run
+// is bit-reproducible and free of atomics:
+//   ba_linearize   one thread per landmark walks its (contiguous, landmark-sorted) edges: e, J, Huber,
+//                  Hll/bl in registers, per-edge Hpl and pose-side terms to SoA arrays; extra blocks do
+//                  the PreEdgeSE2 odometry edges
+//   ba_pose_reduce one warp per free pose sums the pose-side terms of its edges (CSR) -> Hpp diag, bp
+//   ba_lm_prep     per landmark (Hll+lambda I)^-1, Y_e = Hpl_e Hll^-1, g_e = Hpl_e Hll^-1 bl
+//   ba_schur       one warp per non-zero 3x3 block of S gathers its (edge,edge) pair list
+//   ba_chol_solve  one CTA: dense Cholesky of S (in shared memory when it fits) + triangular solves
+//   ba_backsub     per landmark back-substitution, x_trial = x (+) dx, gain-ratio denominator partials
+//   ba_chi2        robust chi2 at x_trial (same code path as ba_linearize without Jacobians)
+//   ba_decide      g2o's rho test / lambda schedule on device; host reads one small struct per trial
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "common.h"
+
+namespace {
+
+using se2gpu::fail;
+
+constexpr int LM_THREADS = 128;   // threads per block in per-landmark kernels
+constexpr int CHOL_THREADS = 1024;
+constexpr int SMEM_CHOL_MAX_N = 159;  // n*n*8 + 2n*8 <= 227 KB
+
+struct Cam {
+    double fx, cx, cy, Rcb[9], tcb[3], delta;
+};
+
+struct LMState {  // device-resident scalars of the LM loop (host mirrors it once per trial)
+    double lambda, ni, chi_cur, chi_before, chi_trial, scale, rho, max_diag;
+    int cur, solve_ok, accepted, trials, terminate, retry, iter, pad;
+};
+
+struct Dev {  // all device pointers of one context (passed by value to kernels)
+    int P, L, E, O, nf, n, nblk;
+    int rank, world;
+    // state
+    double* xp[2];
+    double* xl[2];
+    LMState* st;
+    // edges, landmark-sorted
+    const int *e_pose, *e_hidx, *lm_ptr;
+    const double *e_u, *e_v, *e_w00, *e_w01, *e_w11;
+    const int* hidx;
+    // odometry edges
+    const int *o_i, *o_j;
+    const double *o_m, *o_w;  // [3][O], [6][O]
+    // per-edge / per-landmark outputs (SoA, component-major)
+    double *Hpl, *PH, *Pb, *Y, *g;        // [9][E] [6][E] [3][E] [9][E] [3][E]
+    double *Hll, *bl, *HllInv;            // [6][L] [3][L] [6][L]
+    double *oAii, *oAij, *oAjj, *obi, *obj;  // [6][O] [9][O] [6][O] [3][O] [3][O]
+    // pose-side gathers
+    const int *pose_ptr, *pose_edges, *pose_odo_ptr, *pose_odo;
+    double *Hpp, *bp;                     // [6][nf], [n]
+    // reduced system
+    const int *blk_a, *blk_b, *blk_pair_ptr, *pair_e1, *pair_e2, *blk_odo_ptr, *blk_odo;
+    double *S, *bs, *scal, *dxp, *dxl;    // S [n*n] | bs [n] | scal [8] contiguous (all-reduce buffer)
+    double *part_chi, *part_scale;
+    int nb_lm, nb_odo;
+};
+
+__device__ __forceinline__ double normalize_theta(double theta) {
+    if (theta >= -M_PI && theta < M_PI) return theta;
+    double multiplier = floor(theta / (2 * M_PI));
+    theta = theta - multiplier * 2 * M_PI;
+    if (theta >= M_PI) theta -= 2 * M_PI;
+    if (theta < -M_PI) theta += 2 * M_PI;
+    return theta;
+}
+
+// EdgeSE2XYZ::computeError / linearizeOplus (EdgeSE2XYZ.cpp:61-106), closed form:
+// lc = Rcb Rz(-theta) (lw - (x,y,0)) + tcb ; e = fx*(lc.xy/lc.z) + c - uv ; M = Jpi Rcw ;
+// J_pose = [-M[:,0:2] | M (d.y,-d.x,0)^T] ; J_point = M
+template <bool JAC>
+__device__ __forceinline__ void edge_xyz(const Cam& cam, const double* __restrict__ ps, const double* __restrict__ lw,
+                                         double u, double v, double* err, double* A, double* B) {
+    double s, c;
+    sincos(ps[2], &s, &c);
+    double Rcw[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Rcw[r * 3 + 0] = cam.Rcb[r * 3 + 0] * c - cam.Rcb[r * 3 + 1] * s;
+        Rcw[r * 3 + 1] = cam.Rcb[r * 3 + 0] * s + cam.Rcb[r * 3 + 1] * c;
+        Rcw[r * 3 + 2] = cam.Rcb[r * 3 + 2];
+    }
+    const double d0 = lw[0] - ps[0], d1 = lw[1] - ps[1], d2 = lw[2];
+    double lc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) lc[r] = Rcw[r * 3] * d0 + Rcw[r * 3 + 1] * d1 + Rcw[r * 3 + 2] * d2 + cam.tcb[r];
+    const double zi = 1.0 / lc[2];
+    err[0] = lc[0] * zi * cam.fx + cam.cx - u;
+    err[1] = lc[1] * zi * cam.fx + cam.cy - v;
+    if (JAC) {
+        const double zi2 = zi * zi;
+        const double j00 = cam.fx * zi, j02 = -cam.fx * lc[0] * zi2, j12 = -cam.fx * lc[1] * zi2;
+        double M[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            M[k] = j00 * Rcw[k] + j02 * Rcw[6 + k];
+            M[3 + k] = j00 * Rcw[3 + k] + j12 * Rcw[6 + k];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            A[r * 3 + 0] = -M[r * 3 + 0];
+            A[r * 3 + 1] = -M[r * 3 + 1];
+            A[r * 3 + 2] = M[r * 3 + 0] * d1 - M[r * 3 + 1] * d0;
+            B[r * 3 + 0] = M[r * 3 + 0];
+            B[r * 3 + 1] = M[r * 3 + 1];
+            B[r * 3 + 2] = M[r * 3 + 2];
+        }
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    // deterministic: warp tree (xor shuffles) then warp 0 sums the per-warp values in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0;
+    if (w == 0) {
+        r = l < nw ? sh[l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;  // valid in warp 0
+}
+
+// ------------------------------------------------------------------------------------------------
+// linearise (JAC) or evaluate robust chi2 only (!JAC) at x[xi].  blocks [0,nb_lm): landmarks;
+// blocks [nb_lm, nb_lm+nb_odo): PreEdgeSE2 edges.  part_chi[block] = partial activeRobustChi2.
+template <bool JAC>
+__global__ void __launch_bounds__(LM_THREADS) ba_linearize(Dev d, Cam cam, int use_trial) {
+    __shared__ double sh[32];
+    const int xi = use_trial ? (d.st->cur ^ 1) : d.st->cur;
+    const double* __restrict__ xp = d.xp[xi];
+    const double* __restrict__ xl = d.xl[xi];
+    double chi = 0.0;
+    if ((int)blockIdx.x < d.nb_lm) {
+        const int j = blockIdx.x * LM_THREADS + threadIdx.x;
+        if (j < d.L) {
+            const int beg = d.lm_ptr[j], end = d.lm_ptr[j + 1];
+            if (end > beg) {
+                const double lw[3] = {xl[3 * j], xl[3 * j + 1], xl[3 * j + 2]};
+                double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
+                const double dsqr = cam.delta * cam.delta;
+                const int E = d.E;
+                for (int e = beg; e < end; ++e) {
+                    const int p = d.e_pose[e];
+                    const double ps[3] = {xp[3 * p], xp[3 * p + 1], xp[3 * p + 2]};
+                    double er[2], A[6], B[6];
+                    edge_xyz<JAC>(cam, ps, lw, d.e_u[e], d.e_v[e], er, A, B);
+                    const double w00 = d.e_w00[e], w01 = d.e_w01[e], w11 = d.e_w11[e];
+                    const double we0 = w00 * er[0] + w01 * er[1], we1 = w01 * er[0] + w11 * er[1];
+                    const double c2 = er[0] * we0 + er[1] * we1;
+                    double rho1 = 1.0;
+                    if (c2 <= dsqr) chi += c2;
+                    else { const double sq = sqrt(c2); chi += 2 * sq * cam.delta - dsqr; rho1 = cam.delta / sq; }
+                    if (JAC) {
+                        const double W00 = rho1 * w00, W01 = rho1 * w01, W11 = rho1 * w11;
+                        const double r0 = -rho1 * we0, r1 = -rho1 * we1;
+                        double BtW[6], AtW[6];
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            BtW[r * 2] = B[r] * W00 + B[3 + r] * W01; BtW[r * 2 + 1] = B[r] * W01 + B[3 + r] * W11;
+                            AtW[r * 2] = A[r] * W00 + A[3 + r] * W01; AtW[r * 2 + 1] = A[r] * W01 + A[3 + r] * W11;
+                        }
+                        h00 += BtW[0] * B[0] + BtW[1] * B[3]; h01 += BtW[0] * B[1] + BtW[1] * B[4]; h02 += BtW[0] * B[2] + BtW[1] * B[5];
+                        h11 += BtW[2] * B[1] + BtW[3] * B[4]; h12 += BtW[2] * B[2] + BtW[3] * B[5]; h22 += BtW[4] * B[2] + BtW[5] * B[5];
+                        b0 += B[0] * r0 + B[3] * r1; b1 += B[1] * r0 + B[4] * r1; b2 += B[2] * r0 + B[5] * r1;
+                        if (d.e_hidx[e] >= 0) {
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) d.Hpl[(r * 3 + c) * (size_t)E + e] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
+                            d.PH[0 * (size_t)E + e] = AtW[0] * A[0] + AtW[1] * A[3];
+                            d.PH[1 * (size_t)E + e] = AtW[0] * A[1] + AtW[1] * A[4];
+                            d.PH[2 * (size_t)E + e] = AtW[0] * A[2] + AtW[1] * A[5];
+                            d.PH[3 * (size_t)E + e] = AtW[2] * A[1] + AtW[3] * A[4];
+                            d.PH[4 * (size_t)E + e] = AtW[2] * A[2] + AtW[3] * A[5];
+                            d.PH[5 * (size_t)E + e] = AtW[4] * A[2] + AtW[5] * A[5];
+                            d.Pb[0 * (size_t)E + e] = A[0] * r0 + A[3] * r1;
+                            d.Pb[1 * (size_t)E + e] = A[1] * r0 + A[4] * r1;
+                            d.Pb[2 * (size_t)E + e] = A[2] * r0 + A[5] * r1;
+                        }
+                    }
+                }
+                if (JAC) {
+                    const size_t L = d.L;
+                    d.Hll[0 * L + j] = h00; d.Hll[1 * L + j] = h01; d.Hll[2 * L + j] = h02;
+                    d.Hll[3 * L + j] = h11; d.Hll[4 * L + j] = h12; d.Hll[5 * L + j] = h22;
+                    d.bl[0 * L + j] = b0; d.bl[1 * L + j] = b1; d.bl[2 * L + j] = b2;
+                }
+            }
+        }
+    } else {
+        // PreEdgeSE2 (EdgeSE2XYZ.h:68-99): e = [Ri^T (rj-ri) - m_xy ; thj - thi - m_th], no robust kernel
+        const int o = (blockIdx.x - d.nb_lm) * LM_THREADS + threadIdx.x;
+        if (o < d.O) {
+            const int O = d.O;
+            const int pi = d.o_i[o], pj = d.o_j[o];
+            double s, c;
+            sincos(xp[3 * pi + 2], &s, &c);
+            const double dx = xp[3 * pj] - xp[3 * pi], dy = xp[3 * pj + 1] - xp[3 * pi + 1];
+            const double e0 = c * dx + s * dy - d.o_m[o], e1 = -s * dx + c * dy - d.o_m[O + o];
+            const double e2 = xp[3 * pj + 2] - xp[3 * pi + 2] - d.o_m[2 * O + o];
+            const double w0 = d.o_w[o], w1 = d.o_w[O + o], w2 = d.o_w[2 * O + o], w3 = d.o_w[3 * O + o], w4 = d.o_w[4 * O + o], w5 = d.o_w[5 * O + o];
+            const double W[9] = {w0, w1, w2, w1, w3, w4, w2, w4, w5};
+            const double we[3] = {W[0] * e0 + W[1] * e1 + W[2] * e2, W[3] * e0 + W[4] * e1 + W[5] * e2, W[6] * e0 + W[7] * e1 + W[8] * e2};
+            chi += e0 * we[0] + e1 * we[1] + e2 * we[2];
+            if (JAC) {
+                const double rx = -dy, ry = dx;
+                const double Ai[9] = {-c, -s, -(c * rx + s * ry), s, -c, -(-s * rx + c * ry), 0, 0, -1};
+                const double Aj[9] = {c, s, 0, -s, c, 0, 0, 0, 1};
+                double AiW[9], AjW[9];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        AiW[r * 3 + k] = Ai[r] * W[k] + Ai[3 + r] * W[3 + k] + Ai[6 + r] * W[6 + k];
+                        AjW[r * 3 + k] = Aj[r] * W[k] + Aj[3 + r] * W[3 + k] + Aj[6 + r] * W[6 + k];
+                    }
+                const int u6[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int r = u6[q][0], cc = u6[q][1];
+                    d.oAii[q * (size_t)O + o] = AiW[r * 3] * Ai[cc] + AiW[r * 3 + 1] * Ai[3 + cc] + AiW[r * 3 + 2] * Ai[6 + cc];
+                    d.oAjj[q * (size_t)O + o] = AjW[r * 3] * Aj[cc] + AjW[r * 3 + 1] * Aj[3 + cc] + AjW[r * 3 + 2] * Aj[6 + cc];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        d.oAij[(r * 3 + cc) * (size_t)O + o] = AiW[r * 3] * Aj[cc] + AiW[r * 3 + 1] * Aj[3 + cc] + AiW[r * 3 + 2] * Aj[6 + cc];
+                    d.obi[r * (size_t)O + o] = -(Ai[r] * we[0] + Ai[3 + r] * we[1] + Ai[6 + r] * we[2]);
+                    d.obj[r * (size_t)O + o] = -(Aj[r] * we[0] + Aj[3 + r] * we[1] + Aj[6 + r] * we[2]);
+                }
+            }
+        }
+    }
+    const double tot = block_sum(chi, sh);
+    if (threadIdx.x == 0) d.part_chi[blockIdx.x] = tot;
+}
+
+// one warp per free pose: Hpp diagonal block (6 unique) and bp from its edges (+ its odometry edges)
+__global__ void __launch_bounds__(128) ba_pose_reduce(Dev d) {
+    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (a >= d.nf) return;
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0;
+    const size_t E = d.E, O = d.O;
+    for (int k = d.pose_ptr[a] + lane; k < d.pose_ptr[a + 1]; k += 32) {
+        const int e = d.pose_edges[k];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[q] += d.PH[q * E + e];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[6 + q] += d.Pb[q * E + e];
+    }
+    for (int k = d.pose_odo_ptr[a] + lane; k < d.pose_odo_ptr[a + 1]; k += 32) {
+        const int code = d.pose_odo[k], o = code >> 1;
+        const double* H = (code & 1) ? d.oAjj : d.oAii;
+        const double* b = (code & 1) ? d.obj : d.obi;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[q] += H[q * O + o];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[6 + q] += b[q * O + o];
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) d.Hpp[q * (size_t)d.nf + a] = acc[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) d.bp[3 * a + q] = acc[6 + q];
+    }
+}
+
+// start of an LM iteration: currentChi from the linearisation partials; lambda init at iteration 0
+// (OptimizationAlgorithmLevenberg::computeLambdaInit: 1e-5 * max |diag H| over all free vertices).
+// In sharded mode the host has all-reduced scal[0] (chi) and scal[1] (max diag) before `finish` runs.
+__global__ void __launch_bounds__(256) ba_iter_begin(Dev d, int iter, int phase /*0: local partials -> scal, 1: consume scal*/) {
+    __shared__ double sh[32];
+    if (phase == 0) {
+        double chi = 0;
+        for (int b = threadIdx.x; b < d.nb_lm + d.nb_odo; b += blockDim.x) chi += d.part_chi[b];
+        chi = block_sum(chi, sh);
+        double m = 0;
+        if (iter == 0) {
+            const size_t L = d.L, nf = d.nf;
+            for (int j = threadIdx.x; j < d.L; j += blockDim.x)
+                if (d.lm_ptr[j + 1] > d.lm_ptr[j]) m = fmax(m, fmax(fabs(d.Hll[j]), fmax(fabs(d.Hll[3 * L + j]), fabs(d.Hll[5 * L + j]))));
+            // pose diagonal is only final after the cross-rank sum; in sharded mode it is handled by the host
+            if (d.world == 1)
+                for (int a = threadIdx.x; a < d.nf; a += blockDim.x)
+                    m = fmax(m, fmax(fabs(d.Hpp[a]), fmax(fabs(d.Hpp[3 * nf + a]), fabs(d.Hpp[5 * nf + a]))));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+            __syncthreads();
+            if (threadIdx.x == 0) { m = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]); }
+        }
+        if (threadIdx.x == 0) { d.scal[0] = chi; d.scal[1] = m; }
+    }
+    if (phase == 1 || d.world == 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            LMState& s = *d.st;
+            s.chi_cur = d.scal[0]; s.chi_before = s.chi_cur;
+            if (iter == 0) { s.max_diag = d.scal[1]; s.lambda = 1e-5 * s.max_diag; s.ni = 2.0; }
+            s.trials = 0; s.accepted = 0; s.terminate = 0; s.retry = 0; s.iter = iter; s.rho = 0;
+        }
+    }
+}
+
+// per landmark: (Hll + lambda I)^-1 (symmetric, closed form), Y_e = Hpl_e Hll^-1, g_e = Hpl_e (Hll^-1 bl)
+__global__ void __launch_bounds__(LM_THREADS) ba_lm_prep(Dev d) {
+    const int j = blockIdx.x * LM_THREADS + threadIdx.x;
+    if (j >= d.L) return;
+    const int beg = d.lm_ptr[j], end = d.lm_ptr[j + 1];
+    if (end <= beg) return;
+    const size_t L = d.L, E = d.E;
+    const double lam = d.st->lambda;
+    const double a = d.Hll[j] + lam, b = d.Hll[L + j], c = d.Hll[2 * L + j], e = d.Hll[3 * L + j] + lam, f = d.Hll[4 * L + j], i = d.Hll[5 * L + j] + lam;
+    const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
+    const double det = a * c00 + b * c01 + c * c02;
+    const double id = 1.0 / det;
+    const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id, i11 = (a * i - c * c) * id, i12 = (b * c - a * f) * id, i22 = (a * e - b * b) * id;
+    d.HllInv[j] = i00; d.HllInv[L + j] = i01; d.HllInv[2 * L + j] = i02; d.HllInv[3 * L + j] = i11; d.HllInv[4 * L + j] = i12; d.HllInv[5 * L + j] = i22;
+    const double b0 = d.bl[j], b1 = d.bl[L + j], b2 = d.bl[2 * L + j];
+    const double db0 = i00 * b0 + i01 * b1 + i02 * b2, db1 = i01 * b0 + i11 * b1 + i12 * b2, db2 = i02 * b0 + i12 * b1 + i22 * b2;
+    for (int k = beg; k < end; ++k) {
+        if (d.e_hidx[k] < 0) continue;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double h0 = d.Hpl[(r * 3 + 0) * E + k], h1 = d.Hpl[(r * 3 + 1) * E + k], h2 = d.Hpl[(r * 3 + 2) * E + k];
+            d.Y[(r * 3 + 0) * E + k] = h0 * i00 + h1 * i01 + h2 * i02;
+            d.Y[(r * 3 + 1) * E + k] = h0 * i01 + h1 * i11 + h2 * i12;
+            d.Y[(r * 3 + 2) * E + k] = h0 * i02 + h1 * i12 + h2 * i22;
+            d.g[r * E + k] = h0 * db0 + h1 * db1 + h2 * db2;
+        }
+    }
+}
+
+// one warp per stored 3x3 block (a >= b) of the reduced pose Hessian:
+//   S_ab = [a==b](Hpp_aa + lambda I) + sum(odo blocks) - sum_{(e1,e2)} Y_e1 Hpl_e2^T ;   bs_a = bp_a - sum_e g_e
+__global__ void __launch_bounds__(128) ba_schur(Dev d) {
+    const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (blk >= d.nblk) return;
+    const int a = d.blk_a[blk], b = d.blk_b[blk];
+    const size_t E = d.E, O = d.O;
+    double acc[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = 0;
+    for (int k = d.blk_pair_ptr[blk] + lane; k < d.blk_pair_ptr[blk + 1]; k += 32) {
+        const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
+        double y[9], h[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { y[q] = d.Y[q * E + e1]; h[q] = d.Hpl[q * E + e2]; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
+    }
+    for (int k = d.blk_odo_ptr[blk] + lane; k < d.blk_odo_ptr[blk + 1]; k += 32) {
+        const int code = d.blk_odo[k], o = code >> 1;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + o] : d.oAij[(r * 3 + c) * O + o];
+    }
+    if (a == b)
+        for (int k = d.pose_ptr[a] + lane; k < d.pose_ptr[a + 1]; k += 32) {
+            const int e = d.pose_edges[k];
+            acc[9] -= d.g[e]; acc[10] -= d.g[E + e]; acc[11] -= d.g[2 * E + e];
+        }
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) {
+        const size_t n = d.n, nf = d.nf;
+        if (a == b) {
+            const double lam = (d.rank == 0) ? d.st->lambda : 0.0;   // damping is added once across shards
+            const double H[9] = {d.Hpp[a], d.Hpp[nf + a], d.Hpp[2 * nf + a], d.Hpp[nf + a], d.Hpp[3 * nf + a], d.Hpp[4 * nf + a],
+                                 d.Hpp[2 * nf + a], d.Hpp[4 * nf + a], d.Hpp[5 * nf + a]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d.S[(3 * a + r) * n + 3 * b + c] = acc[r * 3 + c] + H[r * 3 + c] + (r == c ? lam : 0.0);
+                d.bs[3 * a + r] = d.bp[3 * a + r] + acc[9 + r];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d.S[(3 * a + r) * n + 3 * b + c] = acc[r * 3 + c];
+        }
+    }
+}
+
+// one CTA: in-place right-looking Cholesky (lower) of the n x n matrix at A (row-major, leading dim n) with
+// the right-hand side carried as an extra row, followed by back substitution. Writes dxp and st->solve_ok.
+__device__ void chol_solve_body(double* A, double* y, int n, const double* bs, double* dxp, LMState* st) {
+    __shared__ int ok;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) ok = 1;
+    for (int i = tid; i < n; i += nt) y[i] = bs[i];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        const double akk = A[(size_t)k * n + k];
+        if (!(akk > 0.0) || !isfinite(akk)) { if (tid == 0) ok = 0; break; }   // uniform: all threads read the same akk
+        const double dkk = sqrt(akk);
+        const double inv = 1.0 / dkk;
+        // column k scale (rows k+1..n-1) and the rhs entry
+        for (int i = k + 1 + tid; i < n; i += nt) A[(size_t)i * n + k] *= inv;
+        if (tid == 0) { A[(size_t)k * n + k] = dkk; y[k] *= inv; }
+        __syncthreads();
+        // trailing update of the lower triangle (i >= j > k) and of the rhs row
+        const int m = n - k - 1;
+        const int tot = m * (m + 1) / 2;
+        for (int t = tid; t < tot; t += nt) {
+            // map t -> (ii >= jj) in the m x m lower triangle
+            int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+            while (ii * (ii + 1) / 2 > t) --ii;
+            const int jj = t - ii * (ii + 1) / 2;
+            const int i = k + 1 + ii, j = k + 1 + jj;
+            A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        }
+        for (int i = k + 1 + tid; i < n; i += nt) y[i] -= A[(size_t)i * n + k] * y[k];
+        __syncthreads();
+    }
+    __syncthreads();
+    if (ok) {
+        // back substitution L^T x = y
+        for (int k = n - 1; k >= 0; --k) {
+            if (tid == 0) y[k] /= A[(size_t)k * n + k];
+            __syncthreads();
+            const double xk = y[k];
+            for (int i = tid; i < k; i += nt) y[i] -= A[(size_t)k * n + i] * xk;
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += nt) dxp[i] = y[i];
+    } else {
+        for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
+    }
+    if (tid == 0) st->solve_ok = ok;
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
+    extern __shared__ double smem[];
+    const int n = d.n;
+    double* A = smem;
+    double* y = smem + (size_t)n * n;
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = d.S[t];
+    __syncthreads();
+    chol_solve_body(A, y, n, d.bs, d.dxp, d.st);
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_gmem(Dev d, double* ywork) {
+    chol_solve_body(d.S, ywork, d.n, d.bs, d.dxp, d.st);
+}
+
+// back-substitution + oplus into the trial buffers + partial sums of computeScale()
+__global__ void __launch_bounds__(LM_THREADS) ba_backsub_update(Dev d) {
+    __shared__ double sh[32];
+    const int t = blockIdx.x * LM_THREADS + threadIdx.x;
+    const int cur = d.st->cur;
+    const double lam = d.st->lambda;
+    const double lam_pose = (d.rank == 0) ? lam : 0.0;
+    const double* __restrict__ xp = d.xp[cur];
+    const double* __restrict__ xl = d.xl[cur];
+    double* xpt = d.xp[cur ^ 1];
+    double* xlt = d.xl[cur ^ 1];
+    double sc = 0.0;
+    if (t < d.L) {
+        const int j = t;
+        const int beg = d.lm_ptr[j], end = d.lm_ptr[j + 1];
+        const size_t L = d.L, E = d.E;
+        double dl0 = 0, dl1 = 0, dl2 = 0;
+        if (end > beg) {
+            double c0 = d.bl[j], c1 = d.bl[L + j], c2 = d.bl[2 * L + j];
+            for (int k = beg; k < end; ++k) {
+                const int a = d.e_hidx[k];
+                if (a < 0) continue;
+                const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
+                c0 -= d.Hpl[0 * E + k] * p0 + d.Hpl[3 * E + k] * p1 + d.Hpl[6 * E + k] * p2;
+                c1 -= d.Hpl[1 * E + k] * p0 + d.Hpl[4 * E + k] * p1 + d.Hpl[7 * E + k] * p2;
+                c2 -= d.Hpl[2 * E + k] * p0 + d.Hpl[5 * E + k] * p1 + d.Hpl[8 * E + k] * p2;
+            }
+            const double i00 = d.HllInv[j], i01 = d.HllInv[L + j], i02 = d.HllInv[2 * L + j], i11 = d.HllInv[3 * L + j], i12 = d.HllInv[4 * L + j], i22 = d.HllInv[5 * L + j];
+            dl0 = i00 * c0 + i01 * c1 + i02 * c2; dl1 = i01 * c0 + i11 * c1 + i12 * c2; dl2 = i02 * c0 + i12 * c1 + i22 * c2;
+            sc += dl0 * (lam * dl0 + d.bl[j]) + dl1 * (lam * dl1 + d.bl[L + j]) + dl2 * (lam * dl2 + d.bl[2 * L + j]);
+        }
+        d.dxl[3 * j] = dl0; d.dxl[3 * j + 1] = dl1; d.dxl[3 * j + 2] = dl2;
+        xlt[3 * j] = xl[3 * j] + dl0; xlt[3 * j + 1] = xl[3 * j + 1] + dl1; xlt[3 * j + 2] = xl[3 * j + 2] + dl2;
+    }
+    if (t < d.P) {
+        const int a = d.hidx[t];
+        if (a >= 0) {
+            const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
+            xpt[3 * t] = xp[3 * t] + p0; xpt[3 * t + 1] = xp[3 * t + 1] + p1;
+            xpt[3 * t + 2] = normalize_theta(xp[3 * t + 2] + p2);
+            sc += p0 * (lam_pose * p0 + d.bp[3 * a]) + p1 * (lam_pose * p1 + d.bp[3 * a + 1]) + p2 * (lam_pose * p2 + d.bp[3 * a + 2]);
+        } else {
+            xpt[3 * t] = xp[3 * t]; xpt[3 * t + 1] = xp[3 * t + 1]; xpt[3 * t + 2] = xp[3 * t + 2];
+        }
+    }
+    const double tot = block_sum(sc, sh);
+    if (threadIdx.x == 0) d.part_scale[blockIdx.x] = tot;
+}
+
+// g2o's gain-ratio test and lambda schedule (OptimizationAlgorithmLevenberg::solve) for one trial.
+// phase 0 sums the local partials into scal[0..1]; phase 1 (or single GPU) consumes them.
+__global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase, se2gpu_ba_iter_stats* stats_dev) {
+    __shared__ double sh[32];
+    if (phase == 0) {
+        double chi = 0, sc = 0;
+        for (int b = threadIdx.x; b < d.nb_lm + d.nb_odo; b += blockDim.x) chi += d.part_chi[b];
+        for (int b = threadIdx.x; b < nb_scale; b += blockDim.x) sc += d.part_scale[b];
+        chi = block_sum(chi, sh);
+        sc = block_sum(sc, sh);
+        if (threadIdx.x == 0) { d.scal[0] = chi; d.scal[1] = sc; }
+    }
+    if (phase == 1 || d.world == 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            LMState& s = *d.st;
+            const double tempChi = s.solve_ok ? d.scal[0] : DBL_MAX;
+            const double scale = (s.solve_ok ? d.scal[1] : 0.0) + 1e-3;
+            const double rho = (s.chi_cur - tempChi) / scale;
+            s.chi_trial = tempChi; s.scale = scale; s.rho = rho;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                const double sf = fmax(1. / 3., alpha);
+                s.lambda *= sf; s.ni = 2; s.chi_cur = tempChi; s.cur ^= 1; s.accepted = 1;
+            } else {
+                s.lambda *= s.ni; s.ni *= 2;
+            }
+            s.trials += 1;
+            s.retry = (rho < 0 && s.trials < 10) ? 1 : 0;
+            if (!s.retry) {
+                s.terminate = (s.trials == 10 || rho == 0) ? 1 : 0;
+                if (stats_dev) {
+                    se2gpu_ba_iter_stats& o = stats_dev[s.iter];
+                    o.chi2_before = s.chi_before; o.chi2_after = s.chi_cur; o.lambda = s.lambda; o.rho = rho;
+                    o.trials = s.trials; o.accepted = s.accepted; o.terminate = s.terminate; o.pad = 0;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+struct se2gpu_ba {
+    int device = 0;
+    int maxP = 0, maxL = 0, maxE = 0, maxO = 0, maxN = 0;
+    size_t cap_pairs = 0, cap_blk = 0;
+    cudaStream_t stream = nullptr;
+    int rank = 0, world = 1;
+    se2gpu_allreduce_fn allreduce = nullptr;
+    void* ar_user = nullptr;
+    Dev d{};
+    Cam cam{};
+    // owned device buffers
+    std::vector<void*> bufs;
+    int *e_pose = nullptr, *e_hidx = nullptr, *lm_ptr = nullptr, *hidx = nullptr, *o_i = nullptr, *o_j = nullptr;
+    double *e_u = nullptr, *e_v = nullptr, *e_w00 = nullptr, *e_w01 = nullptr, *e_w11 = nullptr, *o_m = nullptr, *o_w = nullptr;
+    int *pose_ptr = nullptr, *pose_edges = nullptr, *pose_odo_ptr = nullptr, *pose_odo = nullptr;
+    int *blk_a = nullptr, *blk_b = nullptr, *blk_pair_ptr = nullptr, *pair_e1 = nullptr, *pair_e2 = nullptr, *blk_odo_ptr = nullptr, *blk_odo = nullptr;
+    double* red = nullptr;     // all-reduce buffer [maxN*maxN + maxN + 8]
+    double* ywork = nullptr;
+    se2gpu_ba_iter_stats* stats_dev = nullptr;
+    int max_stats = 64;
+    LMState* st_host = nullptr;  // pinned
+    std::vector<int> perm;       // sorted edge position -> original edge index
+    int P = 0, L = 0, E = 0, O = 0;
+    int nb_scale = 0;
+    bool loaded = false;
+};
+
+namespace {
+
+template <class T>
+int alloc(se2gpu_ba* h, T** p, size_t count) {
+    if (se2gpu::dev_alloc(p, count) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "cudaMalloc of %zu bytes failed", count * sizeof(T));
+    h->bufs.push_back(*p);
+    return SE2GPU_OK;
+}
+
+template <class T>
+int upload(T* dst, const std::vector<T>& src, cudaStream_t s) {
+    if (src.empty()) return SE2GPU_OK;
+    SE2_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return SE2GPU_OK;
+}
+
+int ensure_cap(se2gpu_ba* h, size_t npairs, size_t nblk, size_t nblk_odo) {
+    if (npairs > h->cap_pairs) {
+        size_t cap = npairs + npairs / 4 + 1024;
+        int *a, *b;
+        if (se2gpu::dev_alloc(&a, cap) != cudaSuccess || se2gpu::dev_alloc(&b, cap) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "pair list alloc failed");
+        h->bufs.push_back(a); h->bufs.push_back(b);
+        h->pair_e1 = a; h->pair_e2 = b; h->cap_pairs = cap;
+    }
+    if (nblk + 1 > h->cap_blk) {
+        size_t cap = nblk + nblk / 4 + 1024;
+        int* p[5];
+        for (int i = 0; i < 5; ++i) { if (se2gpu::dev_alloc(&p[i], cap + 1) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "block list alloc failed"); h->bufs.push_back(p[i]); }
+        h->blk_a = p[0]; h->blk_b = p[1]; h->blk_pair_ptr = p[2]; h->blk_odo_ptr = p[3]; h->blk_odo = p[4];
+        h->cap_blk = cap;
+    }
+    (void)nblk_odo;
+    return SE2GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int max_odo, int device) {
+    if (max_poses <= 0 || max_points <= 0 || max_edges <= 0 || max_odo < 0) { fail(SE2GPU_ERR_INVALID, "bad capacities"); return nullptr; }
+    if (se2gpu::select_device(device) != SE2GPU_OK) return nullptr;
+    const size_t maxN = 3 * (size_t)max_poses;
+    if (maxN * maxN * 8 > (size_t)8 << 30) { fail(SE2GPU_ERR_CAPACITY, "dense reduced system for %d poses exceeds this build's limit", max_poses); return nullptr; }
+    se2gpu_ba* h = new se2gpu_ba;
+    h->device = device; h->maxP = max_poses; h->maxL = max_points; h->maxE = max_edges; h->maxO = max_odo; h->maxN = (int)maxN;
+    const size_t P = max_poses, L = max_points, E = max_edges, O = max_odo ? max_odo : 1;
+    int rc = SE2GPU_OK;
+    Dev& d = h->d;
+    auto A = [&](auto** p, size_t c) { if (rc == SE2GPU_OK) rc = alloc(h, p, c); };
+    A(&d.xp[0], 3 * P); A(&d.xp[1], 3 * P); A(&d.xl[0], 3 * L); A(&d.xl[1], 3 * L); A(&d.st, 1);
+    A(&h->e_pose, E); A(&h->e_hidx, E); A(&h->lm_ptr, L + 1); A(&h->hidx, P);
+    A(&h->e_u, E); A(&h->e_v, E); A(&h->e_w00, E); A(&h->e_w01, E); A(&h->e_w11, E);
+    A(&h->o_i, O); A(&h->o_j, O); A(&h->o_m, 3 * O); A(&h->o_w, 6 * O);
+    A(&d.Hpl, 9 * E); A(&d.PH, 6 * E); A(&d.Pb, 3 * E); A(&d.Y, 9 * E); A(&d.g, 3 * E);
+    A(&d.Hll, 6 * L); A(&d.bl, 3 * L); A(&d.HllInv, 6 * L);
+    A(&d.oAii, 6 * O); A(&d.oAij, 9 * O); A(&d.oAjj, 6 * O); A(&d.obi, 3 * O); A(&d.obj, 3 * O);
+    A(&h->pose_ptr, P + 1); A(&h->pose_edges, E); A(&h->pose_odo_ptr, P + 1); A(&h->pose_odo, 2 * O);
+    A(&d.Hpp, 6 * P); A(&d.bp, 3 * P);
+    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
+    const size_t nb = (L + LM_THREADS - 1) / LM_THREADS + (O + LM_THREADS - 1) / LM_THREADS + (P + LM_THREADS - 1) / LM_THREADS + 4;
+    A(&d.part_chi, nb); A(&d.part_scale, nb);
+    A(&h->stats_dev, h->max_stats);
+    if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
+    if (rc == SE2GPU_OK) {
+        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N) * 8);
+    }
+    if (rc != SE2GPU_OK) { se2gpu_ba_destroy(h); return nullptr; }
+    return h;
+}
+
+void se2gpu_ba_destroy(se2gpu_ba* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->bufs) cudaFree(p);
+    if (h->st_host) cudaFreeHost(h->st_host);
+    delete h;
+}
+
+int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    h->stream = (cudaStream_t)stream;
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_set_shard(se2gpu_ba* h, int rank, int world, se2gpu_allreduce_fn allreduce, void* user) {
+    if (!h || world < 1 || rank < 0 || rank >= world) return fail(SE2GPU_ERR_INVALID, "bad shard %d/%d", rank, world);
+    if (world > 1 && !allreduce) return fail(SE2GPU_ERR_INVALID, "sharded BA needs an allreduce callback");
+    h->rank = rank; h->world = world; h->allreduce = allreduce; h->ar_user = user;
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double* poses, const uint8_t* fixed,
+                          const double* points, const int* edge_pose, const int* edge_point, const double* uv,
+                          const double* info, const int* odo_i, const int* odo_j, const double* odo_meas,
+                          const double* odo_info, double fx, double cx, double cy, const double* Tcb, double huber_delta) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (P <= 0 || L < 0 || E < 0 || O < 0) return fail(SE2GPU_ERR_INVALID, "bad sizes");
+    if (P > h->maxP || L > h->maxL || E > h->maxE || O > h->maxO) return fail(SE2GPU_ERR_CAPACITY, "problem (%d,%d,%d,%d) exceeds capacity (%d,%d,%d,%d)", P, L, E, O, h->maxP, h->maxL, h->maxE, h->maxO);
+    SE2_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    for (int e = 0; e < E; ++e)
+        if (edge_pose[e] < 0 || edge_pose[e] >= P || edge_point[e] < 0 || edge_point[e] >= L) return fail(SE2GPU_ERR_INVALID, "edge %d references a missing vertex", e);
+    for (int o = 0; o < O; ++o)
+        if (odo_i[o] < 0 || odo_i[o] >= P || odo_j[o] < 0 || odo_j[o] >= P) return fail(SE2GPU_ERR_INVALID, "odometry edge %d references a missing vertex", o);
+
+    // --- index mapping (SparseOptimizer::buildIndexMapping): free poses in id order
+    std::vector<int> hidx(P, -1);
+    int nf = 0;
+    for (int i = 0; i < P; ++i) if (!fixed[i]) hidx[i] = nf++;
+    const int n = 3 * nf;
+    // --- shard: this rank keeps the edges of landmarks j % world == rank; odometry lives on rank 0
+    const int world = h->world, rank = h->rank;
+    std::vector<int> lm_ptr(L + 1, 0);
+    for (int e = 0; e < E; ++e) if (edge_point[e] % world == rank) lm_ptr[edge_point[e] + 1]++;
+    for (int j = 0; j < L; ++j) lm_ptr[j + 1] += lm_ptr[j];
+    const int El = lm_ptr[L];
+    std::vector<int> perm(El), cursor(lm_ptr.begin(), lm_ptr.end() - 1);
+    for (int e = 0; e < E; ++e) if (edge_point[e] % world == rank) perm[cursor[edge_point[e]]++] = e;
+    const int Ol = (rank == 0) ? O : 0;
+    std::vector<int> e_pose(El), e_hidx(El);
+    std::vector<double> e_u(El), e_v(El), w00(El), w01(El), w11(El);
+    for (int k = 0; k < El; ++k) {
+        const int e = perm[k];
+        e_pose[k] = edge_pose[e]; e_hidx[k] = hidx[edge_pose[e]];
+        e_u[k] = uv[2 * e]; e_v[k] = uv[2 * e + 1];
+        w00[k] = info[3 * e]; w01[k] = info[3 * e + 1]; w11[k] = info[3 * e + 2];
+    }
+    // --- pose CSR over sorted edges, and over odometry edges (code = 2*o + role)
+    std::vector<int> pose_ptr(nf + 1, 0), pose_edges;
+    for (int k = 0; k < El; ++k) if (e_hidx[k] >= 0) pose_ptr[e_hidx[k] + 1]++;
+    for (int a = 0; a < nf; ++a) pose_ptr[a + 1] += pose_ptr[a];
+    pose_edges.resize(pose_ptr[nf]);
+    { std::vector<int> cur(pose_ptr.begin(), pose_ptr.end() - 1); for (int k = 0; k < El; ++k) if (e_hidx[k] >= 0) pose_edges[cur[e_hidx[k]]++] = k; }
+    std::vector<int> pose_odo_ptr(nf + 1, 0), pose_odo;
+    for (int o = 0; o < Ol; ++o) { if (hidx[odo_i[o]] >= 0) pose_odo_ptr[hidx[odo_i[o]] + 1]++; if (hidx[odo_j[o]] >= 0) pose_odo_ptr[hidx[odo_j[o]] + 1]++; }
+    for (int a = 0; a < nf; ++a) pose_odo_ptr[a + 1] += pose_odo_ptr[a];
+    pose_odo.resize(pose_odo_ptr[nf]);
+    { std::vector<int> cur(pose_odo_ptr.begin(), pose_odo_ptr.end() - 1);
+      for (int o = 0; o < Ol; ++o) { int a = hidx[odo_i[o]], b = hidx[odo_j[o]]; if (a >= 0) pose_odo[cur[a]++] = 2 * o; if (b >= 0) pose_odo[cur[b]++] = 2 * o + 1; } }
+    // --- structure of the reduced system (BlockSolver::buildStructure): blocks (a>=b) touched by co-observation or odometry
+    struct Pair { long long key; int e1, e2; };
+    std::vector<Pair> pairs;
+    pairs.reserve((size_t)El * 4);
+    for (int j = 0; j < L; ++j)
+        for (int k1 = lm_ptr[j]; k1 < lm_ptr[j + 1]; ++k1) {
+            const int a = e_hidx[k1];
+            if (a < 0) continue;
+            for (int k2 = lm_ptr[j]; k2 < lm_ptr[j + 1]; ++k2) {
+                const int b = e_hidx[k2];
+                if (b < 0 || b > a) continue;
+                pairs.push_back({(long long)a * nf + b, k1, k2});
+            }
+        }
+    std::stable_sort(pairs.begin(), pairs.end(), [](const Pair& x, const Pair& y) { return x.key < y.key; });
+    struct OdoB { long long key; int code; };
+    std::vector<OdoB> odob;
+    for (int o = 0; o < Ol; ++o) {
+        const int a = hidx[odo_i[o]], b = hidx[odo_j[o]];
+        if (a < 0 || b < 0 || a == b) continue;
+        // oAij has rows = vertex i, cols = vertex j; the stored block has rows = max index
+        if (a > b) odob.push_back({(long long)a * nf + b, 2 * o});
+        else odob.push_back({(long long)b * nf + a, 2 * o + 1});
+    }
+    std::stable_sort(odob.begin(), odob.end(), [](const OdoB& x, const OdoB& y) { return x.key < y.key; });
+    std::vector<long long> keys;
+    for (int a = 0; a < nf; ++a) keys.push_back((long long)a * nf + a);
+    for (auto& p : pairs) keys.push_back(p.key);
+    for (auto& p : odob) keys.push_back(p.key);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const int nblk = (int)keys.size();
+    std::vector<int> blk_a(nblk), blk_b(nblk), blk_pair_ptr(nblk + 1, 0), blk_odo_ptr(nblk + 1, 0), pe1(pairs.size()), pe2(pairs.size()), blk_odo(odob.size());
+    { size_t ip = 0, io = 0;
+      for (int b = 0; b < nblk; ++b) {
+          blk_a[b] = (int)(keys[b] / nf); blk_b[b] = (int)(keys[b] % nf);
+          blk_pair_ptr[b] = (int)ip; blk_odo_ptr[b] = (int)io;
+          while (ip < pairs.size() && pairs[ip].key == keys[b]) { pe1[ip] = pairs[ip].e1; pe2[ip] = pairs[ip].e2; ++ip; }
+          while (io < odob.size() && odob[io].key == keys[b]) { blk_odo[io] = odob[io].code; ++io; }
+      }
+      blk_pair_ptr[nblk] = (int)ip; blk_odo_ptr[nblk] = (int)io; }
+    if (odob.size() + 1 > (size_t)2 * (h->maxO ? h->maxO : 1) + 1) return fail(SE2GPU_ERR_CAPACITY, "too many odometry blocks");
+    int rc = ensure_cap(h, pairs.size(), std::max<size_t>(nblk, odob.size()), odob.size());
+    if (rc != SE2GPU_OK) return rc;
+
+    // --- odometry SoA
+    std::vector<int> oi(Ol), oj(Ol);
+    std::vector<double> om(3 * (size_t)Ol), ow(6 * (size_t)Ol);
+    for (int o = 0; o < Ol; ++o) {
+        oi[o] = odo_i[o]; oj[o] = odo_j[o];
+        for (int q = 0; q < 3; ++q) om[q * (size_t)Ol + o] = odo_meas[3 * o + q];
+        for (int q = 0; q < 6; ++q) ow[q * (size_t)Ol + o] = odo_info[6 * o + q];
+    }
+    // --- upload
+    SE2_CUDA(cudaMemcpyAsync(h->d.xp[0], poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d.xp[1], poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d.xl[0], points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d.xl[1], points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
+#define UP(dst, src) do { int _r = upload(dst, src, s); if (_r != SE2GPU_OK) return _r; } while (0)
+    UP(h->e_pose, e_pose); UP(h->e_hidx, e_hidx); UP(h->lm_ptr, lm_ptr); UP(h->hidx, hidx);
+    UP(h->e_u, e_u); UP(h->e_v, e_v); UP(h->e_w00, w00); UP(h->e_w01, w01); UP(h->e_w11, w11);
+    UP(h->o_i, oi); UP(h->o_j, oj); UP(h->o_m, om); UP(h->o_w, ow);
+    UP(h->pose_ptr, pose_ptr); UP(h->pose_edges, pose_edges); UP(h->pose_odo_ptr, pose_odo_ptr); UP(h->pose_odo, pose_odo);
+    UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UP(h->pair_e1, pe1); UP(h->pair_e2, pe2);
+    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo);
+#undef UP
+    SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
+    LMState st0{};
+    st0.ni = 2;
+    *h->st_host = st0;
+    SE2_CUDA(cudaMemcpyAsync(h->d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+
+    Dev& d = h->d;
+    d.P = P; d.L = L; d.E = El; d.O = Ol; d.nf = nf; d.n = n; d.nblk = nblk; d.rank = rank; d.world = world;
+    d.e_pose = h->e_pose; d.e_hidx = h->e_hidx; d.lm_ptr = h->lm_ptr; d.hidx = h->hidx;
+    d.e_u = h->e_u; d.e_v = h->e_v; d.e_w00 = h->e_w00; d.e_w01 = h->e_w01; d.e_w11 = h->e_w11;
+    d.o_i = h->o_i; d.o_j = h->o_j; d.o_m = h->o_m; d.o_w = h->o_w;
+    d.pose_ptr = h->pose_ptr; d.pose_edges = h->pose_edges; d.pose_odo_ptr = h->pose_odo_ptr; d.pose_odo = h->pose_odo;
+    d.blk_a = h->blk_a; d.blk_b = h->blk_b; d.blk_pair_ptr = h->blk_pair_ptr; d.pair_e1 = h->pair_e1; d.pair_e2 = h->pair_e2;
+    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo;
+    d.S = h->red; d.bs = h->red + (size_t)n * n; d.scal = d.bs + n;
+    d.nb_lm = (L + LM_THREADS - 1) / LM_THREADS; d.nb_odo = (Ol + LM_THREADS - 1) / LM_THREADS;
+    h->nb_scale = (std::max(L, P) + LM_THREADS - 1) / LM_THREADS;
+    h->cam.fx = fx; h->cam.cx = cx; h->cam.cy = cy; h->cam.delta = huber_delta;
+    memcpy(h->cam.Rcb, Tcb, sizeof(double) * 9); memcpy(h->cam.tcb, Tcb + 9, sizeof(double) * 3);
+    h->perm = perm; h->P = P; h->L = L; h->E = E; h->O = O;
+    h->loaded = true;
+    return SE2GPU_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int ar(se2gpu_ba* h, double* buf, size_t count, int op) {
+    if (h->world == 1) return SE2GPU_OK;
+    int rc = h->allreduce(h->ar_user, buf, count, op, (void*)h->stream);
+    if (rc != 0) return fail(SE2GPU_ERR_CUDA, "allreduce callback failed (%d)", rc);
+    return SE2GPU_OK;
+}
+
+int launch_linearize(se2gpu_ba* h) {
+    Dev& d = h->d;
+    cudaStream_t s = h->stream;
+    if (d.nb_lm + d.nb_odo > 0) SE2_LAUNCH(ba_linearize<true>, d.nb_lm + d.nb_odo, LM_THREADS, 0, s, d, h->cam, 0);
+    if (d.nf > 0) SE2_LAUNCH(ba_pose_reduce, (d.nf * 32 + 127) / 128, 128, 0, s, d);
+    return SE2GPU_OK;
+}
+
+int launch_solve(se2gpu_ba* h) {
+    Dev& d = h->d;
+    cudaStream_t s = h->stream;
+    if (d.nb_lm > 0) SE2_LAUNCH(ba_lm_prep, d.nb_lm, LM_THREADS, 0, s, d);
+    // the global-memory Cholesky factorises S in place (fill-in outside the block list): re-zero it
+    if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
+    if (d.nblk > 0) SE2_LAUNCH(ba_schur, (d.nblk * 32 + 127) / 128, 128, 0, s, d);
+    int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
+    if (rc != SE2GPU_OK) return rc;
+    if (d.n > 0) {
+        if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n) * 8, s, d);
+        else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
+    }
+    return SE2GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char* stop_flag, se2gpu_ba_iter_stats* stats,
+                       double* trace_poses, double* trace_points) {
+    if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
+    if (max_iters < 0) return fail(SE2GPU_ERR_INVALID, "max_iters < 0");
+    if (max_iters > h->max_stats) return fail(SE2GPU_ERR_CAPACITY, "max_iters > %d", h->max_stats);
+    SE2_CUDA(cudaSetDevice(h->device));
+    Dev& d = h->d;
+    cudaStream_t s = h->stream;
+    int done = 0;
+    bool ok = true;
+    for (int it = 0; it < max_iters && !(stop_flag && *stop_flag) && ok; ++it) {
+        int rc = launch_linearize(h);
+        if (rc != SE2GPU_OK) return rc;
+        SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 0);
+        if (h->world > 1) {
+            // chi2 is summed; lambda_init needs max|diag| over the SUMMED pose diagonal and all landmarks
+            if ((rc = ar(h, d.scal, 1, 0)) != SE2GPU_OK) return rc;
+            if (it == 0) {
+                if ((rc = ar(h, d.scal + 1, 1, 1)) != SE2GPU_OK) return rc;   // max over ranks of the landmark diagonal
+                // pose diagonal: sum the 6 x nf block array across ranks on a scratch copy, take its max on the host
+                std::vector<double> hpp(6 * (size_t)d.nf);
+                double* scratch = d.dxl;  // free at this point; 3L >= 6nf is not guaranteed -> use S as scratch instead
+                scratch = d.S;
+                SE2_CUDA(cudaMemcpyAsync(scratch, d.Hpp, sizeof(double) * 6 * d.nf, cudaMemcpyDeviceToDevice, s));
+                if ((rc = ar(h, scratch, 6 * (size_t)d.nf, 0)) != SE2GPU_OK) return rc;
+                SE2_CUDA(cudaMemcpyAsync(hpp.data(), scratch, sizeof(double) * 6 * d.nf, cudaMemcpyDeviceToHost, s));
+                double lmmax = 0;
+                SE2_CUDA(cudaMemcpyAsync(&lmmax, d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+                SE2_CUDA(cudaStreamSynchronize(s));
+                double m = lmmax;
+                for (int a = 0; a < d.nf; ++a) m = std::max(m, std::max(std::fabs(hpp[a]), std::max(std::fabs(hpp[3 * (size_t)d.nf + a]), std::fabs(hpp[5 * (size_t)d.nf + a]))));
+                SE2_CUDA(cudaMemcpyAsync(d.scal + 1, &m, sizeof(double), cudaMemcpyHostToDevice, s));
+                SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * 6 * d.nf, s));
+            }
+            SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 1);
+        }
+        bool retry = true;
+        while (retry) {
+            if ((rc = launch_solve(h)) != SE2GPU_OK) return rc;
+            SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
+            if (d.nb_lm + d.nb_odo > 0) SE2_LAUNCH(ba_linearize<false>, d.nb_lm + d.nb_odo, LM_THREADS, 0, s, d, h->cam, 1);
+            SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 0, h->stats_dev);
+            if (h->world > 1) {
+                if ((rc = ar(h, d.scal, 2, 0)) != SE2GPU_OK) return rc;
+                SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 1, h->stats_dev);
+            }
+            SE2_CUDA(cudaMemcpyAsync(h->st_host, d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+            SE2_CUDA(cudaStreamSynchronize(s));
+            retry = h->st_host->retry && !(stop_flag && *stop_flag);
+        }
+        const LMState& st = *h->st_host;
+        if (stats) {
+            se2gpu_ba_iter_stats o{st.chi_before, st.chi_cur, st.lambda, st.rho, st.trials, st.accepted,
+                                   (st.trials == 10 || st.rho == 0) ? 1 : 0, 0};
+            stats[it] = o;
+        }
+        if (trace_poses) SE2_CUDA(cudaMemcpyAsync(trace_poses + (size_t)it * 3 * h->P, d.xp[st.cur], sizeof(double) * 3 * h->P, cudaMemcpyDeviceToHost, s));
+        if (trace_points) SE2_CUDA(cudaMemcpyAsync(trace_points + (size_t)it * 3 * h->L, d.xl[st.cur], sizeof(double) * 3 * h->L, cudaMemcpyDeviceToHost, s));
+        ok = !(st.trials == 10 || st.rho == 0);
+        ++done;
+    }
+    SE2_CUDA(cudaStreamSynchronize(s));
+    return done;
+}
+
+int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points) {
+    if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
+    SE2_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    SE2_CUDA(cudaMemcpyAsync(h->st_host, h->d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    const int cur = h->st_host->cur;
+    if (poses) SE2_CUDA(cudaMemcpyAsync(poses, h->d.xp[cur], sizeof(double) * 3 * h->P, cudaMemcpyDeviceToHost, s));
+    if (points) SE2_CUDA(cudaMemcpyAsync(points, h->d.xl[cur], sizeof(double) * 3 * h->L, cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hpp, double* bp, double* Hll, double* bl,
+                           double* Hpl, double* S, double* bs, double* dx_p, double* dx_l) {
+    if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
+    if (h->world != 1) return fail(SE2GPU_ERR_INVALID, "debug_system is single-GPU only");
+    SE2_CUDA(cudaSetDevice(h->device));
+    Dev& d = h->d;
+    cudaStream_t s = h->stream;
+    const int n = d.n, nf = d.nf, L = d.L, E = d.E;
+    int rc = launch_linearize(h);
+    if (rc != SE2GPU_OK) return rc;
+    SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, 1, 0);   // iter!=0: keeps lambda untouched, sets chi_cur
+    SE2_CUDA(cudaMemcpyAsync(h->st_host, d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    LMState saved = *h->st_host;
+    if (chi2) *chi2 = saved.chi_cur;
+    h->st_host->lambda = lambda;
+    SE2_CUDA(cudaMemcpyAsync(d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+    if (d.nb_lm > 0) SE2_LAUNCH(ba_lm_prep, d.nb_lm, LM_THREADS, 0, s, d);
+    if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
+    if (d.nblk > 0) SE2_LAUNCH(ba_schur, (d.nblk * 32 + 127) / 128, 128, 0, s, d);
+    std::vector<double> tmp;
+    auto get = [&](const double* dev, size_t cnt) { tmp.resize(cnt); return cudaMemcpyAsync(tmp.data(), dev, cnt * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess; };
+    if (S) { if (!get(d.S, (size_t)n * n)) return fail(SE2GPU_ERR_CUDA, "copy S"); memcpy(S, tmp.data(), tmp.size() * 8); }
+    if (bs) { if (!get(d.bs, n)) return fail(SE2GPU_ERR_CUDA, "copy bs"); memcpy(bs, tmp.data(), tmp.size() * 8); }
+    if (d.n > 0) {
+        if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n) * 8, s, d);
+        else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
+    }
+    SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
+    if (Hpp) {
+        if (!get(d.Hpp, 6 * (size_t)nf)) return fail(SE2GPU_ERR_CUDA, "copy Hpp");
+        // diagonal blocks only (off-diagonal odometry blocks are folded into S directly)
+        memset(Hpp, 0, sizeof(double) * n * n);
+        const int u6[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        for (int a = 0; a < nf; ++a)
+            for (int q = 0; q < 6; ++q) {
+                Hpp[(size_t)(3 * a + u6[q][0]) * n + 3 * a + u6[q][1]] = tmp[q * (size_t)nf + a];
+                Hpp[(size_t)(3 * a + u6[q][1]) * n + 3 * a + u6[q][0]] = tmp[q * (size_t)nf + a];
+            }
+    }
+    if (bp) { if (!get(d.bp, n)) return fail(SE2GPU_ERR_CUDA, "copy bp"); memcpy(bp, tmp.data(), tmp.size() * 8); }
+    if (Hll) {
+        if (!get(d.Hll, 6 * (size_t)L)) return fail(SE2GPU_ERR_CUDA, "copy Hll");
+        const int u6[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        std::vector<int> lmp(L + 1);
+        cudaMemcpy(lmp.data(), d.lm_ptr, sizeof(int) * (L + 1), cudaMemcpyDeviceToHost);
+        for (int j = 0; j < L; ++j)
+            for (int q = 0; q < 6; ++q) {
+                double v = lmp[j + 1] > lmp[j] ? tmp[q * (size_t)L + j] : 0.0;
+                Hll[9 * (size_t)j + u6[q][0] * 3 + u6[q][1]] = v; Hll[9 * (size_t)j + u6[q][1] * 3 + u6[q][0]] = v;
+            }
+    }
+    if (bl) {
+        if (!get(d.bl, 3 * (size_t)L)) return fail(SE2GPU_ERR_CUDA, "copy bl");
+        std::vector<int> lmp(L + 1);
+        cudaMemcpy(lmp.data(), d.lm_ptr, sizeof(int) * (L + 1), cudaMemcpyDeviceToHost);
+        for (int j = 0; j < L; ++j) for (int q = 0; q < 3; ++q) bl[3 * (size_t)j + q] = lmp[j + 1] > lmp[j] ? tmp[q * (size_t)L + j] : 0.0;
+    }
+    if (Hpl) {
+        if (!get(d.Hpl, 9 * (size_t)E)) return fail(SE2GPU_ERR_CUDA, "copy Hpl");
+        std::vector<int> eh(E);
+        cudaMemcpy(eh.data(), d.e_hidx, sizeof(int) * E, cudaMemcpyDeviceToHost);
+        memset(Hpl, 0, sizeof(double) * 9 * (size_t)h->E);
+        for (int k = 0; k < E; ++k) if (eh[k] >= 0) for (int q = 0; q < 9; ++q) Hpl[9 * (size_t)h->perm[k] + q] = tmp[q * (size_t)E + k];
+    }
+    if (dx_p) { if (!get(d.dxp, n)) return fail(SE2GPU_ERR_CUDA, "copy dxp"); memcpy(dx_p, tmp.data(), tmp.size() * 8); }
+    if (dx_l) { if (!get(d.dxl, 3 * (size_t)L)) return fail(SE2GPU_ERR_CUDA, "copy dxl"); memcpy(dx_l, tmp.data(), tmp.size() * 8); }
+    // restore the LM scalars (estimates were never swapped: `cur` untouched)
+    *h->st_host = saved;
+    SE2_CUDA(cudaMemcpyAsync(d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    return n;
+}
+
+}  // extern "C"

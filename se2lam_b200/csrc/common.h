@@ -1,0 +1,56 @@
+// Shared host-side helpers of libse2gpu (error reporting, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/se2gpu.h"
+
+namespace se2gpu {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<unsigned long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define SE2_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return ::se2gpu::fail(SE2GPU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// every kernel launch of the library goes through this so that se2gpu_launch_count() is exact
+#define SE2_LAUNCH(kernel, grid, block, smem, stream, ...)      \
+    do {                                                        \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \
+        ::se2gpu::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    } while (0)
+
+inline int select_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(SE2GPU_ERR_NO_DEVICE, "no CUDA device available (%s)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(SE2GPU_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    SE2_CUDA(cudaSetDevice(device));
+    return SE2GPU_OK;
+}
+
+template <class T>
+inline cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+}
+
+}  // namespace se2gpu

@@ -1,0 +1,178 @@
+"""GPU parity of the local-BA path against the CPU oracle, through the C ABI (se2gpu_ba_*).
+
+Bar: pose / landmark updates within 1e-5 relative per LM step, identical
+accept/reject decisions and lambda sequence.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from se2lam_b200 import synth
+from se2lam_b200.ba import LocalBA
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C3", "C4"])
+def test_linear_system_matches_oracle(cfg):
+    prob = synth.ba_config(cfg)
+    o = pyoracle.BAOracle(prob)
+    lin = o.linearize()
+    lam = 1e-5 * max(np.abs(np.diag(lin["Hpp"])).max(), np.abs(lin["Hll"][:, [0, 1, 2], [0, 1, 2]]).max())
+    ss = o.schur_solve(lam)
+    g = LocalBA.from_problem(prob)
+    sysm = g.debug_system(lam)
+    n = sysm["n"]
+    assert n == 3 * o.nf
+    assert sysm["chi2"] == pytest.approx(lin["chi2"], rel=1e-12)
+    free = np.flatnonzero(prob.fixed == 0)
+    for a in range(len(free)):  # diagonal blocks of Hpp (odometry off-diagonals are folded into S)
+        blk = slice(3 * a, 3 * a + 3)
+        np.testing.assert_allclose(sysm["Hpp"][blk, blk], lin["Hpp"][blk, blk], rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(sysm["bp"], lin["bp"], rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(sysm["Hll"], lin["Hll"], rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(sysm["bl"], lin["bl"], rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(sysm["Hpl"], lin["Hpl"], rtol=1e-11, atol=1e-9)
+    tril = np.tril(np.ones((n, n), bool))
+    assert rel_err(sysm["S"][tril], ss["S"][tril]) < 1e-10
+    assert rel_err(sysm["bs"], ss["bs"]) < 1e-9
+    assert rel_err(sysm["dx_p"], ss["dx_p"]) < REL
+    assert rel_err(sysm["dx_l"], ss["dx_l"]) < REL
+
+
+@pytest.mark.parametrize("cfg,iters", [("C1", 10), ("C3", 10), ("C4", 10)])
+def test_lm_trajectory_matches_oracle_per_step(cfg, iters):
+    prob = synth.ba_config(cfg)
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o, tp_o, tl_o = o.optimize(iters, trace=True)
+    g = LocalBA.from_problem(prob)
+    n_g, st_g, tp_g, tl_g = g.optimize(iters, trace=True)
+    assert n_g == n_o
+    np.testing.assert_array_equal(st_g["trials"], st_o["trials"])
+    np.testing.assert_array_equal(st_g["accepted"], st_o["accepted"])
+    np.testing.assert_array_equal(st_g["terminate"], st_o["terminate"])
+    np.testing.assert_allclose(st_g["lambda"], st_o["lambda"], rtol=1e-6)
+    np.testing.assert_allclose(st_g["chi2_after"], st_o["chi2_after"], rtol=1e-8)
+    prev_p, prev_l = prob.poses, prob.points
+    for k in range(n_o):
+        # per-step update parity: the step taken from the oracle's previous estimate, relative to its size
+        dp_o, dp_g = tp_o[k] - prev_p, tp_g[k] - prev_p
+        dl_o, dl_g = tl_o[k] - prev_l, tl_g[k] - prev_l
+        assert np.abs(dp_g - dp_o).max() <= REL * max(np.abs(dp_o).max(), 1e-12), f"pose step {k}"
+        assert np.abs(dl_g - dl_o).max() <= REL * max(np.abs(dl_o).max(), 1e-12), f"landmark step {k}"
+        prev_p, prev_l = tp_o[k], tl_o[k]
+    poses, pts = g.get()
+    np.testing.assert_array_equal(poses, tp_g[-1])
+    np.testing.assert_array_equal(poses[prob.fixed == 1], prob.poses[prob.fixed == 1])  # gauge
+
+
+def test_rejected_trials_follow_the_oracle():
+    """A badly initialised window makes LM reject steps: lambda/nu schedule and restores must agree."""
+    prob = synth.ba_window(n_kf=10, n_lm=400, seed=11)
+    rng = np.random.default_rng(1)
+    prob.points = prob.points + rng.normal(0, 1.5, prob.points.shape)
+    prob.poses[1:, :2] += rng.normal(0, 0.5, (prob.P - 1, 2))
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o, tp_o, tl_o = o.optimize(12, trace=True)
+    g = LocalBA.from_problem(prob)
+    n_g, st_g, tp_g, tl_g = g.optimize(12, trace=True)
+    assert st_o["trials"].max() > 1, "test input no longer triggers a rejected step"
+    assert n_g == n_o
+    np.testing.assert_array_equal(st_g["trials"], st_o["trials"])
+    np.testing.assert_allclose(st_g["lambda"], st_o["lambda"], rtol=1e-6)
+    np.testing.assert_allclose(tp_g[-1], tp_o[-1], rtol=0, atol=1e-6)
+
+
+def test_edge_cases_unobserved_landmarks_and_all_poses_fixed():
+    prob = synth.ba_window(n_kf=4, n_lm=50, seed=2)
+    keep = prob.edge_point != 0  # landmark 0 loses all its edges: inactive vertex, must stay untouched
+    prob.edge_pose, prob.edge_point, prob.uv, prob.info = prob.edge_pose[keep], prob.edge_point[keep], prob.uv[keep], prob.info[keep]
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o = o.optimize(5)
+    g = LocalBA.from_problem(prob)
+    n_g, st_g = g.optimize(5)
+    assert n_g == n_o
+    po, lo = o.get(); pg, lg = g.get()
+    np.testing.assert_array_equal(lg[0], prob.points[0])
+    np.testing.assert_allclose(pg, po, atol=1e-7)
+    np.testing.assert_allclose(lg, lo, atol=1e-6)
+    prob2 = synth.ba_window(n_kf=3, n_lm=30, seed=4)
+    prob2.fixed[:] = 1  # all poses fixed: only landmarks move
+    o2 = pyoracle.BAOracle(prob2); g2 = LocalBA.from_problem(prob2)
+    n_o2, _ = o2.optimize(4); n_g2, _ = g2.optimize(4)
+    assert n_g2 == n_o2
+    np.testing.assert_allclose(g2.get()[1], o2.get()[1], atol=1e-6)
+    np.testing.assert_array_equal(g2.get()[0], prob2.poses)
+
+
+def test_capacity_and_argument_errors_are_reported():
+    from se2lam_b200 import _capi
+    prob = synth.ba_config("C1")
+    g = LocalBA(1, 10, 10, 1)
+    with pytest.raises(_capi.Se2GpuError):
+        g.set_problem(prob)
+    bad = copy.copy(prob)
+    bad.edge_pose = prob.edge_pose.copy(); bad.edge_pose[0] = 99
+    g2 = LocalBA(prob.P, prob.L, prob.E, prob.O)
+    with pytest.raises(_capi.Se2GpuError):
+        g2.set_problem(bad)
+
+
+def test_full_size_properties_c4():
+    """Size-independent properties at BASELINE size: cost never increases, result independent of the
+    order in which edges are handed over (the C ABI re-sorts edges by landmark)."""
+    prob = synth.ba_config("C4")
+    g = LocalBA.from_problem(prob)
+    n, st = g.optimize(10)
+    assert np.all(st["chi2_after"] <= st["chi2_before"] * (1 + 1e-12))
+    p1, l1 = g.get()
+    perm = np.random.default_rng(0).permutation(prob.E)
+    q = copy.copy(prob)
+    q.edge_pose, q.edge_point, q.uv, q.info = prob.edge_pose[perm], prob.edge_point[perm], prob.uv[perm], prob.info[perm]
+    g2 = LocalBA.from_problem(q)
+    g2.optimize(10)
+    p2, l2 = g2.get()
+    np.testing.assert_allclose(p2, p1, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(l2, l1, rtol=0, atol=1e-8)
+
+
+def test_graph_facade_reads_like_the_reference_loader():
+    """Drive the reference-style helper API exactly the way Map::loadLocalGraph does (Map.cpp:891-1053)."""
+    from se2lam_b200 import ba as B
+    prob = synth.ba_config("C1")
+    Rbc, tbc = synth.default_Tbc()
+    opt = B.SlamOptimizer()
+    B.initOptimizer(opt)
+    K = np.array([[prob.fx, 0, prob.cx], [0, prob.fx, prob.cy], [0, 0, 1]], np.float32)
+    campr = B.addCamPara(opt, K, 0)
+    for i in range(prob.P):
+        B.addVertexSE2(opt, prob.poses[i], i, bool(prob.fixed[i]))
+    for k in range(prob.O):
+        w = prob.odo_info[k]
+        info = np.array([[w[0], w[1], w[2]], [w[1], w[3], w[4]], [w[2], w[4], w[5]]])
+        B.addEdgeSE2(opt, prob.odo_meas[k], int(prob.odo_i[k]), int(prob.odo_j[k]), info)
+    maxKFid = prob.P + 1
+    for j in range(prob.L):
+        B.addVertexSBAXYZ(opt, prob.points[j], maxKFid + j)
+    for e in range(prob.E):
+        w = prob.info[e]
+        B.addEdgeSE2XYZ(opt, prob.uv[e], int(prob.edge_pose[e]), maxKFid + int(prob.edge_point[e]), campr, (Rbc, tbc),
+                        np.array([[w[0], w[1]], [w[1], w[2]]]), prob.huber_delta)
+    opt.initializeOptimization(0)
+    n = opt.optimize(10)
+    o = pyoracle.BAOracle(prob)
+    n_o, _ = o.optimize(10)
+    assert n == n_o
+    po, lo = o.get()
+    for i in range(prob.P):
+        np.testing.assert_allclose(B.estimateVertexSE2(opt, i), po[i], atol=1e-8)
+    for j in range(0, prob.L, 17):
+        np.testing.assert_allclose(B.estimateVertexSBAXYZ(opt, maxKFid + j), lo[j], atol=1e-7)
