@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""Benchmark of the two hot paths named by BASELINE.json (one JSON line on stdout, rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU algorithm (oracle port)
+
+Primary line  = ORB keypoints/s, BASELINE configs[1]: 640x480, 8 levels, 1000 kps/frame, batch of 64 frames / GPU.
+`secondary`   = LM iterations/s, BASELINE configs[3]: 50 KF / 5000 landmarks / ~29k edges, Huber, 10 LM iterations.
+A "step" is one pass of the hot path over one batch (ORB: one 64-frame batch; BA: one optimize(10) of the window).
+
+value : device-resident throughput (inputs already in HBM, CUDA events on the launching stream)
+e2e   : the same metric through the host-buffer C-ABI call (H2D of inputs + D2H of results inside the timed region)
+roofline / cpu_baseline : see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from se2lam_b200 import synth  # noqa: E402
+
+ORB_METRIC = "ORB keypoints/sec at 640x480 (8-level pyramid, 1000 kps/frame)"
+BA_METRIC = "LM iterations/sec on 50-KF/5k-point local BA"
+W, H, NFEAT, NLEV, BATCH = 640, 480, 1000, 8, 64
+BA_ITERS = 10
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# =================================================================================================
+# reference arm: the reference's CPU algorithm (oracle port; the reference itself needs OpenCV/g2o/ROS, absent here)
+# =================================================================================================
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    nframes = max(cores, 8)
+    imgs = synth.orb_batch(min(nframes, BATCH))
+    exts = [pyoracle.OrbOracle(NFEAT, 1.2, NLEV, 20) for _ in range(cores)]
+
+    def work(k):
+        kps, _ = exts[k % cores].extract(imgs[k % len(imgs)])
+        return len(kps)
+    pool = ThreadPoolExecutor(cores)
+    for _ in range(args.warmup):
+        list(pool.map(work, range(nframes)))
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        tot += sum(pool.map(work, range(nframes)))
+    dt = time.perf_counter() - t0
+    orb_v = tot / dt
+    # BA: g2o is single-threaded -> 1 core
+    prob = synth.ba_config("C4")
+    t_ba, it_ba = 0.0, 0
+    for k in range(args.warmup + args.steps):
+        o = pyoracle.BAOracle(prob)
+        t1 = time.perf_counter()
+        n, _ = o.optimize(BA_ITERS)
+        if k >= args.warmup:
+            t_ba += time.perf_counter() - t1; it_ba += n
+    ba_v = it_ba / t_ba
+    line = {
+        "impl": "reference", "metric": ORB_METRIC, "value": orb_v, "unit": "keypoints/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "ORB extraction 640x480, 8 levels, 1000 kps/frame", "sample": f"{nframes} frames per step"},
+        "cpu_baseline": {"value": orb_v, "unit": "keypoints/s", "cores": cores, "kind": "port",
+                         "sample": f"{nframes} frames/step x {args.steps} steps, one extractor per thread"},
+        "e2e": {"value": orb_v, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "secondary": {"metric": BA_METRIC, "value": ba_v, "unit": "LM iterations/s", "higher_is_better": True, "dtype": "f64",
+                      "config": {"workload": f"local BA {prob.P} KF / {prob.L} landmarks / {prob.E} edges, Huber, {BA_ITERS} LM iterations"},
+                      "cpu_baseline": {"value": ba_v, "unit": "LM iterations/s", "cores": 1, "kind": "port",
+                                       "sample": f"{args.steps} x optimize({BA_ITERS})"},
+                      "e2e": {"value": ba_v, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+    }
+    print(json.dumps(line))
+
+
+# =================================================================================================
+# this repo's arm
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from se2lam_b200 import _capi
+    from se2lam_b200.ba import LocalBA
+    from se2lam_b200.orb import ORBextractor
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.lib()
+    hbm_peak, peak_src = peaks()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ------------------------------------------------------------------------------------------ ORB
+    NROT = 8   # distinct 64-frame input batches: 8 x 19.7 MB = 157 MB > 126 MB L2
+    base = synth.orb_batch(BATCH, first_seed=1000 + 64 * rank)
+    host_batches = []
+    for r in range(NROT):
+        b = np.roll(base, r * 7, axis=2) if r else base          # cheap distinct content, same statistics
+        host_batches.append(torch.from_numpy(np.ascontiguousarray(b)).pin_memory())
+    dev_batches = [hb.to(dev, non_blocking=True) for hb in host_batches]
+    ext = ORBextractor(NFEAT, 1.2, NLEV, fastTh=20, max_width=W, max_height=H, max_batch=BATCH, device=local_rank)
+    d_kps = torch.empty(BATCH * NFEAT * 28, dtype=torch.uint8, device=dev)
+    d_desc = torch.empty(BATCH * NFEAT * 32, dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros((max(args.steps, args.warmup) + 1, BATCH), dtype=torch.int32, device=dev)   # one row per step
+    sptr = stream.cuda_stream
+
+    def orb_step(k):
+        ext.extract_device(dev_batches[k % NROT], BATCH, H, W, d_kps, d_desc, d_counts[k], stream=sptr)
+
+    for k in range(args.warmup):
+        orb_step(k)
+    barrier()
+    ext.profile(True)
+    launches0 = lib.se2gpu_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record(stream)
+        for k in range(args.steps):
+            orb_step(k)
+        e1.record(stream)
+        barrier()
+    kp_total = d_counts[:args.steps].sum()
+    orb_ms = max_over_ranks(e0.elapsed_time(e1))
+    orb_launches = lib.se2gpu_launch_count() - launches0
+    prof = ext.profile_read()
+    ext.profile(False)
+    kps_done = sum_over_ranks(float(kp_total.item()))
+    orb_value = kps_done / (orb_ms * 1e-3)
+    # algorithmic bytes per frame: pyramid pixels P_pyr, 60 B per returned keypoint
+    P_pyr = 0
+    for l in range(NLEV):
+        wl, hl, _ = C.c_int(), C.c_int(), C.c_int()
+        lib.se2gpu_orb_level_dims(ext.h, l, C.byref(wl), C.byref(hl), C.byref(_))
+        P_pyr += wl.value * hl.value
+    kp_per_frame = kps_done / (world * args.steps * BATCH)
+    alg = {"pyramid": P_pyr, "orb_fast_cells": P_pyr, "orb_blur": P_pyr, "orb_orient_describe": 60 * kp_per_frame, "orb_select": 8 * kp_per_frame}
+    single = {g: v for g, v in prof.items() if v[1] > 0}
+    dom = max(single, key=lambda g: single[g][0])
+    dom_ms = single[dom][0] / single[dom][1]
+    achieved = alg[dom] * BATCH / (dom_ms * 1e-3) / 1e9
+    step_alg_bytes = (3 * P_pyr + 60 * kp_per_frame) * BATCH
+    roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms,
+            "kernel_share_of_step": single[dom][0] / sum(v[0] for v in single.values()),
+            "per_kernel_ms": {g: v[0] / v[1] for g, v in single.items()},
+            "whole_path_GBps": step_alg_bytes / (orb_ms / args.steps * 1e-3) / 1e9}
+    clocks = clk.summary()
+
+    # e2e: host buffers through se2gpu_orb_extract (H2D + D2H inside the timed region)
+    kps_h = torch.empty(BATCH * NFEAT * 28, dtype=torch.uint8).pin_memory().numpy().view(_capi.KP_DTYPE)
+    desc_h = torch.empty(BATCH * NFEAT * 32, dtype=torch.uint8).pin_memory().numpy()
+    counts_h = np.zeros(BATCH, np.int32)
+
+    def orb_e2e(k):
+        hb = host_batches[k % NROT].numpy()
+        _capi.check(lib.se2gpu_orb_extract(ext.h, hb.ctypes.data, BATCH, W, H, W, W * H, kps_h.ctypes.data, desc_h.ctypes.data,
+                                           counts_h.ctypes.data), "se2gpu_orb_extract")
+        return int(counts_h.sum())
+    for k in range(max(args.warmup, 1)):
+        orb_e2e(k)
+    barrier()
+    t0 = time.perf_counter()
+    tot = 0
+    for k in range(args.steps):
+        tot += orb_e2e(k)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    orb_e2e_value = sum_over_ranks(float(tot)) / (e2e_ms * 1e-3)
+
+    # ------------------------------------------------------------------------------------------ BA
+    prob = synth.ba_config("C4")
+    ar_bufs = {}
+
+    def allreduce(ptr_, count, op, strm):
+        # wrap the library's device buffer as a torch tensor (no copy) and reduce it in place on `strm`
+        key = (ptr_, count)
+        if key not in ar_bufs:
+            class _A:  # __cuda_array_interface__ holder
+                pass
+            a = _A()
+            a.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr_, False), "version": 2}
+            ar_bufs[key] = torch.as_tensor(a, device=dev)
+        t = ar_bufs[key]
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
+    ba = LocalBA.from_problem(prob, device=local_rank, rank=rank, world=world, allreduce=allreduce if world > 1 else None,
+                              stream=sptr)
+    for _ in range(max(args.warmup, 1)):
+        ba.reset(); ba.optimize(BA_ITERS)
+    barrier()
+    ba.profile(True)
+    bl0 = lib.se2gpu_launch_count()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 0
+    barrier()
+    b0.record(stream)
+    for _ in range(args.steps):
+        ba.reset()
+        n, st = ba.optimize(BA_ITERS)
+        iters += n
+    b1.record(stream)
+    barrier()
+    ba_ms = max_over_ranks(b0.elapsed_time(b1))
+    ba_launches = lib.se2gpu_launch_count() - bl0
+    bprof = ba.profile_read()
+    ba.profile(False)
+    trials = int(st["trials"].sum())
+    ba_value = iters / (ba_ms * 1e-3)
+    E, L, P, O = prob.E, prob.L, prob.P, prob.O
+    nS = (3 * (P - 1)) * (3 * (P - 1) + 1) // 2
+    # algorithmic bytes per kernel per launch (SURVEY.md section 8d terms)
+    balg = {"ba_linearize": E * (56 + 48 + 72) + L * 72, "ba_pose_reduce": P * 72 + E * 72, "ba_lm_prep": L * 72 + E * 72,
+            "ba_schur": E * 72 + L * 72 + nS * 8, "ba_chol_solve": nS * 8 * 2, "ba_backsub_update": E * 72 + L * (72 + 24) + (P + L) * 48,
+            "ba_lm_control": 0}
+    bs = {g: v for g, v in bprof.items() if v[1] > 0}
+    bdom = max(bs, key=lambda g: bs[g][0])
+    bdom_ms = bs[bdom][0] / bs[bdom][1]
+    bach = balg[bdom] / (bdom_ms * 1e-3) / 1e9
+    iter_alg = E * 424 + L * 288 + P * 120 + O * 112 + nS * 8
+    ba_roof = {"bound": "hbm", "kernel": bdom, "achieved": bach, "peak": hbm_peak, "unit": "GB/s", "frac": bach / hbm_peak, "traffic": None,
+               "peak_source": peak_src, "kernel_ms": bdom_ms, "kernel_share_of_step": bs[bdom][0] / sum(v[0] for v in bs.values()),
+               "per_kernel_ms": {g: v[0] / v[1] for g, v in bs.items()},
+               "whole_path_GBps": iter_alg / (ba_ms / max(iters, 1) * 1e-3) / 1e9,
+               "note": "the window (14 MB/iteration) is L2-resident and launch/latency bound; see DESIGN.md"}
+    # e2e: upload the window, optimise, read the estimates back, every step
+    t0 = time.perf_counter()
+    it2 = 0
+    for _ in range(args.steps):
+        ba.set_problem(prob)
+        n, _ = ba.optimize(BA_ITERS)
+        ba.get()
+        it2 += n
+    ba_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    h2d = sum(a.nbytes for a in (prob.poses, prob.points, prob.uv, prob.info, prob.odo_meas, prob.odo_info)) + 4 * (2 * E + 2 * O) + P
+    d2h = 8 * 3 * (P + L)
+
+    if rank == 0:
+        cpu_orb, cpu_ba = cpu_baselines() if world == 1 else (None, None)
+        line = {
+            "metric": ORB_METRIC, "value": orb_value, "unit": "keypoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": orb_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "ORB extraction 640x480, 8-level pyramid (scale 1.2), FAST 20/7, 1000 kps/frame, batch of 64 frames per GPU",
+                       "frames_per_step_per_gpu": BATCH, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                       "l2": f"inputs rotate over {NROT} distinct batches = {NROT * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
+                       "keypoints_per_frame": kp_per_frame},
+            "e2e": {"value": orb_e2e_value, "unit": "keypoints/s", "h2d_bytes_per_step": BATCH * W * H,
+                    "d2h_bytes_per_step": BATCH * NFEAT * 60 + BATCH * 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(orb_launches + ba_launches),
+            "roofline": roof, "clocks": clocks,
+            "secondary": {
+                "metric": BA_METRIC, "value": ba_value, "unit": "LM iterations/s", "higher_is_better": True, "dtype": "f64",
+                "scaling": "strong", "ms_per_step": ba_ms / args.steps, "iterations_per_step": iters / args.steps,
+                "lambda_trials_per_step": trials,
+                "config": {"workload": f"local BA {P} KF / {L} landmarks / {E} EdgeSE2XYZ + {O} PreEdgeSE2, Huber, {BA_ITERS} LM iterations",
+                           "parallelism": "single GPU" if world == 1 else f"landmark-sharded over {world} GPUs, 1 all-reduce of [S|b] + 1 of [chi2,scale] per trial"},
+                "e2e": {"value": it2 / (ba_e2e_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(ba_launches), "roofline": ba_roof},
+        }
+        if cpu_orb:
+            line["cpu_baseline"] = cpu_orb
+            line["secondary"]["cpu_baseline"] = cpu_ba
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baselines():
+    """The oracle port timed on this box's host cores on a bounded sample (reported baseline, not the target)."""
+    from oracle import pyoracle
+    imgs = synth.orb_batch(4)
+    o = pyoracle.OrbOracle(NFEAT, 1.2, NLEV, 20)
+    o.extract(imgs[0])
+    t0 = time.perf_counter()
+    tot = 0
+    reps = 0
+    while time.perf_counter() - t0 < 8.0:
+        for im in imgs:
+            tot += len(o.extract(im)[0])
+        reps += 1
+    dt = time.perf_counter() - t0
+    cpu_orb = {"value": tot / dt, "unit": "keypoints/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+               "sample": f"{reps * len(imgs)} frames (seeds 1000-1003 repeated), single thread, oracle -O2 no -march"}
+    prob = synth.ba_config("C4")
+    t_ba, it_ba, reps = 0.0, 0, 0
+    while t_ba < 4.0:
+        ob = pyoracle.BAOracle(prob)
+        t1 = time.perf_counter()
+        n, _ = ob.optimize(BA_ITERS)
+        t_ba += time.perf_counter() - t1; it_ba += n; reps += 1
+    cpu_ba = {"value": it_ba / t_ba, "unit": "LM iterations/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+              "sample": f"{reps} x optimize({BA_ITERS}) of the same window, single thread"}
+    return cpu_orb, cpu_ba
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

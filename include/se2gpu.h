@@ -90,6 +90,14 @@ int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w
 int se2gpu_orb_level_dims(se2gpu_orb* h, int level, int* w, int* hgt, int* pitch);
 int se2gpu_orb_get_level(se2gpu_orb* h, int frame, int level, int blurred, uint8_t* out);
 
+/* per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline line.
+ * groups: 0 pyramid (orb_pyr0 + orb_resize), 1 orb_fast_cells, 2 orb_select, 3 orb_blur, 4 orb_orient_describe.
+ * enable!=0 starts/restarts accumulation; read returns accumulated milliseconds and launch counts per group
+ * (synchronises the events it reads). */
+#define SE2GPU_ORB_PROFILE_GROUPS 5
+int se2gpu_orb_profile(se2gpu_orb* h, int enable);
+int se2gpu_orb_profile_read(se2gpu_orb* h, double* ms, int* launches);
+
 /* ------------------------------------------------------------------------------------------ matcher */
 /* DescriptorDistance for n pairs of 32-byte descriptors in HOST memory: out[i] = popcount(a_i ^ b_i) */
 int se2gpu_hamming_distance(const uint8_t* a, const uint8_t* b, int n, int* out, int device);
@@ -172,6 +180,10 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
 int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char* stop_flag,
                        se2gpu_ba_iter_stats* stats, double* trace_poses, double* trace_points);
 
+/* restore the estimates loaded by the last se2gpu_ba_set_problem (device-side copy; lets a caller re-run
+ * optimize on the same window without re-uploading it) */
+int se2gpu_ba_reset(se2gpu_ba* h);
+
 /* current estimates -> host (poses [P*3], points [L*3]) */
 int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points);
 
@@ -187,6 +199,12 @@ int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream);
  * is non-NULL. Hpp, S: [n*n] row-major (lower triangle valid), n = 3*#free poses; bp, bs, dx_p: [n];
  * Hll [L*9], bl [L*3], dx_l [L*3]; Hpl [E*9] (3x3 per edge, rows = pose, cols = point; original edge order).
  * Returns n (>=0) or a negative error. Does not change the estimates. */
+/* per-kernel device timing for bench.py's roofline line; groups: 0 ba_linearize (+chi2 evaluation), 1 ba_pose_reduce,
+ * 2 ba_lm_prep, 3 ba_schur, 4 ba_chol_solve, 5 ba_backsub_update, 6 ba_iter_begin/ba_decide */
+#define SE2GPU_BA_PROFILE_GROUPS 7
+int se2gpu_ba_profile(se2gpu_ba* h, int enable);
+int se2gpu_ba_profile_read(se2gpu_ba* h, double* ms, int* launches);
+
 int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hpp, double* bp, double* Hll, double* bl,
                            double* Hpl, double* S, double* bs, double* dx_p, double* dx_l);
 

@@ -78,6 +78,19 @@ class LocalBA:
         n = check(lib().se2gpu_ba_optimize(self.h, iters, ptr(stop_flag), ptr(st), ptr(tp), ptr(tl)), "se2gpu_ba_optimize")
         return (n, st[:n], tp[:n], tl[:n]) if trace else (n, st[:n])
 
+    PROFILE_GROUPS = ("ba_linearize", "ba_pose_reduce", "ba_lm_prep", "ba_schur", "ba_chol_solve", "ba_backsub_update", "ba_lm_control")
+
+    def reset(self):
+        check(lib().se2gpu_ba_reset(self.h), "se2gpu_ba_reset")
+
+    def profile(self, enable=True):
+        check(lib().se2gpu_ba_profile(self.h, int(enable)), "se2gpu_ba_profile")
+
+    def profile_read(self):
+        ms = np.zeros(len(self.PROFILE_GROUPS)); n = np.zeros(len(self.PROFILE_GROUPS), np.int32)
+        check(lib().se2gpu_ba_profile_read(self.h, ptr(ms), ptr(n)), "se2gpu_ba_profile_read")
+        return {g: (float(ms[i]), int(n[i])) for i, g in enumerate(self.PROFILE_GROUPS)}
+
     def get(self):
         poses = np.zeros((self.P, 3)); pts = np.zeros((self.L, 3))
         check(lib().se2gpu_ba_get(self.h, ptr(poses), ptr(pts)), "se2gpu_ba_get")

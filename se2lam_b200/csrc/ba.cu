@@ -600,6 +600,8 @@ struct se2gpu_ba {
     int P = 0, L = 0, E = 0, O = 0;
     int nb_scale = 0;
     bool loaded = false;
+    double *xp0 = nullptr, *xl0 = nullptr;   // estimates as loaded (se2gpu_ba_reset)
+    se2gpu::Profiler prof;
 };
 
 namespace {
@@ -665,6 +667,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     const size_t nb = (L + LM_THREADS - 1) / LM_THREADS + (O + LM_THREADS - 1) / LM_THREADS + (P + LM_THREADS - 1) / LM_THREADS + 4;
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
+    A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
         cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N) * 8);
@@ -800,6 +803,8 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     SE2_CUDA(cudaMemcpyAsync(h->d.xp[1], poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d.xl[0], points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d.xl[1], points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->xp0, poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->xl0, points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
 #define UP(dst, src) do { int _r = upload(dst, src, s); if (_r != SE2GPU_OK) return _r; } while (0)
     UP(h->e_pose, e_pose); UP(h->e_hidx, e_hidx); UP(h->lm_ptr, lm_ptr); UP(h->hidx, hidx);
     UP(h->e_u, e_u); UP(h->e_v, e_v); UP(h->e_w00, w00); UP(h->e_w01, w01); UP(h->e_w11, w11);
@@ -847,24 +852,34 @@ int ar(se2gpu_ba* h, double* buf, size_t count, int op) {
 int launch_linearize(se2gpu_ba* h) {
     Dev& d = h->d;
     cudaStream_t s = h->stream;
+    h->prof.begin(0, s);
     if (d.nb_lm + d.nb_odo > 0) SE2_LAUNCH(ba_linearize<true>, d.nb_lm + d.nb_odo, LM_THREADS, 0, s, d, h->cam, 0);
+    h->prof.end(s);
+    h->prof.begin(1, s);
     if (d.nf > 0) SE2_LAUNCH(ba_pose_reduce, (d.nf * 32 + 127) / 128, 128, 0, s, d);
+    h->prof.end(s);
     return SE2GPU_OK;
 }
 
 int launch_solve(se2gpu_ba* h) {
     Dev& d = h->d;
     cudaStream_t s = h->stream;
+    h->prof.begin(2, s);
     if (d.nb_lm > 0) SE2_LAUNCH(ba_lm_prep, d.nb_lm, LM_THREADS, 0, s, d);
+    h->prof.end(s);
     // the global-memory Cholesky factorises S in place (fill-in outside the block list): re-zero it
     if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
+    h->prof.begin(3, s);
     if (d.nblk > 0) SE2_LAUNCH(ba_schur, (d.nblk * 32 + 127) / 128, 128, 0, s, d);
+    h->prof.end(s);
     int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
     if (rc != SE2GPU_OK) return rc;
+    h->prof.begin(4, s);
     if (d.n > 0) {
         if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n) * 8, s, d);
         else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     }
+    h->prof.end(s);
     return SE2GPU_OK;
 }
 
@@ -885,7 +900,9 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
     for (int it = 0; it < max_iters && !(stop_flag && *stop_flag) && ok; ++it) {
         int rc = launch_linearize(h);
         if (rc != SE2GPU_OK) return rc;
+        h->prof.begin(6, s);
         SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 0);
+        h->prof.end(s);
         if (h->world > 1) {
             // chi2 is summed; lambda_init needs max|diag| over the SUMMED pose diagonal and all landmarks
             if ((rc = ar(h, d.scal, 1, 0)) != SE2GPU_OK) return rc;
@@ -911,9 +928,15 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         bool retry = true;
         while (retry) {
             if ((rc = launch_solve(h)) != SE2GPU_OK) return rc;
+            h->prof.begin(5, s);
             SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
+            h->prof.end(s);
+            h->prof.begin(0, s);
             if (d.nb_lm + d.nb_odo > 0) SE2_LAUNCH(ba_linearize<false>, d.nb_lm + d.nb_odo, LM_THREADS, 0, s, d, h->cam, 1);
+            h->prof.end(s);
+            h->prof.begin(6, s);
             SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 0, h->stats_dev);
+            h->prof.end(s);
             if (h->world > 1) {
                 if ((rc = ar(h, d.scal, 2, 0)) != SE2GPU_OK) return rc;
                 SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 1, h->stats_dev);
@@ -935,6 +958,34 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
     }
     SE2_CUDA(cudaStreamSynchronize(s));
     return done;
+}
+
+int se2gpu_ba_reset(se2gpu_ba* h) {
+    if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
+    SE2_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    LMState st0{};
+    st0.ni = 2;
+    *h->st_host = st0;
+    SE2_CUDA(cudaMemcpyAsync(h->d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d.xp[0], h->xp0, sizeof(double) * 3 * h->P, cudaMemcpyDeviceToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d.xl[0], h->xl0, sizeof(double) * 3 * h->L, cudaMemcpyDeviceToDevice, s));
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_profile(se2gpu_ba* h, int enable) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->prof.enable(enable != 0);
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_profile_read(se2gpu_ba* h, double* ms, int* launches) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->prof.flush();
+    for (int g = 0; g < SE2GPU_BA_PROFILE_GROUPS; ++g) { if (ms) ms[g] = h->prof.ms[g]; if (launches) launches[g] = h->prof.launches[g]; }
+    return SE2GPU_OK;
 }
 
 int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points) {

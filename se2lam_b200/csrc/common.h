@@ -48,6 +48,35 @@ inline int select_device(int device) {
     return SE2GPU_OK;
 }
 
+// Accumulates per-group kernel time with CUDA events recorded on the launching stream.
+struct Profiler {
+    static constexpr int MAXG = 8, MAXEV = 4096;
+    bool on = false;
+    int nev = 0;
+    cudaEvent_t ev[MAXEV][2];
+    int grp[MAXEV];
+    bool created = false;
+    double ms[MAXG] = {0};
+    int launches[MAXG] = {0};
+    void enable(bool e) {
+        if (e && !created) { for (int i = 0; i < MAXEV; ++i) { cudaEventCreate(&ev[i][0]); cudaEventCreate(&ev[i][1]); } created = true; }
+        on = e; nev = 0;
+        for (int g = 0; g < MAXG; ++g) { ms[g] = 0; launches[g] = 0; }
+    }
+    void flush() {
+        for (int i = 0; i < nev; ++i) {
+            cudaEventSynchronize(ev[i][1]);
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[i][0], ev[i][1]);
+            ms[grp[i]] += t; launches[grp[i]]++;
+        }
+        nev = 0;
+    }
+    inline void begin(int g, cudaStream_t s) { if (on) { if (nev == MAXEV) flush(); grp[nev] = g; cudaEventRecord(ev[nev][0], s); } }
+    inline void end(cudaStream_t s) { if (on) { cudaEventRecord(ev[nev][1], s); ++nev; } }
+    ~Profiler() { if (created) for (int i = 0; i < MAXEV; ++i) { cudaEventDestroy(ev[i][0]); cudaEventDestroy(ev[i][1]); } }
+};
+
 template <class T>
 inline cudaError_t dev_alloc(T** p, size_t count) {
     return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));

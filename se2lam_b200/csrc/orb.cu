@@ -1,0 +1,774 @@
+// ORB front-end on sm_100a — kernels + C ABI (include/se2gpu.h, se2gpu_orb_*).
+//
+// Replaces se2lam::ORBextractor::operator() (reference src/ORBextractor.cpp:727-788) and the OpenCV
+// primitives underneath it, for batches of frames, bit-exactly (keypoint order included):
+//   orb_pyr0 / orb_resize   ComputePyramid :790-831 (copyMakeBorder REFLECT_101, resize INTER_LINEAR: 11-bit
+//                           fixed point, each level from the previous one)
+//   orb_fast_cells          per-cell cv::FAST(…,fastTh)/FAST(…,7) :608-623 — one CTA per grid cell: the cell and
+//                           its 3 px apron are staged in shared memory once, a threshold-free arc score
+//                           M = max over the 16 nine-pixel arcs of min(+-diff) is computed per pixel
+//                           (corner at t <=> M > t, score = M-1), cell-local 3x3 strict NMS, ordered emission
+//   orb_select              quota redistribution :631-679 + KeyPointsFilter::retainBest twice :687-710 — the
+//                           libstdc++ introselect permutation is reproduced exactly (introselect.h)
+//   orb_blur                GaussianBlur 7x7 sigma 2 :769 (float32 separable, fused multiply-add, RNE to u8)
+//   orb_orient_describe     IC_Angle :130-157 + computeOrbDescriptor :160-200, one warp per keypoint; keypoint
+//                           records are written as 28-byte cv::KeyPoint and 32-byte descriptors
+// Data layout in HBM (per frame): every pyramid level is a bordered u8 plane (w+32) x (h+32) with row pitch
+// rounded up to 32 B; two copies (plain, blurred); candidates are packed 32-bit records x:12|y:12|score:8.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "introselect.h"
+
+namespace {
+
+using se2gpu::fail;
+
+constexpr int EDGE = 16;           // EDGE_THRESHOLD, ORBextractor.cpp:83
+constexpr int HALF_PATCH = 15;     // HALF_PATCH_SIZE :82
+constexpr int PATCH = 31;          // PATCH_SIZE :81
+constexpr int MAX_LEVELS = 16;
+constexpr int FAST_THREADS = 256;
+constexpr int BLUR_TW = 64, BLUR_TH = 32;
+
+__device__ const signed char d_pattern[1024] = {
+#include "orb_pattern_31.inc"
+};
+__constant__ int c_umax[16];
+__constant__ float c_gauss[7];
+
+struct LevelGeo {
+    int w, h, pitch;
+    size_t plane_off;   // byte offset of the bordered plane inside a frame's plane block
+    int nDesired, cols, rows, nCells, nfeaturesCell;
+    int cell_base;      // first cell of this level in the cell table
+    int kp_off, kp_cap; // slot range in the per-frame level keypoint buffer
+    float scale, kp_size;
+    int tab_off;        // offset of this level's resize tables (xofs | yofs) in the int table
+    int tile_base, tiles_x, tiles_y;
+};
+
+struct CellGeo {
+    int level, x0, y0, x1, y1;  // interior [x0,x1) x [y0,y1) in level ROI coordinates
+    int skipped;                // the reference's `continue` cells (:579-580, :603-604)
+    int cand_off, cand_cap;     // slot range in the per-frame candidate buffer
+};
+
+struct TileGeo { int level, x0, y0; };  // blur tile origin in bordered-plane coordinates
+
+struct CellHdr { int n_base, n_a, n_b, pad; };
+
+struct OrbDev {  // passed by value to kernels
+    int nlevels, nfeatures, fast_th, t_lo;
+    int n_cells, n_tiles;
+    const LevelGeo* levels;
+    const CellGeo* cells;
+    const TileGeo* tiles;
+    const int* itab;            // xofs/yofs tables
+    const short* stab;          // ialpha/ibeta tables (2 per entry)
+    uint8_t* plain;             // [B][frame_plane_bytes]
+    uint8_t* blurred;
+    size_t frame_plane_bytes;
+    uint32_t* cand;             // [B][cand_total]
+    size_t cand_total;
+    CellHdr* hdr;               // [B][n_cells]
+    uint32_t* lkp;              // [B][lkp_total]
+    int lkp_total;
+    int* lcount;                // [B][nlevels]
+    int* err;                   // device error flag
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101)
+__global__ void orb_pyr0(OrbDev d, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride) {
+    const LevelGeo& L = d.levels[0];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int f = blockIdx.z;
+    if (x >= L.w + 2 * EDGE) return;
+    const int sx = reflect101(x - EDGE, L.w), sy = reflect101(y - EDGE, L.h);
+    uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    plane[(size_t)y * L.pitch + x] = imgs[f * frame_stride + (size_t)sy * stride + sx];
+}
+
+// level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass
+__global__ void orb_resize(OrbDev d, int level) {
+    const LevelGeo& L = d.levels[level];
+    const LevelGeo& S = d.levels[level - 1];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int f = blockIdx.z;
+    if (x >= L.w + 2 * EDGE) return;
+    const int dx = reflect101(x - EDGE, L.w), dy = reflect101(y - EDGE, L.h);
+    const int* xofs = d.itab + L.tab_off;
+    const int* yofs = xofs + L.w;
+    const short* ialpha = d.stab + 2 * (size_t)L.tab_off;
+    const short* ibeta = ialpha + 2 * L.w;
+    const int sx = xofs[dx], sx1 = min(sx + 1, S.w - 1);
+    const int sy = yofs[dy];
+    const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+    const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
+    const int a0 = ialpha[2 * dx], a1 = ialpha[2 * dx + 1], b0 = ibeta[2 * dy], b1 = ibeta[2 * dy + 1];
+    const int r0 = src[(size_t)sy0 * S.pitch + sx] * a0 + src[(size_t)sy0 * S.pitch + sx1] * a1;
+    const int r1 = src[(size_t)sy1 * S.pitch + sx] * a0 + src[(size_t)sy1 * S.pitch + sx1] * a1;
+    int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    v = min(max(v, 0), 255);
+    uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    plane[(size_t)y * L.pitch + x] = (uint8_t)v;
+}
+
+// threshold-free FAST-9-16 arc score: M = max over the 16 nine-pixel arcs of min(+-(v - ring))
+__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int pw, int t_lo) {
+    const int v = p[0];
+    // quick reject: every 9-arc contains two adjacent compass points
+    const int c0 = v - p[3 * pw], c4 = v - p[3], c8 = v - p[-3 * pw], c12 = v - p[-3];
+    const int nd = (c0 > t_lo) + (c4 > t_lo) + (c8 > t_lo) + (c12 > t_lo);
+    const int nb = (c0 < -t_lo) + (c4 < -t_lo) + (c8 < -t_lo) + (c12 < -t_lo);
+    if (nd < 2 && nb < 2) return 0;
+    int dd[16];
+    dd[0] = c0;                      dd[1] = v - p[3 * pw + 1];   dd[2] = v - p[2 * pw + 2];   dd[3] = v - p[pw + 3];
+    dd[4] = c4;                      dd[5] = v - p[-pw + 3];      dd[6] = v - p[-2 * pw + 2];  dd[7] = v - p[-3 * pw + 1];
+    dd[8] = c8;                      dd[9] = v - p[-3 * pw - 1];  dd[10] = v - p[-2 * pw - 2]; dd[11] = v - p[-pw - 3];
+    dd[12] = c12;                    dd[13] = v - p[pw - 3];      dd[14] = v - p[2 * pw - 2];  dd[15] = v - p[3 * pw - 1];
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo2[k] = min(dd[k], dd[(k + 1) & 15]); hi2[k] = max(dd[k], dd[(k + 1) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+    int mdark = -256, mbright_neg = 256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int lo8 = min(lo4[k], lo4[(k + 4) & 15]), hi8 = max(hi4[k], hi4[(k + 4) & 15]);
+        mdark = max(mdark, min(lo8, dd[(k + 8) & 15]));
+        mbright_neg = min(mbright_neg, max(hi8, dd[(k + 8) & 15]));
+    }
+    return max(mdark, -mbright_neg);
+}
+
+// one CTA per (cell, frame)
+__global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
+    extern __shared__ uint8_t smem[];
+    __shared__ int warp_cnt[FAST_THREADS / 32];
+    __shared__ int s_base, s_na, s_nb;
+    const CellGeo c = d.cells[blockIdx.x];
+    const int f = blockIdx.y;
+    CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
+    const int cw = c.x1 - c.x0, ch = c.y1 - c.y0;
+    if (c.skipped || cw <= 0 || ch <= 0) {
+        if (threadIdx.x == 0) { hdr->n_base = 0; hdr->n_a = 0; hdr->n_b = 0; }
+        return;
+    }
+    const LevelGeo& L = d.levels[c.level];
+    const uint8_t* roi = d.plain + f * d.frame_plane_bytes + L.plane_off + (size_t)EDGE * L.pitch + EDGE;
+    const int pw = cw + 6, ph = ch + 6, sw = cw + 2, sh = ch + 2;
+    uint8_t* patch = smem;
+    uint8_t* score = smem + ((pw * ph + 15) & ~15);
+    for (int i = threadIdx.x; i < pw * ph; i += FAST_THREADS) {
+        const int py = i / pw, px = i - py * pw;
+        patch[i] = roi[(ptrdiff_t)(c.y0 - 3 + py) * L.pitch + (c.x0 - 3 + px)];
+    }
+    for (int i = threadIdx.x; i < sw * sh; i += FAST_THREADS) score[i] = 0;
+    if (threadIdx.x == 0) { s_base = 0; s_na = 0; s_nb = 0; }
+    __syncthreads();
+    const int t_lo = d.t_lo;
+    for (int i = threadIdx.x; i < cw * ch; i += FAST_THREADS) {
+        const int y = i / cw, x = i - y * cw;
+        const int m = fast_arc_score(patch + (y + 3) * pw + (x + 3), pw, t_lo);
+        if (m > t_lo) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
+    }
+    __syncthreads();
+    uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int na = 0, nb = 0;
+    for (int i0 = 0; i0 < cw * ch; i0 += FAST_THREADS) {
+        const int i = i0 + threadIdx.x;
+        int s = 0, x = 0, y = 0;
+        bool keep = false;
+        if (i < cw * ch) {
+            y = i / cw; x = i - y * cw;
+            const uint8_t* q = score + (y + 1) * sw + (x + 1);
+            s = q[0];
+            keep = s > 0 && s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base, tot = 0;
+#pragma unroll
+        for (int w = 0; w < FAST_THREADS / 32; ++w) { const int cnt = warp_cnt[w]; if (w < wid) off += cnt; tot += cnt; }
+        if (keep) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1));
+            if (pos < c.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
+            else *d.err = 1;
+            na += (s >= d.fast_th); nb += (s >= 7);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+    }
+    if (na) atomicAdd(&s_na, na);
+    if (nb) atomicAdd(&s_nb, nb);
+    __syncthreads();
+    if (threadIdx.x == 0) { hdr->n_base = s_base; hdr->n_a = s_na; hdr->n_b = s_nb; }
+}
+
+// one CTA per (level, frame): FAST fallback choice, quota redistribution, retainBest per cell and per level
+__global__ void __launch_bounds__(128) orb_select(OrbDev d) {
+    extern __shared__ uint32_t sbuf[];   // [kp_cap_smem] level list, then int arrays
+    const int level = blockIdx.x, f = blockIdx.y;
+    const LevelGeo& L = d.levels[level];
+    const int nCells = L.nCells;
+    const int cap = 2 * L.nDesired + 4 * nCells + 64;
+    uint32_t* lbuf = sbuf;
+    int* nTotal = (int*)(sbuf + cap);
+    int* nToRetain = nTotal + nCells;
+    int* kept = nToRetain + nCells;
+    int* koff = kept + nCells;
+    __shared__ int s_total;
+    const CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + L.cell_base;
+    uint32_t* cand = d.cand + (size_t)f * d.cand_total;
+    for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
+        const CellGeo& cg = d.cells[L.cell_base + c];
+        int n = 0;
+        if (!cg.skipped) {
+            const CellHdr h = hdr[c];
+            // FAST(cell, fastTh); if (size <= 3) FAST(cell, 7)   (:616-623); both are subsets of the base list
+            const int thr = (h.n_a > 3) ? d.fast_th : 7;
+            n = (h.n_a > 3) ? h.n_a : h.n_b;
+            if (n != h.n_base) {
+                uint32_t* v = cand + cg.cand_off;
+                int m = 0;
+                for (int i = 0; i < h.n_base; ++i) { const uint32_t e = v[i]; if ((int)(e >> 24) >= thr) v[m++] = e; }
+            }
+        }
+        nTotal[c] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // :625-679 (skipped cells never enter the first pass: nToRetain/nTotal stay 0, bNoMore stays false)
+        const int nfeaturesCell = L.nfeaturesCell;
+        int nNoMore = 0, nToDistribute = 0;
+        for (int c = 0; c < nCells; ++c) {
+            const bool skipped = d.cells[L.cell_base + c].skipped;
+            koff[c] = 0;  // bNoMore
+            if (skipped) { nToRetain[c] = 0; continue; }
+            if (nTotal[c] > nfeaturesCell) nToRetain[c] = nfeaturesCell;
+            else { nToRetain[c] = nTotal[c]; nToDistribute += nfeaturesCell - nTotal[c]; koff[c] = 1; nNoMore++; }
+        }
+        while (nToDistribute > 0 && nNoMore < nCells) {
+            const int nNew = (int)((float)nfeaturesCell + ceilf((float)nToDistribute / (float)(nCells - nNoMore)));
+            nToDistribute = 0;
+            for (int c = 0; c < nCells; ++c)
+                if (!koff[c]) {
+                    if (nTotal[c] > nNew) nToRetain[c] = nNew;
+                    else { nToRetain[c] = nTotal[c]; nToDistribute += nNew - nTotal[c]; koff[c] = 1; nNoMore++; }
+                }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
+        const int n = nToRetain[c], tot = nTotal[c];
+        int k = tot;
+        if (tot > n) {  // KeyPointsFilter::retainBest + resize (:692-694)
+            k = n;
+            if (n > 0) se2gpu::kp_nth_element(cand + d.cells[L.cell_base + c].cand_off, tot, n - 1);
+        }
+        kept[c] = k;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int c = 0; c < nCells; ++c) { koff[c] = o; o += kept[c]; }
+        if (o > cap) { *d.err = 2; o = cap; }
+        s_total = o;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
+        const uint32_t* v = cand + d.cells[L.cell_base + c].cand_off;
+        const int o = koff[c];
+        for (int i = 0; i < kept[c] && o + i < cap; ++i) lbuf[o + i] = v[i];
+    }
+    __syncthreads();
+    int total = s_total;
+    if (total > L.nDesired) {  // :706-710
+        if (threadIdx.x == 0) se2gpu::kp_nth_element(lbuf, total, L.nDesired - 1);
+        total = L.nDesired;
+        __syncthreads();
+    }
+    uint32_t* out = d.lkp + (size_t)f * d.lkp_total + L.kp_off;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) out[i] = lbuf[i];
+    if (threadIdx.x == 0) d.lcount[f * d.nlevels + level] = total;
+}
+
+// GaussianBlur 7x7 sigma 2 on the level ROI; the 16 px ring keeps its un-blurred reflect-101 copies
+__global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
+    __shared__ uint8_t patch[(BLUR_TH + 6) * (BLUR_TW + 8)];
+    __shared__ float rowp[(BLUR_TH + 6) * BLUR_TW];
+    const TileGeo t = d.tiles[blockIdx.x];
+    const int f = blockIdx.y;
+    const LevelGeo& L = d.levels[t.level];
+    const uint8_t* src = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    uint8_t* dst = d.blurred + f * d.frame_plane_bytes + L.plane_off;
+    const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
+    constexpr int PW = BLUR_TW + 8;
+    // stage tile + 3 px apron (clamped reads; aprons outside the plane are never used by interior pixels)
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
+        const int py = i / (BLUR_TW + 6), px = i - py * (BLUR_TW + 6);
+        const int gy = min(max(t.y0 - 3 + py, 0), H - 1), gx = min(max(t.x0 - 3 + px, 0), W - 1);
+        patch[py * PW + px] = src[(size_t)gy * L.pitch + gx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
+        const int py = i / BLUR_TW, px = i - py * BLUR_TW;
+        const uint8_t* S = patch + py * PW + px;
+        float s = __fmul_rn(c_gauss[0], (float)S[0]);
+#pragma unroll
+        for (int k = 1; k < 7; ++k) s = __fmaf_rn(c_gauss[k], (float)S[k], s);
+        rowp[i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW; i += 256) {
+        const int py = i / BLUR_TW, px = i - py * BLUR_TW;
+        const int gx = t.x0 + px, gy = t.y0 + py;
+        if (gx >= W || gy >= H) continue;
+        uint8_t o;
+        if (gx >= EDGE && gx < EDGE + L.w && gy >= EDGE && gy < EDGE + L.h) {
+            const float* c = rowp + (py + 3) * BLUR_TW + px;
+            float s = __fmul_rn(c_gauss[3], c[0]);
+#pragma unroll
+            for (int k = 1; k <= 3; ++k) s = __fmaf_rn(c_gauss[3 + k], __fadd_rn(c[k * BLUR_TW], c[-k * BLUR_TW]), s);
+            const int iv = __float2int_rn(s);
+            o = (uint8_t)min(max(iv, 0), 255);
+        } else {
+            o = patch[(py + 3) * PW + px + 3];
+        }
+        dst[(size_t)gy * L.pitch + gx] = o;
+    }
+}
+
+// cv::fastAtan2 (degrees), scalar float path without contraction
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float p1 = 0.9997878412794807f * (float)(180 / M_PI);
+    const float p3 = -0.3258083974640975f * (float)(180 / M_PI);
+    const float p5 = 0.1555786518463281f * (float)(180 / M_PI);
+    const float p7 = -0.04432655554792128f * (float)(180 / M_PI);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// one warp per output keypoint slot: orientation on the plain level, descriptor on the blurred level
+__global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
+                                                           int* __restrict__ counts) {
+    __shared__ signed char pat[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) pat[i] = d_pattern[i];
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int* lc = d.lcount + f * d.nlevels;
+    int level = -1, off = 0, total = 0;
+    for (int l = 0; l < d.nlevels; ++l) {
+        const int c = lc[l];
+        if (level < 0 && slot < total + c) { level = l; off = total; }
+        total += c;
+    }
+    if (slot == 0 && lane == 0) counts[f] = total;
+    if (level < 0) return;
+    const LevelGeo& L = d.levels[level];
+    const uint32_t rec = d.lkp[(size_t)f * d.lkp_total + L.kp_off + (slot - off)];
+    const int x = rec & 0xFFF, y = (rec >> 12) & 0xFFF, score = rec >> 24;
+    const size_t base = f * d.frame_plane_bytes + L.plane_off + (size_t)(EDGE + y) * L.pitch + (EDGE + x);
+    const uint8_t* center = d.plain + base;
+    // IC_Angle: lanes own a column u = lane-15 of the 31x31 patch, rows +-v limited by umax
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - HALF_PATCH, au = abs(u);
+        int colsum = 0;
+        for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) {
+            if (au <= c_umax[abs(v)]) {
+                const int val = center[(ptrdiff_t)v * L.pitch + u];
+                colsum += val; m01 += v * val;
+            }
+        }
+        m10 = u * colsum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // steered BRIEF: a = (float)cos((double)angle_rad), b = (float)sin(...)
+    const float factorPI = (float)(M_PI / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
+    const uint8_t* bc = d.blurred + base;
+    const signed char* pp = pat + lane * 32;
+    unsigned val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1], x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = bc[(ptrdiff_t)r0 * L.pitch + c0], t1 = bc[(ptrdiff_t)r1 * L.pitch + c1];
+        val |= (unsigned)(t0 < t1) << k;
+    }
+    // pack 4 bytes per lane group: lane 4q gets bytes 4q..4q+3
+    unsigned w = val;
+    w |= __shfl_down_sync(0xffffffffu, val, 1) << 8;
+    w |= __shfl_down_sync(0xffffffffu, val, 2) << 16;
+    w |= __shfl_down_sync(0xffffffffu, val, 3) << 24;
+    const size_t oslot = (size_t)f * d.nfeatures + slot;
+    if ((lane & 3) == 0) reinterpret_cast<unsigned*>(desc + oslot * 32)[lane >> 2] = w;
+    if (lane == 0) {
+        se2gpu_keypoint kp;
+        kp.x = level ? __fmul_rn((float)x, L.scale) : (float)x;
+        kp.y = level ? __fmul_rn((float)y, L.scale) : (float)y;
+        kp.size = L.kp_size; kp.angle = angle; kp.response = (float)score; kp.octave = level; kp.class_id = -1;
+        kps[oslot] = kp;
+    }
+}
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+}  // namespace
+
+// =================================================================================================
+struct se2gpu_orb {
+    int device = 0, nfeatures = 0, nlevels = 0, fast_th = 20, max_w = 0, max_h = 0, max_batch = 0;
+    double scaleFactor = 1.2;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor;
+    std::vector<int> mnFeaturesPerLevel;
+    // geometry of the current frame size
+    int cur_w = -1, cur_h = -1;
+    std::vector<LevelGeo> levels;
+    std::vector<CellGeo> cells;
+    std::vector<TileGeo> tiles;
+    size_t fast_smem = 0, select_smem = 0;
+    // capacities (computed for max_w x max_h)
+    size_t cap_plane = 0, cap_cand = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0, cap_lkp = 0;
+    OrbDev d{};
+    LevelGeo* d_levels = nullptr; CellGeo* d_cells = nullptr; TileGeo* d_tiles = nullptr; int* d_itab = nullptr; short* d_stab = nullptr;
+    uint8_t* d_in = nullptr; se2gpu_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_counts = nullptr;
+    std::vector<void*> bufs;
+    int last_n = 0;
+    se2gpu::Profiler prof;
+};
+
+namespace {
+
+// level geometry exactly as ORBextractor::ComputePyramid / ComputeKeyPoints derive it (float32 arithmetic)
+int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes, size_t* cand_total, size_t* n_cells,
+                   size_t* n_tiles, size_t* tab_total, size_t* max_fast_smem, size_t* max_select_smem,
+                   std::vector<LevelGeo>* Lv, std::vector<CellGeo>* Cv, std::vector<TileGeo>* Tv) {
+    (void)dry;
+    const int nl = h->nlevels;
+    std::vector<LevelGeo> L(nl);
+    std::vector<CellGeo> C;
+    std::vector<TileGeo> T;
+    size_t poff = 0, coff = 0, toff = 0, fsm = 0, ssm = 0;
+    int kp_off = 0;
+    const float imageRatio = (float)w / (float)hgt;   // mvImagePyramid[0].cols/rows (:538)
+    for (int l = 0; l < nl; ++l) {
+        LevelGeo& g = L[l];
+        const float scale = h->mvInvScaleFactor[l];
+        g.w = cv_round_f((float)w * scale); g.h = cv_round_f((float)hgt * scale);   // :794-795
+        if (g.w < 2 * EDGE + 7 || g.h < 2 * EDGE + 7) return fail(SE2GPU_ERR_INVALID, "level %d of a %dx%d frame is %dx%d: too small for the 16 px border", l, w, hgt, g.w, g.h);
+        if (g.w + 2 * EDGE > 4095 || g.h + 2 * EDGE > 4095) return fail(SE2GPU_ERR_CAPACITY, "frames wider/taller than 4063 px are not supported");
+        g.pitch = (g.w + 2 * EDGE + 31) & ~31;
+        g.plane_off = poff;
+        poff += (size_t)g.pitch * (g.h + 2 * EDGE);
+        poff = (poff + 255) & ~(size_t)255;
+        g.nDesired = h->mnFeaturesPerLevel[l];
+        g.cols = (int)sqrtf((float)g.nDesired / (5 * imageRatio));   // :542
+        g.rows = (int)(imageRatio * g.cols);                          // :543
+        if (g.cols < 1 || g.rows < 1) return fail(SE2GPU_ERR_INVALID, "level %d has a %dx%d cell grid (nfeatures too small): undefined in the reference", l, g.cols, g.rows);
+        const int minB = EDGE, maxBX = g.w - EDGE, maxBY = g.h - EDGE;
+        const int W = maxBX - minB, H = maxBY - minB;
+        const int cellW = (int)ceilf((float)W / g.cols), cellH = (int)ceilf((float)H / g.rows);
+        g.nCells = g.rows * g.cols;
+        g.nfeaturesCell = (int)ceilf((float)g.nDesired / g.nCells);
+        g.cell_base = (int)C.size();
+        g.kp_off = kp_off; g.kp_cap = g.nDesired; kp_off += g.nDesired;
+        g.scale = h->mvScaleFactor[l];
+        g.kp_size = (float)(int)(PATCH * h->mvScaleFactor[l]);
+        g.tab_off = (int)toff; toff += (size_t)g.w + g.h;
+        std::vector<int> iniXCol(g.cols, 0);
+        float hY = cellH + 6;
+        for (int i = 0; i < g.rows; ++i) {
+            const float iniY = minB + i * cellH - 3;
+            bool rowSkipped = false;
+            if (i == g.rows - 1) { hY = maxBY + 3 - iniY; if (hY <= 0) rowSkipped = true; }
+            float hX = cellW + 6;
+            for (int j = 0; j < g.cols; ++j) {
+                CellGeo c{};
+                c.level = l;
+                if (rowSkipped) { c.skipped = 1; C.push_back(c); continue; }
+                float iniX;
+                if (i == 0) { iniX = minB + j * cellW - 3; iniXCol[j] = (int)iniX; } else iniX = iniXCol[j];
+                if (j == g.cols - 1) { hX = maxBX + 3 - iniX; if (hX <= 0) { c.skipped = 1; C.push_back(c); continue; } }
+                const int r0 = (int)iniY, r1 = (int)(iniY + hY), c0 = (int)iniX, c1 = (int)(iniX + hX);
+                if (r1 > g.h || c1 > g.w || r0 < 0 || c0 < 0) return fail(SE2GPU_ERR_INVALID, "cell grid of level %d leaves the image (the reference asserts here)", l);
+                c.x0 = c0 + 3; c.x1 = c1 - 3; c.y0 = r0 + 3; c.y1 = r1 - 3;
+                const int cw = std::max(c.x1 - c.x0, 0), chh = std::max(c.y1 - c.y0, 0);
+                c.cand_off = (int)coff;
+                c.cand_cap = ((cw + 1) / 2) * ((chh + 1) / 2) + 8;   // strict 3x3 maxima: at most one per 2x2 block
+                coff += c.cand_cap;
+                if (cw > 0 && chh > 0) fsm = std::max(fsm, (size_t)(((cw + 6) * (chh + 6) + 15) & ~15) + (size_t)(cw + 2) * (chh + 2));
+                C.push_back(c);
+            }
+        }
+        ssm = std::max(ssm, (size_t)(2 * g.nDesired + 4 * g.nCells + 64) * 4 + (size_t)g.nCells * 16);
+        g.tile_base = (int)T.size();
+        g.tiles_x = (g.w + 2 * EDGE + BLUR_TW - 1) / BLUR_TW; g.tiles_y = (g.h + 2 * EDGE + BLUR_TH - 1) / BLUR_TH;
+        for (int ty = 0; ty < g.tiles_y; ++ty) for (int tx = 0; tx < g.tiles_x; ++tx) T.push_back(TileGeo{l, tx * BLUR_TW, ty * BLUR_TH});
+    }
+    *plane_bytes = poff; *cand_total = coff; *n_cells = C.size(); *n_tiles = T.size(); *tab_total = toff;
+    *max_fast_smem = fsm; *max_select_smem = ssm;
+    if (Lv) *Lv = L;
+    if (Cv) *Cv = C;
+    if (Tv) *Tv = T;
+    return SE2GPU_OK;
+}
+
+int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
+    if (w == h->cur_w && hgt == h->cur_h) return SE2GPU_OK;
+    size_t pb, ct, nc, nt, tt, fsm, ssm;
+    int rc = build_geometry(h, w, hgt, false, &pb, &ct, &nc, &nt, &tt, &fsm, &ssm, &h->levels, &h->cells, &h->tiles);
+    if (rc != SE2GPU_OK) return rc;
+    if (pb > h->cap_plane || ct > h->cap_cand || nc > h->cap_cells || nt > h->cap_tiles || tt > h->cap_tab)
+        return fail(SE2GPU_ERR_CAPACITY, "frame %dx%d exceeds the capacity this extractor was created with (%dx%d)", w, hgt, h->max_w, h->max_h);
+    if (fsm > 227 * 1024) return fail(SE2GPU_ERR_CAPACITY, "a FAST cell of a %dx%d frame needs %zu B of shared memory", w, hgt, fsm);
+    // resize tables [upstream OpenCV resize.cpp: fixed-point bilinear coefficient tables]
+    std::vector<int> itab(tt, 0);
+    std::vector<short> stab(2 * tt, 0);
+    for (int l = 1; l < h->nlevels; ++l) {
+        const LevelGeo& g = h->levels[l];
+        const LevelGeo& sg = h->levels[l - 1];
+        const double scale_x = 1. / ((double)g.w / sg.w), scale_y = 1. / ((double)g.h / sg.h);
+        int* xofs = itab.data() + g.tab_off; int* yofs = xofs + g.w;
+        short* ialpha = stab.data() + 2 * (size_t)g.tab_off; short* ibeta = ialpha + 2 * g.w;
+        for (int dx = 0; dx < g.w; ++dx) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= sg.w - 1) { fx = 0; sx = sg.w - 1; }
+            xofs[dx] = sx;
+            ialpha[2 * dx] = (short)std::min(std::max(cv_round_f((1.f - fx) * 2048.f), -32768), 32767);
+            ialpha[2 * dx + 1] = (short)std::min(std::max(cv_round_f(fx * 2048.f), -32768), 32767);
+        }
+        for (int dy = 0; dy < g.h; ++dy) {
+            float fy = (float)((dy + 0.5) * scale_y - 0.5);
+            int sy = (int)floorf(fy);
+            fy -= sy;
+            yofs[dy] = sy;
+            ibeta[2 * dy] = (short)cv_round_f((1.f - fy) * 2048.f);
+            ibeta[2 * dy + 1] = (short)cv_round_f(fy * 2048.f);
+        }
+    }
+    SE2_CUDA(cudaMemcpyAsync(h->d_levels, h->levels.data(), sizeof(LevelGeo) * h->levels.size(), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d_cells, h->cells.data(), sizeof(CellGeo) * h->cells.size(), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d_tiles, h->tiles.data(), sizeof(TileGeo) * h->tiles.size(), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d_itab, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d_stab, stab.data(), sizeof(short) * stab.size(), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    h->fast_smem = fsm; h->select_smem = ssm;
+    SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
+    SE2_CUDA(cudaFuncSetAttribute(orb_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ssm, 1024)));
+    OrbDev& d = h->d;
+    d.n_cells = (int)h->cells.size(); d.n_tiles = (int)h->tiles.size();
+    d.frame_plane_bytes = pb; d.cand_total = ct;
+    int lk = 0; for (auto& g : h->levels) lk += g.kp_cap;
+    d.lkp_total = lk;
+    h->cur_w = w; h->cur_h = hgt;
+    return SE2GPU_OK;
+}
+
+int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+               se2gpu_keypoint* d_kps, uint8_t* d_desc, int* d_counts, cudaStream_t s) {
+    int rc = set_geometry(h, w, hgt, s);
+    if (rc != SE2GPU_OK) return rc;
+    OrbDev& d = h->d;
+    se2gpu::Profiler& pr = h->prof;
+    pr.begin(0, s);
+    {
+        const LevelGeo& g = h->levels[0];
+        dim3 grid((g.w + 2 * EDGE + 127) / 128, g.h + 2 * EDGE, n);
+        SE2_LAUNCH(orb_pyr0, grid, 128, 0, s, d, d_imgs, stride, frame_stride);
+    }
+    for (int l = 1; l < h->nlevels; ++l) {
+        const LevelGeo& g = h->levels[l];
+        dim3 grid((g.w + 2 * EDGE + 127) / 128, g.h + 2 * EDGE, n);
+        SE2_LAUNCH(orb_resize, grid, 128, 0, s, d, l);
+    }
+    pr.end(s);
+    pr.begin(1, s);
+    SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
+    pr.end(s);
+    pr.begin(2, s);
+    SE2_LAUNCH(orb_select, dim3(h->nlevels, n), 128, h->select_smem, s, d);
+    pr.end(s);
+    pr.begin(3, s);
+    SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, s, d);
+    pr.end(s);
+    const int warps = 8;
+    pr.begin(4, s);
+    SE2_LAUNCH(orb_orient_describe, dim3((h->nfeatures + warps - 1) / warps, n), warps * 32, 0, s, d, d_kps, d_desc, d_counts);
+    pr.end(s);
+    h->last_n = n;
+    return SE2GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, int fast_th, int max_w, int max_h,
+                              int max_batch, int device) {
+    if (nfeatures <= 0 || nlevels <= 0 || nlevels > MAX_LEVELS || !(scale_factor > 1.0f) || fast_th < 1 || fast_th > 254 ||
+        max_w <= 0 || max_h <= 0 || max_batch <= 0) { fail(SE2GPU_ERR_INVALID, "bad ORB parameters"); return nullptr; }
+    if (se2gpu::select_device(device) != SE2GPU_OK) return nullptr;
+    se2gpu_orb* h = new se2gpu_orb;
+    h->device = device; h->nfeatures = nfeatures; h->nlevels = nlevels; h->fast_th = fast_th;
+    h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch;
+    h->scaleFactor = scale_factor;   // the reference keeps it in a double member (ORBextractor.h:67)
+    // ORBextractor::ORBextractor, ORBextractor.cpp:463-520
+    h->mvScaleFactor.resize(nlevels); h->mvInvScaleFactor.resize(nlevels); h->mnFeaturesPerLevel.resize(nlevels);
+    h->mvScaleFactor[0] = 1;
+    for (int i = 1; i < nlevels; i++) h->mvScaleFactor[i] = (float)(h->mvScaleFactor[i - 1] * h->scaleFactor);
+    const float invScaleFactor = (float)(1.0f / h->scaleFactor);
+    h->mvInvScaleFactor[0] = 1;
+    for (int i = 1; i < nlevels; i++) h->mvInvScaleFactor[i] = h->mvInvScaleFactor[i - 1] * invScaleFactor;
+    const float factor = (float)(1.0 / h->scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) { h->mnFeaturesPerLevel[l] = cv_round_f(nDesired); sum += h->mnFeaturesPerLevel[l]; nDesired *= factor; }
+    h->mnFeaturesPerLevel[nlevels - 1] = std::max(nfeatures - sum, 0);
+    if (sum > nfeatures) { fail(SE2GPU_ERR_INVALID, "per-level quotas sum to %d > nfeatures %d for these parameters", sum, nfeatures); delete h; return nullptr; }
+    int umax[16];
+    {
+        int v, v0, vmax = (int)floorf(HALF_PATCH * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(HALF_PATCH * sqrtf(2.f) / 2);
+        const double hp2 = HALF_PATCH * HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) umax[v] = (int)lrint(sqrt(hp2 - v * v));
+        for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) { while (umax[v0] == umax[v0 + 1]) ++v0; umax[v] = v0; ++v0; }
+    }
+    float gk[7];
+    { double g[7], s = 0; for (int i = 0; i < 7; ++i) { double x = i - 3; g[i] = std::exp(-0.5 * x * x / 4.0); s += g[i]; } for (int i = 0; i < 7; ++i) gk[i] = (float)(g[i] * (1. / s)); }
+    size_t pb, ct, nc, nt, tt, fsm, ssm;
+    int rc = build_geometry(h, max_w, max_h, true, &pb, &ct, &nc, &nt, &tt, &fsm, &ssm, nullptr, nullptr, nullptr);
+    if (rc != SE2GPU_OK) { delete h; return nullptr; }
+    // head-room so that smaller frames (different cell rounding) always fit
+    h->cap_plane = pb + 4096; h->cap_cand = ct + ct / 8 + 4096; h->cap_cells = nc + 64; h->cap_tiles = nt + 64; h->cap_tab = tt + 64;
+    h->cap_lkp = nfeatures + 64;
+    const size_t B = max_batch;
+    bool ok = true;
+    auto A = [&](auto** p, size_t c) { if (ok && se2gpu::dev_alloc(p, c) == cudaSuccess) h->bufs.push_back(*p); else ok = false; };
+    OrbDev& d = h->d;
+    A(&h->d_levels, (size_t)nlevels); A(&h->d_cells, h->cap_cells); A(&h->d_tiles, h->cap_tiles); A(&h->d_itab, h->cap_tab); A(&h->d_stab, 2 * h->cap_tab);
+    A(&d.plain, B * h->cap_plane); A(&d.blurred, B * h->cap_plane);
+    A(&d.cand, B * h->cap_cand); A(&d.hdr, B * h->cap_cells); A(&d.lkp, B * h->cap_lkp); A(&d.lcount, B * nlevels); A(&d.err, 1);
+    A(&h->d_in, B * (size_t)max_w * max_h); A(&h->d_kps, B * nfeatures); A(&h->d_desc, B * nfeatures * 32); A(&h->d_counts, B);
+    if (!ok) { fail(SE2GPU_ERR_CUDA, "device allocation failed (%s)", cudaGetErrorString(cudaGetLastError())); se2gpu_orb_destroy(h); return nullptr; }
+    cudaMemset(d.err, 0, sizeof(int));
+    cudaMemcpyToSymbol(c_umax, umax, sizeof umax);
+    cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
+    d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
+    d.levels = h->d_levels; d.cells = h->d_cells; d.tiles = h->d_tiles; d.itab = h->d_itab; d.stab = h->d_stab;
+    if (cudaDeviceSynchronize() != cudaSuccess) { fail(SE2GPU_ERR_CUDA, "init failed"); se2gpu_orb_destroy(h); return nullptr; }
+    return h;
+}
+
+void se2gpu_orb_destroy(se2gpu_orb* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void* p : h->bufs) cudaFree(p);
+    delete h;
+}
+
+int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+                              se2gpu_keypoint* d_kps, uint8_t* d_desc, int* d_counts, void* stream) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (n < 0 || n > h->max_batch) return fail(SE2GPU_ERR_CAPACITY, "batch %d exceeds max_batch %d", n, h->max_batch);
+    SE2_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return SE2GPU_OK;
+    if (!d_imgs || w <= 0 || hgt <= 0) { SE2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * n, s)); return SE2GPU_OK; }
+    if (stride < w) return fail(SE2GPU_ERR_INVALID, "stride < width");
+    return run_device(h, d_imgs, n, w, hgt, stride, frame_stride, d_kps, d_desc, d_counts, s);
+}
+
+int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+                       se2gpu_keypoint* kps, uint8_t* desc, int* counts) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (n < 0 || n > h->max_batch) return fail(SE2GPU_ERR_CAPACITY, "batch %d exceeds max_batch %d", n, h->max_batch);
+    if (n == 0) return SE2GPU_OK;
+    if (!imgs || w <= 0 || hgt <= 0) { for (int i = 0; i < n; ++i) counts[i] = 0; return SE2GPU_OK; }   // :730-731
+    if (stride < w) return fail(SE2GPU_ERR_INVALID, "stride < width");
+    if (w > h->max_w || hgt > h->max_h) return fail(SE2GPU_ERR_CAPACITY, "frame %dx%d exceeds %dx%d", w, hgt, h->max_w, h->max_h);
+    SE2_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = nullptr;
+    // pack rows tightly on the device (pitch = w)
+    for (int i = 0; i < n; ++i)
+        SE2_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)i * w * hgt, w, imgs + i * frame_stride, stride, w, hgt, cudaMemcpyHostToDevice, s));
+    int rc = run_device(h, h->d_in, n, w, hgt, w, (size_t)w * hgt, h->d_kps, h->d_desc, h->d_counts, s);
+    if (rc != SE2GPU_OK) return rc;
+    SE2_CUDA(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaMemcpyAsync(kps, h->d_kps, sizeof(se2gpu_keypoint) * (size_t)n * h->nfeatures, cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)32 * n * h->nfeatures, cudaMemcpyDeviceToHost, s));
+    int err = 0;
+    SE2_CUDA(cudaMemcpyAsync(&err, h->d.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    if (err) { cudaMemset(h->d.err, 0, sizeof(int)); return fail(SE2GPU_ERR_CAPACITY, "internal candidate buffer overflow (code %d)", err); }
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_profile(se2gpu_orb* h, int enable) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->prof.enable(enable != 0);
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_profile_read(se2gpu_orb* h, double* ms, int* launches) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->prof.flush();
+    for (int g = 0; g < SE2GPU_ORB_PROFILE_GROUPS; ++g) { if (ms) ms[g] = h->prof.ms[g]; if (launches) launches[g] = h->prof.launches[g]; }
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_level_dims(se2gpu_orb* h, int level, int* w, int* hgt, int* pitch) {
+    if (!h || level < 0 || level >= h->nlevels || h->cur_w < 0) return fail(SE2GPU_ERR_INVALID, "no geometry");
+    *w = h->levels[level].w; *hgt = h->levels[level].h; *pitch = h->levels[level].pitch;
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_get_level(se2gpu_orb* h, int frame, int level, int blurred, uint8_t* out) {
+    if (!h || level < 0 || level >= h->nlevels || h->cur_w < 0 || frame < 0 || frame >= h->last_n) return fail(SE2GPU_ERR_INVALID, "bad frame/level");
+    SE2_CUDA(cudaSetDevice(h->device));
+    const LevelGeo& g = h->levels[level];
+    const uint8_t* src = (blurred ? h->d.blurred : h->d.plain) + (size_t)frame * h->d.frame_plane_bytes + g.plane_off;
+    SE2_CUDA(cudaMemcpy(out, src, (size_t)g.pitch * (g.h + 2 * EDGE), cudaMemcpyDeviceToHost));
+    return SE2GPU_OK;
+}
+
+}  // extern "C"

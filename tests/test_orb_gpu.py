@@ -1,0 +1,115 @@
+"""GPU parity of the ORB front-end against the CPU oracle and the committed golden vectors, through the C ABI.
+
+Bar: bit-exact keypoints (x, y, octave, response, angle, size) in identical order and
+bit-exact 32-byte descriptors.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from se2lam_b200 import synth
+from se2lam_b200.orb import ORBextractor
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "orb_golden.npz"))
+CASES = {
+    "synth1000": lambda: synth.orb_frame(1000), "synth1001": lambda: synth.orb_frame(1001),
+    "constant": lambda: synth.orb_adversarial("constant"), "noise": lambda: synth.orb_adversarial("noise"),
+    "lowcontrast": lambda: synth.orb_adversarial("lowcontrast"), "gradient": lambda: synth.orb_adversarial("gradient"),
+    "small_320x240": lambda: synth.orb_frame(5, 320, 240), "odd_501x377": lambda: synth.orb_frame(6, 501, 377),
+}
+
+
+def assert_same(kg, dg, ko, do_, what=""):
+    assert len(kg) == len(ko), f"{what}: {len(kg)} vs {len(ko)} keypoints"
+    for field in ("octave", "x", "y", "response", "angle", "size", "class_id"):
+        bad = np.flatnonzero(kg[field].view(np.int32) != ko[field].view(np.int32))
+        assert bad.size == 0, f"{what}: {field} differs at {bad[:5]} ({kg[field][bad[:5]]} vs {ko[field][bad[:5]]})"
+    bad = np.flatnonzero((dg != do_).any(axis=1))
+    assert bad.size == 0, f"{what}: {bad.size} descriptors differ, first at {bad[:5]}"
+
+
+@pytest.fixture(scope="module")
+def ext():
+    return ORBextractor(1000, 1.2, 8, fastTh=20, max_width=640, max_height=480, max_batch=8)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_matches_golden_vectors(ext, name):
+    img = CASES[name]()
+    kps, desc = ext(img)
+    assert_same(kps, desc, GOLD[name + "_kps"], GOLD[name + "_desc"], name)
+
+
+def test_pyramid_and_blur_planes_bit_exact(ext):
+    img = synth.orb_frame(1003)
+    o = pyoracle.OrbOracle()
+    ko, do_ = o.extract(img)
+    kg, dg = ext(img)
+    for level in range(8):
+        po, w, h = o.level(level, False)
+        pg, wg, hg = ext.level(0, level, False)
+        assert (w, h) == (wg, hg)
+        np.testing.assert_array_equal(pg[:, :w + 32], po[:, :w + 32], err_msg=f"plain level {level}")
+        bo, _, _ = o.level(level, True)
+        if bo is not None:
+            bg, _, _ = ext.level(0, level, True)
+            np.testing.assert_array_equal(bg[:, :w + 32], bo[:, :w + 32], err_msg=f"blurred level {level}")
+    assert_same(kg, dg, ko, do_, "synth1003")
+
+
+def test_batch_equals_single_frames_and_oracle(ext):
+    imgs = synth.orb_batch(8, first_seed=2000)
+    kps, desc, counts = ext.extract_batch(imgs)
+    o = pyoracle.OrbOracle()
+    for i in range(8):
+        ko, do_ = o.extract(imgs[i])
+        assert counts[i] == len(ko)
+        assert_same(kps[i, :counts[i]], desc[i, :counts[i]], ko, do_, f"batch frame {i}")
+
+
+@pytest.mark.parametrize("params", [dict(nfeatures=500, scaleFactor=1.2, nlevels=8, fastTh=20),
+                                    dict(nfeatures=2000, scaleFactor=1.15, nlevels=6, fastTh=12),
+                                    dict(nfeatures=800, scaleFactor=1.3, nlevels=5, fastTh=5),
+                                    dict(nfeatures=1000, scaleFactor=1.2, nlevels=8, fastTh=40)])
+def test_other_parameters(params):
+    img = synth.orb_frame(77)
+    e = ORBextractor(params["nfeatures"], params["scaleFactor"], params["nlevels"], fastTh=params["fastTh"])
+    o = pyoracle.OrbOracle(params["nfeatures"], params["scaleFactor"], params["nlevels"], params["fastTh"])
+    ko, do_ = o.extract(img)
+    kg, dg = e(img)
+    assert_same(kg, dg, ko, do_, str(params))
+
+
+def test_strided_input_and_empty_image(ext):
+    big = np.zeros((480, 704), np.uint8)
+    img = synth.orb_frame(1004)
+    big[:, 32:672] = img
+    view = big[:, 32:672]
+    kps = np.zeros((1, 1000), pyoracle.KP_DTYPE)
+    from se2lam_b200._capi import lib, ptr, check
+    desc = np.zeros((1, 1000, 32), np.uint8); counts = np.zeros(1, np.int32)
+    check(lib().se2gpu_orb_extract(ext.h, view.ctypes.data, 1, 640, 480, big.strides[0], 0, ptr(kps), ptr(desc), ptr(counts)), "strided")
+    ko, do_ = pyoracle.OrbOracle().extract(img)
+    assert_same(kps[0, :counts[0]], desc[0, :counts[0]], ko, do_, "strided")
+    k0, d0 = ext(np.zeros((0, 0), np.uint8))
+    assert len(k0) == 0 and d0.shape == (0, 32)
+
+
+def test_full_batch_properties():
+    """BASELINE configs[1] size (64 frames): determinism (two runs identical), frame independence (a frame's
+    result does not depend on its batch neighbours), every frame returns exactly nfeatures keypoints."""
+    imgs = synth.orb_batch(64)
+    e = ORBextractor(1000, 1.2, 8, max_batch=64)
+    k1, d1, c1 = e.extract_batch(imgs)
+    k2, d2, c2 = e.extract_batch(imgs[::-1].copy())
+    assert np.all(c1 == 1000)
+    assert k1.tobytes() == k2[::-1].tobytes() and d1.tobytes() == d2[::-1].tobytes()
+    o = pyoracle.OrbOracle()
+    for i in (0, 31, 63):
+        ko, do_ = o.extract(imgs[i])
+        assert_same(k1[i], d1[i], ko, do_, f"frame {i} of 64")
