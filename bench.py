@@ -245,12 +245,13 @@ def run_ours(args):
         _capi.check(lib.se2gpu_orb_extract(ext.h, hb.ctypes.data, BATCH, W, H, W, W * H, kps_h.ctypes.data, desc_h.ctypes.data,
                                            counts_h.ctypes.data), "se2gpu_orb_extract")
         return int(counts_h.sum())
-    for k in range(max(args.warmup, 1)):
+    e2e_steps = 0 if args.quick else args.steps
+    for k in range(0 if args.quick else max(args.warmup, 1)):
         orb_e2e(k)
     barrier()
     t0 = time.perf_counter()
     tot = 0
-    for k in range(args.steps):
+    for k in range(e2e_steps):
         tot += orb_e2e(k)
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -313,7 +314,7 @@ def run_ours(args):
     # e2e: upload the window, optimise, read the estimates back, every step
     t0 = time.perf_counter()
     it2 = 0
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         ba.set_problem(prob)
         n, _ = ba.optimize(BA_ITERS)
         ba.get()
@@ -323,7 +324,7 @@ def run_ours(args):
     d2h = 8 * 3 * (P + L)
 
     if rank == 0:
-        cpu_orb, cpu_ba = cpu_baselines() if world == 1 else (None, None)
+        cpu_orb, cpu_ba = cpu_baselines() if (world == 1 and not args.quick) else (None, None)
         line = {
             "metric": ORB_METRIC, "value": orb_value, "unit": "keypoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": orb_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -387,6 +388,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the CPU baseline and the e2e legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

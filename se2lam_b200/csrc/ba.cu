@@ -31,7 +31,7 @@ namespace {
 using se2gpu::fail;
 
 constexpr int LM_THREADS = 128;   // threads per block in per-landmark kernels
-constexpr int CHOL_THREADS = 1024;
+constexpr int CHOL_THREADS = 512;
 constexpr int SMEM_CHOL_MAX_N = 159;  // n*n*8 + 2n*8 <= 227 KB
 
 struct Cam {
@@ -66,6 +66,7 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     double *Hpp, *bp;                     // [6][nf], [n]
     // reduced system
     const int *blk_a, *blk_b, *blk_pair_ptr, *pair_e1, *pair_e2, *blk_odo_ptr, *blk_odo;
+    const int* colmax;                    // [n] envelope of the reduced system (last structurally non-zero row per column)
     double *S, *bs, *scal, *dxp, *dxl;    // S [n*n] | bs [n] | scal [8] contiguous (all-reduce buffer)
     double *part_chi, *part_scale;
     int nb_lm, nb_odo;
@@ -256,23 +257,25 @@ __global__ void __launch_bounds__(LM_THREADS) ba_linearize(Dev d, Cam cam, int u
     if (threadIdx.x == 0) d.part_chi[blockIdx.x] = tot;
 }
 
-// one warp per free pose: Hpp diagonal block (6 unique) and bp from its edges (+ its odometry edges)
-__global__ void __launch_bounds__(128) ba_pose_reduce(Dev d) {
-    const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (a >= d.nf) return;
+// one CTA (POSE_THREADS threads) per free pose: Hpp diagonal block (6 unique) and bp from its edges (+ its odometry
+// edges); fixed summation order: thread-strided partials, warp xor-tree, then the per-warp sums in warp order
+constexpr int POSE_THREADS = 256;
+__global__ void __launch_bounds__(POSE_THREADS) ba_pose_reduce(Dev d) {
+    __shared__ double sh[POSE_THREADS / 32][9];
+    const int a = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double acc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[q] = 0;
     const size_t E = d.E, O = d.O;
-    for (int k = d.pose_ptr[a] + lane; k < d.pose_ptr[a + 1]; k += 32) {
+    for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += POSE_THREADS) {
         const int e = d.pose_edges[k];
 #pragma unroll
         for (int q = 0; q < 6; ++q) acc[q] += d.PH[q * E + e];
 #pragma unroll
         for (int q = 0; q < 3; ++q) acc[6 + q] += d.Pb[q * E + e];
     }
-    for (int k = d.pose_odo_ptr[a] + lane; k < d.pose_odo_ptr[a + 1]; k += 32) {
+    for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += POSE_THREADS) {
         const int code = d.pose_odo[k], o = code >> 1;
         const double* H = (code & 1) ? d.oAjj : d.oAii;
         const double* b = (code & 1) ? d.obj : d.obi;
@@ -285,11 +288,16 @@ __global__ void __launch_bounds__(128) ba_pose_reduce(Dev d) {
     for (int q = 0; q < 9; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-    if (lane == 0) {
+    if (lane == 0)
 #pragma unroll
-        for (int q = 0; q < 6; ++q) d.Hpp[q * (size_t)d.nf + a] = acc[q];
+        for (int q = 0; q < 9; ++q) sh[wid][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) d.bp[3 * a + q] = acc[6 + q];
+        for (int w = 0; w < POSE_THREADS / 32; ++w) v += sh[w][threadIdx.x];
+        if (threadIdx.x < 6) d.Hpp[threadIdx.x * (size_t)d.nf + a] = v;
+        else d.bp[3 * a + threadIdx.x - 6] = v;
     }
 }
 
@@ -360,18 +368,19 @@ __global__ void __launch_bounds__(LM_THREADS) ba_lm_prep(Dev d) {
     }
 }
 
-// one warp per stored 3x3 block (a >= b) of the reduced pose Hessian:
+// one CTA (SCHUR_THREADS threads) per stored 3x3 block (a >= b) of the reduced pose Hessian:
 //   S_ab = [a==b](Hpp_aa + lambda I) + sum(odo blocks) - sum_{(e1,e2)} Y_e1 Hpl_e2^T ;   bs_a = bp_a - sum_e g_e
-__global__ void __launch_bounds__(128) ba_schur(Dev d) {
-    const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (blk >= d.nblk) return;
+constexpr int SCHUR_THREADS = 128;
+__global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
+    __shared__ double sh[SCHUR_THREADS / 32][12];
+    const int blk = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int a = d.blk_a[blk], b = d.blk_b[blk];
     const size_t E = d.E, O = d.O;
     double acc[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) acc[q] = 0;
-    for (int k = d.blk_pair_ptr[blk] + lane; k < d.blk_pair_ptr[blk + 1]; k += 32) {
+    for (int k = d.blk_pair_ptr[blk] + threadIdx.x; k < d.blk_pair_ptr[blk + 1]; k += SCHUR_THREADS) {
         const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
         double y[9], h[9];
 #pragma unroll
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(128) ba_schur(Dev d) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
     }
-    for (int k = d.blk_odo_ptr[blk] + lane; k < d.blk_odo_ptr[blk + 1]; k += 32) {
+    for (int k = d.blk_odo_ptr[blk] + threadIdx.x; k < d.blk_odo_ptr[blk + 1]; k += SCHUR_THREADS) {
         const int code = d.blk_odo[k], o = code >> 1;
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(128) ba_schur(Dev d) {
             for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + o] : d.oAij[(r * 3 + c) * O + o];
     }
     if (a == b)
-        for (int k = d.pose_ptr[a] + lane; k < d.pose_ptr[a + 1]; k += 32) {
+        for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += SCHUR_THREADS) {
             const int e = d.pose_edges[k];
             acc[9] -= d.g[e]; acc[10] -= d.g[E + e]; acc[11] -= d.g[2 * E + e];
         }
@@ -397,7 +406,13 @@ __global__ void __launch_bounds__(128) ba_schur(Dev d) {
     for (int q = 0; q < 12; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-    if (lane == 0) {
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 12; ++q) sh[wid][q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) { double v = 0; for (int w = 0; w < SCHUR_THREADS / 32; ++w) v += sh[w][q]; acc[q] = v; }
         const size_t n = d.n, nf = d.nf;
         if (a == b) {
             const double lam = (d.rank == 0) ? d.st->lambda : 0.0;   // damping is added once across shards
@@ -418,48 +433,53 @@ __global__ void __launch_bounds__(128) ba_schur(Dev d) {
     }
 }
 
-// one CTA: in-place right-looking Cholesky (lower) of the n x n matrix at A (row-major, leading dim n) with
-// the right-hand side carried as an extra row, followed by back substitution. Writes dxp and st->solve_ok.
-__device__ void chol_solve_body(double* A, double* y, int n, const double* bs, double* dxp, LMState* st) {
+// one CTA: in-place LDL^T (== Cholesky with positive pivots) of the n x n matrix at A (row-major, leading dim n,
+// lower triangle) restricted to its envelope: colmax[k] is the last row with a structural non-zero in column k
+// (monotone closure computed on the host from the block list), so fill-in stays inside [k+1, colmax[k]]^2.
+// One __syncthreads per pivot: the column is kept unscaled (L*D form) and the trailing update divides by the pivot.
+// The right-hand side rides along as an extra row (forward substitution for free); the back substitution is done
+// by warp 0 alone (warp-synchronous, no block barriers). Writes dxp and st->solve_ok.
+__device__ void ldlt_solve_body(double* A, double* y, double* dinv, int n, const int* __restrict__ colmax,
+                                const double* bs, double* dxp, LMState* st) {
     __shared__ int ok;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
     if (tid == 0) ok = 1;
     for (int i = tid; i < n; i += nt) y[i] = bs[i];
     __syncthreads();
     for (int k = 0; k < n; ++k) {
         const double akk = A[(size_t)k * n + k];
-        if (!(akk > 0.0) || !isfinite(akk)) { if (tid == 0) ok = 0; break; }   // uniform: all threads read the same akk
-        const double dkk = sqrt(akk);
-        const double inv = 1.0 / dkk;
-        // column k scale (rows k+1..n-1) and the rhs entry
-        for (int i = k + 1 + tid; i < n; i += nt) A[(size_t)i * n + k] *= inv;
-        if (tid == 0) { A[(size_t)k * n + k] = dkk; y[k] *= inv; }
-        __syncthreads();
-        // trailing update of the lower triangle (i >= j > k) and of the rhs row
-        const int m = n - k - 1;
-        const int tot = m * (m + 1) / 2;
-        for (int t = tid; t < tot; t += nt) {
-            // map t -> (ii >= jj) in the m x m lower triangle
-            int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-            while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
-            while (ii * (ii + 1) / 2 > t) --ii;
-            const int jj = t - ii * (ii + 1) / 2;
-            const int i = k + 1 + ii, j = k + 1 + jj;
-            A[(size_t)i * n + j] -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+        if (!(akk > 0.0) || !isfinite(akk)) { if (tid == 0) ok = 0; break; }   // uniform: every thread reads the same pivot
+        const double inv = 1.0 / akk;
+        const int hi = colmax[k];                 // rows/cols k+1..hi are touched by column k
+        const int m = hi - k;
+        const double yk = y[k];
+        // no barrier needed here: this step only writes A[i][j], y[i] with i,j > k, never the pivot, y[k] or column k
+        for (int ii = ty; ii < m; ii += nty) {
+            const int i = k + 1 + ii;
+            const double lik = A[(size_t)i * n + k] * inv;
+            for (int jj = tx; jj <= ii; jj += 32) {
+                const int j = k + 1 + jj;
+                A[(size_t)i * n + j] -= lik * A[(size_t)j * n + k];
+            }
+            if (tx == 0) y[i] -= lik * yk;
         }
-        for (int i = k + 1 + tid; i < n; i += nt) y[i] -= A[(size_t)i * n + k] * y[k];
+        if (tid == 0) dinv[k] = inv;
         __syncthreads();
     }
     __syncthreads();
     if (ok) {
-        // back substitution L^T x = y
-        for (int k = n - 1; k >= 0; --k) {
-            if (tid == 0) y[k] /= A[(size_t)k * n + k];
-            __syncthreads();
-            const double xk = y[k];
-            for (int i = tid; i < k; i += nt) y[i] -= A[(size_t)k * n + i] * xk;
-            __syncthreads();
+        if (ty == 0) {
+            // L^T x = D^-1 w, L unit lower with L[i][k] = A[i][k] * dinv[k]; rows are contiguous
+            for (int i = tx; i < n; i += 32) y[i] *= dinv[i];
+            __syncwarp();
+            for (int k = n - 1; k > 0; --k) {
+                const double xk = y[k];
+                for (int i = tx; i < k; i += 32) y[i] -= A[(size_t)k * n + i] * dinv[i] * xk;
+                __syncwarp();
+            }
         }
+        __syncthreads();
         for (int i = tid; i < n; i += nt) dxp[i] = y[i];
     } else {
         for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
@@ -472,13 +492,14 @@ __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
     const int n = d.n;
     double* A = smem;
     double* y = smem + (size_t)n * n;
+    double* dinv = y + n;
     for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = d.S[t];
     __syncthreads();
-    chol_solve_body(A, y, n, d.bs, d.dxp, d.st);
+    ldlt_solve_body(A, y, dinv, n, d.colmax, d.bs, d.dxp, d.st);
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_gmem(Dev d, double* ywork) {
-    chol_solve_body(d.S, ywork, d.n, d.bs, d.dxp, d.st);
+    ldlt_solve_body(d.S, ywork, ywork + d.n, d.n, d.colmax, d.bs, d.dxp, d.st);
 }
 
 // back-substitution + oplus into the trial buffers + partial sums of computeScale()
@@ -593,6 +614,7 @@ struct se2gpu_ba {
     int *blk_a = nullptr, *blk_b = nullptr, *blk_pair_ptr = nullptr, *pair_e1 = nullptr, *pair_e2 = nullptr, *blk_odo_ptr = nullptr, *blk_odo = nullptr;
     double* red = nullptr;     // all-reduce buffer [maxN*maxN + maxN + 8]
     double* ywork = nullptr;
+    int* colmax = nullptr;
     se2gpu_ba_iter_stats* stats_dev = nullptr;
     int max_stats = 64;
     LMState* st_host = nullptr;  // pinned
@@ -663,14 +685,14 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.oAii, 6 * O); A(&d.oAij, 9 * O); A(&d.oAjj, 6 * O); A(&d.obi, 3 * O); A(&d.obj, 3 * O);
     A(&h->pose_ptr, P + 1); A(&h->pose_edges, E); A(&h->pose_odo_ptr, P + 1); A(&h->pose_odo, 2 * O);
     A(&d.Hpp, 6 * P); A(&d.bp, 3 * P);
-    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
+    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 2 * maxN); A(&h->colmax, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
     const size_t nb = (L + LM_THREADS - 1) / LM_THREADS + (O + LM_THREADS - 1) / LM_THREADS + (P + LM_THREADS - 1) / LM_THREADS + 4;
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
     A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
-        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N) * 8);
+        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8);
     }
     if (rc != SE2GPU_OK) { se2gpu_ba_destroy(h); return nullptr; }
     return h;
@@ -787,6 +809,20 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
       }
       blk_pair_ptr[nblk] = (int)ip; blk_odo_ptr[nblk] = (int)io; }
     if (odob.size() + 1 > (size_t)2 * (h->maxO ? h->maxO : 1) + 1) return fail(SE2GPU_ERR_CAPACITY, "too many odometry blocks");
+    // envelope of the reduced system: last block row touching each block column, made monotone so that the
+    // fill-in of an LDL^T without pivoting stays inside it; in sharded mode every rank needs the envelope of the
+    // SUMMED system, i.e. of all landmarks, so it is rebuilt here from the unsharded edge list
+    std::vector<int> bmax(nf);
+    for (int a = 0; a < nf; ++a) bmax[a] = a;
+    {
+        std::vector<int> lo(L, nf), hi(L, -1);
+        for (int e = 0; e < E; ++e) { const int a = hidx[edge_pose[e]]; if (a < 0) continue; const int j = edge_point[e]; lo[j] = std::min(lo[j], a); hi[j] = std::max(hi[j], a); }
+        for (int j = 0; j < L; ++j) if (hi[j] >= 0) bmax[lo[j]] = std::max(bmax[lo[j]], hi[j]);
+        for (int o = 0; o < O; ++o) { const int a = hidx[odo_i[o]], b = hidx[odo_j[o]]; if (a < 0 || b < 0) continue; bmax[std::min(a, b)] = std::max(bmax[std::min(a, b)], std::max(a, b)); }
+        for (int a = 1; a < nf; ++a) bmax[a] = std::max(bmax[a], bmax[a - 1]);
+    }
+    std::vector<int> colmax(n);
+    for (int a = 0; a < nf; ++a) for (int r = 0; r < 3; ++r) colmax[3 * a + r] = 3 * bmax[a] + 2;
     int rc = ensure_cap(h, pairs.size(), std::max<size_t>(nblk, odob.size()), odob.size());
     if (rc != SE2GPU_OK) return rc;
 
@@ -811,7 +847,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     UP(h->o_i, oi); UP(h->o_j, oj); UP(h->o_m, om); UP(h->o_w, ow);
     UP(h->pose_ptr, pose_ptr); UP(h->pose_edges, pose_edges); UP(h->pose_odo_ptr, pose_odo_ptr); UP(h->pose_odo, pose_odo);
     UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UP(h->pair_e1, pe1); UP(h->pair_e2, pe2);
-    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo);
+    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax);
 #undef UP
     SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
     LMState st0{};
@@ -827,7 +863,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     d.o_i = h->o_i; d.o_j = h->o_j; d.o_m = h->o_m; d.o_w = h->o_w;
     d.pose_ptr = h->pose_ptr; d.pose_edges = h->pose_edges; d.pose_odo_ptr = h->pose_odo_ptr; d.pose_odo = h->pose_odo;
     d.blk_a = h->blk_a; d.blk_b = h->blk_b; d.blk_pair_ptr = h->blk_pair_ptr; d.pair_e1 = h->pair_e1; d.pair_e2 = h->pair_e2;
-    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo;
+    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax;
     d.S = h->red; d.bs = h->red + (size_t)n * n; d.scal = d.bs + n;
     d.nb_lm = (L + LM_THREADS - 1) / LM_THREADS; d.nb_odo = (Ol + LM_THREADS - 1) / LM_THREADS;
     h->nb_scale = (std::max(L, P) + LM_THREADS - 1) / LM_THREADS;
@@ -856,7 +892,7 @@ int launch_linearize(se2gpu_ba* h) {
     if (d.nb_lm + d.nb_odo > 0) SE2_LAUNCH(ba_linearize<true>, d.nb_lm + d.nb_odo, LM_THREADS, 0, s, d, h->cam, 0);
     h->prof.end(s);
     h->prof.begin(1, s);
-    if (d.nf > 0) SE2_LAUNCH(ba_pose_reduce, (d.nf * 32 + 127) / 128, 128, 0, s, d);
+    if (d.nf > 0) SE2_LAUNCH(ba_pose_reduce, d.nf, POSE_THREADS, 0, s, d);
     h->prof.end(s);
     return SE2GPU_OK;
 }
@@ -870,15 +906,13 @@ int launch_solve(se2gpu_ba* h) {
     // the global-memory Cholesky factorises S in place (fill-in outside the block list): re-zero it
     if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
     h->prof.begin(3, s);
-    if (d.nblk > 0) SE2_LAUNCH(ba_schur, (d.nblk * 32 + 127) / 128, 128, 0, s, d);
+    if (d.nblk > 0) SE2_LAUNCH(ba_schur, d.nblk, SCHUR_THREADS, 0, s, d);
     h->prof.end(s);
     int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
     if (rc != SE2GPU_OK) return rc;
     h->prof.begin(4, s);
-    if (d.n > 0) {
-        if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n) * 8, s, d);
-        else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
-    }
+    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8, s, d);   // n == 0: trivially ok
+    else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     h->prof.end(s);
     return SE2GPU_OK;
 }
@@ -1020,15 +1054,13 @@ int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hp
     SE2_CUDA(cudaMemcpyAsync(d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
     if (d.nb_lm > 0) SE2_LAUNCH(ba_lm_prep, d.nb_lm, LM_THREADS, 0, s, d);
     if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
-    if (d.nblk > 0) SE2_LAUNCH(ba_schur, (d.nblk * 32 + 127) / 128, 128, 0, s, d);
+    if (d.nblk > 0) SE2_LAUNCH(ba_schur, d.nblk, SCHUR_THREADS, 0, s, d);
     std::vector<double> tmp;
     auto get = [&](const double* dev, size_t cnt) { tmp.resize(cnt); return cudaMemcpyAsync(tmp.data(), dev, cnt * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess; };
     if (S) { if (!get(d.S, (size_t)n * n)) return fail(SE2GPU_ERR_CUDA, "copy S"); memcpy(S, tmp.data(), tmp.size() * 8); }
     if (bs) { if (!get(d.bs, n)) return fail(SE2GPU_ERR_CUDA, "copy bs"); memcpy(bs, tmp.data(), tmp.size() * 8); }
-    if (d.n > 0) {
-        if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n) * 8, s, d);
-        else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
-    }
+    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8, s, d);
+    else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
     if (Hpp) {
         if (!get(d.Hpp, 6 * (size_t)nf)) return fail(SE2GPU_ERR_CUDA, "copy Hpp");

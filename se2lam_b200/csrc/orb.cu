@@ -123,19 +123,29 @@ __global__ void orb_resize(OrbDev d, int level) {
     plane[(size_t)y * L.pitch + x] = (uint8_t)v;
 }
 
-// threshold-free FAST-9-16 arc score: M = max over the 16 nine-pixel arcs of min(+-(v - ring))
-__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int pw, int t_lo) {
+// FAST-9-16 arc score M = max over the 16 nine-pixel arcs of min(+-(v - ring)); corner at t <=> M > t,
+// cv::FAST's stored score == M-1 whatever t was. Returns 0 early when the pixel cannot be a corner at t:
+// a 9-arc always contains one pixel of each opposite pair (k, k+8), so all 4 tested pairs must have a
+// member beyond +-t of the centre.
+__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int pw, int t) {
     const int v = p[0];
-    // quick reject: every 9-arc contains two adjacent compass points
-    const int c0 = v - p[3 * pw], c4 = v - p[3], c8 = v - p[-3 * pw], c12 = v - p[-3];
-    const int nd = (c0 > t_lo) + (c4 > t_lo) + (c8 > t_lo) + (c12 > t_lo);
-    const int nb = (c0 < -t_lo) + (c4 < -t_lo) + (c8 < -t_lo) + (c12 < -t_lo);
-    if (nd < 2 && nb < 2) return 0;
+    const int c0 = v - p[3 * pw], c8 = v - p[-3 * pw];
+    bool dk = (c0 > t) | (c8 > t), br = (c0 < -t) | (c8 < -t);
+    if (!(dk | br)) return 0;
+    const int c4 = v - p[3], c12 = v - p[-3];
+    dk &= (c4 > t) | (c12 > t); br &= (c4 < -t) | (c12 < -t);
+    if (!(dk | br)) return 0;
+    const int c2 = v - p[2 * pw + 2], c10 = v - p[-2 * pw - 2];
+    dk &= (c2 > t) | (c10 > t); br &= (c2 < -t) | (c10 < -t);
+    if (!(dk | br)) return 0;
+    const int c6 = v - p[-2 * pw + 2], c14 = v - p[2 * pw - 2];
+    dk &= (c6 > t) | (c14 > t); br &= (c6 < -t) | (c14 < -t);
+    if (!(dk | br)) return 0;
     int dd[16];
-    dd[0] = c0;                      dd[1] = v - p[3 * pw + 1];   dd[2] = v - p[2 * pw + 2];   dd[3] = v - p[pw + 3];
-    dd[4] = c4;                      dd[5] = v - p[-pw + 3];      dd[6] = v - p[-2 * pw + 2];  dd[7] = v - p[-3 * pw + 1];
-    dd[8] = c8;                      dd[9] = v - p[-3 * pw - 1];  dd[10] = v - p[-2 * pw - 2]; dd[11] = v - p[-pw - 3];
-    dd[12] = c12;                    dd[13] = v - p[pw - 3];      dd[14] = v - p[2 * pw - 2];  dd[15] = v - p[3 * pw - 1];
+    dd[0] = c0;   dd[1] = v - p[3 * pw + 1];   dd[2] = c2;    dd[3] = v - p[pw + 3];
+    dd[4] = c4;   dd[5] = v - p[-pw + 3];      dd[6] = c6;    dd[7] = v - p[-3 * pw + 1];
+    dd[8] = c8;   dd[9] = v - p[-3 * pw - 1];  dd[10] = c10;  dd[11] = v - p[-pw - 3];
+    dd[12] = c12; dd[13] = v - p[pw - 3];      dd[14] = c14;  dd[15] = v - p[3 * pw - 1];
     int lo2[16], hi2[16], lo4[16], hi4[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) { lo2[k] = min(dd[k], dd[(k + 1) & 15]); hi2[k] = max(dd[k], dd[(k + 1) & 15]); }
@@ -151,11 +161,12 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int
     return max(mdark, -mbright_neg);
 }
 
-// one CTA per (cell, frame)
+// one CTA per (cell, frame): cv::FAST(cell, fastTh, NMS) and, if that yields <= 3 keypoints, cv::FAST(cell, 7, NMS)
+// (ORBextractor.cpp:616-623). The cell and its 3 px apron are staged once in shared memory with aligned
+// 32-bit loads; keypoints are emitted in raster order with one block-wide scan (two barrier-free passes).
 __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     extern __shared__ uint8_t smem[];
-    __shared__ int warp_cnt[FAST_THREADS / 32];
-    __shared__ int s_base, s_na, s_nb;
+    __shared__ int s_total;
     const CellGeo c = d.cells[blockIdx.x];
     const int f = blockIdx.y;
     CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
@@ -165,61 +176,90 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
         return;
     }
     const LevelGeo& L = d.levels[c.level];
-    const uint8_t* roi = d.plain + f * d.frame_plane_bytes + L.plane_off + (size_t)EDGE * L.pitch + EDGE;
-    const int pw = cw + 6, ph = ch + 6, sw = cw + 2, sh = ch + 2;
+    const uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    // patch columns start at the 4-aligned bordered-plane column ax0 <= x0-3 (plane base and pitch are 32 B aligned)
+    const int bx0 = c.x0 - 3 + EDGE, by0 = c.y0 - 3 + EDGE;
+    const int ax0 = bx0 & ~3, shift = bx0 - ax0;
+    const int ph = ch + 6, sw = cw + 2, sh = ch + 2;
+    const int pww = (shift + cw + 6 + 3) >> 2, pw = pww * 4;
     uint8_t* patch = smem;
     uint8_t* score = smem + ((pw * ph + 15) & ~15);
-    for (int i = threadIdx.x; i < pw * ph; i += FAST_THREADS) {
-        const int py = i / pw, px = i - py * pw;
-        patch[i] = roi[(ptrdiff_t)(c.y0 - 3 + py) * L.pitch + (c.x0 - 3 + px)];
+    const int npix = cw * ch, nchunk = (npix + FAST_THREADS - 1) / FAST_THREADS;
+    int* cnt = reinterpret_cast<int*>(score + ((sw * sh + 15) & ~15));   // [nchunk][8 warps] -> exclusive offsets
+    for (int i = threadIdx.x; i < pww * ph; i += FAST_THREADS) {
+        const int py = i / pww, pxw = i - py * pww;
+        reinterpret_cast<uint32_t*>(patch)[i] = *reinterpret_cast<const uint32_t*>(plane + (size_t)(by0 + py) * L.pitch + ax0 + 4 * pxw);
     }
-    for (int i = threadIdx.x; i < sw * sh; i += FAST_THREADS) score[i] = 0;
-    if (threadIdx.x == 0) { s_base = 0; s_na = 0; s_nb = 0; }
-    __syncthreads();
-    const int t_lo = d.t_lo;
-    for (int i = threadIdx.x; i < cw * ch; i += FAST_THREADS) {
-        const int y = i / cw, x = i - y * cw;
-        const int m = fast_arc_score(patch + (y + 3) * pw + (x + 3), pw, t_lo);
-        if (m > t_lo) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
-    }
-    __syncthreads();
-    uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int na = 0, nb = 0;
-    for (int i0 = 0; i0 < cw * ch; i0 += FAST_THREADS) {
-        const int i = i0 + threadIdx.x;
-        int s = 0, x = 0, y = 0;
+    const uint8_t* p0 = patch + 3 * pw + 3 + shift;
+    int thr = d.fast_th;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < sw * sh; i += FAST_THREADS) score[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < npix; i += FAST_THREADS) {
+            const int y = i / cw, x = i - y * cw;
+            const int m = fast_arc_score(p0 + y * pw + x, pw, thr);
+            if (m > thr) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
+        }
+        __syncthreads();
+        for (int k = 0; k < nchunk; ++k) {
+            const int i = k * FAST_THREADS + threadIdx.x;
+            bool keep = false;
+            if (i < npix) {
+                const int y = i / cw, x = i - y * cw;
+                const uint8_t* q = score + (y + 1) * sw + (x + 1);
+                const int s = q[0];
+                keep = s > 0 && s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) cnt[k * (FAST_THREADS / 32) + wid] = __popc(bal);
+        }
+        __syncthreads();
+        if (wid == 0) {   // exclusive scan of the nchunk*8 counts, in raster order
+            int run = 0;
+            const int n = nchunk * (FAST_THREADS / 32);
+            for (int b0 = 0; b0 < n; b0 += 32) {
+                const int v = (b0 + lane < n) ? cnt[b0 + lane] : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (b0 + lane < n) cnt[b0 + lane] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_total = run;
+        }
+        __syncthreads();
+        if (s_total > 3 || thr == 7) break;
+        thr = 7;                 // cellKeyPoints.size() <= 3: clear and retry with the fixed fallback threshold
+        __syncthreads();
+    }
+    uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
+    for (int k = 0; k < nchunk; ++k) {
+        const int i = k * FAST_THREADS + threadIdx.x;
         bool keep = false;
-        if (i < cw * ch) {
+        int s = 0, x = 0, y = 0;
+        if (i < npix) {
             y = i / cw; x = i - y * cw;
             const uint8_t* q = score + (y + 1) * sw + (x + 1);
             s = q[0];
             keep = s > 0 && s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_cnt[wid] = __popc(bal);
-        __syncthreads();
-        int off = s_base, tot = 0;
-#pragma unroll
-        for (int w = 0; w < FAST_THREADS / 32; ++w) { const int cnt = warp_cnt[w]; if (w < wid) off += cnt; tot += cnt; }
         if (keep) {
-            const int pos = off + __popc(bal & ((1u << lane) - 1));
+            const int pos = cnt[k * (FAST_THREADS / 32) + wid] + __popc(bal & ((1u << lane) - 1));
             if (pos < c.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
             else *d.err = 1;
-            na += (s >= d.fast_th); nb += (s >= 7);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_base += tot;
     }
-    if (na) atomicAdd(&s_na, na);
-    if (nb) atomicAdd(&s_nb, nb);
-    __syncthreads();
-    if (threadIdx.x == 0) { hdr->n_base = s_base; hdr->n_a = s_na; hdr->n_b = s_nb; }
+    if (threadIdx.x == 0) { hdr->n_base = s_total; hdr->n_a = s_total; hdr->n_b = s_total; }
 }
 
-// one CTA per (level, frame): FAST fallback choice, quota redistribution, retainBest per cell and per level
+// one CTA per (level, frame): quota redistribution, retainBest per cell and per level. The cells' candidate lists
+// are staged in shared memory when the level's total fits (SEL_STAGE entries), so the serial introselect of each
+// cell (one thread per cell) runs at shared-memory latency; otherwise it runs in place in global memory.
+constexpr int SEL_STAGE = 12288;
 __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
-    extern __shared__ uint32_t sbuf[];   // [kp_cap_smem] level list, then int arrays
+    extern __shared__ uint32_t sbuf[];   // [cap] level list | [4*nCells] ints | [SEL_STAGE] staged candidates
     const int level = blockIdx.x, f = blockIdx.y;
     const LevelGeo& L = d.levels[level];
     const int nCells = L.nCells;
@@ -229,33 +269,20 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
     int* nToRetain = nTotal + nCells;
     int* kept = nToRetain + nCells;
     int* koff = kept + nCells;
-    __shared__ int s_total;
+    uint32_t* stage = (uint32_t*)(koff + nCells);
+    __shared__ int s_total, s_staged;
     const CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + L.cell_base;
     uint32_t* cand = d.cand + (size_t)f * d.cand_total;
-    for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
-        const CellGeo& cg = d.cells[L.cell_base + c];
-        int n = 0;
-        if (!cg.skipped) {
-            const CellHdr h = hdr[c];
-            // FAST(cell, fastTh); if (size <= 3) FAST(cell, 7)   (:616-623); both are subsets of the base list
-            const int thr = (h.n_a > 3) ? d.fast_th : 7;
-            n = (h.n_a > 3) ? h.n_a : h.n_b;
-            if (n != h.n_base) {
-                uint32_t* v = cand + cg.cand_off;
-                int m = 0;
-                for (int i = 0; i < h.n_base; ++i) { const uint32_t e = v[i]; if ((int)(e >> 24) >= thr) v[m++] = e; }
-            }
-        }
-        nTotal[c] = n;
-    }
+    for (int c = threadIdx.x; c < nCells; c += blockDim.x) nTotal[c] = d.cells[L.cell_base + c].skipped ? 0 : hdr[c].n_base;
     __syncthreads();
     if (threadIdx.x == 0) {
         // :625-679 (skipped cells never enter the first pass: nToRetain/nTotal stay 0, bNoMore stays false)
         const int nfeaturesCell = L.nfeaturesCell;
-        int nNoMore = 0, nToDistribute = 0;
+        int nNoMore = 0, nToDistribute = 0, tot = 0;
         for (int c = 0; c < nCells; ++c) {
             const bool skipped = d.cells[L.cell_base + c].skipped;
             koff[c] = 0;  // bNoMore
+            tot += nTotal[c];
             if (skipped) { nToRetain[c] = 0; continue; }
             if (nTotal[c] > nfeaturesCell) nToRetain[c] = nfeaturesCell;
             else { nToRetain[c] = nTotal[c]; nToDistribute += nfeaturesCell - nTotal[c]; koff[c] = 1; nNoMore++; }
@@ -269,29 +296,37 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
                     else { nToRetain[c] = nTotal[c]; nToDistribute += nNew - nTotal[c]; koff[c] = 1; nNoMore++; }
                 }
         }
+        s_staged = tot <= SEL_STAGE;
+        int o = 0;
+        for (int c = 0; c < nCells; ++c) { kept[c] = o; o += nTotal[c]; }   // staging offsets (reused below)
     }
     __syncthreads();
+    const bool staged = s_staged;
+    if (staged) {
+        for (int c = 0; c < nCells; ++c) {
+            const uint32_t* v = cand + d.cells[L.cell_base + c].cand_off;
+            for (int i = threadIdx.x; i < nTotal[c]; i += blockDim.x) stage[kept[c] + i] = v[i];
+        }
+        __syncthreads();
+    }
     for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
         const int n = nToRetain[c], tot = nTotal[c];
-        int k = tot;
-        if (tot > n) {  // KeyPointsFilter::retainBest + resize (:692-694)
-            k = n;
-            if (n > 0) se2gpu::kp_nth_element(cand + d.cells[L.cell_base + c].cand_off, tot, n - 1);
-        }
-        kept[c] = k;
+        uint32_t* v = staged ? stage + kept[c] : cand + d.cells[L.cell_base + c].cand_off;
+        koff[c] = (int)(v - (staged ? stage : cand));   // remember where the list lives
+        if (tot > n && n > 0) se2gpu::kp_nth_element(v, tot, n - 1);   // KeyPointsFilter::retainBest + resize (:692-694)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int o = 0;
-        for (int c = 0; c < nCells; ++c) { koff[c] = o; o += kept[c]; }
+        for (int c = 0; c < nCells; ++c) { const int k = min(nTotal[c], nToRetain[c]); nTotal[c] = k; kept[c] = o; o += k; }
         if (o > cap) { *d.err = 2; o = cap; }
         s_total = o;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
-        const uint32_t* v = cand + d.cells[L.cell_base + c].cand_off;
-        const int o = koff[c];
-        for (int i = 0; i < kept[c] && o + i < cap; ++i) lbuf[o + i] = v[i];
+        const uint32_t* v = (staged ? stage : cand) + koff[c];
+        const int o = kept[c];
+        for (int i = 0; i < nTotal[c] && o + i < cap; ++i) lbuf[o + i] = v[i];
     }
     __syncthreads();
     int total = s_total;
@@ -305,49 +340,57 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
     if (threadIdx.x == 0) d.lcount[f * d.nlevels + level] = total;
 }
 
-// GaussianBlur 7x7 sigma 2 on the level ROI; the 16 px ring keeps its un-blurred reflect-101 copies
+// GaussianBlur 7x7 sigma 2 on the level ROI; the 16 px ring keeps its un-blurred reflect-101 copies.
+// Tile = 64 x 32 outputs; the tile and its apron are staged with aligned 32-bit loads (tile origins are multiples
+// of 64 and the plane pitch a multiple of 32), each thread produces 4 adjacent outputs and stores them as one word.
 __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
-    __shared__ uint8_t patch[(BLUR_TH + 6) * (BLUR_TW + 8)];
+    constexpr int PWW = (BLUR_TW + 8) / 4, PW = BLUR_TW + 8;   // staged columns: x0-4 .. x0+67
+    __shared__ uint32_t patchw[(BLUR_TH + 6) * PWW];
     __shared__ float rowp[(BLUR_TH + 6) * BLUR_TW];
+    const uint8_t* patch = reinterpret_cast<const uint8_t*>(patchw);
     const TileGeo t = d.tiles[blockIdx.x];
     const int f = blockIdx.y;
     const LevelGeo& L = d.levels[t.level];
     const uint8_t* src = d.plain + f * d.frame_plane_bytes + L.plane_off;
     uint8_t* dst = d.blurred + f * d.frame_plane_bytes + L.plane_off;
     const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
-    constexpr int PW = BLUR_TW + 8;
-    // stage tile + 3 px apron (clamped reads; aprons outside the plane are never used by interior pixels)
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW + 6); i += 256) {
-        const int py = i / (BLUR_TW + 6), px = i - py * (BLUR_TW + 6);
-        const int gy = min(max(t.y0 - 3 + py, 0), H - 1), gx = min(max(t.x0 - 3 + px, 0), W - 1);
-        patch[py * PW + px] = src[(size_t)gy * L.pitch + gx];
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * PWW; i += 256) {
+        const int py = i / PWW, pxw = i - py * PWW;
+        const int gy = min(max(t.y0 - 3 + py, 0), H - 1), gx = t.x0 - 4 + 4 * pxw;
+        // words left of the plane or beyond the pitch are never consumed by an interior pixel
+        patchw[i] = (gx >= 0 && gx + 4 <= L.pitch) ? *reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx) : 0u;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
         const int py = i / BLUR_TW, px = i - py * BLUR_TW;
-        const uint8_t* S = patch + py * PW + px;
+        const uint8_t* S = patch + py * PW + px + 1;    // taps px-3..px+3 -> staged columns px+1..px+7
         float s = __fmul_rn(c_gauss[0], (float)S[0]);
 #pragma unroll
         for (int k = 1; k < 7; ++k) s = __fmaf_rn(c_gauss[k], (float)S[k], s);
         rowp[i] = s;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW; i += 256) {
-        const int py = i / BLUR_TW, px = i - py * BLUR_TW;
-        const int gx = t.x0 + px, gy = t.y0 + py;
-        if (gx >= W || gy >= H) continue;
-        uint8_t o;
-        if (gx >= EDGE && gx < EDGE + L.w && gy >= EDGE && gy < EDGE + L.h) {
-            const float* c = rowp + (py + 3) * BLUR_TW + px;
-            float s = __fmul_rn(c_gauss[3], c[0]);
+    for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW / 4; i += 256) {
+        const int py = i / (BLUR_TW / 4), px4 = (i - py * (BLUR_TW / 4)) * 4;
+        const int gy = t.y0 + py, gx0 = t.x0 + px4;
+        if (gy >= H || gx0 >= L.pitch) continue;
+        uint32_t word = 0;
 #pragma unroll
-            for (int k = 1; k <= 3; ++k) s = __fmaf_rn(c_gauss[3 + k], __fadd_rn(c[k * BLUR_TW], c[-k * BLUR_TW]), s);
-            const int iv = __float2int_rn(s);
-            o = (uint8_t)min(max(iv, 0), 255);
-        } else {
-            o = patch[(py + 3) * PW + px + 3];
+        for (int q = 0; q < 4; ++q) {
+            const int px = px4 + q, gx = gx0 + q;
+            uint32_t o;
+            if (gx >= EDGE && gx < EDGE + L.w && gy >= EDGE && gy < EDGE + L.h) {
+                const float* c = rowp + (py + 3) * BLUR_TW + px;
+                float s = __fmul_rn(c_gauss[3], c[0]);
+#pragma unroll
+                for (int k = 1; k <= 3; ++k) s = __fmaf_rn(c_gauss[3 + k], __fadd_rn(c[k * BLUR_TW], c[-k * BLUR_TW]), s);
+                o = (uint32_t)min(max(__float2int_rn(s), 0), 255);
+            } else {
+                o = patch[(py + 3) * PW + px + 4];
+            }
+            word |= o << (8 * q);
         }
-        dst[(size_t)gy * L.pitch + gx] = o;
+        *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx0) = word;
     }
 }
 
@@ -532,11 +575,15 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 c.cand_off = (int)coff;
                 c.cand_cap = ((cw + 1) / 2) * ((chh + 1) / 2) + 8;   // strict 3x3 maxima: at most one per 2x2 block
                 coff += c.cand_cap;
-                if (cw > 0 && chh > 0) fsm = std::max(fsm, (size_t)(((cw + 6) * (chh + 6) + 15) & ~15) + (size_t)(cw + 2) * (chh + 2));
+                if (cw > 0 && chh > 0) {
+                    const size_t pwb = (size_t)((cw + 6 + 3 + 3) / 4 + 1) * 4;   // worst-case alignment shift
+                    const size_t nchunk = ((size_t)cw * chh + FAST_THREADS - 1) / FAST_THREADS;
+                    fsm = std::max(fsm, ((pwb * (chh + 6) + 15) & ~(size_t)15) + (((size_t)(cw + 2) * (chh + 2) + 15) & ~(size_t)15) + nchunk * (FAST_THREADS / 32) * 4 + 64);
+                }
                 C.push_back(c);
             }
         }
-        ssm = std::max(ssm, (size_t)(2 * g.nDesired + 4 * g.nCells + 64) * 4 + (size_t)g.nCells * 16);
+        ssm = std::max(ssm, (size_t)(2 * g.nDesired + 4 * g.nCells + 64) * 4 + (size_t)g.nCells * 16 + (size_t)SEL_STAGE * 4);
         g.tile_base = (int)T.size();
         g.tiles_x = (g.w + 2 * EDGE + BLUR_TW - 1) / BLUR_TW; g.tiles_y = (g.h + 2 * EDGE + BLUR_TH - 1) / BLUR_TH;
         for (int ty = 0; ty < g.tiles_y; ++ty) for (int tx = 0; tx < g.tiles_x; ++tx) T.push_back(TileGeo{l, tx * BLUR_TW, ty * BLUR_TH});

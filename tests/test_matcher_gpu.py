@@ -67,6 +67,6 @@ def test_search_by_bow(seed, mp_only, ori):
 
 
 def test_empty_inputs():
-    f1, f2, prev = make_frame_pair(seed=1, n=50)
+    f1, f2, prev = make_frame_pair(seed=1, n=200)
     n, m = ORBmatcher(0.9).MatchByWindow(FrameView(f1["kp"], f1["desc"]), FrameView(f2["kp"][:0], f2["desc"][:0]), prev.copy(), 20)
     assert n == 0 and np.all(m == -1)
