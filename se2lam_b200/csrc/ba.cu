@@ -31,8 +31,8 @@ namespace {
 using se2gpu::fail;
 
 constexpr int LM_THREADS = 128;   // threads per block in per-landmark kernels
-constexpr int CHOL_THREADS = 512;
-constexpr int SMEM_CHOL_MAX_N = 159;  // n*n*8 + 2n*8 <= 227 KB
+constexpr int CHOL_THREADS = 256;
+constexpr int SMEM_CHOL_MAX_N = 158;  // (n*n + 2n + 2)*8 + n*4 <= 227 KB
 
 struct Cam {
     double fx, cx, cy, Rcb[9], tcb[3], delta;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
 // One __syncthreads per pivot: the column is kept unscaled (L*D form) and the trailing update divides by the pivot.
 // The right-hand side rides along as an extra row (forward substitution for free); the back substitution is done
 // by warp 0 alone (warp-synchronous, no block barriers). Writes dxp and st->solve_ok.
-__device__ void ldlt_solve_body(double* A, double* y, double* dinv, int n, const int* __restrict__ colmax,
+__device__ void ldlt_solve_body(double* A, double* y, double* dinv, int n, const int* colmax,
                                 const double* bs, double* dxp, LMState* st) {
     __shared__ int ok;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -493,9 +493,11 @@ __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
     double* A = smem;
     double* y = smem + (size_t)n * n;
     double* dinv = y + n;
+    int* cmax = reinterpret_cast<int*>(dinv + n + 2);   // keep the per-pivot envelope lookup out of the L2 latency path
     for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = d.S[t];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
     __syncthreads();
-    ldlt_solve_body(A, y, dinv, n, d.colmax, d.bs, d.dxp, d.st);
+    ldlt_solve_body(A, y, dinv, n, cmax, d.bs, d.dxp, d.st);
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_gmem(Dev d, double* ywork) {
@@ -692,7 +694,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
-        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8);
+        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8 + SMEM_CHOL_MAX_N * 4 + 16);
     }
     if (rc != SE2GPU_OK) { se2gpu_ba_destroy(h); return nullptr; }
     return h;
@@ -911,7 +913,7 @@ int launch_solve(se2gpu_ba* h) {
     int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
     if (rc != SE2GPU_OK) return rc;
     h->prof.begin(4, s);
-    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8, s, d);   // n == 0: trivially ok
+    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8 + (size_t)d.n * 4 + 16, s, d);   // n == 0: trivially ok
     else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     h->prof.end(s);
     return SE2GPU_OK;
@@ -1059,7 +1061,7 @@ int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hp
     auto get = [&](const double* dev, size_t cnt) { tmp.resize(cnt); return cudaMemcpyAsync(tmp.data(), dev, cnt * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess; };
     if (S) { if (!get(d.S, (size_t)n * n)) return fail(SE2GPU_ERR_CUDA, "copy S"); memcpy(S, tmp.data(), tmp.size() * 8); }
     if (bs) { if (!get(d.bs, n)) return fail(SE2GPU_ERR_CUDA, "copy bs"); memcpy(bs, tmp.data(), tmp.size() * 8); }
-    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8, s, d);
+    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8 + (size_t)d.n * 4 + 16, s, d);
     else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
     if (Hpp) {

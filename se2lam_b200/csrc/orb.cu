@@ -87,40 +87,62 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101)
+// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101); 4 output pixels per thread, one word store
 __global__ void orb_pyr0(OrbDev d, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride) {
     const LevelGeo& L = d.levels[0];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     const int f = blockIdx.z;
-    if (x >= L.w + 2 * EDGE) return;
-    const int sx = reflect101(x - EDGE, L.w), sy = reflect101(y - EDGE, L.h);
+    if (x4 >= L.pitch) return;
+    const int sy = reflect101(y - EDGE, L.h);
+    const uint8_t* row = imgs + f * frame_stride + (size_t)sy * stride;
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int x = x4 + q;
+        const uint32_t v = (x < L.w + 2 * EDGE) ? row[reflect101(x - EDGE, L.w)] : 0u;
+        word |= v << (8 * q);
+    }
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    plane[(size_t)y * L.pitch + x] = imgs[f * frame_stride + (size_t)sy * stride + sx];
+    *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
 }
 
-// level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass
+// level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass;
+// 4 output pixels per thread (row-dependent terms computed once), one word store
 __global__ void orb_resize(OrbDev d, int level) {
     const LevelGeo& L = d.levels[level];
     const LevelGeo& S = d.levels[level - 1];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     const int f = blockIdx.z;
-    if (x >= L.w + 2 * EDGE) return;
-    const int dx = reflect101(x - EDGE, L.w), dy = reflect101(y - EDGE, L.h);
+    if (x4 >= L.pitch) return;
+    const int dy = reflect101(y - EDGE, L.h);
     const int* xofs = d.itab + L.tab_off;
     const int* yofs = xofs + L.w;
-    const short* ialpha = d.stab + 2 * (size_t)L.tab_off;
-    const short* ibeta = ialpha + 2 * L.w;
-    const int sx = xofs[dx], sx1 = min(sx + 1, S.w - 1);
+    const short2* ialpha = reinterpret_cast<const short2*>(d.stab + 2 * (size_t)L.tab_off);
+    const short2* ibeta = ialpha + L.w;
     const int sy = yofs[dy];
     const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
+    const short2 bb = ibeta[dy];
     const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
-    const int a0 = ialpha[2 * dx], a1 = ialpha[2 * dx + 1], b0 = ibeta[2 * dy], b1 = ibeta[2 * dy + 1];
-    const int r0 = src[(size_t)sy0 * S.pitch + sx] * a0 + src[(size_t)sy0 * S.pitch + sx1] * a1;
-    const int r1 = src[(size_t)sy1 * S.pitch + sx] * a0 + src[(size_t)sy1 * S.pitch + sx1] * a1;
-    int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-    v = min(max(v, 0), 255);
+    const uint8_t* r0p = src + (size_t)sy0 * S.pitch;
+    const uint8_t* r1p = src + (size_t)sy1 * S.pitch;
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int x = x4 + q;
+        uint32_t o = 0;
+        if (x < L.w + 2 * EDGE) {
+            const int dx = reflect101(x - EDGE, L.w);
+            const int sx = xofs[dx], sx1 = min(sx + 1, S.w - 1);
+            const short2 aa = ialpha[dx];
+            const int r0 = r0p[sx] * aa.x + r0p[sx1] * aa.y;
+            const int r1 = r1p[sx] * aa.x + r1p[sx1] * aa.y;
+            const int v = (((bb.x * (r0 >> 4)) >> 16) + ((bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
+            o = (uint32_t)min(max(v, 0), 255);
+        }
+        word |= o << (8 * q);
+    }
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    plane[(size_t)y * L.pitch + x] = (uint8_t)v;
+    *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
 }
 
 // FAST-9-16 arc score M = max over the 16 nine-pixel arcs of min(+-(v - ring)); corner at t <=> M > t,
@@ -162,8 +184,9 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int
 }
 
 // one CTA per (cell, frame): cv::FAST(cell, fastTh, NMS) and, if that yields <= 3 keypoints, cv::FAST(cell, 7, NMS)
-// (ORBextractor.cpp:616-623). The cell and its 3 px apron are staged once in shared memory with aligned
-// 32-bit loads; keypoints are emitted in raster order with one block-wide scan (two barrier-free passes).
+// (ORBextractor.cpp:616-623). The cell and its 3 px apron are staged once in shared memory with aligned 32-bit loads.
+// Work unit = one 32-pixel row segment per warp iteration (no per-pixel division); segments are numbered in raster
+// order, so one exclusive scan over the per-segment survivor counts gives every keypoint its raster-order slot.
 __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     extern __shared__ uint8_t smem[];
     __shared__ int s_total;
@@ -184,46 +207,51 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     const int pww = (shift + cw + 6 + 3) >> 2, pw = pww * 4;
     uint8_t* patch = smem;
     uint8_t* score = smem + ((pw * ph + 15) & ~15);
-    const int npix = cw * ch, nchunk = (npix + FAST_THREADS - 1) / FAST_THREADS;
-    int* cnt = reinterpret_cast<int*>(score + ((sw * sh + 15) & ~15));   // [nchunk][8 warps] -> exclusive offsets
+    const int nseg = (cw + 31) >> 5, nchunk = ch * nseg;
+    int* cnt = reinterpret_cast<int*>(score + ((sw * sh + 15) & ~15));   // [nchunk] survivors per segment -> exclusive offsets
     for (int i = threadIdx.x; i < pww * ph; i += FAST_THREADS) {
         const int py = i / pww, pxw = i - py * pww;
         reinterpret_cast<uint32_t*>(patch)[i] = *reinterpret_cast<const uint32_t*>(plane + (size_t)(by0 + py) * L.pitch + ax0 + 4 * pxw);
     }
+    constexpr int NW = FAST_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint8_t* p0 = patch + 3 * pw + 3 + shift;
     int thr = d.fast_th;
+    unsigned long long keepmask = 0;   // bit t: this lane's pixel of the warp's t-th segment survived NMS (first 64 segments)
     for (int pass = 0; pass < 2; ++pass) {
-        for (int i = threadIdx.x; i < sw * sh; i += FAST_THREADS) score[i] = 0;
+        for (int i = threadIdx.x; i < (sw * sh + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
         __syncthreads();
-        for (int i = threadIdx.x; i < npix; i += FAST_THREADS) {
-            const int y = i / cw, x = i - y * cw;
-            const int m = fast_arc_score(p0 + y * pw + x, pw, thr);
-            if (m > thr) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
+        for (int cidx = wid; cidx < nchunk; cidx += NW) {
+            const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
+            if (x < cw) {
+                const int m = fast_arc_score(p0 + y * pw + x, pw, thr);
+                if (m > thr) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
+            }
         }
         __syncthreads();
-        for (int k = 0; k < nchunk; ++k) {
-            const int i = k * FAST_THREADS + threadIdx.x;
+        keepmask = 0;
+        int t = 0;
+        for (int cidx = wid; cidx < nchunk; cidx += NW, ++t) {
+            const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
             bool keep = false;
-            if (i < npix) {
-                const int y = i / cw, x = i - y * cw;
+            if (x < cw) {
                 const uint8_t* q = score + (y + 1) * sw + (x + 1);
                 const int s = q[0];
-                keep = s > 0 && s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+                if (s) keep = s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) cnt[k * (FAST_THREADS / 32) + wid] = __popc(bal);
+            if (lane == 0) cnt[cidx] = __popc(bal);
+            if (keep && t < 64) keepmask |= 1ull << t;
         }
         __syncthreads();
-        if (wid == 0) {   // exclusive scan of the nchunk*8 counts, in raster order
+        if (wid == 0) {   // exclusive scan of the per-segment counts, in raster order
             int run = 0;
-            const int n = nchunk * (FAST_THREADS / 32);
-            for (int b0 = 0; b0 < n; b0 += 32) {
-                const int v = (b0 + lane < n) ? cnt[b0 + lane] : 0;
+            for (int b0 = 0; b0 < nchunk; b0 += 32) {
+                const int v = (b0 + lane < nchunk) ? cnt[b0 + lane] : 0;
                 int inc = v;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                if (b0 + lane < n) cnt[b0 + lane] = run + inc - v;
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                if (b0 + lane < nchunk) cnt[b0 + lane] = run + inc - v;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
             if (lane == 0) s_total = run;
@@ -234,19 +262,25 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
         __syncthreads();
     }
     uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
-    for (int k = 0; k < nchunk; ++k) {
-        const int i = k * FAST_THREADS + threadIdx.x;
-        bool keep = false;
-        int s = 0, x = 0, y = 0;
-        if (i < npix) {
-            y = i / cw; x = i - y * cw;
-            const uint8_t* q = score + (y + 1) * sw + (x + 1);
-            s = q[0];
-            keep = s > 0 && s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+    int t = 0;
+    for (int cidx = wid; cidx < nchunk; cidx += NW, ++t) {
+        const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
+        bool keep;
+        int s = 0;
+        if (t < 64) {
+            keep = (keepmask >> t) & 1ull;
+        } else {
+            keep = false;
+            if (x < cw) {
+                const uint8_t* q = score + (y + 1) * sw + (x + 1);
+                s = q[0];
+                if (s) keep = s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+            }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            const int pos = cnt[k * (FAST_THREADS / 32) + wid] + __popc(bal & ((1u << lane) - 1));
+            s = score[(y + 1) * sw + (x + 1)];
+            const int pos = cnt[cidx] + __popc(bal & ((1u << lane) - 1));
             if (pos < c.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
             else *d.err = 1;
         }
@@ -577,8 +611,8 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 coff += c.cand_cap;
                 if (cw > 0 && chh > 0) {
                     const size_t pwb = (size_t)((cw + 6 + 3 + 3) / 4 + 1) * 4;   // worst-case alignment shift
-                    const size_t nchunk = ((size_t)cw * chh + FAST_THREADS - 1) / FAST_THREADS;
-                    fsm = std::max(fsm, ((pwb * (chh + 6) + 15) & ~(size_t)15) + (((size_t)(cw + 2) * (chh + 2) + 15) & ~(size_t)15) + nchunk * (FAST_THREADS / 32) * 4 + 64);
+                    const size_t nchunk = (size_t)chh * ((cw + 31) / 32);
+                    fsm = std::max(fsm, ((pwb * (chh + 6) + 15) & ~(size_t)15) + (((size_t)(cw + 2) * (chh + 2) + 15) & ~(size_t)15) + nchunk * 4 + 64);
                 }
                 C.push_back(c);
             }
@@ -659,12 +693,12 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     pr.begin(0, s);
     {
         const LevelGeo& g = h->levels[0];
-        dim3 grid((g.w + 2 * EDGE + 127) / 128, g.h + 2 * EDGE, n);
+        dim3 grid((g.pitch / 4 + 127) / 128, g.h + 2 * EDGE, n);
         SE2_LAUNCH(orb_pyr0, grid, 128, 0, s, d, d_imgs, stride, frame_stride);
     }
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
-        dim3 grid((g.w + 2 * EDGE + 127) / 128, g.h + 2 * EDGE, n);
+        dim3 grid((g.pitch / 4 + 127) / 128, g.h + 2 * EDGE, n);
         SE2_LAUNCH(orb_resize, grid, 128, 0, s, d, l);
     }
     pr.end(s);
