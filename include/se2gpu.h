@@ -199,9 +199,13 @@ int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream);
  * is non-NULL. Hpp, S: [n*n] row-major (lower triangle valid), n = 3*#free poses; bp, bs, dx_p: [n];
  * Hll [L*9], bl [L*3], dx_l [L*3]; Hpl [E*9] (3x3 per edge, rows = pose, cols = point; original edge order).
  * Returns n (>=0) or a negative error. Does not change the estimates. */
+/* execution mode of se2gpu_ba_optimize: 0 = auto (persistent cooperative kernel when available: single GPU, reduced system
+ * fits one CTA's shared memory), 1 = one kernel per phase (always used for sharded runs), 2 = persistent or fail */
+int se2gpu_ba_set_mode(se2gpu_ba* h, int mode);
+
 /* per-kernel device timing for bench.py's roofline line; groups: 0 ba_linearize (+chi2 evaluation), 1 ba_pose_reduce,
- * 2 ba_lm_prep, 3 ba_schur, 4 ba_chol_solve, 5 ba_backsub_update, 6 ba_iter_begin/ba_decide */
-#define SE2GPU_BA_PROFILE_GROUPS 7
+ * 2 ba_lm_prep, 3 ba_schur, 4 ba_chol_solve, 5 ba_backsub_update, 6 ba_iter_begin/ba_decide, 7 ba_persistent (whole optimize) */
+#define SE2GPU_BA_PROFILE_GROUPS 8
 int se2gpu_ba_profile(se2gpu_ba* h, int enable);
 int se2gpu_ba_profile_read(se2gpu_ba* h, double* ms, int* launches);
 

@@ -43,7 +43,7 @@ SYMBOLS = [
     "se2gpu_hamming_distance", "se2gpu_match_by_window", "se2gpu_match_by_projection", "se2gpu_search_by_bow",
     "se2gpu_ba_create", "se2gpu_ba_destroy", "se2gpu_ba_set_problem", "se2gpu_ba_optimize", "se2gpu_ba_get",
     "se2gpu_ba_set_shard", "se2gpu_ba_set_stream", "se2gpu_ba_debug_system", "se2gpu_ba_reset", "se2gpu_ba_profile",
-    "se2gpu_ba_profile_read",
+    "se2gpu_ba_profile_read", "se2gpu_ba_set_mode",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.se2gpu_orb_profile_read.argtypes = [vp, vp, vp]
     L.se2gpu_ba_reset.argtypes = [vp]
     L.se2gpu_ba_profile.argtypes = [vp, i]
+    L.se2gpu_ba_set_mode.argtypes = [vp, i]
     L.se2gpu_ba_profile_read.argtypes = [vp, vp, vp]
     L.se2gpu_hamming_distance.argtypes = [vp, vp, i, vp, i]
     L.se2gpu_match_by_window.argtypes = [vp, vp, i, vp, vp, i, vp, GridParams, i, i, i, i, f, vp, i]

@@ -36,8 +36,9 @@ class LocalBA:
         self.close()
 
     @classmethod
-    def from_problem(cls, prob, device=0, rank=0, world=1, allreduce=None, stream=None):
+    def from_problem(cls, prob, device=0, rank=0, world=1, allreduce=None, stream=None, mode=0):
         ba = cls(prob.P, max(prob.L, 1), max(prob.E, 1), max(prob.O, 1), device)
+        ba.set_mode(mode)
         if stream is not None:
             ba.set_stream(stream)
         if world > 1:
@@ -78,7 +79,12 @@ class LocalBA:
         n = check(lib().se2gpu_ba_optimize(self.h, iters, ptr(stop_flag), ptr(st), ptr(tp), ptr(tl)), "se2gpu_ba_optimize")
         return (n, st[:n], tp[:n], tl[:n]) if trace else (n, st[:n])
 
-    PROFILE_GROUPS = ("ba_linearize", "ba_pose_reduce", "ba_lm_prep", "ba_schur", "ba_chol_solve", "ba_backsub_update", "ba_lm_control")
+    PROFILE_GROUPS = ("ba_linearize", "ba_pose_reduce", "ba_lm_prep", "ba_schur", "ba_chol_solve", "ba_backsub_update", "ba_lm_control",
+                      "ba_persistent")
+    MODE_AUTO, MODE_MULTI_LAUNCH, MODE_PERSISTENT = 0, 1, 2
+
+    def set_mode(self, mode):
+        check(lib().se2gpu_ba_set_mode(self.h, int(mode)), "se2gpu_ba_set_mode")
 
     def reset(self):
         check(lib().se2gpu_ba_reset(self.h), "se2gpu_ba_reset")

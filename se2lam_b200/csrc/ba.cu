@@ -18,6 +18,7 @@
 //   ba_backsub     per landmark back-substitution, x_trial = x (+) dx, gain-ratio denominator partials
 //   ba_chi2        robust chi2 at x_trial (same code path as ba_linearize without Jacobians)
 //   ba_decide      g2o's rho test / lambda schedule on device; host reads one small struct per trial
+#include <cooperative_groups.h>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -595,6 +596,462 @@ __global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase,
     }
 }
 
+
+// =================================================================================================
+// Persistent cooperative variant: the WHOLE optimize() call is one kernel launch. All CTAs are co-resident (one per
+// SM, cooperative launch); phases are separated by grid-wide barriers instead of kernel boundaries, and the LM
+// control (rho test, lambda schedule, accept/reject, termination) is evaluated redundantly and identically by every
+// CTA from the same fixed-order partial sums, so no host round trip happens inside an optimize() call.
+// Per-landmark work is spread over LPL lanes (edges strided over the lanes, xor-tree over the lane group).
+namespace cg = cooperative_groups;
+constexpr int PK_THREADS = 256;
+constexpr int LPL = 8;
+
+struct PKArgs {
+    int max_iters;
+    se2gpu_ba_iter_stats* stats;
+    double* trace_p;          // [max_iters][3P] or null
+    double* trace_l;          // [max_iters][3L] or null
+    const volatile int* abort_host;   // mapped pinned word written by the host watcher
+    int* abort_dev;           // published copy (read by all CTAs after a grid barrier)
+    double* part_chi;         // [gridDim.x]
+    double* part_scale;       // [gridDim.x]
+    double* part_max;         // [gridDim.x]
+    long long* phase_cycles;  // [8] SM cycles CTA 0 spent per phase incl. the barrier that ends it (profiling aid)
+};
+
+__device__ __forceinline__ double group_sum(double v) {   // sum over the LPL-lane group, fixed order
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// block-wide sum / max of a global array, same order in every CTA; result broadcast to all threads
+__device__ double cta_sum_array(const double* a, int n, double* sh) {
+    double v = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += a[i];
+    const double r = block_sum(v, sh);
+    __syncthreads();
+    if (threadIdx.x == 0) sh[0] = r;
+    __syncthreads();
+    const double out = sh[0];
+    __syncthreads();
+    return out;
+}
+__device__ double cta_max(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double m = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]);
+    __syncthreads();
+    return m;
+}
+
+// one (landmark j, lane sub) slice of the linearisation / chi2 evaluation; all LPL lanes of a group call it together
+template <bool JAC>
+__device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, const double* xp, const double* xl, int j, int sub) {
+    double chi = 0, h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
+    int beg = 0, end = 0;
+    if (j < d.L) { beg = d.lm_ptr[j]; end = d.lm_ptr[j + 1]; }
+    if (end > beg) {
+        const double lw[3] = {xl[3 * j], xl[3 * j + 1], xl[3 * j + 2]};
+        const double dsqr = cam.delta * cam.delta;
+        const size_t E = d.E;
+        for (int e = beg + sub; e < end; e += LPL) {
+            const int p = d.e_pose[e];
+            const double ps[3] = {xp[3 * p], xp[3 * p + 1], xp[3 * p + 2]};
+            double er[2], A[6], B[6];
+            edge_xyz<JAC>(cam, ps, lw, d.e_u[e], d.e_v[e], er, A, B);
+            const double w00 = d.e_w00[e], w01 = d.e_w01[e], w11 = d.e_w11[e];
+            const double we0 = w00 * er[0] + w01 * er[1], we1 = w01 * er[0] + w11 * er[1];
+            const double c2 = er[0] * we0 + er[1] * we1;
+            double rho1 = 1.0;
+            if (c2 <= dsqr) chi += c2;
+            else { const double sq = sqrt(c2); chi += 2 * sq * cam.delta - dsqr; rho1 = cam.delta / sq; }
+            if (JAC) {
+                const double W00 = rho1 * w00, W01 = rho1 * w01, W11 = rho1 * w11;
+                const double r0 = -rho1 * we0, r1 = -rho1 * we1;
+                double BtW[6], AtW[6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    BtW[r * 2] = B[r] * W00 + B[3 + r] * W01; BtW[r * 2 + 1] = B[r] * W01 + B[3 + r] * W11;
+                    AtW[r * 2] = A[r] * W00 + A[3 + r] * W01; AtW[r * 2 + 1] = A[r] * W01 + A[3 + r] * W11;
+                }
+                h00 += BtW[0] * B[0] + BtW[1] * B[3]; h01 += BtW[0] * B[1] + BtW[1] * B[4]; h02 += BtW[0] * B[2] + BtW[1] * B[5];
+                h11 += BtW[2] * B[1] + BtW[3] * B[4]; h12 += BtW[2] * B[2] + BtW[3] * B[5]; h22 += BtW[4] * B[2] + BtW[5] * B[5];
+                b0 += B[0] * r0 + B[3] * r1; b1 += B[1] * r0 + B[4] * r1; b2 += B[2] * r0 + B[5] * r1;
+                if (d.e_hidx[e] >= 0) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) d.Hpl[(r * 3 + c) * E + e] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
+                    d.PH[0 * E + e] = AtW[0] * A[0] + AtW[1] * A[3]; d.PH[1 * E + e] = AtW[0] * A[1] + AtW[1] * A[4];
+                    d.PH[2 * E + e] = AtW[0] * A[2] + AtW[1] * A[5]; d.PH[3 * E + e] = AtW[2] * A[1] + AtW[3] * A[4];
+                    d.PH[4 * E + e] = AtW[2] * A[2] + AtW[3] * A[5]; d.PH[5 * E + e] = AtW[4] * A[2] + AtW[5] * A[5];
+                    d.Pb[0 * E + e] = A[0] * r0 + A[3] * r1; d.Pb[1 * E + e] = A[1] * r0 + A[4] * r1; d.Pb[2 * E + e] = A[2] * r0 + A[5] * r1;
+                }
+            }
+        }
+    }
+    if (JAC) {
+        h00 = group_sum(h00); h01 = group_sum(h01); h02 = group_sum(h02); h11 = group_sum(h11); h12 = group_sum(h12); h22 = group_sum(h22);
+        b0 = group_sum(b0); b1 = group_sum(b1); b2 = group_sum(b2);
+        if (sub == 0 && end > beg) {
+            const size_t L = d.L;
+            d.Hll[j] = h00; d.Hll[L + j] = h01; d.Hll[2 * L + j] = h02; d.Hll[3 * L + j] = h11; d.Hll[4 * L + j] = h12; d.Hll[5 * L + j] = h22;
+            d.bl[j] = b0; d.bl[L + j] = b1; d.bl[2 * L + j] = b2;
+        }
+    }
+    return chi;
+}
+
+// PreEdgeSE2 (EdgeSE2XYZ.h:68-99) for one odometry edge
+template <bool JAC>
+__device__ __forceinline__ double pk_odo(const Dev& d, const double* xp, int o) {
+    const size_t O = d.O;
+    const int pi = d.o_i[o], pj = d.o_j[o];
+    double s, c;
+    sincos(xp[3 * pi + 2], &s, &c);
+    const double dx = xp[3 * pj] - xp[3 * pi], dy = xp[3 * pj + 1] - xp[3 * pi + 1];
+    const double e0 = c * dx + s * dy - d.o_m[o], e1 = -s * dx + c * dy - d.o_m[O + o];
+    const double e2 = xp[3 * pj + 2] - xp[3 * pi + 2] - d.o_m[2 * O + o];
+    const double w0 = d.o_w[o], w1 = d.o_w[O + o], w2 = d.o_w[2 * O + o], w3 = d.o_w[3 * O + o], w4 = d.o_w[4 * O + o], w5 = d.o_w[5 * O + o];
+    const double W[9] = {w0, w1, w2, w1, w3, w4, w2, w4, w5};
+    const double we[3] = {W[0] * e0 + W[1] * e1 + W[2] * e2, W[3] * e0 + W[4] * e1 + W[5] * e2, W[6] * e0 + W[7] * e1 + W[8] * e2};
+    if (JAC) {
+        const double rx = -dy, ry = dx;
+        const double Ai[9] = {-c, -s, -(c * rx + s * ry), s, -c, -(-s * rx + c * ry), 0, 0, -1};
+        const double Aj[9] = {c, s, 0, -s, c, 0, 0, 0, 1};
+        double AiW[9], AjW[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                AiW[r * 3 + k] = Ai[r] * W[k] + Ai[3 + r] * W[3 + k] + Ai[6 + r] * W[6 + k];
+                AjW[r * 3 + k] = Aj[r] * W[k] + Aj[3 + r] * W[3 + k] + Aj[6 + r] * W[6 + k];
+            }
+        const int u6[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int r = u6[q][0], cc = u6[q][1];
+            d.oAii[q * O + o] = AiW[r * 3] * Ai[cc] + AiW[r * 3 + 1] * Ai[3 + cc] + AiW[r * 3 + 2] * Ai[6 + cc];
+            d.oAjj[q * O + o] = AjW[r * 3] * Aj[cc] + AjW[r * 3 + 1] * Aj[3 + cc] + AjW[r * 3 + 2] * Aj[6 + cc];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) d.oAij[(r * 3 + cc) * O + o] = AiW[r * 3] * Aj[cc] + AiW[r * 3 + 1] * Aj[3 + cc] + AiW[r * 3 + 2] * Aj[6 + cc];
+            d.obi[r * O + o] = -(Ai[r] * we[0] + Ai[3 + r] * we[1] + Ai[6 + r] * we[2]);
+            d.obj[r * O + o] = -(Aj[r] * we[0] + Aj[3 + r] * we[1] + Aj[6 + r] * we[2]);
+        }
+    }
+    return e0 * we[0] + e1 * we[1] + e2 * we[2];
+}
+
+template <bool JAC>
+__device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double* part, double* sh) {
+    const double* xp = d.xp[xi];
+    const double* xl = d.xl[xi];
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    double chi = 0;
+    const int nwork = ((d.L * LPL + 31) / 32) * 32;   // whole warps iterate together (the lane-group shuffles need them)
+    for (int g = gtid; g < nwork; g += gthreads) chi += pk_landmark<JAC>(d, cam, xp, xl, g / LPL, g % LPL);
+    for (int o = gtid; o < d.O; o += gthreads) chi += pk_odo<JAC>(d, xp, o);
+    const double tot = block_sum(chi, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = tot;
+}
+
+__device__ void pk_phase_pose_reduce(const Dev& d, double* sh9 /*[8][9]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t E = d.E, O = d.O;
+    for (int a = blockIdx.x; a < d.nf; a += gridDim.x) {
+        double acc[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) acc[q] = 0;
+        for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += blockDim.x) {
+            const int e = d.pose_edges[k];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[q] += d.PH[q * E + e];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[6 + q] += d.Pb[q * E + e];
+        }
+        for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += blockDim.x) {
+            const int code = d.pose_odo[k], o = code >> 1;
+            const double* H = (code & 1) ? d.oAjj : d.oAii;
+            const double* b = (code & 1) ? d.obj : d.obi;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[q] += H[q * O + o];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[6 + q] += b[q * O + o];
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        __syncthreads();
+        if (lane == 0)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) sh9[wid * 9 + q] = acc[q];
+        __syncthreads();
+        if (threadIdx.x < 9) {
+            double v = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh9[w * 9 + threadIdx.x];
+            if (threadIdx.x < 6) d.Hpp[threadIdx.x * (size_t)d.nf + a] = v;
+            else d.bp[3 * a + threadIdx.x - 6] = v;
+        }
+    }
+}
+
+__device__ void pk_phase_lm_prep(const Dev& d, double lam) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const size_t L = d.L, E = d.E;
+    for (int g = gtid; g < d.L * LPL; g += gthreads) {
+        const int j = g / LPL, sub = g % LPL;
+        const int beg = d.lm_ptr[j], end = d.lm_ptr[j + 1];
+        if (end <= beg) continue;
+        const double a = d.Hll[j] + lam, b = d.Hll[L + j], c = d.Hll[2 * L + j], e = d.Hll[3 * L + j] + lam, f = d.Hll[4 * L + j], i = d.Hll[5 * L + j] + lam;
+        const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
+        const double id = 1.0 / (a * c00 + b * c01 + c * c02);
+        const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id, i11 = (a * i - c * c) * id, i12 = (b * c - a * f) * id, i22 = (a * e - b * b) * id;
+        if (sub == 0) { d.HllInv[j] = i00; d.HllInv[L + j] = i01; d.HllInv[2 * L + j] = i02; d.HllInv[3 * L + j] = i11; d.HllInv[4 * L + j] = i12; d.HllInv[5 * L + j] = i22; }
+        const double b0 = d.bl[j], b1 = d.bl[L + j], b2 = d.bl[2 * L + j];
+        const double db0 = i00 * b0 + i01 * b1 + i02 * b2, db1 = i01 * b0 + i11 * b1 + i12 * b2, db2 = i02 * b0 + i12 * b1 + i22 * b2;
+        for (int k = beg + sub; k < end; k += LPL) {
+            if (d.e_hidx[k] < 0) continue;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double h0 = d.Hpl[(r * 3 + 0) * E + k], h1 = d.Hpl[(r * 3 + 1) * E + k], h2 = d.Hpl[(r * 3 + 2) * E + k];
+                d.Y[(r * 3 + 0) * E + k] = h0 * i00 + h1 * i01 + h2 * i02;
+                d.Y[(r * 3 + 1) * E + k] = h0 * i01 + h1 * i11 + h2 * i12;
+                d.Y[(r * 3 + 2) * E + k] = h0 * i02 + h1 * i12 + h2 * i22;
+                d.g[r * E + k] = h0 * db0 + h1 * db1 + h2 * db2;
+            }
+        }
+    }
+}
+
+__device__ void pk_phase_schur(const Dev& d, double lam, double* sh12 /*[8][12]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t E = d.E, O = d.O, n = d.n, nf = d.nf;
+    for (int blk = blockIdx.x; blk < d.nblk; blk += gridDim.x) {
+        const int a = d.blk_a[blk], b = d.blk_b[blk];
+        double acc[12];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) acc[q] = 0;
+        for (int k = d.blk_pair_ptr[blk] + threadIdx.x; k < d.blk_pair_ptr[blk + 1]; k += blockDim.x) {
+            const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
+            double y[9], h[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { y[q] = d.Y[q * E + e1]; h[q] = d.Hpl[q * E + e2]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
+        }
+        for (int k = d.blk_odo_ptr[blk] + threadIdx.x; k < d.blk_odo_ptr[blk + 1]; k += blockDim.x) {
+            const int code = d.blk_odo[k], o = code >> 1;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + o] : d.oAij[(r * 3 + c) * O + o];
+        }
+        if (a == b)
+            for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += blockDim.x) {
+                const int e = d.pose_edges[k];
+                acc[9] -= d.g[e]; acc[10] -= d.g[E + e]; acc[11] -= d.g[2 * E + e];
+            }
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        __syncthreads();
+        if (lane == 0)
+#pragma unroll
+            for (int q = 0; q < 12; ++q) sh12[wid * 12 + q] = acc[q];
+        __syncthreads();
+        if (threadIdx.x < 12) {
+            double v = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh12[w * 12 + threadIdx.x];
+            const int q = threadIdx.x;
+            if (q < 9) {
+                const int r = q / 3, c = q % 3;
+                if (a == b) {
+                    const int u6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+                    v += d.Hpp[u6[r][c] * nf + a] + (r == c ? lam : 0.0);
+                }
+                d.S[(3 * a + r) * n + 3 * b + c] = v;
+            } else if (a == b) {
+                d.bs[3 * a + q - 9] = d.bp[3 * a + q - 9] + v;
+            }
+        }
+    }
+}
+
+__device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const double* xp = d.xp[cur];
+    const double* xl = d.xl[cur];
+    double* xpt = d.xp[cur ^ 1];
+    double* xlt = d.xl[cur ^ 1];
+    const size_t L = d.L, E = d.E;
+    double sc = 0;
+    const int nwork = ((d.L * LPL + 31) / 32) * 32;
+    for (int g = gtid; g < nwork; g += gthreads) {
+        const int j = g / LPL, sub = g % LPL;
+        int beg = 0, end = 0;
+        if (j < d.L) { beg = d.lm_ptr[j]; end = d.lm_ptr[j + 1]; }
+        double c0 = 0, c1 = 0, c2 = 0;
+        for (int k = beg + sub; k < end; k += LPL) {
+            const int a = d.e_hidx[k];
+            if (a < 0) continue;
+            const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
+            c0 -= d.Hpl[0 * E + k] * p0 + d.Hpl[3 * E + k] * p1 + d.Hpl[6 * E + k] * p2;
+            c1 -= d.Hpl[1 * E + k] * p0 + d.Hpl[4 * E + k] * p1 + d.Hpl[7 * E + k] * p2;
+            c2 -= d.Hpl[2 * E + k] * p0 + d.Hpl[5 * E + k] * p1 + d.Hpl[8 * E + k] * p2;
+        }
+        c0 = group_sum(c0); c1 = group_sum(c1); c2 = group_sum(c2);
+        if (sub == 0 && j < d.L) {
+            double dl0 = 0, dl1 = 0, dl2 = 0;
+            if (end > beg) {
+                c0 += d.bl[j]; c1 += d.bl[L + j]; c2 += d.bl[2 * L + j];
+                const double i00 = d.HllInv[j], i01 = d.HllInv[L + j], i02 = d.HllInv[2 * L + j], i11 = d.HllInv[3 * L + j], i12 = d.HllInv[4 * L + j], i22 = d.HllInv[5 * L + j];
+                dl0 = i00 * c0 + i01 * c1 + i02 * c2; dl1 = i01 * c0 + i11 * c1 + i12 * c2; dl2 = i02 * c0 + i12 * c1 + i22 * c2;
+                sc += dl0 * (lam * dl0 + d.bl[j]) + dl1 * (lam * dl1 + d.bl[L + j]) + dl2 * (lam * dl2 + d.bl[2 * L + j]);
+            }
+            d.dxl[3 * j] = dl0; d.dxl[3 * j + 1] = dl1; d.dxl[3 * j + 2] = dl2;
+            xlt[3 * j] = xl[3 * j] + dl0; xlt[3 * j + 1] = xl[3 * j + 1] + dl1; xlt[3 * j + 2] = xl[3 * j + 2] + dl2;
+        }
+    }
+    for (int t = gtid; t < d.P; t += gthreads) {
+        const int a = d.hidx[t];
+        if (a >= 0) {
+            const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
+            xpt[3 * t] = xp[3 * t] + p0; xpt[3 * t + 1] = xp[3 * t + 1] + p1;
+            xpt[3 * t + 2] = normalize_theta(xp[3 * t + 2] + p2);
+            sc += p0 * (lam * p0 + d.bp[3 * a]) + p1 * (lam * p1 + d.bp[3 * a + 1]) + p2 * (lam * p2 + d.bp[3 * a + 2]);
+        } else {
+            xpt[3 * t] = xp[3 * t]; xpt[3 * t + 1] = xp[3 * t + 1]; xpt[3 * t + 2] = xp[3 * t + 2];
+        }
+    }
+    return sc;
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, PKArgs pa) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double smem[];            // LDL^T workspace (used by CTA 0)
+    __shared__ double sh[32];
+    __shared__ double shv[8 * 12];
+    const int n = d.n, nparts = gridDim.x;
+    double lambda = 0, ni = 2, chi_cur = 0;
+    int cur = d.st->cur, done = 0;
+    bool stop = false;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define PK_TICK(g) do { const long long _t = clock64(); tacc[g] += _t - tprev; tprev = _t; } while (0)
+    for (int it = 0; it < pa.max_iters && !stop; ++it) {
+        // ---- A: linearise at x_cur (computeActiveErrors + buildSystem)
+        pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
+        grid.sync();
+        PK_TICK(0);
+        if (*pa.abort_dev) break;
+        // ---- B: pose-side gather (+ landmark diagonal maximum for lambda_0)
+        pk_phase_pose_reduce(d, shv);
+        if (it == 0) {
+            double m = 0;
+            const size_t L = d.L;
+            for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.L; j += gridDim.x * blockDim.x)
+                if (d.lm_ptr[j + 1] > d.lm_ptr[j]) m = fmax(m, fmax(fabs(d.Hll[j]), fmax(fabs(d.Hll[3 * L + j]), fabs(d.Hll[5 * L + j]))));
+            m = cta_max(m, sh);
+            if (threadIdx.x == 0) pa.part_max[blockIdx.x] = m;
+        }
+        grid.sync();
+        PK_TICK(1);
+        chi_cur = cta_sum_array(pa.part_chi, nparts, sh);
+        const double chi_before = chi_cur;
+        if (it == 0) {
+            double m = 0;
+            for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = fmax(m, pa.part_max[i]);
+            const size_t nf = d.nf;
+            for (int a = threadIdx.x; a < d.nf; a += blockDim.x) m = fmax(m, fmax(fabs(d.Hpp[a]), fmax(fabs(d.Hpp[3 * nf + a]), fabs(d.Hpp[5 * nf + a]))));
+            m = cta_max(m, sh);
+            lambda = 1e-5 * m; ni = 2;
+        }
+        int trials = 0, accepted = 0;
+        double rho = 0;
+        do {
+            // ---- P: damping-dependent per-landmark terms
+            PK_TICK(6);
+            pk_phase_lm_prep(d, lambda);
+            grid.sync();
+            PK_TICK(2);
+            // ---- C: Schur complement gather
+            pk_phase_schur(d, lambda, shv);
+            grid.sync();
+            PK_TICK(3);
+            // ---- D: reduced solve (one CTA; S staged into its shared memory)
+            if (blockIdx.x == 0) {
+                double* A = smem; double* y = smem + (size_t)n * n; double* dinv = y + n;
+                int* cmax = reinterpret_cast<int*>(dinv + n + 2);
+                for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = d.S[t];
+                for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
+                __syncthreads();
+                ldlt_solve_body(A, y, dinv, n, cmax, d.bs, d.dxp, d.st);
+            }
+            grid.sync();
+            PK_TICK(4);
+            const int solve_ok = d.st->solve_ok;
+            // ---- E: back-substitution, oplus into the trial buffers, computeScale partials
+            {
+                const double sc = pk_phase_backsub(d, cur, lambda);
+                const double tot = block_sum(sc, sh);
+                if (threadIdx.x == 0) pa.part_scale[blockIdx.x] = tot;
+            }
+            grid.sync();
+            PK_TICK(5);
+            // ---- F: robust chi2 at the trial point
+            pk_phase_linearize<false>(d, cam, cur ^ 1, pa.part_chi, sh);
+            if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
+            grid.sync();
+            PK_TICK(0);
+            // ---- LM decision (identical in every CTA)
+            const double tempChi = solve_ok ? cta_sum_array(pa.part_chi, nparts, sh) : DBL_MAX;
+            const double scale = (solve_ok ? cta_sum_array(pa.part_scale, nparts, sh) : 0.0) + 1e-3;
+            rho = (chi_cur - tempChi) / scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha); ni = 2; chi_cur = tempChi; cur ^= 1; accepted = 1;
+            } else {
+                lambda *= ni; ni *= 2;
+            }
+            ++trials;
+            stop = (*pa.abort_dev != 0);
+        } while (rho < 0 && trials < 10 && !stop);
+        const int terminate = (trials == 10 || rho == 0) ? 1 : 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && pa.stats) {
+            se2gpu_ba_iter_stats& o = pa.stats[it];
+            o.chi2_before = chi_before; o.chi2_after = chi_cur; o.lambda = lambda; o.rho = rho;
+            o.trials = trials; o.accepted = accepted; o.terminate = terminate; o.pad = 0;
+        }
+        if (pa.trace_p) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * d.P; i += gridDim.x * blockDim.x) pa.trace_p[(size_t)it * 3 * d.P + i] = d.xp[cur][i];
+        if (pa.trace_l) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * d.L; i += gridDim.x * blockDim.x) pa.trace_l[(size_t)it * 3 * d.L + i] = d.xl[cur][i];
+        ++done;
+        if (terminate) stop = true;
+    }
+    PK_TICK(6);
+#undef PK_TICK
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        LMState& s = *d.st;
+        s.cur = cur; s.lambda = lambda; s.ni = ni; s.chi_cur = chi_cur; s.iter = done;
+        if (pa.phase_cycles) for (int g = 0; g < 8; ++g) pa.phase_cycles[g] += tacc[g];
+    }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -626,6 +1083,14 @@ struct se2gpu_ba {
     bool loaded = false;
     double *xp0 = nullptr, *xl0 = nullptr;   // estimates as loaded (se2gpu_ba_reset)
     se2gpu::Profiler prof;
+    // persistent cooperative path
+    int mode = 0;              // 0 auto, 1 multi-launch, 2 persistent
+    int pk_grid = 0;           // co-resident CTAs (0 = unavailable)
+    double *pk_part_chi = nullptr, *pk_part_scale = nullptr, *pk_part_max = nullptr;
+    int* abort_host = nullptr; int* abort_host_dev = nullptr; int* abort_dev = nullptr;
+    double *trace_p = nullptr, *trace_l = nullptr; size_t trace_cap_p = 0, trace_cap_l = 0;
+    long long* phase_cycles = nullptr;   // device [8]
+    int pk_launches = 0, clock_khz = 0;
 };
 
 namespace {
@@ -692,9 +1157,26 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
     A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
+    A(&h->pk_part_chi, 1024); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 1); A(&h->phase_cycles, 8);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
         cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8 + SMEM_CHOL_MAX_N * 4 + 16);
+    }
+    if (rc == SE2GPU_OK) {
+        // persistent cooperative kernel: one CTA per SM, all co-resident
+        const int smem_max = (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8 + SMEM_CHOL_MAX_N * 4 + 16;
+        int coop = 0, nsm = 0, occ = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+        cudaMemset(h->phase_cycles, 0, 8 * sizeof(long long));
+        if (coop && cudaFuncSetAttribute(ba_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent, PK_THREADS, smem_max) == cudaSuccess && occ >= 1)
+            h->pk_grid = std::min(nsm, 1024);
+        cudaGetLastError();
+        if (cudaHostAlloc((void**)&h->abort_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&h->abort_host_dev, h->abort_host, 0) != cudaSuccess) { h->pk_grid = 0; cudaGetLastError(); }
+        else *h->abort_host = 0;
     }
     if (rc != SE2GPU_OK) { se2gpu_ba_destroy(h); return nullptr; }
     return h;
@@ -704,6 +1186,9 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->bufs) cudaFree(p);
+    if (h->trace_p) cudaFree(h->trace_p);
+    if (h->trace_l) cudaFree(h->trace_l);
+    if (h->abort_host) cudaFreeHost(h->abort_host);
     if (h->st_host) cudaFreeHost(h->st_host);
     delete h;
 }
@@ -931,6 +1416,43 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
     SE2_CUDA(cudaSetDevice(h->device));
     Dev& d = h->d;
     cudaStream_t s = h->stream;
+    const bool can_persist = h->world == 1 && h->pk_grid > 0 && d.n <= SMEM_CHOL_MAX_N;
+    if (h->mode == 2 && !can_persist) return fail(SE2GPU_ERR_INVALID, "persistent mode unavailable (sharded run, %d unknowns > %d, or no cooperative launch)", d.n, SMEM_CHOL_MAX_N);
+    if (can_persist && h->mode != 1) {
+        if (max_iters == 0 || (stop_flag && *stop_flag)) return 0;
+        // the whole optimize() is ONE cooperative launch; the host only forwards the abort flag while it runs
+        if (trace_poses && h->trace_cap_p < (size_t)max_iters * 3 * h->P) {
+            if (h->trace_p) cudaFree(h->trace_p);
+            h->trace_cap_p = (size_t)max_iters * 3 * h->P;
+            SE2_CUDA(cudaMalloc((void**)&h->trace_p, h->trace_cap_p * sizeof(double)));
+        }
+        if (trace_points && h->trace_cap_l < (size_t)max_iters * 3 * h->L) {
+            if (h->trace_l) cudaFree(h->trace_l);
+            h->trace_cap_l = (size_t)max_iters * 3 * h->L;
+            SE2_CUDA(cudaMalloc((void**)&h->trace_l, h->trace_cap_l * sizeof(double)));
+        }
+        *h->abort_host = 0;
+        PKArgs pa{max_iters, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
+                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr};
+        if (h->prof.on) h->pk_launches++;
+        const size_t smem = ((size_t)d.n * d.n + 2 * d.n + 2) * 8 + (size_t)d.n * 4 + 16;
+        void* args[] = {(void*)&d, (void*)&h->cam, (void*)&pa};
+        h->prof.begin(7, s);
+        SE2_CUDA(cudaLaunchCooperativeKernel((void*)ba_persistent, dim3(h->pk_grid), dim3(PK_THREADS), args, smem, s));
+        se2gpu::g_launches.fetch_add(1, std::memory_order_relaxed);
+        h->prof.end(s);
+        SE2_CUDA(cudaMemcpyAsync(h->st_host, d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+        if (stop_flag) {
+            while (cudaStreamQuery(s) == cudaErrorNotReady) if (*stop_flag) *(volatile int*)h->abort_host = 1;
+        }
+        SE2_CUDA(cudaStreamSynchronize(s));
+        const int done = h->st_host->iter;
+        if (stats && done > 0) SE2_CUDA(cudaMemcpyAsync(stats, h->stats_dev, sizeof(se2gpu_ba_iter_stats) * done, cudaMemcpyDeviceToHost, s));
+        if (trace_poses && done > 0) SE2_CUDA(cudaMemcpyAsync(trace_poses, h->trace_p, sizeof(double) * (size_t)done * 3 * h->P, cudaMemcpyDeviceToHost, s));
+        if (trace_points && done > 0) SE2_CUDA(cudaMemcpyAsync(trace_points, h->trace_l, sizeof(double) * (size_t)done * 3 * h->L, cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaStreamSynchronize(s));
+        return done;
+    }
     int done = 0;
     bool ok = true;
     for (int it = 0; it < max_iters && !(stop_flag && *stop_flag) && ok; ++it) {
@@ -1009,10 +1531,18 @@ int se2gpu_ba_reset(se2gpu_ba* h) {
     return SE2GPU_OK;
 }
 
+int se2gpu_ba_set_mode(se2gpu_ba* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(SE2GPU_ERR_INVALID, "mode must be 0 (auto), 1 (multi-launch) or 2 (persistent)");
+    h->mode = mode;
+    return SE2GPU_OK;
+}
+
 int se2gpu_ba_profile(se2gpu_ba* h, int enable) {
     if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
     SE2_CUDA(cudaSetDevice(h->device));
     h->prof.enable(enable != 0);
+    h->pk_launches = 0;
+    SE2_CUDA(cudaMemset(h->phase_cycles, 0, 8 * sizeof(long long)));
     return SE2GPU_OK;
 }
 
@@ -1021,6 +1551,12 @@ int se2gpu_ba_profile_read(se2gpu_ba* h, double* ms, int* launches) {
     SE2_CUDA(cudaSetDevice(h->device));
     h->prof.flush();
     for (int g = 0; g < SE2GPU_BA_PROFILE_GROUPS; ++g) { if (ms) ms[g] = h->prof.ms[g]; if (launches) launches[g] = h->prof.launches[g]; }
+    if (h->pk_launches > 0) {
+        // persistent mode: groups 0..6 are the in-kernel phase times of CTA 0 (SM cycles / nominal max clock), one "launch" per optimize()
+        long long cyc[8];
+        SE2_CUDA(cudaMemcpy(cyc, h->phase_cycles, sizeof cyc, cudaMemcpyDeviceToHost));
+        for (int g = 0; g < 7; ++g) { if (ms) ms[g] = (double)cyc[g] / (double)(h->clock_khz > 0 ? h->clock_khz : 1965000); if (launches) launches[g] = h->pk_launches; }
+    }
     return SE2GPU_OK;
 }
 

@@ -163,24 +163,28 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int
     const int c6 = v - p[-2 * pw + 2], c14 = v - p[2 * pw - 2];
     dk &= (c6 > t) | (c14 > t); br &= (c6 < -t) | (c14 < -t);
     if (!(dk | br)) return 0;
-    int dd[16];
-    dd[0] = c0;   dd[1] = v - p[3 * pw + 1];   dd[2] = c2;    dd[3] = v - p[pw + 3];
-    dd[4] = c4;   dd[5] = v - p[-pw + 3];      dd[6] = c6;    dd[7] = v - p[-3 * pw + 1];
-    dd[8] = c8;   dd[9] = v - p[-3 * pw - 1];  dd[10] = c10;  dd[11] = v - p[-pw - 3];
-    dd[12] = c12; dd[13] = v - p[pw - 3];      dd[14] = c14;  dd[15] = v - p[3 * pw - 1];
-    int lo2[16], hi2[16], lo4[16], hi4[16];
+    // both polarities at once: each ring difference d is packed as the s16x2 pair (d, -d); an arc's score for the
+    // "darker" / "brighter" test is the min over its 9 packed entries, computed with Blackwell's 3-input packed min
+    // (VIMNMX3.S16x2): m3_k = min(q_k,q_k+1,q_k+2), m9_k = min(m3_k, m3_k+3, m3_k+6); M = max over k and both halves.
+#define SE2_PK(dv) ((static_cast<unsigned>(dv) & 0xFFFFu) | (static_cast<unsigned>(-(dv)) << 16))
+    unsigned q[16];
+    q[0] = SE2_PK(c0);   q[1] = SE2_PK(v - p[3 * pw + 1]);    q[2] = SE2_PK(c2);    q[3] = SE2_PK(v - p[pw + 3]);
+    q[4] = SE2_PK(c4);   q[5] = SE2_PK(v - p[-pw + 3]);       q[6] = SE2_PK(c6);    q[7] = SE2_PK(v - p[-3 * pw + 1]);
+    q[8] = SE2_PK(c8);   q[9] = SE2_PK(v - p[-3 * pw - 1]);   q[10] = SE2_PK(c10);  q[11] = SE2_PK(v - p[-pw - 3]);
+    q[12] = SE2_PK(c12); q[13] = SE2_PK(v - p[pw - 3]);       q[14] = SE2_PK(c14);  q[15] = SE2_PK(v - p[3 * pw - 1]);
+#undef SE2_PK
+    unsigned m3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { lo2[k] = min(dd[k], dd[(k + 1) & 15]); hi2[k] = max(dd[k], dd[(k + 1) & 15]); }
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
+    unsigned best = 0x80008000u;   // (-32768, -32768)
 #pragma unroll
-    for (int k = 0; k < 16; ++k) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-    int mdark = -256, mbright_neg = 256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int lo8 = min(lo4[k], lo4[(k + 4) & 15]), hi8 = max(hi4[k], hi4[(k + 4) & 15]);
-        mdark = max(mdark, min(lo8, dd[(k + 8) & 15]));
-        mbright_neg = min(mbright_neg, max(hi8, dd[(k + 8) & 15]));
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned a9 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const unsigned b9 = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a9, b9);
     }
-    return max(mdark, -mbright_neg);
+    const int mdark = static_cast<short>(best & 0xFFFFu), mbright = static_cast<short>(best >> 16);
+    return max(mdark, mbright);
 }
 
 // one CTA per (cell, frame): cv::FAST(cell, fastTh, NMS) and, if that yields <= 3 keypoints, cv::FAST(cell, 7, NMS)
@@ -375,12 +379,13 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
 }
 
 // GaussianBlur 7x7 sigma 2 on the level ROI; the 16 px ring keeps its un-blurred reflect-101 copies.
-// Tile = 64 x 32 outputs; the tile and its apron are staged with aligned 32-bit loads (tile origins are multiples
-// of 64 and the plane pitch a multiple of 32), each thread produces 4 adjacent outputs and stores them as one word.
+// Tile = 64 x 32 outputs. Staging: aligned 32-bit loads (tile origins are multiples of 64, pitch of 32).
+// Row pass: one thread = 4 adjacent outputs from three staged words (12 bytes), stored as one float4.
+// Column pass: one thread = one column x 8 rows with a sliding window (14 loads for 8 outputs, conflict-free).
 __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
     constexpr int PWW = (BLUR_TW + 8) / 4, PW = BLUR_TW + 8;   // staged columns: x0-4 .. x0+67
     __shared__ uint32_t patchw[(BLUR_TH + 6) * PWW];
-    __shared__ float rowp[(BLUR_TH + 6) * BLUR_TW];
+    __shared__ __align__(16) float rowp[(BLUR_TH + 6) * BLUR_TW];
     const uint8_t* patch = reinterpret_cast<const uint8_t*>(patchw);
     const TileGeo t = d.tiles[blockIdx.x];
     const int f = blockIdx.y;
@@ -395,36 +400,49 @@ __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
         patchw[i] = (gx >= 0 && gx + 4 <= L.pitch) ? *reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx) : 0u;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * BLUR_TW; i += 256) {
-        const int py = i / BLUR_TW, px = i - py * BLUR_TW;
-        const uint8_t* S = patch + py * PW + px + 1;    // taps px-3..px+3 -> staged columns px+1..px+7
-        float s = __fmul_rn(c_gauss[0], (float)S[0]);
+    const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3], g4 = c_gauss[4], g5 = c_gauss[5], g6 = c_gauss[6];
+    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
+        const int py = i / (BLUR_TW / 4), pg = i - py * (BLUR_TW / 4);
+        const uint32_t* wp = patchw + py * PWW + pg;           // bytes 4*pg .. 4*pg+11 of the staged row
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        float b[12];
 #pragma unroll
-        for (int k = 1; k < 7; ++k) s = __fmaf_rn(c_gauss[k], (float)S[k], s);
-        rowp[i] = s;
+        for (int k = 0; k < 4; ++k) { b[k] = (float)((w0 >> (8 * k)) & 255u); b[4 + k] = (float)((w1 >> (8 * k)) & 255u); b[8 + k] = (float)((w2 >> (8 * k)) & 255u); }
+        float4 o;
+        float* op = &o.x;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {        // output column 4*pg+qd <- staged bytes (4*pg+qd+1 .. +7)
+            float s = __fmul_rn(g0, b[qd + 1]);
+            s = __fmaf_rn(g1, b[qd + 2], s); s = __fmaf_rn(g2, b[qd + 3], s); s = __fmaf_rn(g3, b[qd + 4], s);
+            s = __fmaf_rn(g4, b[qd + 5], s); s = __fmaf_rn(g5, b[qd + 6], s); s = __fmaf_rn(g6, b[qd + 7], s);
+            op[qd] = s;
+        }
+        *reinterpret_cast<float4*>(rowp + py * BLUR_TW + 4 * pg) = o;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < BLUR_TH * BLUR_TW / 4; i += 256) {
-        const int py = i / (BLUR_TW / 4), px4 = (i - py * (BLUR_TW / 4)) * 4;
-        const int gy = t.y0 + py, gx0 = t.x0 + px4;
-        if (gy >= H || gx0 >= L.pitch) continue;
-        uint32_t word = 0;
+    {
+        const int px = threadIdx.x & (BLUR_TW - 1), rg = threadIdx.x / BLUR_TW;      // 64 columns x 4 row groups of 8
+        const int gx = t.x0 + px;
+        float win[14];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int px = px4 + q, gx = gx0 + q;
-            uint32_t o;
-            if (gx >= EDGE && gx < EDGE + L.w && gy >= EDGE && gy < EDGE + L.h) {
-                const float* c = rowp + (py + 3) * BLUR_TW + px;
-                float s = __fmul_rn(c_gauss[3], c[0]);
+        for (int k = 0; k < 14; ++k) win[k] = rowp[(rg * 8 + k) * BLUR_TW + px];
+        const bool colin = gx >= EDGE && gx < EDGE + L.w;
 #pragma unroll
-                for (int k = 1; k <= 3; ++k) s = __fmaf_rn(c_gauss[3 + k], __fadd_rn(c[k * BLUR_TW], c[-k * BLUR_TW]), s);
-                o = (uint32_t)min(max(__float2int_rn(s), 0), 255);
+        for (int r = 0; r < 8; ++r) {
+            const int py = rg * 8 + r, gy = t.y0 + py;
+            if (gy >= H || gx >= L.pitch) continue;
+            uint8_t o;
+            if (colin && gy >= EDGE && gy < EDGE + L.h) {
+                float s = __fmul_rn(g3, win[r + 3]);
+                s = __fmaf_rn(g4, __fadd_rn(win[r + 4], win[r + 2]), s);
+                s = __fmaf_rn(g5, __fadd_rn(win[r + 5], win[r + 1]), s);
+                s = __fmaf_rn(g6, __fadd_rn(win[r + 6], win[r]), s);
+                o = (uint8_t)min(max(__float2int_rn(s), 0), 255);
             } else {
                 o = patch[(py + 3) * PW + px + 4];
             }
-            word |= o << (8 * q);
+            dst[(size_t)gy * L.pitch + gx] = o;
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)gy * L.pitch + gx0) = word;
     }
 }
 
@@ -548,6 +566,8 @@ struct se2gpu_orb {
     std::vector<void*> bufs;
     int last_n = 0;
     se2gpu::Profiler prof;
+    cudaStream_t side = nullptr;          // blur runs here, concurrently with FAST + selection
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
 };
 
 namespace {
@@ -702,15 +722,29 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         SE2_LAUNCH(orb_resize, grid, 128, 0, s, d, l);
     }
     pr.end(s);
+    // the blur only depends on the pyramid: fork it onto the side stream so that it overlaps the (latency-bound)
+    // selection kernel; join before the descriptors are sampled. With the profiler on everything stays on one
+    // stream so that the per-kernel event times are not polluted by the overlap.
+    const bool overlap = !pr.on && h->side != nullptr;
+    if (overlap) {
+        SE2_CUDA(cudaEventRecord(h->ev_pyr, s));
+        SE2_CUDA(cudaStreamWaitEvent(h->side, h->ev_pyr, 0));
+        SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, h->side, d);
+        SE2_CUDA(cudaEventRecord(h->ev_blur, h->side));
+    }
     pr.begin(1, s);
     SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     pr.end(s);
     pr.begin(2, s);
     SE2_LAUNCH(orb_select, dim3(h->nlevels, n), 128, h->select_smem, s, d);
     pr.end(s);
-    pr.begin(3, s);
-    SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, s, d);
-    pr.end(s);
+    if (overlap) {
+        SE2_CUDA(cudaStreamWaitEvent(s, h->ev_blur, 0));
+    } else {
+        pr.begin(3, s);
+        SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, s, d);
+        pr.end(s);
+    }
     const int warps = 8;
     pr.begin(4, s);
     SE2_LAUNCH(orb_orient_describe, dim3((h->nfeatures + warps - 1) / warps, n), warps * 32, 0, s, d, d_kps, d_desc, d_counts);
@@ -770,6 +804,8 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     A(&h->d_in, B * (size_t)max_w * max_h); A(&h->d_kps, B * nfeatures); A(&h->d_desc, B * nfeatures * 32); A(&h->d_counts, B);
     if (!ok) { fail(SE2GPU_ERR_CUDA, "device allocation failed (%s)", cudaGetErrorString(cudaGetLastError())); se2gpu_orb_destroy(h); return nullptr; }
     cudaMemset(d.err, 0, sizeof(int));
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
     cudaMemcpyToSymbol(c_umax, umax, sizeof umax);
     cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
     d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
@@ -782,6 +818,9 @@ void se2gpu_orb_destroy(se2gpu_orb* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (void* p : h->bufs) cudaFree(p);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
+    if (h->ev_blur) cudaEventDestroy(h->ev_blur);
     delete h;
 }
 

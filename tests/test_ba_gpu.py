@@ -15,6 +15,7 @@ from se2lam_b200.ba import LocalBA
 pytestmark = pytest.mark.gpu
 
 REL = 1e-5
+MODES = [pytest.param(1, id="multi-launch"), pytest.param(2, id="persistent")]
 
 
 def rel_err(a, b):
@@ -48,12 +49,13 @@ def test_linear_system_matches_oracle(cfg):
     assert rel_err(sysm["dx_l"], ss["dx_l"]) < REL
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cfg,iters", [("C1", 10), ("C3", 10), ("C4", 10)])
-def test_lm_trajectory_matches_oracle_per_step(cfg, iters):
+def test_lm_trajectory_matches_oracle_per_step(cfg, iters, mode):
     prob = synth.ba_config(cfg)
     o = pyoracle.BAOracle(prob)
     n_o, st_o, tp_o, tl_o = o.optimize(iters, trace=True)
-    g = LocalBA.from_problem(prob)
+    g = LocalBA.from_problem(prob, mode=mode)
     n_g, st_g, tp_g, tl_g = g.optimize(iters, trace=True)
     assert n_g == n_o
     np.testing.assert_array_equal(st_g["trials"], st_o["trials"])
@@ -74,8 +76,9 @@ def test_lm_trajectory_matches_oracle_per_step(cfg, iters):
     np.testing.assert_array_equal(poses[prob.fixed == 1], prob.poses[prob.fixed == 1])  # gauge
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("seed,sp,sl,sth", [(14, 0.5, 1.5, 0.0), (17, 1.0, 3.0, 0.2), (16, 0.5, 1.5, 0.0)])
-def test_rejected_trials_follow_the_oracle(seed, sp, sl, sth):
+def test_rejected_trials_follow_the_oracle(seed, sp, sl, sth, mode):
     """Badly initialised windows make LM reject steps: lambda/nu schedule, restores and retries must agree."""
     prob = synth.ba_window(n_kf=10, n_lm=400, seed=seed)
     rng = np.random.default_rng(1)
@@ -84,7 +87,7 @@ def test_rejected_trials_follow_the_oracle(seed, sp, sl, sth):
     prob.poses[1:, 2] += rng.normal(0, sth, prob.P - 1)
     o = pyoracle.BAOracle(prob)
     n_o, st_o, tp_o, tl_o = o.optimize(12, trace=True)
-    g = LocalBA.from_problem(prob)
+    g = LocalBA.from_problem(prob, mode=mode)
     n_g, st_g, tp_g, tl_g = g.optimize(12, trace=True)
     assert st_o["trials"].max() > 1, "test input no longer triggers a rejected step"
     assert n_g == n_o
@@ -101,13 +104,14 @@ def test_rejected_trials_follow_the_oracle(seed, sp, sl, sth):
         assert np.abs(tl_g[k] - tl_o[k]).max() <= 1e-3 * max(np.abs(ref_l).max(), 1e-6), f"landmark state {k}"
 
 
-def test_edge_cases_unobserved_landmarks_and_all_poses_fixed():
+@pytest.mark.parametrize("mode", MODES)
+def test_edge_cases_unobserved_landmarks_and_all_poses_fixed(mode):
     prob = synth.ba_window(n_kf=4, n_lm=50, seed=2)
     keep = prob.edge_point != 0  # landmark 0 loses all its edges: inactive vertex, must stay untouched
     prob.edge_pose, prob.edge_point, prob.uv, prob.info = prob.edge_pose[keep], prob.edge_point[keep], prob.uv[keep], prob.info[keep]
     o = pyoracle.BAOracle(prob)
     n_o, st_o = o.optimize(5)
-    g = LocalBA.from_problem(prob)
+    g = LocalBA.from_problem(prob, mode=mode)
     n_g, st_g = g.optimize(5)
     assert n_g == n_o
     po, lo = o.get(); pg, lg = g.get()
@@ -116,7 +120,7 @@ def test_edge_cases_unobserved_landmarks_and_all_poses_fixed():
     np.testing.assert_allclose(lg, lo, atol=1e-6)
     prob2 = synth.ba_window(n_kf=3, n_lm=30, seed=4)
     prob2.fixed[:] = 1  # all poses fixed: only landmarks move
-    o2 = pyoracle.BAOracle(prob2); g2 = LocalBA.from_problem(prob2)
+    o2 = pyoracle.BAOracle(prob2); g2 = LocalBA.from_problem(prob2, mode=mode)
     n_o2, _ = o2.optimize(4); n_g2, _ = g2.optimize(4)
     assert n_g2 == n_o2
     np.testing.assert_allclose(g2.get()[1], o2.get()[1], atol=1e-6)
@@ -186,3 +190,29 @@ def test_graph_facade_reads_like_the_reference_loader():
         np.testing.assert_allclose(B.estimateVertexSE2(opt, i), po[i], atol=1e-8)
     for j in range(0, prob.L, 17):
         np.testing.assert_allclose(B.estimateVertexSBAXYZ(opt, maxKFid + j), lo[j], atol=1e-7)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_reset_and_stop_flag(mode):
+    """se2gpu_ba_reset restores the loaded window bit for bit; a raised abort flag stops the optimiser
+    (setForceStopFlag semantics: no iteration is started once the flag is set)."""
+    prob = synth.ba_config("C3")
+    g = LocalBA.from_problem(prob, mode=mode)
+    n1, st1 = g.optimize(6)
+    p1, l1 = g.get()
+    g.reset()
+    p0, l0 = g.get()
+    np.testing.assert_array_equal(p0, prob.poses); np.testing.assert_array_equal(l0, prob.points)
+    n2, st2 = g.optimize(6)
+    p2, l2 = g.get()
+    assert n1 == n2 and p1.tobytes() == p2.tobytes() and l1.tobytes() == l2.tobytes()      # bit-reproducible runs
+    np.testing.assert_array_equal(st1["chi2_after"], st2["chi2_after"])
+    g.reset()
+    flag = np.ones(1, np.uint8)
+    n3, _ = g.optimize(6, stop_flag=flag)
+    assert n3 == 0
+    np.testing.assert_array_equal(g.get()[0], prob.poses)
+    # continuing after a finished optimize restarts the lambda schedule (g2o: iteration==0 of a new optimize call)
+    flag[0] = 0
+    n4, st4 = g.optimize(3, stop_flag=flag)
+    assert n4 == 3 and st4["chi2_before"][0] == st1["chi2_before"][0]
