@@ -31,9 +31,10 @@ namespace {
 
 using se2gpu::fail;
 
+constexpr int EB = 12;             // doubles per edge record (9 used + padding to 96 B = 3 L2 sectors)
 constexpr int LM_THREADS = 128;   // threads per block in per-landmark kernels
-constexpr int CHOL_THREADS = 256;
-constexpr int SMEM_CHOL_MAX_N = 158;  // (n*n + 2n + 2)*8 + n*4 <= 227 KB
+constexpr int CHOL_THREADS = 512;
+constexpr int SMEM_CHOL_MAX_N = 156;  // ldlt_smem_bytes(n) <= 227 KB, n a multiple of 3
 
 struct Cam {
     double fx, cx, cy, Rcb[9], tcb[3], delta;
@@ -59,7 +60,9 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     const int *o_i, *o_j;
     const double *o_m, *o_w;  // [3][O], [6][O]
     // per-edge / per-landmark outputs (SoA, component-major)
-    double *Hpl, *PH, *Pb, *Y, *g;        // [9][E] [6][E] [3][E] [9][E] [3][E]
+    // per-edge records, array-of-structures with a 96 B stride so that one record is exactly 3 L2 sectors:
+    //   Hpl[e] = 3x3 pose-landmark block; PH[e] = pose-side Hessian (6 unique) + gradient (3); Y[e] = Hpl Hll^-1 (9) + g (3)
+    double *Hpl, *PH, *Y;
     double *Hll, *bl, *HllInv;            // [6][L] [3][L] [6][L]
     double *oAii, *oAij, *oAjj, *obi, *obj;  // [6][O] [9][O] [6][O] [3][O] [3][O]
     // pose-side gathers
@@ -188,16 +191,16 @@ __global__ void __launch_bounds__(LM_THREADS) ba_linearize(Dev d, Cam cam, int u
 #pragma unroll
                             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) d.Hpl[(r * 3 + c) * (size_t)E + e] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
-                            d.PH[0 * (size_t)E + e] = AtW[0] * A[0] + AtW[1] * A[3];
-                            d.PH[1 * (size_t)E + e] = AtW[0] * A[1] + AtW[1] * A[4];
-                            d.PH[2 * (size_t)E + e] = AtW[0] * A[2] + AtW[1] * A[5];
-                            d.PH[3 * (size_t)E + e] = AtW[2] * A[1] + AtW[3] * A[4];
-                            d.PH[4 * (size_t)E + e] = AtW[2] * A[2] + AtW[3] * A[5];
-                            d.PH[5 * (size_t)E + e] = AtW[4] * A[2] + AtW[5] * A[5];
-                            d.Pb[0 * (size_t)E + e] = A[0] * r0 + A[3] * r1;
-                            d.Pb[1 * (size_t)E + e] = A[1] * r0 + A[4] * r1;
-                            d.Pb[2 * (size_t)E + e] = A[2] * r0 + A[5] * r1;
+                                for (int c = 0; c < 3; ++c) d.Hpl[(size_t)e * EB + ((r * 3 + c))] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
+                            d.PH[(size_t)e * EB + (0)] = AtW[0] * A[0] + AtW[1] * A[3];
+                            d.PH[(size_t)e * EB + (1)] = AtW[0] * A[1] + AtW[1] * A[4];
+                            d.PH[(size_t)e * EB + (2)] = AtW[0] * A[2] + AtW[1] * A[5];
+                            d.PH[(size_t)e * EB + (3)] = AtW[2] * A[1] + AtW[3] * A[4];
+                            d.PH[(size_t)e * EB + (4)] = AtW[2] * A[2] + AtW[3] * A[5];
+                            d.PH[(size_t)e * EB + (5)] = AtW[4] * A[2] + AtW[5] * A[5];
+                            d.PH[(size_t)e * EB + 6 + (0)] = A[0] * r0 + A[3] * r1;
+                            d.PH[(size_t)e * EB + 6 + (1)] = A[1] * r0 + A[4] * r1;
+                            d.PH[(size_t)e * EB + 6 + (2)] = A[2] * r0 + A[5] * r1;
                         }
                     }
                 }
@@ -272,9 +275,9 @@ __global__ void __launch_bounds__(POSE_THREADS) ba_pose_reduce(Dev d) {
     for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += POSE_THREADS) {
         const int e = d.pose_edges[k];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) acc[q] += d.PH[q * E + e];
+        for (int q = 0; q < 6; ++q) acc[q] += d.PH[(size_t)e * EB + (q)];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) acc[6 + q] += d.Pb[q * E + e];
+        for (int q = 0; q < 3; ++q) acc[6 + q] += d.PH[(size_t)e * EB + 6 + (q)];
     }
     for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += POSE_THREADS) {
         const int code = d.pose_odo[k], o = code >> 1;
@@ -360,11 +363,11 @@ __global__ void __launch_bounds__(LM_THREADS) ba_lm_prep(Dev d) {
         if (d.e_hidx[k] < 0) continue;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const double h0 = d.Hpl[(r * 3 + 0) * E + k], h1 = d.Hpl[(r * 3 + 1) * E + k], h2 = d.Hpl[(r * 3 + 2) * E + k];
-            d.Y[(r * 3 + 0) * E + k] = h0 * i00 + h1 * i01 + h2 * i02;
-            d.Y[(r * 3 + 1) * E + k] = h0 * i01 + h1 * i11 + h2 * i12;
-            d.Y[(r * 3 + 2) * E + k] = h0 * i02 + h1 * i12 + h2 * i22;
-            d.g[r * E + k] = h0 * db0 + h1 * db1 + h2 * db2;
+            const double h0 = d.Hpl[(size_t)k * EB + ((r * 3 + 0))], h1 = d.Hpl[(size_t)k * EB + ((r * 3 + 1))], h2 = d.Hpl[(size_t)k * EB + ((r * 3 + 2))];
+            d.Y[(size_t)k * EB + ((r * 3 + 0))] = h0 * i00 + h1 * i01 + h2 * i02;
+            d.Y[(size_t)k * EB + ((r * 3 + 1))] = h0 * i01 + h1 * i11 + h2 * i12;
+            d.Y[(size_t)k * EB + ((r * 3 + 2))] = h0 * i02 + h1 * i12 + h2 * i22;
+            d.Y[(size_t)k * EB + 9 + (r)] = h0 * db0 + h1 * db1 + h2 * db2;
         }
     }
 }
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
         const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
         double y[9], h[9];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) { y[q] = d.Y[q * E + e1]; h[q] = d.Hpl[q * E + e2]; }
+        for (int q = 0; q < 9; ++q) { y[q] = d.Y[(size_t)e1 * EB + (q)]; h[q] = d.Hpl[(size_t)e2 * EB + (q)]; }
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -401,7 +404,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
     if (a == b)
         for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += SCHUR_THREADS) {
             const int e = d.pose_edges[k];
-            acc[9] -= d.g[e]; acc[10] -= d.g[E + e]; acc[11] -= d.g[2 * E + e];
+            acc[9] -= d.Y[(size_t)e * EB + 9]; acc[10] -= d.Y[(size_t)e * EB + 10]; acc[11] -= d.Y[(size_t)e * EB + 9 + (2)];
         }
 #pragma unroll
     for (int q = 0; q < 12; ++q)
@@ -434,49 +437,79 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
     }
 }
 
-// one CTA: in-place LDL^T (== Cholesky with positive pivots) of the n x n matrix at A (row-major, leading dim n,
-// lower triangle) restricted to its envelope: colmax[k] is the last row with a structural non-zero in column k
-// (monotone closure computed on the host from the block list), so fill-in stays inside [k+1, colmax[k]]^2.
-// One __syncthreads per pivot: the column is kept unscaled (L*D form) and the trailing update divides by the pivot.
-// The right-hand side rides along as an extra row (forward substitution for free); the back substitution is done
-// by warp 0 alone (warp-synchronous, no block barriers). Writes dxp and st->solve_ok.
-__device__ void ldlt_solve_body(double* A, double* y, double* dinv, int n, const int* colmax,
-                                const double* bs, double* dxp, LMState* st) {
+// Reduced solve, one CTA: block LDL^T with 3x3 pivot blocks (one pose per block) restricted to the envelope of S.
+//   S = L D L^T, D block diagonal, L unit block lower. Per block step k: W = D_k^-1 (closed-form symmetric inverse; the
+//   leading principal minors double as the positive-definiteness test == CHOLMOD's "not PD"), every trailing entry
+//   A[i][j] -= a_i . (W a_j) with a_i = A[i][k..k+2] left UNSCALED in place, the right-hand side rides along as an
+//   extra column. One block barrier per pose (n/3 barriers instead of n), a short FP64 dependency chain per step
+//   (measured on B200: dependent DFMA 8 cycles, 1/x 67, LDS 29, barrier 29 -> ~300 cycles per step).
+// Back substitution: x_k = W_k (u_k - sum_{i>k} a_i^T x_i), warp 0 only, warp-synchronous.
+// SMEM=true indexes the dynamic shared array directly (LDS, no generic-address conversion in the loops);
+// SMEM=false works in place in global memory (reduced systems too large for one CTA's shared memory).
+template <bool SMEM>
+__device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
+    extern __shared__ double sm[];
     __shared__ int ok;
+    // layout (SMEM): A [n*n] | y [n] | Wb [3n] | cmax (int) [n]
+    double* A = SMEM ? sm : G;
+    double* y = SMEM ? sm + (size_t)n * n : ywork;
+    double* Wb = SMEM ? sm + (size_t)n * n + n : ywork + n;          // 9 doubles per pose
+    const int* cmax = SMEM ? reinterpret_cast<const int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2) : colmax_g;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int tx = tid & 31, ty = tid >> 5, nty = nt >> 5;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     if (tid == 0) ok = 1;
     for (int i = tid; i < n; i += nt) y[i] = bs[i];
     __syncthreads();
-    for (int k = 0; k < n; ++k) {
-        const double akk = A[(size_t)k * n + k];
-        if (!(akk > 0.0) || !isfinite(akk)) { if (tid == 0) ok = 0; break; }   // uniform: every thread reads the same pivot
-        const double inv = 1.0 / akk;
-        const int hi = colmax[k];                 // rows/cols k+1..hi are touched by column k
-        const int m = hi - k;
-        const double yk = y[k];
-        // no barrier needed here: this step only writes A[i][j], y[i] with i,j > k, never the pivot, y[k] or column k
-        for (int ii = ty; ii < m; ii += nty) {
-            const int i = k + 1 + ii;
-            const double lik = A[(size_t)i * n + k] * inv;
-            for (int jj = tx; jj <= ii; jj += 32) {
-                const int j = k + 1 + jj;
-                A[(size_t)i * n + j] -= lik * A[(size_t)j * n + k];
+    const int nb = n / 3;
+    for (int kb = 0; kb < nb; ++kb) {
+        const int k = 3 * kb;
+        // pivot block (lower part) and its inverse, redundantly in every thread
+        const double a = A[(size_t)k * n + k], b = A[(size_t)(k + 1) * n + k], c = A[(size_t)(k + 2) * n + k];
+        const double e = A[(size_t)(k + 1) * n + k + 1], f = A[(size_t)(k + 2) * n + k + 1], i2 = A[(size_t)(k + 2) * n + k + 2];
+        const double c00 = e * i2 - f * f, c01 = c * f - b * i2, c02 = b * f - c * e;
+        const double det = a * c00 + b * c01 + c * c02, m2 = a * e - b * b;
+        if (!(a > 0.0) || !(m2 > 0.0) || !(det > 0.0) || !isfinite(det)) { if (tid == 0) ok = 0; break; }   // uniform
+        const double id = 1.0 / det;
+        const double w00 = c00 * id, w01 = c01 * id, w02 = c02 * id, w11 = (a * i2 - c * c) * id, w12 = (b * c - a * f) * id, w22 = m2 * id;
+        const double u0 = y[k], u1 = y[k + 1], u2 = y[k + 2];
+        const double t0 = w00 * u0 + w01 * u1 + w02 * u2, t1 = w01 * u0 + w11 * u1 + w12 * u2, t2 = w02 * u0 + w12 * u1 + w22 * u2;
+        const int hi = cmax[k + 2];
+        const int m = hi - (k + 2);                 // trailing rows/cols k+3 .. hi
+        for (int ii = wid; ii < m; ii += nw) {
+            const int i = k + 3 + ii;
+            const double a0 = A[(size_t)i * n + k], a1 = A[(size_t)i * n + k + 1], a2 = A[(size_t)i * n + k + 2];
+            for (int jj = lane; jj <= ii + 1; jj += 32) {
+                if (jj <= ii) {
+                    const int j = k + 3 + jj;
+                    const double b0 = A[(size_t)j * n + k], b1 = A[(size_t)j * n + k + 1], b2 = A[(size_t)j * n + k + 2];
+                    const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
+                    A[(size_t)i * n + j] -= a0 * v0 + a1 * v1 + a2 * v2;
+                } else {
+                    y[i] -= a0 * t0 + a1 * t1 + a2 * t2;        // the right-hand side as an extra column
+                }
             }
-            if (tx == 0) y[i] -= lik * yk;
         }
-        if (tid == 0) dinv[k] = inv;
+        if (tid < 9) {
+            const double W9[9] = {w00, w01, w02, w01, w11, w12, w02, w12, w22};
+            Wb[9 * kb + tid] = W9[tid];
+        }
         __syncthreads();
     }
     __syncthreads();
     if (ok) {
-        if (ty == 0) {
-            // L^T x = D^-1 w, L unit lower with L[i][k] = A[i][k] * dinv[k]; rows are contiguous
-            for (int i = tx; i < n; i += 32) y[i] *= dinv[i];
-            __syncwarp();
-            for (int k = n - 1; k > 0; --k) {
-                const double xk = y[k];
-                for (int i = tx; i < k; i += 32) y[i] -= A[(size_t)k * n + i] * dinv[i] * xk;
+        if (wid == 0) {
+            for (int kb = nb - 1; kb >= 0; --kb) {
+                const int k = 3 * kb, hi = cmax[k + 2];
+                double r = 0;
+                if (lane < 3) {
+                    double s0 = 0, s1 = 0;
+                    int i = k + 3;
+                    for (; i + 1 <= hi; i += 2) { s0 += A[(size_t)i * n + k + lane] * y[i]; s1 += A[(size_t)(i + 1) * n + k + lane] * y[i + 1]; }
+                    if (i <= hi) s0 += A[(size_t)i * n + k + lane] * y[i];
+                    r = y[k + lane] - (s0 + s1);
+                }
+                const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2);
+                if (lane < 3) y[k + lane] = Wb[9 * kb + 3 * lane] * r0 + Wb[9 * kb + 3 * lane + 1] * r1 + Wb[9 * kb + 3 * lane + 2] * r2;
                 __syncwarp();
             }
         }
@@ -488,21 +521,25 @@ __device__ void ldlt_solve_body(double* A, double* y, double* dinv, int n, const
     if (tid == 0) st->solve_ok = ok;
 }
 
-__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
-    extern __shared__ double smem[];
+// bytes of dynamic shared memory the SMEM variant needs for n unknowns
+__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16; }
+
+__device__ __forceinline__ void ldlt_stage(const Dev& d) {   // S, envelope -> shared memory
+    extern __shared__ double sm[];
     const int n = d.n;
-    double* A = smem;
-    double* y = smem + (size_t)n * n;
-    double* dinv = y + n;
-    int* cmax = reinterpret_cast<int*>(dinv + n + 2);   // keep the per-pivot envelope lookup out of the L2 latency path
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = d.S[t];
+    int* cmax = reinterpret_cast<int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2);
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) sm[t] = d.S[t];
     for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
     __syncthreads();
-    ldlt_solve_body(A, y, dinv, n, cmax, d.bs, d.dxp, d.st);
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
+    ldlt_stage(d);
+    ldlt_block_solve<true>(nullptr, nullptr, d.n, nullptr, d.bs, d.dxp, d.st);
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_gmem(Dev d, double* ywork) {
-    ldlt_solve_body(d.S, ywork, ywork + d.n, d.n, d.colmax, d.bs, d.dxp, d.st);
+    ldlt_block_solve<false>(d.S, ywork, d.n, d.colmax, d.bs, d.dxp, d.st);
 }
 
 // back-substitution + oplus into the trial buffers + partial sums of computeScale()
@@ -528,9 +565,9 @@ __global__ void __launch_bounds__(LM_THREADS) ba_backsub_update(Dev d) {
                 const int a = d.e_hidx[k];
                 if (a < 0) continue;
                 const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
-                c0 -= d.Hpl[0 * E + k] * p0 + d.Hpl[3 * E + k] * p1 + d.Hpl[6 * E + k] * p2;
-                c1 -= d.Hpl[1 * E + k] * p0 + d.Hpl[4 * E + k] * p1 + d.Hpl[7 * E + k] * p2;
-                c2 -= d.Hpl[2 * E + k] * p0 + d.Hpl[5 * E + k] * p1 + d.Hpl[8 * E + k] * p2;
+                c0 -= d.Hpl[(size_t)k * EB + (0)] * p0 + d.Hpl[(size_t)k * EB + (3)] * p1 + d.Hpl[(size_t)k * EB + (6)] * p2;
+                c1 -= d.Hpl[(size_t)k * EB + (1)] * p0 + d.Hpl[(size_t)k * EB + (4)] * p1 + d.Hpl[(size_t)k * EB + (7)] * p2;
+                c2 -= d.Hpl[(size_t)k * EB + (2)] * p0 + d.Hpl[(size_t)k * EB + (5)] * p1 + d.Hpl[(size_t)k * EB + (8)] * p2;
             }
             const double i00 = d.HllInv[j], i01 = d.HllInv[L + j], i02 = d.HllInv[2 * L + j], i11 = d.HllInv[3 * L + j], i12 = d.HllInv[4 * L + j], i22 = d.HllInv[5 * L + j];
             dl0 = i00 * c0 + i01 * c1 + i02 * c2; dl1 = i01 * c0 + i11 * c1 + i12 * c2; dl2 = i02 * c0 + i12 * c1 + i22 * c2;
@@ -688,11 +725,11 @@ __device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, cons
 #pragma unroll
                     for (int r = 0; r < 3; ++r)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) d.Hpl[(r * 3 + c) * E + e] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
-                    d.PH[0 * E + e] = AtW[0] * A[0] + AtW[1] * A[3]; d.PH[1 * E + e] = AtW[0] * A[1] + AtW[1] * A[4];
-                    d.PH[2 * E + e] = AtW[0] * A[2] + AtW[1] * A[5]; d.PH[3 * E + e] = AtW[2] * A[1] + AtW[3] * A[4];
-                    d.PH[4 * E + e] = AtW[2] * A[2] + AtW[3] * A[5]; d.PH[5 * E + e] = AtW[4] * A[2] + AtW[5] * A[5];
-                    d.Pb[0 * E + e] = A[0] * r0 + A[3] * r1; d.Pb[1 * E + e] = A[1] * r0 + A[4] * r1; d.Pb[2 * E + e] = A[2] * r0 + A[5] * r1;
+                        for (int c = 0; c < 3; ++c) d.Hpl[(size_t)e * EB + ((r * 3 + c))] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
+                    d.PH[(size_t)e * EB + (0)] = AtW[0] * A[0] + AtW[1] * A[3]; d.PH[(size_t)e * EB + (1)] = AtW[0] * A[1] + AtW[1] * A[4];
+                    d.PH[(size_t)e * EB + (2)] = AtW[0] * A[2] + AtW[1] * A[5]; d.PH[(size_t)e * EB + (3)] = AtW[2] * A[1] + AtW[3] * A[4];
+                    d.PH[(size_t)e * EB + (4)] = AtW[2] * A[2] + AtW[3] * A[5]; d.PH[(size_t)e * EB + (5)] = AtW[4] * A[2] + AtW[5] * A[5];
+                    d.PH[(size_t)e * EB + 6 + (0)] = A[0] * r0 + A[3] * r1; d.PH[(size_t)e * EB + 6 + (1)] = A[1] * r0 + A[4] * r1; d.PH[(size_t)e * EB + 6 + (2)] = A[2] * r0 + A[5] * r1;
                 }
             }
         }
@@ -775,9 +812,9 @@ __device__ void pk_phase_pose_reduce(const Dev& d, double* sh9 /*[8][9]*/) {
         for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += blockDim.x) {
             const int e = d.pose_edges[k];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q] += d.PH[q * E + e];
+            for (int q = 0; q < 6; ++q) acc[q] += d.PH[(size_t)e * EB + (q)];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) acc[6 + q] += d.Pb[q * E + e];
+            for (int q = 0; q < 3; ++q) acc[6 + q] += d.PH[(size_t)e * EB + 6 + (q)];
         }
         for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += blockDim.x) {
             const int code = d.pose_odo[k], o = code >> 1;
@@ -824,11 +861,11 @@ __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
             if (d.e_hidx[k] < 0) continue;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const double h0 = d.Hpl[(r * 3 + 0) * E + k], h1 = d.Hpl[(r * 3 + 1) * E + k], h2 = d.Hpl[(r * 3 + 2) * E + k];
-                d.Y[(r * 3 + 0) * E + k] = h0 * i00 + h1 * i01 + h2 * i02;
-                d.Y[(r * 3 + 1) * E + k] = h0 * i01 + h1 * i11 + h2 * i12;
-                d.Y[(r * 3 + 2) * E + k] = h0 * i02 + h1 * i12 + h2 * i22;
-                d.g[r * E + k] = h0 * db0 + h1 * db1 + h2 * db2;
+                const double h0 = d.Hpl[(size_t)k * EB + ((r * 3 + 0))], h1 = d.Hpl[(size_t)k * EB + ((r * 3 + 1))], h2 = d.Hpl[(size_t)k * EB + ((r * 3 + 2))];
+                d.Y[(size_t)k * EB + ((r * 3 + 0))] = h0 * i00 + h1 * i01 + h2 * i02;
+                d.Y[(size_t)k * EB + ((r * 3 + 1))] = h0 * i01 + h1 * i11 + h2 * i12;
+                d.Y[(size_t)k * EB + ((r * 3 + 2))] = h0 * i02 + h1 * i12 + h2 * i22;
+                d.Y[(size_t)k * EB + 9 + (r)] = h0 * db0 + h1 * db1 + h2 * db2;
             }
         }
     }
@@ -846,7 +883,7 @@ __device__ void pk_phase_schur(const Dev& d, double lam, double* sh12 /*[8][12]*
             const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
             double y[9], h[9];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { y[q] = d.Y[q * E + e1]; h[q] = d.Hpl[q * E + e2]; }
+            for (int q = 0; q < 9; ++q) { y[q] = d.Y[(size_t)e1 * EB + (q)]; h[q] = d.Hpl[(size_t)e2 * EB + (q)]; }
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -862,7 +899,7 @@ __device__ void pk_phase_schur(const Dev& d, double lam, double* sh12 /*[8][12]*
         if (a == b)
             for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += blockDim.x) {
                 const int e = d.pose_edges[k];
-                acc[9] -= d.g[e]; acc[10] -= d.g[E + e]; acc[11] -= d.g[2 * E + e];
+                acc[9] -= d.Y[(size_t)e * EB + 9]; acc[10] -= d.Y[(size_t)e * EB + 10]; acc[11] -= d.Y[(size_t)e * EB + 9 + (2)];
             }
 #pragma unroll
         for (int q = 0; q < 12; ++q)
@@ -909,9 +946,9 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
             const int a = d.e_hidx[k];
             if (a < 0) continue;
             const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
-            c0 -= d.Hpl[0 * E + k] * p0 + d.Hpl[3 * E + k] * p1 + d.Hpl[6 * E + k] * p2;
-            c1 -= d.Hpl[1 * E + k] * p0 + d.Hpl[4 * E + k] * p1 + d.Hpl[7 * E + k] * p2;
-            c2 -= d.Hpl[2 * E + k] * p0 + d.Hpl[5 * E + k] * p1 + d.Hpl[8 * E + k] * p2;
+            c0 -= d.Hpl[(size_t)k * EB + (0)] * p0 + d.Hpl[(size_t)k * EB + (3)] * p1 + d.Hpl[(size_t)k * EB + (6)] * p2;
+            c1 -= d.Hpl[(size_t)k * EB + (1)] * p0 + d.Hpl[(size_t)k * EB + (4)] * p1 + d.Hpl[(size_t)k * EB + (7)] * p2;
+            c2 -= d.Hpl[(size_t)k * EB + (2)] * p0 + d.Hpl[(size_t)k * EB + (5)] * p1 + d.Hpl[(size_t)k * EB + (8)] * p2;
         }
         c0 = group_sum(c0); c1 = group_sum(c1); c2 = group_sum(c2);
         if (sub == 0 && j < d.L) {
@@ -942,7 +979,6 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
 
 __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, PKArgs pa) {
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ double smem[];            // LDL^T workspace (used by CTA 0)
     __shared__ double sh[32];
     __shared__ double shv[8 * 12];
     const int n = d.n, nparts = gridDim.x;
@@ -995,12 +1031,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             PK_TICK(3);
             // ---- D: reduced solve (one CTA; S staged into its shared memory)
             if (blockIdx.x == 0) {
-                double* A = smem; double* y = smem + (size_t)n * n; double* dinv = y + n;
-                int* cmax = reinterpret_cast<int*>(dinv + n + 2);
-                for (int t = threadIdx.x; t < n * n; t += blockDim.x) A[t] = d.S[t];
-                for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
-                __syncthreads();
-                ldlt_solve_body(A, y, dinv, n, cmax, d.bs, d.dxp, d.st);
+                ldlt_stage(d);
+                ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, d.bs, d.dxp, d.st);
             }
             grid.sync();
             PK_TICK(4);
@@ -1147,12 +1179,12 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&h->e_pose, E); A(&h->e_hidx, E); A(&h->lm_ptr, L + 1); A(&h->hidx, P);
     A(&h->e_u, E); A(&h->e_v, E); A(&h->e_w00, E); A(&h->e_w01, E); A(&h->e_w11, E);
     A(&h->o_i, O); A(&h->o_j, O); A(&h->o_m, 3 * O); A(&h->o_w, 6 * O);
-    A(&d.Hpl, 9 * E); A(&d.PH, 6 * E); A(&d.Pb, 3 * E); A(&d.Y, 9 * E); A(&d.g, 3 * E);
+    A(&d.Hpl, EB * E); A(&d.PH, EB * E); A(&d.Y, EB * E);
     A(&d.Hll, 6 * L); A(&d.bl, 3 * L); A(&d.HllInv, 6 * L);
     A(&d.oAii, 6 * O); A(&d.oAij, 9 * O); A(&d.oAjj, 6 * O); A(&d.obi, 3 * O); A(&d.obj, 3 * O);
     A(&h->pose_ptr, P + 1); A(&h->pose_edges, E); A(&h->pose_odo_ptr, P + 1); A(&h->pose_odo, 2 * O);
     A(&d.Hpp, 6 * P); A(&d.bp, 3 * P);
-    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 2 * maxN); A(&h->colmax, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
+    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 4 * maxN + 16); A(&h->colmax, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
     const size_t nb = (L + LM_THREADS - 1) / LM_THREADS + (O + LM_THREADS - 1) / LM_THREADS + (P + LM_THREADS - 1) / LM_THREADS + 4;
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
@@ -1160,11 +1192,11 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&h->pk_part_chi, 1024); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 1); A(&h->phase_cycles, 8);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
-        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8 + SMEM_CHOL_MAX_N * 4 + 16);
+        cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N));
     }
     if (rc == SE2GPU_OK) {
         // persistent cooperative kernel: one CTA per SM, all co-resident
-        const int smem_max = (SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + 2 * SMEM_CHOL_MAX_N + 2) * 8 + SMEM_CHOL_MAX_N * 4 + 16;
+        const int smem_max = (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N);
         int coop = 0, nsm = 0, occ = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
@@ -1398,7 +1430,7 @@ int launch_solve(se2gpu_ba* h) {
     int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
     if (rc != SE2GPU_OK) return rc;
     h->prof.begin(4, s);
-    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8 + (size_t)d.n * 4 + 16, s, d);   // n == 0: trivially ok
+    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ldlt_smem_bytes(d.n), s, d);   // n == 0: trivially ok
     else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     h->prof.end(s);
     return SE2GPU_OK;
@@ -1435,7 +1467,7 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         PKArgs pa{max_iters, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
                   h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr};
         if (h->prof.on) h->pk_launches++;
-        const size_t smem = ((size_t)d.n * d.n + 2 * d.n + 2) * 8 + (size_t)d.n * 4 + 16;
+        const size_t smem = ldlt_smem_bytes(d.n);
         void* args[] = {(void*)&d, (void*)&h->cam, (void*)&pa};
         h->prof.begin(7, s);
         SE2_CUDA(cudaLaunchCooperativeKernel((void*)ba_persistent, dim3(h->pk_grid), dim3(PK_THREADS), args, smem, s));
@@ -1597,7 +1629,7 @@ int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hp
     auto get = [&](const double* dev, size_t cnt) { tmp.resize(cnt); return cudaMemcpyAsync(tmp.data(), dev, cnt * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess; };
     if (S) { if (!get(d.S, (size_t)n * n)) return fail(SE2GPU_ERR_CUDA, "copy S"); memcpy(S, tmp.data(), tmp.size() * 8); }
     if (bs) { if (!get(d.bs, n)) return fail(SE2GPU_ERR_CUDA, "copy bs"); memcpy(bs, tmp.data(), tmp.size() * 8); }
-    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ((size_t)d.n * d.n + 2 * d.n + 2) * 8 + (size_t)d.n * 4 + 16, s, d);
+    if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ldlt_smem_bytes(d.n), s, d);
     else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
     if (Hpp) {
@@ -1630,11 +1662,11 @@ int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hp
         for (int j = 0; j < L; ++j) for (int q = 0; q < 3; ++q) bl[3 * (size_t)j + q] = lmp[j + 1] > lmp[j] ? tmp[q * (size_t)L + j] : 0.0;
     }
     if (Hpl) {
-        if (!get(d.Hpl, 9 * (size_t)E)) return fail(SE2GPU_ERR_CUDA, "copy Hpl");
+        if (!get(d.Hpl, EB * (size_t)E)) return fail(SE2GPU_ERR_CUDA, "copy Hpl");
         std::vector<int> eh(E);
         cudaMemcpy(eh.data(), d.e_hidx, sizeof(int) * E, cudaMemcpyDeviceToHost);
         memset(Hpl, 0, sizeof(double) * 9 * (size_t)h->E);
-        for (int k = 0; k < E; ++k) if (eh[k] >= 0) for (int q = 0; q < 9; ++q) Hpl[9 * (size_t)h->perm[k] + q] = tmp[q * (size_t)E + k];
+        for (int k = 0; k < E; ++k) if (eh[k] >= 0) for (int q = 0; q < 9; ++q) Hpl[9 * (size_t)h->perm[k] + q] = tmp[(size_t)k * EB + q];
     }
     if (dx_p) { if (!get(d.dxp, n)) return fail(SE2GPU_ERR_CUDA, "copy dxp"); memcpy(dx_p, tmp.data(), tmp.size() * 8); }
     if (dx_l) { if (!get(d.dxl, 3 * (size_t)L)) return fail(SE2GPU_ERR_CUDA, "copy dxl"); memcpy(dx_l, tmp.data(), tmp.size() * 8); }
