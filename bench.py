@@ -306,13 +306,13 @@ def run_ours(args):
     # algorithmic bytes per kernel per launch (SURVEY.md section 8d terms)
     balg = {"ba_linearize": E * (56 + 48 + 72) + L * 72, "ba_pose_reduce": P * 72 + E * 72, "ba_lm_prep": L * 72 + E * 72,
             "ba_schur": E * 72 + L * 72 + nS * 8, "ba_chol_solve": nS * 8 * 2, "ba_backsub_update": E * 72 + L * (72 + 24) + (P + L) * 48,
-            "ba_lm_control": 0, "ba_persistent": 0}
+            "ba_lm_control": 0, "ba_persistent": 0, "ba_stage_S": nS * 8}
     iter_alg = E * 424 + L * 288 + P * 120 + O * 112 + nS * 8
     balg["ba_persistent"] = iter_alg * iters / max(args.steps, 1)      # one launch = one optimize() = `iters/steps` LM iterations
     bs = {g: v for g, v in bprof.items() if v[1] > 0}
     persistent = "ba_persistent" in bs
     if persistent:   # one launch per optimize(): the roofline kernel is the whole persistent kernel, phases are reported beside it
-        phases = {g: v for g, v in bs.items() if g != "ba_persistent"}
+        phases = {g: v for g, v in bs.items() if g != "ba_persistent"}   # incl. ba_stage_S (TMA bulk copy of S)
         bs = {"ba_persistent": bs["ba_persistent"]}
     bdom = max(bs, key=lambda g: bs[g][0])
     bdom_ms = bs[bdom][0] / bs[bdom][1]

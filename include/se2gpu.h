@@ -204,8 +204,9 @@ int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream);
 int se2gpu_ba_set_mode(se2gpu_ba* h, int mode);
 
 /* per-kernel device timing for bench.py's roofline line; groups: 0 ba_linearize (+chi2 evaluation), 1 ba_pose_reduce,
- * 2 ba_lm_prep, 3 ba_schur, 4 ba_chol_solve, 5 ba_backsub_update, 6 ba_iter_begin/ba_decide, 7 ba_persistent (whole optimize) */
-#define SE2GPU_BA_PROFILE_GROUPS 8
+ * 2 ba_lm_prep, 3 ba_schur, 4 ba_chol_solve, 5 ba_backsub_update, 6 ba_iter_begin/ba_decide, 7 ba_persistent (whole optimize),
+ * 8 TMA staging of S inside the persistent kernel. In persistent mode groups 0-6 and 8 are in-kernel phase times of CTA 0. */
+#define SE2GPU_BA_PROFILE_GROUPS 9
 int se2gpu_ba_profile(se2gpu_ba* h, int enable);
 int se2gpu_ba_profile_read(se2gpu_ba* h, double* ms, int* launches);
 

@@ -80,7 +80,7 @@ class LocalBA:
         return (n, st[:n], tp[:n], tl[:n]) if trace else (n, st[:n])
 
     PROFILE_GROUPS = ("ba_linearize", "ba_pose_reduce", "ba_lm_prep", "ba_schur", "ba_chol_solve", "ba_backsub_update", "ba_lm_control",
-                      "ba_persistent")
+                      "ba_persistent", "ba_stage_S")
     MODE_AUTO, MODE_MULTI_LAUNCH, MODE_PERSISTENT = 0, 1, 2
 
     def set_mode(self, mode):

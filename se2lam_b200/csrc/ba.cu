@@ -524,17 +524,50 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
 // bytes of dynamic shared memory the SMEM variant needs for n unknowns
 __host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16; }
 
-__device__ __forceinline__ void ldlt_stage(const Dev& d) {   // S, envelope -> shared memory
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: stage the reduced system into shared memory
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("fence.proxy.async;" ::: "memory");   // order earlier generic-proxy accesses before the async-proxy copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// S (n*n doubles, rounded up to 16 B: the tail lands in y, which is initialised afterwards) and the envelope -> shared
+// memory. One elected thread issues a single bulk copy; everybody waits on the mbarrier phase `parity`.
+__device__ __forceinline__ void ldlt_stage(const Dev& d, unsigned long long* bar, unsigned parity) {
     extern __shared__ double sm[];
     const int n = d.n;
     int* cmax = reinterpret_cast<int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2);
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) sm[t] = d.S[t];
-    for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
+    const unsigned bytes = (unsigned)(((size_t)n * n * 8 + 15) & ~(size_t)15);
+    if (bytes) {
+        if (threadIdx.x == 0) bulk_g2s(sm, d.S, bytes, bar);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
+        mbar_wait(bar, parity);
+    }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
-    ldlt_stage(d);
+    __shared__ __align__(8) unsigned long long bar;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    ldlt_stage(d, &bar, 0);
     ldlt_block_solve<true>(nullptr, nullptr, d.n, nullptr, d.bs, d.dxp, d.st);
 }
 
@@ -655,6 +688,7 @@ struct PKArgs {
     double* part_scale;       // [gridDim.x]
     double* part_max;         // [gridDim.x]
     long long* phase_cycles;  // [8] SM cycles CTA 0 spent per phase incl. the barrier that ends it (profiling aid)
+    int dyn_smem_bytes;       // dynamic shared memory of the launch (arena size of the non-zero CTAs)
 };
 
 __device__ __forceinline__ double group_sum(double v) {   // sum over the LPL-lane group, fixed order
@@ -802,43 +836,141 @@ __device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double*
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
 
-__device__ void pk_phase_pose_reduce(const Dev& d, double* sh9 /*[8][9]*/) {
+// Static work lists of a persistent CTA, cached once per optimize() in its (otherwise unused) dynamic shared memory:
+// the (edge, edge) pair lists of the blocks of S it owns and, for diagonal blocks, the pose's edge list. This removes
+// the dependent L2 round trips for index data from every Schur / pose-gather phase (only the payload is gathered).
+constexpr int PK_MAXOWN = 16;
+struct PKOwn { int blk, a, b, p0, np, e0, ne; };
+
+// pose a: Hpp diagonal block (6 unique) + bp from its edges (list in `edges`, shared or global) and odometry edges
+__device__ void pk_pose_item(const Dev& d, int a, const int* edges, int ne, double* sh9 /*[8][9]*/) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t E = d.E, O = d.O;
-    for (int a = blockIdx.x; a < d.nf; a += gridDim.x) {
-        double acc[9];
+    const size_t O = d.O;
+    double acc[9];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) acc[q] = 0;
-        for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += blockDim.x) {
-            const int e = d.pose_edges[k];
+    for (int q = 0; q < 9; ++q) acc[q] = 0;
+    for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+        const double* rec = d.PH + (size_t)edges[k] * EB;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q] += d.PH[(size_t)e * EB + (q)];
+        for (int q = 0; q < 9; ++q) acc[q] += rec[q];
+    }
+    for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += blockDim.x) {
+        const int code = d.pose_odo[k], o = code >> 1;
+        const double* H = (code & 1) ? d.oAjj : d.oAii;
+        const double* b = (code & 1) ? d.obj : d.obi;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) acc[6 + q] += d.PH[(size_t)e * EB + 6 + (q)];
+        for (int q = 0; q < 6; ++q) acc[q] += H[q * O + o];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[6 + q] += b[q * O + o];
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 9; ++q) sh9[wid * 9 + q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh9[w * 9 + threadIdx.x];
+        if (threadIdx.x < 6) d.Hpp[threadIdx.x * (size_t)d.nf + a] = v;
+        else d.bp[3 * a + threadIdx.x - 6] = v;
+    }
+}
+
+// block (a >= b) of the reduced system; pairs interleaved (e1,e2) in `pairs` (shared) or null -> global lists at gp0
+__device__ void pk_schur_item(const Dev& d, double lam, int blk, int a, int b, const int* pairs, int gp0, int np, const int* edges, int ne,
+                              double* sh12 /*[8][12]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t O = d.O, n = d.n, nf = d.nf;
+    double acc[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = 0;
+    for (int k = threadIdx.x; k < np; k += blockDim.x) {
+        const int e1 = pairs ? pairs[2 * k] : d.pair_e1[gp0 + k], e2 = pairs ? pairs[2 * k + 1] : d.pair_e2[gp0 + k];
+        const double* yr = d.Y + (size_t)e1 * EB;
+        const double* hr = d.Hpl + (size_t)e2 * EB;
+        double y[9], h[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { y[q] = yr[q]; h[q] = hr[q]; }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
+    }
+    for (int k = d.blk_odo_ptr[blk] + threadIdx.x; k < d.blk_odo_ptr[blk + 1]; k += blockDim.x) {
+        const int code = d.blk_odo[k], o = code >> 1;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + o] : d.oAij[(r * 3 + c) * O + o];
+    }
+    if (a == b)
+        for (int k = threadIdx.x; k < ne; k += blockDim.x) {
+            const double* yr = d.Y + (size_t)edges[k] * EB;
+            acc[9] -= yr[9]; acc[10] -= yr[10]; acc[11] -= yr[11];
         }
-        for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += blockDim.x) {
-            const int code = d.pose_odo[k], o = code >> 1;
-            const double* H = (code & 1) ? d.oAjj : d.oAii;
-            const double* b = (code & 1) ? d.obj : d.obi;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) acc[q] += H[q * O + o];
+    for (int q = 0; q < 12; ++q)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) acc[6 + q] += b[q * O + o];
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 12; ++q) sh12[wid * 12 + q] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        double v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh12[w * 12 + threadIdx.x];
+        const int q = threadIdx.x;
+        if (q < 9) {
+            const int r = q / 3, c = q % 3;
+            if (a == b) {
+                const int u6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+                v += d.Hpp[u6[r][c] * nf + a] + (r == c ? lam : 0.0);
+            }
+            d.S[(3 * a + r) * n + 3 * b + c] = v;
+        } else if (a == b) {
+            d.bs[3 * a + q - 9] = d.bp[3 * a + q - 9] + v;
         }
-#pragma unroll
-        for (int q = 0; q < 9; ++q)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        __syncthreads();
-        if (lane == 0)
-#pragma unroll
-            for (int q = 0; q < 9; ++q) sh9[wid * 9 + q] = acc[q];
-        __syncthreads();
-        if (threadIdx.x < 9) {
-            double v = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh9[w * 9 + threadIdx.x];
-            if (threadIdx.x < 6) d.Hpp[threadIdx.x * (size_t)d.nf + a] = v;
-            else d.bp[3 * a + threadIdx.x - 6] = v;
+    }
+}
+
+// work split of the gather phases: CTA 0 runs the reduced solve and owns no blocks when the grid has other CTAs
+struct PKWork {
+    int first, stride;     // this CTA's blocks: first, first+stride, ... ; first < 0 -> none
+    int n_own;             // of which the first n_own are cached in shared memory
+    const PKOwn* own;
+    const int* arena;
+};
+
+__device__ void pk_phase_pose_reduce(const Dev& d, const PKWork& w, double* sh9) {
+    if (w.first < 0) return;
+    int i = 0;
+    for (int blk = w.first; blk < d.nblk; blk += w.stride, ++i) {
+        if (i < w.n_own) {
+            const PKOwn o = w.own[i];
+            if (o.a == o.b) pk_pose_item(d, o.a, w.arena + o.e0, o.ne, sh9);
+        } else {
+            const int a = d.blk_a[blk];
+            if (a == d.blk_b[blk]) pk_pose_item(d, a, d.pose_edges + d.pose_ptr[a], d.pose_ptr[a + 1] - d.pose_ptr[a], sh9);
+        }
+    }
+}
+
+__device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double* sh12) {
+    if (w.first < 0) return;
+    int i = 0;
+    for (int blk = w.first; blk < d.nblk; blk += w.stride, ++i) {
+        if (i < w.n_own) {
+            const PKOwn o = w.own[i];
+            pk_schur_item(d, lam, o.blk, o.a, o.b, w.arena + o.p0, 0, o.np, w.arena + o.e0, o.ne, sh12);
+        } else {
+            const int a = d.blk_a[blk], b = d.blk_b[blk];
+            pk_schur_item(d, lam, blk, a, b, nullptr, d.blk_pair_ptr[blk], d.blk_pair_ptr[blk + 1] - d.blk_pair_ptr[blk],
+                          d.pose_edges + d.pose_ptr[a], a == b ? d.pose_ptr[a + 1] - d.pose_ptr[a] : 0, sh12);
         }
     }
 }
@@ -866,63 +998,6 @@ __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
                 d.Y[(size_t)k * EB + ((r * 3 + 1))] = h0 * i01 + h1 * i11 + h2 * i12;
                 d.Y[(size_t)k * EB + ((r * 3 + 2))] = h0 * i02 + h1 * i12 + h2 * i22;
                 d.Y[(size_t)k * EB + 9 + (r)] = h0 * db0 + h1 * db1 + h2 * db2;
-            }
-        }
-    }
-}
-
-__device__ void pk_phase_schur(const Dev& d, double lam, double* sh12 /*[8][12]*/) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t E = d.E, O = d.O, n = d.n, nf = d.nf;
-    for (int blk = blockIdx.x; blk < d.nblk; blk += gridDim.x) {
-        const int a = d.blk_a[blk], b = d.blk_b[blk];
-        double acc[12];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) acc[q] = 0;
-        for (int k = d.blk_pair_ptr[blk] + threadIdx.x; k < d.blk_pair_ptr[blk + 1]; k += blockDim.x) {
-            const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
-            double y[9], h[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) { y[q] = d.Y[(size_t)e1 * EB + (q)]; h[q] = d.Hpl[(size_t)e2 * EB + (q)]; }
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
-        }
-        for (int k = d.blk_odo_ptr[blk] + threadIdx.x; k < d.blk_odo_ptr[blk + 1]; k += blockDim.x) {
-            const int code = d.blk_odo[k], o = code >> 1;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + o] : d.oAij[(r * 3 + c) * O + o];
-        }
-        if (a == b)
-            for (int k = d.pose_ptr[a] + threadIdx.x; k < d.pose_ptr[a + 1]; k += blockDim.x) {
-                const int e = d.pose_edges[k];
-                acc[9] -= d.Y[(size_t)e * EB + 9]; acc[10] -= d.Y[(size_t)e * EB + 10]; acc[11] -= d.Y[(size_t)e * EB + 9 + (2)];
-            }
-#pragma unroll
-        for (int q = 0; q < 12; ++q)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        __syncthreads();
-        if (lane == 0)
-#pragma unroll
-            for (int q = 0; q < 12; ++q) sh12[wid * 12 + q] = acc[q];
-        __syncthreads();
-        if (threadIdx.x < 12) {
-            double v = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh12[w * 12 + threadIdx.x];
-            const int q = threadIdx.x;
-            if (q < 9) {
-                const int r = q / 3, c = q % 3;
-                if (a == b) {
-                    const int u6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-                    v += d.Hpp[u6[r][c] * nf + a] + (r == c ? lam : 0.0);
-                }
-                d.S[(3 * a + r) * n + 3 * b + c] = v;
-            } else if (a == b) {
-                d.bs[3 * a + q - 9] = d.bp[3 * a + q - 9] + v;
             }
         }
     }
@@ -981,6 +1056,46 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
     __shared__ double shv[8 * 12];
+    __shared__ __align__(8) unsigned long long stage_bar;
+    unsigned stage_parity = 0;
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
+    // ---- static work lists of this CTA -> shared memory (CTA 0 keeps its shared memory for the reduced solve)
+    extern __shared__ double sm[];
+    __shared__ PKOwn own[PK_MAXOWN];
+    __shared__ int s_nown;
+    PKWork work;
+    {
+        const int G = gridDim.x;
+        work.stride = G > 1 ? G - 1 : 1;
+        work.first = G > 1 ? (int)blockIdx.x - 1 : 0;      // -1 for CTA 0 of a multi-CTA grid
+        work.own = own;
+        work.arena = reinterpret_cast<const int*>(sm);
+        int* arena = reinterpret_cast<int*>(sm);
+        const int arena_ints = (G > 1 && blockIdx.x > 0) ? pa.dyn_smem_bytes / 4 : 0;
+        if (threadIdx.x == 0) {
+            int off = 0, no = 0;
+            if (work.first >= 0)
+                for (int blk = work.first; blk < d.nblk && no < PK_MAXOWN; blk += work.stride) {
+                    const int a = d.blk_a[blk], b = d.blk_b[blk];
+                    const int np = d.blk_pair_ptr[blk + 1] - d.blk_pair_ptr[blk];
+                    const int ne = (a == b) ? d.pose_ptr[a + 1] - d.pose_ptr[a] : 0;
+                    if (off + 2 * np + ne > arena_ints) break;
+                    own[no] = PKOwn{blk, a, b, off, np, off + 2 * np, ne};
+                    off += 2 * np + ne; ++no;
+                }
+            s_nown = no;
+        }
+        __syncthreads();
+        work.n_own = s_nown;
+        for (int i = 0; i < work.n_own; ++i) {
+            const PKOwn o = own[i];
+            const int g0 = d.blk_pair_ptr[o.blk];
+            for (int k = threadIdx.x; k < o.np; k += blockDim.x) { arena[o.p0 + 2 * k] = d.pair_e1[g0 + k]; arena[o.p0 + 2 * k + 1] = d.pair_e2[g0 + k]; }
+            const int q0 = d.pose_ptr[o.a];
+            for (int k = threadIdx.x; k < o.ne; k += blockDim.x) arena[o.e0 + k] = d.pose_edges[q0 + k];
+        }
+    }
+    __syncthreads();
     const int n = d.n, nparts = gridDim.x;
     double lambda = 0, ni = 2, chi_cur = 0;
     int cur = d.st->cur, done = 0;
@@ -995,8 +1110,10 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         grid.sync();
         PK_TICK(0);
         if (*pa.abort_dev) break;
-        // ---- B: pose-side gather (+ landmark diagonal maximum for lambda_0)
-        pk_phase_pose_reduce(d, shv);
+        // ---- B: pose-side gather (+ landmark diagonal maximum for lambda_0); for it > 0 the damping of the first trial is
+        // already known, so the damping-dependent per-landmark terms are prepared in the same phase (one barrier less)
+        pk_phase_pose_reduce(d, work, shv);
+        if (it > 0) pk_phase_lm_prep(d, lambda);
         if (it == 0) {
             double m = 0;
             const size_t L = d.L;
@@ -1020,18 +1137,22 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         int trials = 0, accepted = 0;
         double rho = 0;
         do {
-            // ---- P: damping-dependent per-landmark terms
+            // ---- P: damping-dependent per-landmark terms (first trial of it > 0: done in phase B)
             PK_TICK(6);
-            pk_phase_lm_prep(d, lambda);
-            grid.sync();
+            if (it == 0 || trials > 0) {
+                pk_phase_lm_prep(d, lambda);
+                grid.sync();
+            }
             PK_TICK(2);
             // ---- C: Schur complement gather
-            pk_phase_schur(d, lambda, shv);
+            pk_phase_schur(d, lambda, work, shv);
             grid.sync();
             PK_TICK(3);
             // ---- D: reduced solve (one CTA; S staged into its shared memory)
             if (blockIdx.x == 0) {
-                ldlt_stage(d);
+                ldlt_stage(d, &stage_bar, stage_parity);
+                stage_parity ^= 1;
+                PK_TICK(7);
                 ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, d.bs, d.dxp, d.st);
             }
             grid.sync();
@@ -1465,9 +1586,10 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         }
         *h->abort_host = 0;
         PKArgs pa{max_iters, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
-                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr};
+                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0};
         if (h->prof.on) h->pk_launches++;
-        const size_t smem = ldlt_smem_bytes(d.n);
+        const size_t smem = std::max(ldlt_smem_bytes(d.n), (size_t)96 * 1024);
+        pa.dyn_smem_bytes = (int)smem;
         void* args[] = {(void*)&d, (void*)&h->cam, (void*)&pa};
         h->prof.begin(7, s);
         SE2_CUDA(cudaLaunchCooperativeKernel((void*)ba_persistent, dim3(h->pk_grid), dim3(PK_THREADS), args, smem, s));
@@ -1588,6 +1710,8 @@ int se2gpu_ba_profile_read(se2gpu_ba* h, double* ms, int* launches) {
         long long cyc[8];
         SE2_CUDA(cudaMemcpy(cyc, h->phase_cycles, sizeof cyc, cudaMemcpyDeviceToHost));
         for (int g = 0; g < 7; ++g) { if (ms) ms[g] = (double)cyc[g] / (double)(h->clock_khz > 0 ? h->clock_khz : 1965000); if (launches) launches[g] = h->pk_launches; }
+        if (ms) ms[8] = (double)cyc[7] / (double)(h->clock_khz > 0 ? h->clock_khz : 1965000);
+        if (launches) launches[8] = h->pk_launches;
     }
     return SE2GPU_OK;
 }

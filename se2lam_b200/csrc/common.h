@@ -50,7 +50,7 @@ inline int select_device(int device) {
 
 // Accumulates per-group kernel time with CUDA events recorded on the launching stream.
 struct Profiler {
-    static constexpr int MAXG = 8, MAXEV = 4096;
+    static constexpr int MAXG = 16, MAXEV = 4096;
     bool on = false;
     int nev = 0;
     cudaEvent_t ev[MAXEV][2];
