@@ -20,6 +20,7 @@
 //   ba_decide      g2o's rho test / lambda schedule on device; host reads one small struct per trial
 #include <cooperative_groups.h>
 #include <cfloat>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -450,10 +451,11 @@ template <bool SMEM>
 __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
     extern __shared__ double sm[];
     __shared__ int ok;
+    __shared__ double tb[3];                                     // W_k u_k of the current pivot block
     // layout (SMEM): A [n*n] | y [n] | Wb [3n] | cmax (int) [n]
     double* A = SMEM ? sm : G;
     double* y = SMEM ? sm + (size_t)n * n : ywork;
-    double* Wb = SMEM ? sm + (size_t)n * n + n : ywork + n;          // 9 doubles per pose
+    double* Wb = SMEM ? sm + (size_t)n * n + n : ywork + n;          // 9 doubles per pose: W_k = D_k^-1
     const int* cmax = SMEM ? reinterpret_cast<const int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2) : colmax_g;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
@@ -461,37 +463,77 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
     for (int i = tid; i < n; i += nt) y[i] = bs[i];
     __syncthreads();
     const int nb = n / 3;
-    for (int kb = 0; kb < nb; ++kb) {
-        const int k = 3 * kb;
-        // pivot block (lower part) and its inverse, redundantly in every thread
-        const double a = A[(size_t)k * n + k], b = A[(size_t)(k + 1) * n + k], c = A[(size_t)(k + 2) * n + k];
-        const double e = A[(size_t)(k + 1) * n + k + 1], f = A[(size_t)(k + 2) * n + k + 1], i2 = A[(size_t)(k + 2) * n + k + 2];
+    // The FP64 pipe issues one warp instruction every ~2 cycles per SM sub-partition, so the pivot-block inverse must
+    // not be recomputed by every warp: warp 0 ("pivot warp") updates the NEXT pivot block + its rhs entries first,
+    // inverts it and publishes W_{k+1}, W_{k+1} u_{k+1} to shared memory before the step's barrier, while the other
+    // warps update the rest of the trailing envelope (one row per warp). After the barrier everybody just reads W.
+    auto invert_and_publish = [&](int kb, double a, double b, double c, double e, double f, double i2, double u0, double u1, double u2) {
         const double c00 = e * i2 - f * f, c01 = c * f - b * i2, c02 = b * f - c * e;
         const double det = a * c00 + b * c01 + c * c02, m2 = a * e - b * b;
-        if (!(a > 0.0) || !(m2 > 0.0) || !(det > 0.0) || !isfinite(det)) { if (tid == 0) ok = 0; break; }   // uniform
+        const bool pd = (a > 0.0) && (m2 > 0.0) && (det > 0.0) && isfinite(det);   // leading minors: CHOLMOD's "not positive definite"
         const double id = 1.0 / det;
         const double w00 = c00 * id, w01 = c01 * id, w02 = c02 * id, w11 = (a * i2 - c * c) * id, w12 = (b * c - a * f) * id, w22 = m2 * id;
-        const double u0 = y[k], u1 = y[k + 1], u2 = y[k + 2];
-        const double t0 = w00 * u0 + w01 * u1 + w02 * u2, t1 = w01 * u0 + w11 * u1 + w12 * u2, t2 = w02 * u0 + w12 * u1 + w22 * u2;
+        double* W = Wb + 9 * kb;
+        if (lane == 0) { W[0] = w00; W[1] = w01; W[2] = w02; W[3] = w01; W[4] = w11; W[5] = w12; W[6] = w02; W[7] = w12; W[8] = w22;
+                         tb[0] = w00 * u0 + w01 * u1 + w02 * u2; tb[1] = w01 * u0 + w11 * u1 + w12 * u2; tb[2] = w02 * u0 + w12 * u1 + w22 * u2;
+                         if (!pd) ok = 0; }
+    };
+    if (wid == 0 && nb > 0)
+        invert_and_publish(0, A[0], A[(size_t)n], A[2 * (size_t)n], A[(size_t)n + 1], A[2 * (size_t)n + 1], A[2 * (size_t)n + 2], y[0], y[1], y[2]);
+    __syncthreads();
+    for (int kb = 0; kb < nb; ++kb) {
+        if (!ok) break;                                          // uniform: written before the barrier that precedes this read
+        const int k = 3 * kb;
+        const double* W = Wb + 9 * kb;
+        const double w00 = W[0], w01 = W[1], w02 = W[2], w11 = W[4], w12 = W[5], w22 = W[8];
+        const double t0 = tb[0], t1 = tb[1], t2 = tb[2];
         const int hi = cmax[k + 2];
         const int m = hi - (k + 2);                 // trailing rows/cols k+3 .. hi
-        for (int ii = wid; ii < m; ii += nw) {
-            const int i = k + 3 + ii;
-            const double a0 = A[(size_t)i * n + k], a1 = A[(size_t)i * n + k + 1], a2 = A[(size_t)i * n + k + 2];
-            for (int jj = lane; jj <= ii + 1; jj += 32) {
-                if (jj <= ii) {
-                    const int j = k + 3 + jj;
-                    const double b0 = A[(size_t)j * n + k], b1 = A[(size_t)j * n + k + 1], b2 = A[(size_t)j * n + k + 2];
-                    const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
-                    A[(size_t)i * n + j] -= a0 * v0 + a1 * v1 + a2 * v2;
-                } else {
-                    y[i] -= a0 * t0 + a1 * t1 + a2 * t2;        // the right-hand side as an extra column
+        __syncthreads();                            // everyone holds W_k / t_k in registers: warp 0 may overwrite tb
+        if (wid == 0) {
+            // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
+            double val = 0;
+            if (kb + 1 < nb && lane < 9) {
+                const int q = lane;                 // 0..5: (ii,jj) = (0,0)(1,0)(1,1)(2,0)(2,1)(2,2); 6..8: rhs of row q-6
+                const int ii = q < 1 ? 0 : (q < 3 ? 1 : (q < 6 ? 2 : q - 6));
+                const int jj = q < 1 ? 0 : (q < 3 ? q - 1 : (q < 6 ? q - 3 : 0));
+                const int i = k + 3 + ii, j = k + 3 + jj;
+                val = (q < 6) ? A[(size_t)i * n + j] : y[i];
+                if (ii < m) {                       // rows beyond the envelope of this block column are structurally untouched
+                    const double a0 = A[(size_t)i * n + k], a1 = A[(size_t)i * n + k + 1], a2 = A[(size_t)i * n + k + 2];
+                    if (q < 6) {
+                        const double b0 = A[(size_t)j * n + k], b1 = A[(size_t)j * n + k + 1], b2 = A[(size_t)j * n + k + 2];
+                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
+                        val -= a0 * v0 + a1 * v1 + a2 * v2;
+                        A[(size_t)i * n + j] = val;
+                    } else {
+                        val -= a0 * t0 + a1 * t1 + a2 * t2;
+                        y[i] = val;
+                    }
                 }
             }
-        }
-        if (tid < 9) {
-            const double W9[9] = {w00, w01, w02, w01, w11, w12, w02, w12, w22};
-            Wb[9 * kb + tid] = W9[tid];
+            if (kb + 1 < nb) {
+                const double pa = __shfl_sync(0xffffffffu, val, 0), pb = __shfl_sync(0xffffffffu, val, 1), pe = __shfl_sync(0xffffffffu, val, 2);
+                const double pc = __shfl_sync(0xffffffffu, val, 3), pf = __shfl_sync(0xffffffffu, val, 4), pi = __shfl_sync(0xffffffffu, val, 5);
+                const double q0 = __shfl_sync(0xffffffffu, val, 6), q1 = __shfl_sync(0xffffffffu, val, 7), q2 = __shfl_sync(0xffffffffu, val, 8);
+                invert_and_publish(kb + 1, pa, pb, pc, pe, pf, pi, q0, q1, q2);
+            }
+        } else {
+            // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs)
+            for (int ii = 3 + (wid - 1); ii < m; ii += nw - 1) {
+                const int i = k + 3 + ii;
+                const double a0 = A[(size_t)i * n + k], a1 = A[(size_t)i * n + k + 1], a2 = A[(size_t)i * n + k + 2];
+                for (int jj = lane; jj <= ii + 1; jj += 32) {
+                    if (jj <= ii) {
+                        const int j = k + 3 + jj;
+                        const double b0 = A[(size_t)j * n + k], b1 = A[(size_t)j * n + k + 1], b2 = A[(size_t)j * n + k + 2];
+                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
+                        A[(size_t)i * n + j] -= a0 * v0 + a1 * v1 + a2 * v2;
+                    } else {
+                        y[i] -= a0 * t0 + a1 * t1 + a2 * t2;        // the right-hand side as an extra column
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -674,7 +716,7 @@ __global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase,
 // CTA from the same fixed-order partial sums, so no host round trip happens inside an optimize() call.
 // Per-landmark work is spread over LPL lanes (edges strided over the lanes, xor-tree over the lane group).
 namespace cg = cooperative_groups;
-constexpr int PK_THREADS = 256;
+constexpr int PK_THREADS = 512;
 constexpr int LPL = 8;
 
 struct PKArgs {
@@ -689,6 +731,7 @@ struct PKArgs {
     double* part_max;         // [gridDim.x]
     long long* phase_cycles;  // [8] SM cycles CTA 0 spent per phase incl. the barrier that ends it (profiling aid)
     int dyn_smem_bytes;       // dynamic shared memory of the launch (arena size of the non-zero CTAs)
+    long long* cta_work;      // [gridDim.x][8] per-CTA busy cycles per phase (debug aid, null = off)
 };
 
 __device__ __forceinline__ double group_sum(double v) {   // sum over the LPL-lane group, fixed order
@@ -1100,13 +1143,16 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     double lambda = 0, ni = 2, chi_cur = 0;
     int cur = d.st->cur, done = 0;
     bool stop = false;
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = clock64();
-#define PK_TICK(g) do { const long long _t = clock64(); tacc[g] += _t - tprev; tprev = _t; } while (0)
+    // phase timers live in shared memory and are touched by thread 0 only (keeps them out of the register budget)
+    __shared__ long long tacc[8], wacc[8], tprev_s, wprev_s;
+    if (threadIdx.x == 0) { for (int g = 0; g < 8; ++g) { tacc[g] = 0; wacc[g] = 0; } tprev_s = wprev_s = clock64(); }
+#define PK_TICK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); tacc[g] += _t - tprev_s; tprev_s = _t; wprev_s = _t; } } while (0)
+#define PK_WORK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); wacc[g] += _t - wprev_s; wprev_s = _t; } } while (0)
     for (int it = 0; it < pa.max_iters && !stop; ++it) {
         // ---- A: linearise at x_cur (computeActiveErrors + buildSystem)
         pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh);
         if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
+        PK_WORK(0);
         grid.sync();
         PK_TICK(0);
         if (*pa.abort_dev) break;
@@ -1122,6 +1168,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             m = cta_max(m, sh);
             if (threadIdx.x == 0) pa.part_max[blockIdx.x] = m;
         }
+        PK_WORK(1);
         grid.sync();
         PK_TICK(1);
         chi_cur = cta_sum_array(pa.part_chi, nparts, sh);
@@ -1141,11 +1188,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             PK_TICK(6);
             if (it == 0 || trials > 0) {
                 pk_phase_lm_prep(d, lambda);
+                PK_WORK(2);
                 grid.sync();
             }
             PK_TICK(2);
             // ---- C: Schur complement gather
             pk_phase_schur(d, lambda, work, shv);
+            PK_WORK(3);
             grid.sync();
             PK_TICK(3);
             // ---- D: reduced solve (one CTA; S staged into its shared memory)
@@ -1155,6 +1204,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 PK_TICK(7);
                 ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, d.bs, d.dxp, d.st);
             }
+            PK_WORK(4);
             grid.sync();
             PK_TICK(4);
             const int solve_ok = d.st->solve_ok;
@@ -1164,11 +1214,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 const double tot = block_sum(sc, sh);
                 if (threadIdx.x == 0) pa.part_scale[blockIdx.x] = tot;
             }
+            PK_WORK(5);
             grid.sync();
             PK_TICK(5);
             // ---- F: robust chi2 at the trial point
             pk_phase_linearize<false>(d, cam, cur ^ 1, pa.part_chi, sh);
             if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
+            PK_WORK(7);
             grid.sync();
             PK_TICK(0);
             // ---- LM decision (identical in every CTA)
@@ -1198,6 +1250,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     }
     PK_TICK(6);
 #undef PK_TICK
+#undef PK_WORK
+    if (pa.cta_work && threadIdx.x == 0) for (int g = 0; g < 8; ++g) pa.cta_work[blockIdx.x * 8 + g] = wacc[g];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         LMState& s = *d.st;
         s.cur = cur; s.lambda = lambda; s.ni = ni; s.chi_cur = chi_cur; s.iter = done;
@@ -1243,6 +1297,7 @@ struct se2gpu_ba {
     int* abort_host = nullptr; int* abort_host_dev = nullptr; int* abort_dev = nullptr;
     double *trace_p = nullptr, *trace_l = nullptr; size_t trace_cap_p = 0, trace_cap_l = 0;
     long long* phase_cycles = nullptr;   // device [8]
+    long long* cta_work = nullptr;       // device [1024][8]
     int pk_launches = 0, clock_khz = 0;
 };
 
@@ -1310,7 +1365,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
     A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
-    A(&h->pk_part_chi, 1024); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 1); A(&h->phase_cycles, 8);
+    A(&h->pk_part_chi, 1024); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 1); A(&h->phase_cycles, 8); A(&h->cta_work, 1024 * 8);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
         cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N));
@@ -1586,7 +1641,7 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         }
         *h->abort_host = 0;
         PKArgs pa{max_iters, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
-                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0};
+                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0, getenv("SE2GPU_BA_DEBUG") ? h->cta_work : nullptr};
         if (h->prof.on) h->pk_launches++;
         const size_t smem = std::max(ldlt_smem_bytes(d.n), (size_t)96 * 1024);
         pa.dyn_smem_bytes = (int)smem;
@@ -1601,6 +1656,16 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         }
         SE2_CUDA(cudaStreamSynchronize(s));
         const int done = h->st_host->iter;
+        if (pa.cta_work) {   // SE2GPU_BA_DEBUG=1: per-phase busy cycles of every CTA (max / mean / who) to stderr
+            std::vector<long long> w((size_t)h->pk_grid * 8);
+            cudaMemcpy(w.data(), h->cta_work, w.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            const char* names[8] = {"linearize", "pose+prep", "lm_prep", "schur", "solve", "backsub", "-", "chi2"};
+            for (int g = 0; g < 8; ++g) {
+                long long mx = 0, sum = 0; int who = 0;
+                for (int c = 0; c < h->pk_grid; ++c) { const long long v = w[(size_t)c * 8 + g]; sum += v; if (v > mx) { mx = v; who = c; } }
+                fprintf(stderr, "[se2gpu_ba] phase %-10s busy cycles: max %lld (CTA %d) mean %lld  (per optimize of %d iters)\n", names[g], mx, who, sum / h->pk_grid, done);
+            }
+        }
         if (stats && done > 0) SE2_CUDA(cudaMemcpyAsync(stats, h->stats_dev, sizeof(se2gpu_ba_iter_stats) * done, cudaMemcpyDeviceToHost, s));
         if (trace_poses && done > 0) SE2_CUDA(cudaMemcpyAsync(trace_poses, h->trace_p, sizeof(double) * (size_t)done * 3 * h->P, cudaMemcpyDeviceToHost, s));
         if (trace_points && done > 0) SE2_CUDA(cudaMemcpyAsync(trace_points, h->trace_l, sizeof(double) * (size_t)done * 3 * h->L, cudaMemcpyDeviceToHost, s));
