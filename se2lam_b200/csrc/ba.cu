@@ -1098,7 +1098,7 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
 __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, PKArgs pa) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
-    __shared__ double shv[8 * 12];
+    __shared__ double shv[(PK_THREADS / 32) * 12];
     __shared__ __align__(8) unsigned long long stage_bar;
     unsigned stage_parity = 0;
     if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
