@@ -447,9 +447,6 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
 // Back substitution: x_k = W_k (u_k - sum_{i>k} a_i^T x_i), warp 0 only, warp-synchronous.
 // SMEM=true indexes the dynamic shared array directly (LDS, no generic-address conversion in the loops);
 // SMEM=false works in place in global memory (reduced systems too large for one CTA's shared memory).
-__device__ long long g_solve_dbg[8];   // SE2GPU_BA_DEBUG: cycles of thread 0 inside the reduced solve
-#define SOLVE_TICK(g) do { if (tid == 0) { const long long _t = clock64(); g_solve_dbg[g] += _t - sprev; sprev = _t; } } while (0)
-
 template <bool SMEM>
 __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
     extern __shared__ double sm[];
@@ -462,7 +459,6 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
     const int* cmax = SMEM ? reinterpret_cast<const int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2) : colmax_g;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-    long long sprev = clock64();
     if (tid == 0) ok = 1;
     for (int i = tid; i < n; i += nt) y[i] = bs[i];
     __syncthreads();
@@ -485,7 +481,6 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
     if (wid == 0 && nb > 0)
         invert_and_publish(0, A[0], A[(size_t)n], A[2 * (size_t)n], A[(size_t)n + 1], A[2 * (size_t)n + 1], A[2 * (size_t)n + 2], y[0], y[1], y[2]);
     __syncthreads();
-    SOLVE_TICK(0);
     for (int kb = 0; kb < nb; ++kb) {
         if (!ok) break;                                          // uniform: written before the barrier that precedes this read
         const int k = 3 * kb;
@@ -495,7 +490,6 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
         const int hi = cmax[k + 2];
         const int m = hi - (k + 2);                 // trailing rows/cols k+3 .. hi
         __syncthreads();                            // everyone holds W_k / t_k in registers: warp 0 may overwrite tb
-        SOLVE_TICK(1);
         if (wid == 0) {
             // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
             double val = 0;
@@ -519,12 +513,12 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
                 }
             }
             if (kb + 1 < nb) {
-                const double pa = __shfl_sync(0xffffffffu, val, 0), pb = __shfl_sync(0xffffffffu, val, 1), pe = __shfl_sync(0xffffffffu, val, 2);
-                const double pc = __shfl_sync(0xffffffffu, val, 3), pf = __shfl_sync(0xffffffffu, val, 4), pi = __shfl_sync(0xffffffffu, val, 5);
-                const double q0 = __shfl_sync(0xffffffffu, val, 6), q1 = __shfl_sync(0xffffffffu, val, 7), q2 = __shfl_sync(0xffffffffu, val, 8);
-                invert_and_publish(kb + 1, pa, pb, pc, pe, pf, pi, q0, q1, q2);
+                // the 6 + 3 freshly updated values are already in shared memory: re-read them instead of shuffling
+                __syncwarp();
+                const int r = k + 3;
+                invert_and_publish(kb + 1, A[r * n + r], A[(r + 1) * n + r], A[(r + 2) * n + r], A[(r + 1) * n + r + 1], A[(r + 2) * n + r + 1],
+                                   A[(r + 2) * n + r + 2], y[r], y[r + 1], y[r + 2]);
             }
-            SOLVE_TICK(2);
         } else {
             // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs)
             for (int ii = 3 + (wid - 1); ii < m; ii += nw - 1) {
@@ -543,30 +537,29 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
             }
         }
         __syncthreads();
-        SOLVE_TICK(3);
     }
     __syncthreads();
     if (ok) {
         if (wid == 0) {
+            // lanes = 3 columns x 8 row slots; each 8-lane group sums its column's dot product with an xor tree
+            const int c = lane >> 3, rs = lane & 7;
             for (int kb = nb - 1; kb >= 0; --kb) {
-                const int k = 3 * kb, hi = cmax[k + 2];
-                double r = 0;
-                if (lane < 3) {
-                    double s0 = 0, s1 = 0;
-                    int i = k + 3;
-                    for (; i + 1 <= hi; i += 2) { s0 += A[(size_t)i * n + k + lane] * y[i]; s1 += A[(size_t)(i + 1) * n + k + lane] * y[i + 1]; }
-                    if (i <= hi) s0 += A[(size_t)i * n + k + lane] * y[i];
-                    r = y[k + lane] - (s0 + s1);
-                }
-                const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1), r2 = __shfl_sync(0xffffffffu, r, 2);
-                if (lane < 3) y[k + lane] = Wb[9 * kb + 3 * lane] * r0 + Wb[9 * kb + 3 * lane + 1] * r1 + Wb[9 * kb + 3 * lane + 2] * r2;
+                const int k = 3 * kb, m = cmax[k + 2] - (k + 2);
+                const double* W = Wb + 9 * kb;
+                double sdot = 0;
+                if (c < 3)
+                    for (int ii = rs; ii < m; ii += 8) sdot += A[(k + 3 + ii) * n + k + c] * y[k + 3 + ii];
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                const double rc = (c < 3) ? y[k + c] - sdot : 0.0;
+                const double r0 = __shfl_sync(0xffffffffu, rc, 0), r1 = __shfl_sync(0xffffffffu, rc, 8), r2 = __shfl_sync(0xffffffffu, rc, 16);
+                if (lane < 3) y[k + lane] = W[3 * lane] * r0 + W[3 * lane + 1] * r1 + W[3 * lane + 2] * r2;
                 __syncwarp();
             }
-            SOLVE_TICK(4);
         }
         __syncthreads();
         for (int i = tid; i < n; i += nt) dxp[i] = y[i];
-        SOLVE_TICK(5);
     } else {
         for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
     }
@@ -1669,10 +1662,6 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         if (pa.cta_work) {   // SE2GPU_BA_DEBUG=1: per-phase busy cycles of every CTA (max / mean / who) to stderr
             std::vector<long long> w((size_t)h->pk_grid * 8);
             cudaMemcpy(w.data(), h->cta_work, w.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-            long long sd[8];
-            cudaMemcpyFromSymbol(sd, g_solve_dbg, sizeof sd);
-            fprintf(stderr, "[se2gpu_ba] solve (cumulative cycles, thread 0): init %lld | read W + barrier %lld | pivot-warp work %lld | end-of-step barrier %lld | back-substitution %lld | copy-out %lld\n",
-                    sd[0], sd[1], sd[2], sd[3], sd[4], sd[5]);
             const char* names[8] = {"linearize", "pose+prep", "lm_prep", "schur", "solve", "backsub", "-", "chi2"};
             for (int g = 0; g < 8; ++g) {
                 long long mx = 0, sum = 0; int who = 0;
