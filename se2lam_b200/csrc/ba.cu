@@ -447,6 +447,13 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
 // Back substitution: x_k = W_k (u_k - sum_{i>k} a_i^T x_i), warp 0 only, warp-synchronous.
 // SMEM=true indexes the dynamic shared array directly (LDS, no generic-address conversion in the loops);
 // SMEM=false works in place in global memory (reduced systems too large for one CTA's shared memory).
+#ifdef SE2_SOLVE_STAMPS
+__device__ long long g_stamps[64];
+#define STAMP(i) do { if (threadIdx.x == 0) s_stamp[i] = clock64(); } while (0)
+#else
+#define STAMP(i) do { } while (0)
+#endif
+
 template <bool SMEM>
 __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
     extern __shared__ double sm[];
@@ -459,10 +466,15 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
     const int* cmax = SMEM ? reinterpret_cast<const int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2) : colmax_g;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+#ifdef SE2_SOLVE_STAMPS
+    __shared__ long long s_stamp[64];
+#endif
+    STAMP(0);
     if (tid == 0) ok = 1;
     for (int i = tid; i < n; i += nt) y[i] = bs[i];
     __syncthreads();
     const int nb = n / 3;
+    STAMP(1);
     // The FP64 pipe issues one warp instruction every ~2 cycles per SM sub-partition, so the pivot-block inverse must
     // not be recomputed by every warp: warp 0 ("pivot warp") updates the NEXT pivot block + its rhs entries first,
     // inverts it and publishes W_{k+1}, W_{k+1} u_{k+1} to shared memory before the step's barrier, while the other
@@ -481,15 +493,18 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
     if (wid == 0 && nb > 0)
         invert_and_publish(0, A[0], A[(size_t)n], A[2 * (size_t)n], A[(size_t)n + 1], A[2 * (size_t)n + 1], A[2 * (size_t)n + 2], y[0], y[1], y[2]);
     __syncthreads();
+    STAMP(2);
     for (int kb = 0; kb < nb; ++kb) {
         if (!ok) break;                                          // uniform: written before the barrier that precedes this read
         const int k = 3 * kb;
+        if (kb < 8) STAMP(10 + 4 * kb);
         const double* W = Wb + 9 * kb;
         const double w00 = W[0], w01 = W[1], w02 = W[2], w11 = W[4], w12 = W[5], w22 = W[8];
         const double t0 = tb[0], t1 = tb[1], t2 = tb[2];
         const int hi = cmax[k + 2];
         const int m = hi - (k + 2);                 // trailing rows/cols k+3 .. hi
         __syncthreads();                            // everyone holds W_k / t_k in registers: warp 0 may overwrite tb
+        if (kb < 8) STAMP(11 + 4 * kb);
         if (wid == 0) {
             // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
             double val = 0;
@@ -519,6 +534,7 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
                 invert_and_publish(kb + 1, A[r * n + r], A[(r + 1) * n + r], A[(r + 2) * n + r], A[(r + 1) * n + r + 1], A[(r + 2) * n + r + 1],
                                    A[(r + 2) * n + r + 2], y[r], y[r + 1], y[r + 2]);
             }
+            if (kb < 8) STAMP(12 + 4 * kb);
         } else {
             // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs)
             for (int ii = 3 + (wid - 1); ii < m; ii += nw - 1) {
@@ -537,8 +553,10 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
             }
         }
         __syncthreads();
+        if (kb < 8) STAMP(13 + 4 * kb);
     }
     __syncthreads();
+    STAMP(3);
     if (ok) {
         if (wid == 0) {
             // lanes = 3 columns x 8 row slots; each 8-lane group sums its column's dot product with an xor tree
@@ -559,11 +577,17 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
             }
         }
         __syncthreads();
+        STAMP(4);
         for (int i = tid; i < n; i += nt) dxp[i] = y[i];
     } else {
         for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
     }
     if (tid == 0) st->solve_ok = ok;
+    STAMP(5);
+#ifdef SE2_SOLVE_STAMPS
+    __syncthreads();
+    if (tid < 64) g_stamps[tid] = s_stamp[tid];
+#endif
 }
 
 // bytes of dynamic shared memory the SMEM variant needs for n unknowns
