@@ -25,6 +25,7 @@ import time
 
 import numpy as np
 
+_OUT = sys.stdout
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -34,6 +35,18 @@ ORB_METRIC = "ORB keypoints/sec at 640x480 (8-level pyramid, 1000 kps/frame)"
 BA_METRIC = "LM iterations/sec on 50-KF/5k-point local BA"
 W, H, NFEAT, NLEV, BATCH = 640, 480, 1000, 8, 64
 BA_ITERS = 10
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this round (None if not captured)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None
+    try:
+        return json.load(open(files[-1])).get(kernel)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -135,7 +148,7 @@ def run_reference(args):
                                        "sample": f"{args.steps} x optimize({BA_ITERS})"},
                       "e2e": {"value": ba_v, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
 
 
 # =================================================================================================
@@ -234,7 +247,7 @@ def run_ours(args):
     achieved = alg[dom] * BATCH / (dom_ms * 1e-3) / 1e9
     step_alg_bytes = (3 * P_pyr + 60 * kp_per_frame) * BATCH
     roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms,
+            "traffic": ncu_traffic(dom), "algorithmic_bytes_per_launch": alg[dom] * BATCH, "peak_source": peak_src, "kernel_ms": dom_ms,
             "kernel_share_of_step": single[dom][0] / sum(v[0] for v in single.values()),
             "per_kernel_ms": {g: v[0] / v[1] for g, v in single.items()},
             "per_kernel_note": "second, event-instrumented pass (kernels serialised); the timed pass overlaps orb_blur with orb_fast_cells+orb_select",
@@ -317,7 +330,8 @@ def run_ours(args):
     bdom = max(bs, key=lambda g: bs[g][0])
     bdom_ms = bs[bdom][0] / bs[bdom][1]
     bach = balg[bdom] / (bdom_ms * 1e-3) / 1e9
-    ba_roof = {"bound": "hbm", "kernel": bdom, "achieved": bach, "peak": hbm_peak, "unit": "GB/s", "frac": bach / hbm_peak, "traffic": None,
+    ba_roof = {"bound": "hbm", "kernel": bdom, "achieved": bach, "peak": hbm_peak, "unit": "GB/s", "frac": bach / hbm_peak,
+               "traffic": ncu_traffic(bdom), "algorithmic_bytes_per_launch": balg[bdom],
                "peak_source": peak_src, "kernel_ms": bdom_ms, "kernel_share_of_step": bs[bdom][0] / sum(v[0] for v in bs.values()),
                "per_kernel_ms": {g: v[0] / v[1] for g, v in bs.items()},
                "per_phase_ms_per_optimize": ({g: v[0] / v[1] for g, v in phases.items()} if persistent else None),
@@ -361,7 +375,7 @@ def run_ours(args):
         if cpu_orb:
             line["cpu_baseline"] = cpu_orb
             line["secondary"]["cpu_baseline"] = cpu_ba
-        print(json.dumps(line))
+        _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -394,7 +408,18 @@ def cpu_baselines():
     return cpu_orb, cpu_ba
 
 
+def _reserve_stdout():
+    """Only the final JSON line may reach stdout (NCCL / torch print banners there): point fd 1 at stderr for the
+    duration of the run and return a writer bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    global _OUT
+    _OUT = _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
