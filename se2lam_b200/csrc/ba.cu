@@ -448,150 +448,11 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
 // SMEM=true indexes the dynamic shared array directly (LDS, no generic-address conversion in the loops);
 // SMEM=false works in place in global memory (reduced systems too large for one CTA's shared memory).
 #ifdef SE2_SOLVE_STAMPS
-__device__ long long g_stamps[64];
-#define STAMP(i) do { if (threadIdx.x == 0) s_stamp[i] = clock64(); } while (0)
+__device__ long long g_stamps[64];   // tools/solve_bench.cu: clock64 stamps of thread 0 (plain stores, no read-modify-write)
+#define STAMP(i) do { if (threadIdx.x == 0) g_stamps[i] = clock64(); } while (0)
 #else
 #define STAMP(i) do { } while (0)
 #endif
-
-template <bool SMEM>
-__device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
-    extern __shared__ double sm[];
-    __shared__ int ok;
-    __shared__ double tb[3];                                     // W_k u_k of the current pivot block
-    // layout (SMEM): A [n*n] | y [n] | Wb [3n] | cmax (int) [n]
-    double* A = SMEM ? sm : G;
-    double* y = SMEM ? sm + (size_t)n * n : ywork;
-    double* Wb = SMEM ? sm + (size_t)n * n + n : ywork + n;          // 9 doubles per pose: W_k = D_k^-1
-    const int* cmax = SMEM ? reinterpret_cast<const int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2) : colmax_g;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-#ifdef SE2_SOLVE_STAMPS
-    __shared__ long long s_stamp[64];
-#endif
-    STAMP(0);
-    if (tid == 0) ok = 1;
-    for (int i = tid; i < n; i += nt) y[i] = bs[i];
-    __syncthreads();
-    const int nb = n / 3;
-    STAMP(1);
-    // The FP64 pipe issues one warp instruction every ~2 cycles per SM sub-partition, so the pivot-block inverse must
-    // not be recomputed by every warp: warp 0 ("pivot warp") updates the NEXT pivot block + its rhs entries first,
-    // inverts it and publishes W_{k+1}, W_{k+1} u_{k+1} to shared memory before the step's barrier, while the other
-    // warps update the rest of the trailing envelope (one row per warp). After the barrier everybody just reads W.
-    auto invert_and_publish = [&](int kb, double a, double b, double c, double e, double f, double i2, double u0, double u1, double u2) {
-        const double c00 = e * i2 - f * f, c01 = c * f - b * i2, c02 = b * f - c * e;
-        const double det = a * c00 + b * c01 + c * c02, m2 = a * e - b * b;
-        const bool pd = (a > 0.0) && (m2 > 0.0) && (det > 0.0) && isfinite(det);   // leading minors: CHOLMOD's "not positive definite"
-        const double id = 1.0 / det;
-        const double w00 = c00 * id, w01 = c01 * id, w02 = c02 * id, w11 = (a * i2 - c * c) * id, w12 = (b * c - a * f) * id, w22 = m2 * id;
-        double* W = Wb + 9 * kb;
-        if (lane == 0) { W[0] = w00; W[1] = w01; W[2] = w02; W[3] = w01; W[4] = w11; W[5] = w12; W[6] = w02; W[7] = w12; W[8] = w22;
-                         tb[0] = w00 * u0 + w01 * u1 + w02 * u2; tb[1] = w01 * u0 + w11 * u1 + w12 * u2; tb[2] = w02 * u0 + w12 * u1 + w22 * u2;
-                         if (!pd) ok = 0; }
-    };
-    if (wid == 0 && nb > 0)
-        invert_and_publish(0, A[0], A[(size_t)n], A[2 * (size_t)n], A[(size_t)n + 1], A[2 * (size_t)n + 1], A[2 * (size_t)n + 2], y[0], y[1], y[2]);
-    __syncthreads();
-    STAMP(2);
-    for (int kb = 0; kb < nb; ++kb) {
-        if (!ok) break;                                          // uniform: written before the barrier that precedes this read
-        const int k = 3 * kb;
-        if (kb < 8) STAMP(10 + 4 * kb);
-        const double* W = Wb + 9 * kb;
-        const double w00 = W[0], w01 = W[1], w02 = W[2], w11 = W[4], w12 = W[5], w22 = W[8];
-        const double t0 = tb[0], t1 = tb[1], t2 = tb[2];
-        const int hi = cmax[k + 2];
-        const int m = hi - (k + 2);                 // trailing rows/cols k+3 .. hi
-        __syncthreads();                            // everyone holds W_k / t_k in registers: warp 0 may overwrite tb
-        if (kb < 8) STAMP(11 + 4 * kb);
-        if (wid == 0) {
-            // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
-            double val = 0;
-            if (kb + 1 < nb && lane < 9) {
-                const int q = lane;                 // 0..5: (ii,jj) = (0,0)(1,0)(1,1)(2,0)(2,1)(2,2); 6..8: rhs of row q-6
-                const int ii = q < 1 ? 0 : (q < 3 ? 1 : (q < 6 ? 2 : q - 6));
-                const int jj = q < 1 ? 0 : (q < 3 ? q - 1 : (q < 6 ? q - 3 : 0));
-                const int i = k + 3 + ii, j = k + 3 + jj;
-                val = (q < 6) ? A[(size_t)i * n + j] : y[i];
-                if (ii < m) {                       // rows beyond the envelope of this block column are structurally untouched
-                    const double a0 = A[(size_t)i * n + k], a1 = A[(size_t)i * n + k + 1], a2 = A[(size_t)i * n + k + 2];
-                    if (q < 6) {
-                        const double b0 = A[(size_t)j * n + k], b1 = A[(size_t)j * n + k + 1], b2 = A[(size_t)j * n + k + 2];
-                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
-                        val -= a0 * v0 + a1 * v1 + a2 * v2;
-                        A[(size_t)i * n + j] = val;
-                    } else {
-                        val -= a0 * t0 + a1 * t1 + a2 * t2;
-                        y[i] = val;
-                    }
-                }
-            }
-            if (kb + 1 < nb) {
-                // the 6 + 3 freshly updated values are already in shared memory: re-read them instead of shuffling
-                __syncwarp();
-                const int r = k + 3;
-                invert_and_publish(kb + 1, A[r * n + r], A[(r + 1) * n + r], A[(r + 2) * n + r], A[(r + 1) * n + r + 1], A[(r + 2) * n + r + 1],
-                                   A[(r + 2) * n + r + 2], y[r], y[r + 1], y[r + 2]);
-            }
-            if (kb < 8) STAMP(12 + 4 * kb);
-        } else {
-            // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs)
-            for (int ii = 3 + (wid - 1); ii < m; ii += nw - 1) {
-                const int i = k + 3 + ii;
-                const double a0 = A[(size_t)i * n + k], a1 = A[(size_t)i * n + k + 1], a2 = A[(size_t)i * n + k + 2];
-                for (int jj = lane; jj <= ii + 1; jj += 32) {
-                    if (jj <= ii) {
-                        const int j = k + 3 + jj;
-                        const double b0 = A[(size_t)j * n + k], b1 = A[(size_t)j * n + k + 1], b2 = A[(size_t)j * n + k + 2];
-                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
-                        A[(size_t)i * n + j] -= a0 * v0 + a1 * v1 + a2 * v2;
-                    } else {
-                        y[i] -= a0 * t0 + a1 * t1 + a2 * t2;        // the right-hand side as an extra column
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (kb < 8) STAMP(13 + 4 * kb);
-    }
-    __syncthreads();
-    STAMP(3);
-    if (ok) {
-        if (wid == 0) {
-            // lanes = 3 columns x 8 row slots; each 8-lane group sums its column's dot product with an xor tree
-            const int c = lane >> 3, rs = lane & 7;
-            for (int kb = nb - 1; kb >= 0; --kb) {
-                const int k = 3 * kb, m = cmax[k + 2] - (k + 2);
-                const double* W = Wb + 9 * kb;
-                double sdot = 0;
-                if (c < 3)
-                    for (int ii = rs; ii < m; ii += 8) sdot += A[(k + 3 + ii) * n + k + c] * y[k + 3 + ii];
-                sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-                sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-                sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-                const double rc = (c < 3) ? y[k + c] - sdot : 0.0;
-                const double r0 = __shfl_sync(0xffffffffu, rc, 0), r1 = __shfl_sync(0xffffffffu, rc, 8), r2 = __shfl_sync(0xffffffffu, rc, 16);
-                if (lane < 3) y[k + lane] = W[3 * lane] * r0 + W[3 * lane + 1] * r1 + W[3 * lane + 2] * r2;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-        STAMP(4);
-        for (int i = tid; i < n; i += nt) dxp[i] = y[i];
-    } else {
-        for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
-    }
-    if (tid == 0) st->solve_ok = ok;
-    STAMP(5);
-#ifdef SE2_SOLVE_STAMPS
-    __syncthreads();
-    if (tid < 64) g_stamps[tid] = s_stamp[tid];
-#endif
-}
-
-// bytes of dynamic shared memory the SMEM variant needs for n unknowns
-__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16; }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: stage the reduced system into shared memory
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -616,6 +477,171 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+// explicit 32-bit shared-window loads / stores: the address register is derived ONCE from the dynamic shared array, so the
+// hot loops contain no generic->shared conversions (nvcc otherwise re-derives the window base from SR_CgaCtaId, an
+// S2UR in front of many LDS, which dominated the per-pivot latency of the first versions of this solve)
+struct SmemIO {
+    static __device__ __forceinline__ double ld(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void st(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+    static __device__ __forceinline__ int ldi(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void sti(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+};
+struct GmemIO {   // same interface on byte offsets from a global base (reduced systems that do not fit one CTA's shared memory)
+    static __device__ __forceinline__ double ld(unsigned long long a) { return *reinterpret_cast<const volatile double*>(a); }
+    static __device__ __forceinline__ void st(unsigned long long a, double v) { *reinterpret_cast<volatile double*>(a) = v; }
+    static __device__ __forceinline__ int ldi(unsigned long long a) { return *reinterpret_cast<const volatile int*>(a); }
+    static __device__ __forceinline__ void sti(unsigned long long a, int v) { *reinterpret_cast<volatile int*>(a) = v; }
+};
+
+// Block LDL^T of the reduced system (see the comment above ldlt_smem_bytes for the algorithm).
+//   ADDR = unsigned (shared window) or unsigned long long (global); aA, aY, aW, aC, aT are the byte addresses of
+//   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int)}.
+template <class IO, class ADDR>
+__device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR aT, int n, const double* bs, double* dxp, LMState* st) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const ADDR aOK = aT + 24;
+#define A_(r, c) (aA + (ADDR)(((r) * n + (c)) * 8))
+#define Y_(i) (aY + (ADDR)((i) * 8))
+#define W_(kb, q) (aW + (ADDR)((9 * (kb) + (q)) * 8))
+    STAMP(0);
+    if (tid == 0) IO::sti(aOK, 1);
+    for (int i = tid; i < n; i += nt) IO::st(Y_(i), bs[i]);
+    __syncthreads();
+    const int nb = n / 3;
+    STAMP(1);
+    // The FP64 pipe issues one warp instruction every ~2 cycles per SM sub-partition, so the pivot-block inverse must
+    // not be recomputed by every warp: warp 0 ("pivot warp") updates the NEXT pivot block + its rhs entries first,
+    // inverts it and publishes W_{k+1}, W_{k+1} u_{k+1} to shared memory before the step's barrier, while the other
+    // warps update the rest of the trailing envelope (one row per warp). After the barrier everybody just reads W.
+    auto invert_and_publish = [&](int kb, int r) {     // pivot block at rows/cols r..r+2 (already final), rhs y[r..r+2]
+        const double a = IO::ld(A_(r, r)), b = IO::ld(A_(r + 1, r)), c = IO::ld(A_(r + 2, r));
+        const double e = IO::ld(A_(r + 1, r + 1)), f = IO::ld(A_(r + 2, r + 1)), i2 = IO::ld(A_(r + 2, r + 2));
+        const double u0 = IO::ld(Y_(r)), u1 = IO::ld(Y_(r + 1)), u2 = IO::ld(Y_(r + 2));
+        const double c00 = e * i2 - f * f, c01 = c * f - b * i2, c02 = b * f - c * e;
+        const double det = a * c00 + b * c01 + c * c02, m2 = a * e - b * b;
+        const bool pd = (a > 0.0) && (m2 > 0.0) && (det > 0.0) && isfinite(det);   // leading minors: CHOLMOD's "not positive definite"
+        const double id = 1.0 / det;
+        const double w00 = c00 * id, w01 = c01 * id, w02 = c02 * id, w11 = (a * i2 - c * c) * id, w12 = (b * c - a * f) * id, w22 = m2 * id;
+        if (lane == 0) {
+            IO::st(W_(kb, 0), w00); IO::st(W_(kb, 1), w01); IO::st(W_(kb, 2), w02); IO::st(W_(kb, 3), w01); IO::st(W_(kb, 4), w11);
+            IO::st(W_(kb, 5), w12); IO::st(W_(kb, 6), w02); IO::st(W_(kb, 7), w12); IO::st(W_(kb, 8), w22);
+            IO::st(aT, w00 * u0 + w01 * u1 + w02 * u2); IO::st(aT + 8, w01 * u0 + w11 * u1 + w12 * u2); IO::st(aT + 16, w02 * u0 + w12 * u1 + w22 * u2);
+            if (!pd) IO::sti(aOK, 0);
+        }
+    };
+    if (wid == 0 && nb > 0) invert_and_publish(0, 0);
+    __syncthreads();
+    STAMP(2);
+    for (int kb = 0; kb < nb; ++kb) {
+        if (!IO::ldi(aOK)) break;                                // uniform: written before the barrier that precedes this read
+        const int k = 3 * kb;
+        if (kb < 8) STAMP(10 + 4 * kb);
+        const double w00 = IO::ld(W_(kb, 0)), w01 = IO::ld(W_(kb, 1)), w02 = IO::ld(W_(kb, 2)), w11 = IO::ld(W_(kb, 4)), w12 = IO::ld(W_(kb, 5)), w22 = IO::ld(W_(kb, 8));
+        const double t0 = IO::ld(aT), t1 = IO::ld(aT + 8), t2 = IO::ld(aT + 16);
+        const int m = IO::ldi(aC + (ADDR)((k + 2) * 4)) - (k + 2);            // trailing rows/cols k+3 .. k+2+m
+        __syncthreads();                            // everyone holds W_k / t_k in registers: warp 0 may overwrite the scratch
+        if (kb < 8) STAMP(11 + 4 * kb);
+        if (wid == 0) {
+            // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
+            if (kb + 1 < nb && lane < 9) {
+                const int q = lane;                 // 0..5: (ii,jj) = (0,0)(1,0)(1,1)(2,0)(2,1)(2,2); 6..8: rhs of row q-6
+                const int ii = q < 1 ? 0 : (q < 3 ? 1 : (q < 6 ? 2 : q - 6));
+                const int jj = q < 1 ? 0 : (q < 3 ? q - 1 : (q < 6 ? q - 3 : 0));
+                const int i = k + 3 + ii, j = k + 3 + jj;
+                if (ii < m) {                       // rows beyond the envelope of this block column are structurally untouched
+                    const ADDR dst = (q < 6) ? A_(i, j) : Y_(i);
+                    double val = IO::ld(dst);
+                    const double a0 = IO::ld(A_(i, k)), a1 = IO::ld(A_(i, k + 1)), a2 = IO::ld(A_(i, k + 2));
+                    if (q < 6) {
+                        const double b0 = IO::ld(A_(j, k)), b1 = IO::ld(A_(j, k + 1)), b2 = IO::ld(A_(j, k + 2));
+                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
+                        val -= a0 * v0 + a1 * v1 + a2 * v2;
+                    } else {
+                        val -= a0 * t0 + a1 * t1 + a2 * t2;
+                    }
+                    IO::st(dst, val);
+                }
+            }
+            if (kb + 1 < nb) {
+                __syncwarp();                       // the 6 + 3 freshly updated values are in memory: re-read, invert, publish
+                invert_and_publish(kb + 1, k + 3);
+            }
+            if (kb < 8) STAMP(12 + 4 * kb);
+        } else {
+            // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs)
+            for (int ii = 3 + (wid - 1); ii < m; ii += nw - 1) {
+                const int i = k + 3 + ii;
+                const double a0 = IO::ld(A_(i, k)), a1 = IO::ld(A_(i, k + 1)), a2 = IO::ld(A_(i, k + 2));
+                for (int jj = lane; jj <= ii + 1; jj += 32) {
+                    if (jj <= ii) {
+                        const int j = k + 3 + jj;
+                        const double b0 = IO::ld(A_(j, k)), b1 = IO::ld(A_(j, k + 1)), b2 = IO::ld(A_(j, k + 2));
+                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
+                        IO::st(A_(i, j), IO::ld(A_(i, j)) - (a0 * v0 + a1 * v1 + a2 * v2));
+                    } else {
+                        IO::st(Y_(i), IO::ld(Y_(i)) - (a0 * t0 + a1 * t1 + a2 * t2));        // the right-hand side as an extra column
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (kb < 8) STAMP(13 + 4 * kb);
+    }
+    __syncthreads();
+    STAMP(3);
+    const int ok = IO::ldi(aOK);
+    if (ok) {
+        if (wid == 0) {
+            // lanes = 3 columns x 8 row slots; each 8-lane group sums its column's dot product with an xor tree
+            const int c = lane >> 3, rs = lane & 7;
+            for (int kb = nb - 1; kb >= 0; --kb) {
+                const int k = 3 * kb, m = IO::ldi(aC + (ADDR)((k + 2) * 4)) - (k + 2);
+                double sdot = 0;
+                if (c < 3)
+                    for (int ii = rs; ii < m; ii += 8) sdot += IO::ld(A_(k + 3 + ii, k + c)) * IO::ld(Y_(k + 3 + ii));
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                const double rc = (c < 3) ? IO::ld(Y_(k + c)) - sdot : 0.0;
+                const double r0 = __shfl_sync(0xffffffffu, rc, 0), r1 = __shfl_sync(0xffffffffu, rc, 8), r2 = __shfl_sync(0xffffffffu, rc, 16);
+                if (lane < 3) IO::st(Y_(k + lane), IO::ld(W_(kb, 3 * lane)) * r0 + IO::ld(W_(kb, 3 * lane + 1)) * r1 + IO::ld(W_(kb, 3 * lane + 2)) * r2);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        STAMP(4);
+        for (int i = tid; i < n; i += nt) dxp[i] = IO::ld(Y_(i));
+    } else {
+        for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
+    }
+    if (tid == 0) st->solve_ok = ok;
+    STAMP(5);
+#undef A_
+#undef Y_
+#undef W_
+}
+
+template <bool SMEM>
+__device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
+    if (SMEM) {
+        extern __shared__ double sm[];
+        // layout: A [n*n] | y [n] | W [3n] | pad [2] | cmax (int) [n] | scratch tb[3], ok
+        const unsigned sA = smem_u32(sm);
+        const unsigned sY = sA + (unsigned)n * n * 8, sW = sY + (unsigned)n * 8, sC = sW + (unsigned)(3 * n + 2) * 8;
+        const unsigned sT = (sC + (unsigned)n * 4 + 15u) & ~15u;
+        ldlt_block_solve_impl<SmemIO, unsigned>(sA, sY, sW, sC, sT, n, bs, dxp, st);
+    } else {
+        // global layout: A = G; ywork holds y [n] | W [3n] | scratch [4]; the envelope stays where it is
+        const unsigned long long gA = (unsigned long long)G, gY = (unsigned long long)ywork, gW = gY + (unsigned long long)n * 8;
+        const unsigned long long gT = gW + (unsigned long long)(3 * n) * 8;
+        ldlt_block_solve_impl<GmemIO, unsigned long long>(gA, gY, gW, (unsigned long long)colmax_g, gT, n, bs, dxp, st);
+    }
+}
+
+// bytes of dynamic shared memory the SMEM variant needs for n unknowns
+__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16 + 48; }
 
 // S (n*n doubles, rounded up to 16 B: the tail lands in y, which is initialised afterwards) and the envelope -> shared
 // memory. One elected thread issues a single bulk copy; everybody waits on the mbarrier phase `parity`.
@@ -1387,7 +1413,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.oAii, 6 * O); A(&d.oAij, 9 * O); A(&d.oAjj, 6 * O); A(&d.obi, 3 * O); A(&d.obj, 3 * O);
     A(&h->pose_ptr, P + 1); A(&h->pose_edges, E); A(&h->pose_odo_ptr, P + 1); A(&h->pose_odo, 2 * O);
     A(&d.Hpp, 6 * P); A(&d.bp, 3 * P);
-    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 4 * maxN + 16); A(&h->colmax, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
+    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 4 * maxN + 32); A(&h->colmax, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
     const size_t nb = (L + LM_THREADS - 1) / LM_THREADS + (O + LM_THREADS - 1) / LM_THREADS + (P + LM_THREADS - 1) / LM_THREADS + 4;
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
