@@ -72,6 +72,7 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     // reduced system
     const int *blk_a, *blk_b, *blk_pair_ptr, *pair_e1, *pair_e2, *blk_odo_ptr, *blk_odo;
     const int* colmax;                    // [n] envelope of the reduced system (last structurally non-zero row per column)
+    const int* blk_order;                 // [nblk] diagonal blocks first: position p is served by persistent worker p % W
     double *S, *bs, *scal, *dxp, *dxl;    // S [n*n] | bs [n] | scal [8] contiguous (all-reduce buffer)
     double *part_chi, *part_scale;
     int nb_lm, nb_odo;
@@ -1045,11 +1046,12 @@ struct PKWork {
 __device__ void pk_phase_pose_reduce(const Dev& d, const PKWork& w, double* sh9) {
     if (w.first < 0) return;
     int i = 0;
-    for (int blk = w.first; blk < d.nblk; blk += w.stride, ++i) {
+    for (int pos = w.first; pos < d.nblk; pos += w.stride, ++i) {
         if (i < w.n_own) {
             const PKOwn o = w.own[i];
             if (o.a == o.b) pk_pose_item(d, o.a, w.arena + o.e0, o.ne, sh9);
         } else {
+            const int blk = d.blk_order[pos];
             const int a = d.blk_a[blk];
             if (a == d.blk_b[blk]) pk_pose_item(d, a, d.pose_edges + d.pose_ptr[a], d.pose_ptr[a + 1] - d.pose_ptr[a], sh9);
         }
@@ -1059,11 +1061,12 @@ __device__ void pk_phase_pose_reduce(const Dev& d, const PKWork& w, double* sh9)
 __device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double* sh12) {
     if (w.first < 0) return;
     int i = 0;
-    for (int blk = w.first; blk < d.nblk; blk += w.stride, ++i) {
+    for (int pos = w.first; pos < d.nblk; pos += w.stride, ++i) {
         if (i < w.n_own) {
             const PKOwn o = w.own[i];
             pk_schur_item(d, lam, o.blk, o.a, o.b, w.arena + o.p0, 0, o.np, w.arena + o.e0, o.ne, sh12);
         } else {
+            const int blk = d.blk_order[pos];
             const int a = d.blk_a[blk], b = d.blk_b[blk];
             pk_schur_item(d, lam, blk, a, b, nullptr, d.blk_pair_ptr[blk], d.blk_pair_ptr[blk + 1] - d.blk_pair_ptr[blk],
                           d.pose_edges + d.pose_ptr[a], a == b ? d.pose_ptr[a + 1] - d.pose_ptr[a] : 0, sh12);
@@ -1171,7 +1174,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         if (threadIdx.x == 0) {
             int off = 0, no = 0;
             if (work.first >= 0)
-                for (int blk = work.first; blk < d.nblk && no < PK_MAXOWN; blk += work.stride) {
+                for (int pos = work.first; pos < d.nblk && no < PK_MAXOWN; pos += work.stride) {
+                    const int blk = d.blk_order[pos];
                     const int a = d.blk_a[blk], b = d.blk_b[blk];
                     const int np = d.blk_pair_ptr[blk + 1] - d.blk_pair_ptr[blk];
                     const int ne = (a == b) ? d.pose_ptr[a + 1] - d.pose_ptr[a] : 0;
@@ -1334,6 +1338,7 @@ struct se2gpu_ba {
     double* red = nullptr;     // all-reduce buffer [maxN*maxN + maxN + 8]
     double* ywork = nullptr;
     int* colmax = nullptr;
+    int* blk_order = nullptr;
     se2gpu_ba_iter_stats* stats_dev = nullptr;
     int max_stats = 64;
     LMState* st_host = nullptr;  // pinned
@@ -1380,9 +1385,9 @@ int ensure_cap(se2gpu_ba* h, size_t npairs, size_t nblk, size_t nblk_odo) {
     }
     if (nblk + 1 > h->cap_blk) {
         size_t cap = nblk + nblk / 4 + 1024;
-        int* p[5];
-        for (int i = 0; i < 5; ++i) { if (se2gpu::dev_alloc(&p[i], cap + 1) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "block list alloc failed"); h->bufs.push_back(p[i]); }
-        h->blk_a = p[0]; h->blk_b = p[1]; h->blk_pair_ptr = p[2]; h->blk_odo_ptr = p[3]; h->blk_odo = p[4];
+        int* p[6];
+        for (int i = 0; i < 6; ++i) { if (se2gpu::dev_alloc(&p[i], cap + 1) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "block list alloc failed"); h->bufs.push_back(p[i]); }
+        h->blk_a = p[0]; h->blk_b = p[1]; h->blk_pair_ptr = p[2]; h->blk_odo_ptr = p[3]; h->blk_odo = p[4]; h->blk_order = p[5];
         h->cap_blk = cap;
     }
     (void)nblk_odo;
@@ -1571,6 +1576,12 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     }
     std::vector<int> colmax(n);
     for (int a = 0; a < nf; ++a) for (int r = 0; r < 3; ++r) colmax[3 * a + r] = 3 * bmax[a] + 2;
+    // serving order of the blocks for the persistent kernel: diagonal blocks (they also carry the pose-side gather) first,
+    // so that round-robin assignment gives every worker CTA at most one of them
+    std::vector<int> blk_order;
+    blk_order.reserve(nblk);
+    for (int b = 0; b < nblk; ++b) if (blk_a[b] == blk_b[b]) blk_order.push_back(b);
+    for (int b = 0; b < nblk; ++b) if (blk_a[b] != blk_b[b]) blk_order.push_back(b);
     int rc = ensure_cap(h, pairs.size(), std::max<size_t>(nblk, odob.size()), odob.size());
     if (rc != SE2GPU_OK) return rc;
 
@@ -1595,7 +1606,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     UP(h->o_i, oi); UP(h->o_j, oj); UP(h->o_m, om); UP(h->o_w, ow);
     UP(h->pose_ptr, pose_ptr); UP(h->pose_edges, pose_edges); UP(h->pose_odo_ptr, pose_odo_ptr); UP(h->pose_odo, pose_odo);
     UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UP(h->pair_e1, pe1); UP(h->pair_e2, pe2);
-    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax);
+    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax); UP(h->blk_order, blk_order);
 #undef UP
     SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
     LMState st0{};
@@ -1611,7 +1622,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     d.o_i = h->o_i; d.o_j = h->o_j; d.o_m = h->o_m; d.o_w = h->o_w;
     d.pose_ptr = h->pose_ptr; d.pose_edges = h->pose_edges; d.pose_odo_ptr = h->pose_odo_ptr; d.pose_odo = h->pose_odo;
     d.blk_a = h->blk_a; d.blk_b = h->blk_b; d.blk_pair_ptr = h->blk_pair_ptr; d.pair_e1 = h->pair_e1; d.pair_e2 = h->pair_e2;
-    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax;
+    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax; d.blk_order = h->blk_order;
     d.S = h->red; d.bs = h->red + (size_t)n * n; d.scal = d.bs + n;
     d.nb_lm = (L + LM_THREADS - 1) / LM_THREADS; d.nb_odo = (Ol + LM_THREADS - 1) / LM_THREADS;
     h->nb_scale = (std::max(L, P) + LM_THREADS - 1) / LM_THREADS;

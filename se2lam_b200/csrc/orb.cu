@@ -79,6 +79,7 @@ struct OrbDev {  // passed by value to kernels
     int lkp_total;
     int* lcount;                // [B][nlevels]
     int* err;                   // device error flag
+    int frame0;                 // first frame of this launch group (pipelined host path processes the batch in chunks)
 };
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -91,7 +92,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 __global__ void orb_pyr0(OrbDev d, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride) {
     const LevelGeo& L = d.levels[0];
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
-    const int f = blockIdx.z;
+    const int f = blockIdx.z + d.frame0;
     if (x4 >= L.pitch) return;
     const int sy = reflect101(y - EDGE, L.h);
     const uint8_t* row = imgs + f * frame_stride + (size_t)sy * stride;
@@ -112,7 +113,7 @@ __global__ void orb_resize(OrbDev d, int level) {
     const LevelGeo& L = d.levels[level];
     const LevelGeo& S = d.levels[level - 1];
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
-    const int f = blockIdx.z;
+    const int f = blockIdx.z + d.frame0;
     if (x4 >= L.pitch) return;
     const int dy = reflect101(y - EDGE, L.h);
     const int* xofs = d.itab + L.tab_off;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     extern __shared__ uint8_t smem[];
     __shared__ int s_total;
     const CellGeo c = d.cells[blockIdx.x];
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + d.frame0;
     CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
     const int cw = c.x1 - c.x0, ch = c.y1 - c.y0;
     if (c.skipped || cw <= 0 || ch <= 0) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
 constexpr int SEL_STAGE = 12288;
 __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
     extern __shared__ uint32_t sbuf[];   // [cap] level list | [4*nCells] ints | [SEL_STAGE] staged candidates
-    const int level = blockIdx.x, f = blockIdx.y;
+    const int level = blockIdx.x, f = blockIdx.y + d.frame0;
     const LevelGeo& L = d.levels[level];
     const int nCells = L.nCells;
     const int cap = 2 * L.nDesired + 4 * nCells + 64;
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
     __shared__ __align__(16) float rowp[(BLUR_TH + 6) * BLUR_TW];
     const uint8_t* patch = reinterpret_cast<const uint8_t*>(patchw);
     const TileGeo t = d.tiles[blockIdx.x];
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + d.frame0;
     const LevelGeo& L = d.levels[t.level];
     const uint8_t* src = d.plain + f * d.frame_plane_bytes + L.plane_off;
     uint8_t* dst = d.blurred + f * d.frame_plane_bytes + L.plane_off;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keyp
     __shared__ signed char pat[1024];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) pat[i] = d_pattern[i];
     __syncthreads();
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + d.frame0;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int* lc = d.lcount + f * d.nlevels;
@@ -568,6 +569,10 @@ struct se2gpu_orb {
     se2gpu::Profiler prof;
     cudaStream_t side = nullptr;          // blur runs here, concurrently with FAST + selection
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    // host-buffer path: two pipeline lanes (stream + side stream + events) so that the H2D of chunk c+1 and the D2H of
+    // chunk c-1 overlap the kernels of chunk c
+    cudaStream_t pipe[2] = {nullptr, nullptr}, pipe_side[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_ev_pyr[2] = {nullptr, nullptr}, pipe_ev_blur[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -705,10 +710,13 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
 }
 
 int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int stride, size_t frame_stride,
-               se2gpu_keypoint* d_kps, uint8_t* d_desc, int* d_counts, cudaStream_t s) {
+               se2gpu_keypoint* d_kps, uint8_t* d_desc, int* d_counts, cudaStream_t s, int frame0 = 0, int lane = -1) {
     int rc = set_geometry(h, w, hgt, s);
     if (rc != SE2GPU_OK) return rc;
-    OrbDev& d = h->d;
+    OrbDev d = h->d;             // by-value copy carrying this launch group's frame offset
+    d.frame0 = frame0;
+    cudaStream_t side = lane < 0 ? h->side : h->pipe_side[lane];
+    cudaEvent_t ev_pyr = lane < 0 ? h->ev_pyr : h->pipe_ev_pyr[lane], ev_blur = lane < 0 ? h->ev_blur : h->pipe_ev_blur[lane];
     se2gpu::Profiler& pr = h->prof;
     pr.begin(0, s);
     {
@@ -725,12 +733,12 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     // the blur only depends on the pyramid: fork it onto the side stream so that it overlaps the (latency-bound)
     // selection kernel; join before the descriptors are sampled. With the profiler on everything stays on one
     // stream so that the per-kernel event times are not polluted by the overlap.
-    const bool overlap = !pr.on && h->side != nullptr;
+    const bool overlap = !pr.on && side != nullptr;
     if (overlap) {
-        SE2_CUDA(cudaEventRecord(h->ev_pyr, s));
-        SE2_CUDA(cudaStreamWaitEvent(h->side, h->ev_pyr, 0));
-        SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, h->side, d);
-        SE2_CUDA(cudaEventRecord(h->ev_blur, h->side));
+        SE2_CUDA(cudaEventRecord(ev_pyr, s));
+        SE2_CUDA(cudaStreamWaitEvent(side, ev_pyr, 0));
+        SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, side, d);
+        SE2_CUDA(cudaEventRecord(ev_blur, side));
     }
     pr.begin(1, s);
     SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
@@ -739,7 +747,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     SE2_LAUNCH(orb_select, dim3(h->nlevels, n), 128, h->select_smem, s, d);
     pr.end(s);
     if (overlap) {
-        SE2_CUDA(cudaStreamWaitEvent(s, h->ev_blur, 0));
+        SE2_CUDA(cudaStreamWaitEvent(s, ev_blur, 0));
     } else {
         pr.begin(3, s);
         SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, s, d);
@@ -749,7 +757,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     pr.begin(4, s);
     SE2_LAUNCH(orb_orient_describe, dim3((h->nfeatures + warps - 1) / warps, n), warps * 32, 0, s, d, d_kps, d_desc, d_counts);
     pr.end(s);
-    h->last_n = n;
+    h->last_n = std::max(h->last_n * (frame0 > 0), frame0 + n);
     return SE2GPU_OK;
 }
 
@@ -806,6 +814,11 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     cudaMemset(d.err, 0, sizeof(int));
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
+    for (int l = 0; l < 2 && h->side; ++l)
+        if (cudaStreamCreateWithFlags(&h->pipe[l], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->pipe_side[l], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->pipe_ev_pyr[l], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->pipe_ev_blur[l], cudaEventDisableTiming) != cudaSuccess) {
+            h->pipe[0] = nullptr; cudaGetLastError(); break;
+        }
     cudaMemcpyToSymbol(c_umax, umax, sizeof umax);
     cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
     d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
@@ -821,6 +834,12 @@ void se2gpu_orb_destroy(se2gpu_orb* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    for (int l = 0; l < 2; ++l) {
+        if (h->pipe[l]) cudaStreamDestroy(h->pipe[l]);
+        if (h->pipe_side[l]) cudaStreamDestroy(h->pipe_side[l]);
+        if (h->pipe_ev_pyr[l]) cudaEventDestroy(h->pipe_ev_pyr[l]);
+        if (h->pipe_ev_blur[l]) cudaEventDestroy(h->pipe_ev_blur[l]);
+    }
     delete h;
 }
 
@@ -845,34 +864,32 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     if (stride < w) return fail(SE2GPU_ERR_INVALID, "stride < width");
     if (w > h->max_w || hgt > h->max_h) return fail(SE2GPU_ERR_CAPACITY, "frame %dx%d exceeds %dx%d", w, hgt, h->max_w, h->max_h);
     SE2_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = nullptr;
-    // pack rows tightly on the device (pitch = w)
-    for (int i = 0; i < n; ++i)
-        SE2_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)i * w * hgt, w, imgs + i * frame_stride, stride, w, hgt, cudaMemcpyHostToDevice, s));
-    int rc = run_device(h, h->d_in, n, w, hgt, w, (size_t)w * hgt, h->d_kps, h->d_desc, h->d_counts, s);
+    int rc = set_geometry(h, w, hgt, nullptr);
     if (rc != SE2GPU_OK) return rc;
-    SE2_CUDA(cudaMemcpyAsync(counts, h->d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
-    SE2_CUDA(cudaMemcpyAsync(kps, h->d_kps, sizeof(se2gpu_keypoint) * (size_t)n * h->nfeatures, cudaMemcpyDeviceToHost, s));
-    SE2_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)32 * n * h->nfeatures, cudaMemcpyDeviceToHost, s));
+    const bool pipelined = h->pipe[0] && h->pipe[1] && !h->prof.on && n > 1;
+    const int chunk = pipelined ? std::max(1, std::min(16, (n + 3) / 4)) : n;
+    int lane = 0;
+    for (int f0 = 0; f0 < n; f0 += chunk, lane ^= 1) {
+        const int m = std::min(chunk, n - f0);
+        cudaStream_t s = pipelined ? h->pipe[lane] : nullptr;
+        // pack rows tightly on the device (pitch = w); frames of different chunks use disjoint device buffers
+        if (stride == w && frame_stride == (size_t)w * hgt)
+            SE2_CUDA(cudaMemcpyAsync(h->d_in + (size_t)f0 * w * hgt, imgs + (size_t)f0 * frame_stride, (size_t)m * w * hgt, cudaMemcpyHostToDevice, s));
+        else
+            for (int i = f0; i < f0 + m; ++i)
+                SE2_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)i * w * hgt, w, imgs + i * frame_stride, stride, w, hgt, cudaMemcpyHostToDevice, s));
+        rc = run_device(h, h->d_in, m, w, hgt, w, (size_t)w * hgt, h->d_kps, h->d_desc, h->d_counts, s, f0, pipelined ? lane : -1);
+        if (rc != SE2GPU_OK) return rc;
+        SE2_CUDA(cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * h->nfeatures, h->d_kps + (size_t)f0 * h->nfeatures, sizeof(se2gpu_keypoint) * (size_t)m * h->nfeatures, cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaMemcpyAsync(desc + (size_t)32 * f0 * h->nfeatures, h->d_desc + (size_t)32 * f0 * h->nfeatures, (size_t)32 * m * h->nfeatures, cudaMemcpyDeviceToHost, s));
+    }
+    if (pipelined) { SE2_CUDA(cudaStreamSynchronize(h->pipe[0])); SE2_CUDA(cudaStreamSynchronize(h->pipe[1])); }
     int err = 0;
-    SE2_CUDA(cudaMemcpyAsync(&err, h->d.err, sizeof(int), cudaMemcpyDeviceToHost, s));
-    SE2_CUDA(cudaStreamSynchronize(s));
+    SE2_CUDA(cudaMemcpyAsync(&err, h->d.err, sizeof(int), cudaMemcpyDeviceToHost, nullptr));
+    SE2_CUDA(cudaStreamSynchronize(nullptr));
+    h->last_n = n;
     if (err) { cudaMemset(h->d.err, 0, sizeof(int)); return fail(SE2GPU_ERR_CAPACITY, "internal candidate buffer overflow (code %d)", err); }
-    return SE2GPU_OK;
-}
-
-int se2gpu_orb_profile(se2gpu_orb* h, int enable) {
-    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
-    SE2_CUDA(cudaSetDevice(h->device));
-    h->prof.enable(enable != 0);
-    return SE2GPU_OK;
-}
-
-int se2gpu_orb_profile_read(se2gpu_orb* h, double* ms, int* launches) {
-    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
-    SE2_CUDA(cudaSetDevice(h->device));
-    h->prof.flush();
-    for (int g = 0; g < SE2GPU_ORB_PROFILE_GROUPS; ++g) { if (ms) ms[g] = h->prof.ms[g]; if (launches) launches[g] = h->prof.launches[g]; }
     return SE2GPU_OK;
 }
 
