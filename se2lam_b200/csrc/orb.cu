@@ -893,6 +893,21 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     return SE2GPU_OK;
 }
 
+int se2gpu_orb_profile(se2gpu_orb* h, int enable) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->prof.enable(enable != 0);
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_profile_read(se2gpu_orb* h, double* ms, int* launches) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->prof.flush();
+    for (int g = 0; g < SE2GPU_ORB_PROFILE_GROUPS; ++g) { if (ms) ms[g] = h->prof.ms[g]; if (launches) launches[g] = h->prof.launches[g]; }
+    return SE2GPU_OK;
+}
+
 int se2gpu_orb_level_dims(se2gpu_orb* h, int level, int* w, int* hgt, int* pitch) {
     if (!h || level < 0 || level >= h->nlevels || h->cur_w < 0) return fail(SE2GPU_ERR_INVALID, "no geometry");
     *w = h->levels[level].w; *hgt = h->levels[level].h; *pitch = h->levels[level].pitch;
