@@ -573,6 +573,9 @@ struct se2gpu_orb {
     // chunk c-1 overlap the kernels of chunk c
     cudaStream_t pipe[2] = {nullptr, nullptr}, pipe_side[2] = {nullptr, nullptr};
     cudaEvent_t pipe_ev_pyr[2] = {nullptr, nullptr}, pipe_ev_blur[2] = {nullptr, nullptr};
+    // pinned staging for results when the caller's buffers are pageable (a D2H copy into pageable memory blocks the
+    // host and would serialise the pipeline)
+    int* pin_counts = nullptr; se2gpu_keypoint* pin_kps = nullptr; uint8_t* pin_desc = nullptr;
 };
 
 namespace {
@@ -834,6 +837,9 @@ void se2gpu_orb_destroy(se2gpu_orb* h) {
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    if (h->pin_counts) cudaFreeHost(h->pin_counts);
+    if (h->pin_kps) cudaFreeHost(h->pin_kps);
+    if (h->pin_desc) cudaFreeHost(h->pin_desc);
     for (int l = 0; l < 2; ++l) {
         if (h->pipe[l]) cudaStreamDestroy(h->pipe[l]);
         if (h->pipe_side[l]) cudaStreamDestroy(h->pipe_side[l]);
@@ -866,8 +872,27 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     SE2_CUDA(cudaSetDevice(h->device));
     int rc = set_geometry(h, w, hgt, nullptr);
     if (rc != SE2GPU_OK) return rc;
-    const bool pipelined = h->pipe[0] && h->pipe[1] && !h->prof.on && n > 1;
-    const int chunk = pipelined ? std::max(1, std::min(16, (n + 3) / 4)) : n;
+    // number of pipeline chunks: SE2GPU_ORB_CHUNKS overrides (1 = one synchronous pass)
+    static const int env_chunks = [] { const char* e = getenv("SE2GPU_ORB_CHUNKS"); return e ? atoi(e) : 0; }();
+    const int nchunks = env_chunks > 0 ? env_chunks : 4;
+    const bool pipelined = h->pipe[0] && h->pipe[1] && !h->prof.on && n > 1 && nchunks > 1;
+    const int chunk = pipelined ? std::max(1, (n + nchunks - 1) / nchunks) : n;
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    se2gpu_keypoint* out_kps = kps; uint8_t* out_desc = desc; int* out_counts = counts;
+    if (pipelined) {
+        if (!h->pin_counts && cudaMallocHost((void**)&h->pin_counts, sizeof(int) * h->max_batch) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
+        out_counts = h->pin_counts;
+        if (!is_pinned(kps) || !is_pinned(desc)) {
+            if (!h->pin_kps && (cudaMallocHost((void**)&h->pin_kps, sizeof(se2gpu_keypoint) * (size_t)h->max_batch * h->nfeatures) != cudaSuccess ||
+                                cudaMallocHost((void**)&h->pin_desc, (size_t)32 * h->max_batch * h->nfeatures) != cudaSuccess))
+                return fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
+            out_kps = h->pin_kps; out_desc = h->pin_desc;
+        }
+    }
     int lane = 0;
     for (int f0 = 0; f0 < n; f0 += chunk, lane ^= 1) {
         const int m = std::min(chunk, n - f0);
@@ -880,11 +905,15 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
                 SE2_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)i * w * hgt, w, imgs + i * frame_stride, stride, w, hgt, cudaMemcpyHostToDevice, s));
         rc = run_device(h, h->d_in, m, w, hgt, w, (size_t)w * hgt, h->d_kps, h->d_desc, h->d_counts, s, f0, pipelined ? lane : -1);
         if (rc != SE2GPU_OK) return rc;
-        SE2_CUDA(cudaMemcpyAsync(counts + f0, h->d_counts + f0, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
-        SE2_CUDA(cudaMemcpyAsync(kps + (size_t)f0 * h->nfeatures, h->d_kps + (size_t)f0 * h->nfeatures, sizeof(se2gpu_keypoint) * (size_t)m * h->nfeatures, cudaMemcpyDeviceToHost, s));
-        SE2_CUDA(cudaMemcpyAsync(desc + (size_t)32 * f0 * h->nfeatures, h->d_desc + (size_t)32 * f0 * h->nfeatures, (size_t)32 * m * h->nfeatures, cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaMemcpyAsync(out_counts + f0, h->d_counts + f0, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaMemcpyAsync(out_kps + (size_t)f0 * h->nfeatures, h->d_kps + (size_t)f0 * h->nfeatures, sizeof(se2gpu_keypoint) * (size_t)m * h->nfeatures, cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaMemcpyAsync(out_desc + (size_t)32 * f0 * h->nfeatures, h->d_desc + (size_t)32 * f0 * h->nfeatures, (size_t)32 * m * h->nfeatures, cudaMemcpyDeviceToHost, s));
     }
-    if (pipelined) { SE2_CUDA(cudaStreamSynchronize(h->pipe[0])); SE2_CUDA(cudaStreamSynchronize(h->pipe[1])); }
+    if (pipelined) {
+        SE2_CUDA(cudaStreamSynchronize(h->pipe[0])); SE2_CUDA(cudaStreamSynchronize(h->pipe[1]));
+        memcpy(counts, out_counts, sizeof(int) * n);
+        if (out_kps != kps) { memcpy(kps, out_kps, sizeof(se2gpu_keypoint) * (size_t)n * h->nfeatures); memcpy(desc, out_desc, (size_t)32 * n * h->nfeatures); }
+    }
     int err = 0;
     SE2_CUDA(cudaMemcpyAsync(&err, h->d.err, sizeof(int), cudaMemcpyDeviceToHost, nullptr));
     SE2_CUDA(cudaStreamSynchronize(nullptr));
