@@ -33,7 +33,10 @@ class LocalBA:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     @classmethod
     def from_problem(cls, prob, device=0, rank=0, world=1, allreduce=None, stream=None, mode=0):

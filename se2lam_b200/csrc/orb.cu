@@ -872,11 +872,14 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     SE2_CUDA(cudaSetDevice(h->device));
     int rc = set_geometry(h, w, hgt, nullptr);
     if (rc != SE2GPU_OK) return rc;
-    // number of pipeline chunks: SE2GPU_ORB_CHUNKS overrides (1 = one synchronous pass)
+    // pipeline shape: `nchunks` chunks, the first one `first_pct` percent of an even share (a short first chunk exposes
+    // less of the initial H2D copy); SE2GPU_ORB_CHUNKS / SE2GPU_ORB_FIRST override, 1 chunk = one synchronous pass
     static const int env_chunks = [] { const char* e = getenv("SE2GPU_ORB_CHUNKS"); return e ? atoi(e) : 0; }();
-    const int nchunks = env_chunks > 0 ? env_chunks : 4;
+    static const int env_first = [] { const char* e = getenv("SE2GPU_ORB_FIRST"); return e ? atoi(e) : 0; }();
+    const int nchunks = env_chunks > 0 ? env_chunks : 2;
     const bool pipelined = h->pipe[0] && h->pipe[1] && !h->prof.on && n > 1 && nchunks > 1;
     const int chunk = pipelined ? std::max(1, (n + nchunks - 1) / nchunks) : n;
+    const int first = pipelined ? std::max(1, std::min(n, chunk * (env_first > 0 ? env_first : 50) / 100)) : n;
     auto is_pinned = [](const void* p) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -894,8 +897,8 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
         }
     }
     int lane = 0;
-    for (int f0 = 0; f0 < n; f0 += chunk, lane ^= 1) {
-        const int m = std::min(chunk, n - f0);
+    for (int f0 = 0, m = 0; f0 < n; f0 += m, lane ^= 1) {
+        m = std::min(f0 == 0 ? first : std::max(chunk, (n - first + nchunks - 2) / std::max(1, nchunks - 1)), n - f0);
         cudaStream_t s = pipelined ? h->pipe[lane] : nullptr;
         // pack rows tightly on the device (pitch = w); frames of different chunks use disjoint device buffers
         if (stride == w && frame_stride == (size_t)w * hgt)

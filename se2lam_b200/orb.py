@@ -37,7 +37,10 @@ class ORBextractor:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def GetLevels(self):
         return self.nlevels

@@ -9,7 +9,7 @@ from se2lam_b200.orb import ORBextractor
 n, NF, W, H = 64, 1000, 640, 480
 ex = ORBextractor(NF, 1.2, 8, max_batch=n)
 lib = _capi.lib()
-hosts = [torch.from_numpy(synth.orb_batch(n, seed=100 + k)).pin_memory() for k in range(4)]
+hosts = [torch.from_numpy(synth.orb_batch(n, first_seed=100 + 64 * k)).pin_memory() for k in range(4)]
 pinned = os.environ.get("PINNED_OUT", "1") == "1"
 mk = (lambda nb: torch.empty(nb, dtype=torch.uint8).pin_memory().numpy()) if pinned else (lambda nb: np.zeros(nb, np.uint8))
 kps, desc, counts = mk(n * NF * 28), mk(n * NF * 32), np.zeros(n, np.int32)
@@ -25,7 +25,7 @@ print(json.dumps({"chunks": os.environ.get("SE2GPU_ORB_CHUNKS"), "pinned_out": p
 '''
 
 for pinned in ("1", "0"):
-    for c in ("1", "2", "3", "4", "6", "8"):
-        env = dict(os.environ, SE2GPU_ORB_CHUNKS=c, PINNED_OUT=pinned)
+    for c, f in (("1", "100"), ("2", "100"), ("2", "75"), ("2", "50"), ("2", "35"), ("3", "100"), ("3", "50"), ("4", "100"), ("4", "50")):
+        env = dict(os.environ, SE2GPU_ORB_CHUNKS=c, SE2GPU_ORB_FIRST=f, PINNED_OUT=pinned)
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
-        print(r.stdout.strip() or r.stderr[-400:], flush=True)
+        print(f, r.stdout.strip() or r.stderr[-400:], flush=True)
