@@ -146,55 +146,56 @@ __global__ void orb_resize(OrbDev d, int level) {
     *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
 }
 
-// FAST-9-16 arc score M = max over the 16 nine-pixel arcs of min(+-(v - ring)); corner at t <=> M > t,
-// cv::FAST's stored score == M-1 whatever t was. Returns 0 early when the pixel cannot be a corner at t:
-// a 9-arc always contains one pixel of each opposite pair (k, k+8), so all 4 tested pairs must have a
-// member beyond +-t of the centre.
-__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int pw, int t) {
-    const int v = p[0];
-    const int c0 = v - p[3 * pw], c8 = v - p[-3 * pw];
-    bool dk = (c0 > t) | (c8 > t), br = (c0 < -t) | (c8 < -t);
-    if (!(dk | br)) return 0;
-    const int c4 = v - p[3], c12 = v - p[-3];
-    dk &= (c4 > t) | (c12 > t); br &= (c4 < -t) | (c12 < -t);
-    if (!(dk | br)) return 0;
-    const int c2 = v - p[2 * pw + 2], c10 = v - p[-2 * pw - 2];
-    dk &= (c2 > t) | (c10 > t); br &= (c2 < -t) | (c10 < -t);
-    if (!(dk | br)) return 0;
-    const int c6 = v - p[-2 * pw + 2], c14 = v - p[2 * pw - 2];
-    dk &= (c6 > t) | (c14 > t); br &= (c6 < -t) | (c14 < -t);
-    if (!(dk | br)) return 0;
-    // both polarities at once: each ring difference d is packed as the s16x2 pair (d, -d); an arc's score for the
-    // "darker" / "brighter" test is the min over its 9 packed entries, computed with Blackwell's 3-input packed min
-    // (VIMNMX3.S16x2): m3_k = min(q_k,q_k+1,q_k+2), m9_k = min(m3_k, m3_k+3, m3_k+6); M = max over k and both halves.
-#define SE2_PK(dv) ((static_cast<unsigned>(dv) & 0xFFFFu) | (static_cast<unsigned>(-(dv)) << 16))
+// FAST-9-16 on packed ring differences. For centre v and ring pixel p the s16x2 word
+//   q = (256 + v - p) | (256 + p - v) << 16  =  p * 0xFFFF + ((256 + v) | (256 - v) << 16)      (one IMAD; both halves in [1,511])
+// carries the "darker" and the "brighter" test side by side, so Blackwell's packed 3-input min/max (VIMNMX3.S16x2)
+// evaluates both polarities at once. Arc score M = max over the 16 nine-pixel arcs of min(+-(v - ring)); corner at
+// t <=> M > t, and cv::FAST's stored score == M-1 whatever t was.
+__device__ __forceinline__ unsigned fast_cv(int v) { return (unsigned)(256 + v) | ((unsigned)(256 - v) << 16); }
+__device__ __forceinline__ unsigned fast_q(unsigned p, unsigned cv) { return p * 0xFFFFu + cv; }
+
+// necessary condition for a corner at threshold t: a 9-arc contains one pixel of each opposite pair (k, k+8), so for
+// one polarity all 4 tested pairs must have a member beyond t. Branch-free: min over the pairs of the pair maxima.
+__device__ __forceinline__ bool fast_maybe_corner(const uint8_t* __restrict__ p, int pw, int t) {
+    const unsigned cv = fast_cv(p[0]);
+    const unsigned a = __vmaxs2(fast_q(p[3 * pw], cv), fast_q(p[-3 * pw], cv));
+    const unsigned b = __vmaxs2(fast_q(p[3], cv), fast_q(p[-3], cv));
+    const unsigned c = __vmaxs2(fast_q(p[2 * pw + 2], cv), fast_q(p[-2 * pw - 2], cv));
+    const unsigned e = __vmaxs2(fast_q(p[-2 * pw + 2], cv), fast_q(p[2 * pw - 2], cv));
+    const unsigned m = __vmins2(__vimin3_s16x2(a, b, c), e);
+    return max(m & 0xFFFFu, m >> 16) > (unsigned)(256 + t);
+}
+
+__device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int pw) {
+    const unsigned cv = fast_cv(p[0]);
     unsigned q[16];
-    q[0] = SE2_PK(c0);   q[1] = SE2_PK(v - p[3 * pw + 1]);    q[2] = SE2_PK(c2);    q[3] = SE2_PK(v - p[pw + 3]);
-    q[4] = SE2_PK(c4);   q[5] = SE2_PK(v - p[-pw + 3]);       q[6] = SE2_PK(c6);    q[7] = SE2_PK(v - p[-3 * pw + 1]);
-    q[8] = SE2_PK(c8);   q[9] = SE2_PK(v - p[-3 * pw - 1]);   q[10] = SE2_PK(c10);  q[11] = SE2_PK(v - p[-pw - 3]);
-    q[12] = SE2_PK(c12); q[13] = SE2_PK(v - p[pw - 3]);       q[14] = SE2_PK(c14);  q[15] = SE2_PK(v - p[3 * pw - 1]);
-#undef SE2_PK
+    q[0] = fast_q(p[3 * pw], cv);       q[1] = fast_q(p[3 * pw + 1], cv);   q[2] = fast_q(p[2 * pw + 2], cv);    q[3] = fast_q(p[pw + 3], cv);
+    q[4] = fast_q(p[3], cv);            q[5] = fast_q(p[-pw + 3], cv);      q[6] = fast_q(p[-2 * pw + 2], cv);   q[7] = fast_q(p[-3 * pw + 1], cv);
+    q[8] = fast_q(p[-3 * pw], cv);      q[9] = fast_q(p[-3 * pw - 1], cv);  q[10] = fast_q(p[-2 * pw - 2], cv);  q[11] = fast_q(p[-pw - 3], cv);
+    q[12] = fast_q(p[-3], cv);          q[13] = fast_q(p[pw - 3], cv);      q[14] = fast_q(p[2 * pw - 2], cv);   q[15] = fast_q(p[3 * pw - 1], cv);
     unsigned m3[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
-    unsigned best = 0x80008000u;   // (-32768, -32768)
+    unsigned best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
         const unsigned a9 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
         const unsigned b9 = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
         best = __vimax3_s16x2(best, a9, b9);
     }
-    const int mdark = static_cast<short>(best & 0xFFFFu), mbright = static_cast<short>(best >> 16);
-    return max(mdark, mbright);
+    return (int)max(best & 0xFFFFu, best >> 16) - 256;
 }
 
 // one CTA per (cell, frame): cv::FAST(cell, fastTh, NMS) and, if that yields <= 3 keypoints, cv::FAST(cell, 7, NMS)
 // (ORBextractor.cpp:616-623). The cell and its 3 px apron are staged once in shared memory with aligned 32-bit loads.
-// Work unit = one 32-pixel row segment per warp iteration (no per-pixel division); segments are numbered in raster
-// order, so one exclusive scan over the per-segment survivor counts gives every keypoint its raster-order slot.
+//   A  every pixel: branch-free 4-pair test, survivors compacted into a shared list (warp ballot + one shared atomic)
+//   B  list entries, full warps: arc score -> score plane (same pitch as the patch, 1 px apron)
+//   C  list entries: strict 3x3 maximum -> one bit per pixel in a raster-order bitmap
+//   D  one warp: exclusive scan of the bitmap words' popcounts = raster-order output slots
+//   E  one thread per bitmap word: emit (score | y | x)
 __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     extern __shared__ uint8_t smem[];
-    __shared__ int s_total;
+    __shared__ int s_total, s_ncand;
     const CellGeo c = d.cells[blockIdx.x];
     const int f = blockIdx.y + d.frame0;
     CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
@@ -208,12 +209,14 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     // patch columns start at the 4-aligned bordered-plane column ax0 <= x0-3 (plane base and pitch are 32 B aligned)
     const int bx0 = c.x0 - 3 + EDGE, by0 = c.y0 - 3 + EDGE;
     const int ax0 = bx0 & ~3, shift = bx0 - ax0;
-    const int ph = ch + 6, sw = cw + 2, sh = ch + 2;
+    const int ph = ch + 6;
     const int pww = (shift + cw + 6 + 3) >> 2, pw = pww * 4;
+    const int nbits = pw * ch, nwords = (nbits + 31) >> 5;
     uint8_t* patch = smem;
-    uint8_t* score = smem + ((pw * ph + 15) & ~15);
-    const int nseg = (cw + 31) >> 5, nchunk = ch * nseg;
-    int* cnt = reinterpret_cast<int*>(score + ((sw * sh + 15) & ~15));   // [nchunk] survivors per segment -> exclusive offsets
+    uint8_t* score = smem + ((pw * ph + 15) & ~15);                                       // [(ch+2) x pw], pixel (x,y) at (y+1)*pw + x+1
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(score + ((pw * (ch + 2) + 15) & ~15)); // [nwords], bit y*pw + x
+    uint32_t* woff = bitmap + nwords;                                                     // [nwords] exclusive popcount scan
+    uint16_t* list = reinterpret_cast<uint16_t*>(woff + nwords);                          // [<= cw*ch] entries y*pw + x
     for (int i = threadIdx.x; i < pww * ph; i += FAST_THREADS) {
         const int py = i / pww, pxw = i - py * pww;
         reinterpret_cast<uint32_t*>(patch)[i] = *reinterpret_cast<const uint32_t*>(plane + (size_t)(by0 + py) * L.pitch + ax0 + 4 * pxw);
@@ -222,41 +225,52 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint8_t* p0 = patch + 3 * pw + 3 + shift;
     int thr = d.fast_th;
-    unsigned long long keepmask = 0;   // bit t: this lane's pixel of the warp's t-th segment survived NMS (first 64 segments)
     for (int pass = 0; pass < 2; ++pass) {
-        for (int i = threadIdx.x; i < (sw * sh + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+        for (int i = threadIdx.x; i < (pw * (ch + 2) + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+        for (int i = threadIdx.x; i < nwords; i += FAST_THREADS) bitmap[i] = 0u;
+        if (threadIdx.x == 0) s_ncand = 0;
         __syncthreads();
-        for (int cidx = wid; cidx < nchunk; cidx += NW) {
-            const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
-            if (x < cw) {
-                const int m = fast_arc_score(p0 + y * pw + x, pw, thr);
-                if (m > thr) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
+        // A
+        for (int y = wid; y < ch; y += NW) {
+            const uint8_t* row = p0 + y * pw;
+            for (int x = lane; x < cw + lane; x += 32) {      // whole warp iterates together (x - lane < cw)
+                const bool ok = x < cw && fast_maybe_corner(row + x, pw, thr);
+                const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (ok) list[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(y * pw + x);
+                }
             }
         }
         __syncthreads();
-        keepmask = 0;
-        int t = 0;
-        for (int cidx = wid; cidx < nchunk; cidx += NW, ++t) {
-            const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
-            bool keep = false;
-            if (x < cw) {
-                const uint8_t* q = score + (y + 1) * sw + (x + 1);
-                const int s = q[0];
-                if (s) keep = s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) cnt[cidx] = __popc(bal);
-            if (keep && t < 64) keepmask |= 1ull << t;
+        const int ncand = s_ncand;
+        // B
+        for (int i = threadIdx.x; i < ncand; i += FAST_THREADS) {
+            const int off = list[i];
+            const int m = fast_arc_score(p0 + off, pw);
+            if (m > thr) score[off + pw + 1] = (uint8_t)(m - 1);
         }
         __syncthreads();
-        if (wid == 0) {   // exclusive scan of the per-segment counts, in raster order
+        // C
+        for (int i = threadIdx.x; i < ncand; i += FAST_THREADS) {
+            const int off = list[i];
+            const uint8_t* q = score + off + pw + 1;
+            const int sc = q[0];
+            if (sc && sc > q[-pw - 1] && sc > q[-pw] && sc > q[-pw + 1] && sc > q[-1] && sc > q[1] && sc > q[pw - 1] && sc > q[pw] && sc > q[pw + 1])
+                atomicOr(&bitmap[off >> 5], 1u << (off & 31));
+        }
+        __syncthreads();
+        // D
+        if (wid == 0) {
             int run = 0;
-            for (int b0 = 0; b0 < nchunk; b0 += 32) {
-                const int v = (b0 + lane < nchunk) ? cnt[b0 + lane] : 0;
+            for (int b0 = 0; b0 < nwords; b0 += 32) {
+                const int v = (b0 + lane < nwords) ? __popc(bitmap[b0 + lane]) : 0;
                 int inc = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-                if (b0 + lane < nchunk) cnt[b0 + lane] = run + inc - v;
+                if (b0 + lane < nwords) woff[b0 + lane] = run + inc - v;
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
             if (lane == 0) s_total = run;
@@ -266,28 +280,18 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
         thr = 7;                 // cellKeyPoints.size() <= 3: clear and retry with the fixed fallback threshold
         __syncthreads();
     }
+    // E
     uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
-    int t = 0;
-    for (int cidx = wid; cidx < nchunk; cidx += NW, ++t) {
-        const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
-        bool keep;
-        int s = 0;
-        if (t < 64) {
-            keep = (keepmask >> t) & 1ull;
-        } else {
-            keep = false;
-            if (x < cw) {
-                const uint8_t* q = score + (y + 1) * sw + (x + 1);
-                s = q[0];
-                if (s) keep = s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
-            }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            s = score[(y + 1) * sw + (x + 1)];
-            const int pos = cnt[cidx] + __popc(bal & ((1u << lane) - 1));
-            if (pos < c.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
+    for (int j = threadIdx.x; j < nwords; j += FAST_THREADS) {
+        uint32_t w = bitmap[j];
+        int pos = woff[j];
+        while (w) {
+            const int off = j * 32 + __ffs(w) - 1;
+            w &= w - 1;
+            const int y = off / pw, x = off - y * pw;
+            if (pos < c.cand_cap) out[pos] = ((uint32_t)score[off + pw + 1] << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
             else *d.err = 1;
+            ++pos;
         }
     }
     if (threadIdx.x == 0) { hdr->n_base = s_total; hdr->n_a = s_total; hdr->n_b = s_total; }
@@ -639,8 +643,9 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 coff += c.cand_cap;
                 if (cw > 0 && chh > 0) {
                     const size_t pwb = (size_t)((cw + 6 + 3 + 3) / 4 + 1) * 4;   // worst-case alignment shift
-                    const size_t nchunk = (size_t)chh * ((cw + 31) / 32);
-                    fsm = std::max(fsm, ((pwb * (chh + 6) + 15) & ~(size_t)15) + (((size_t)(cw + 2) * (chh + 2) + 15) & ~(size_t)15) + nchunk * 4 + 64);
+                    const size_t nwords = (pwb * chh + 31) / 32;
+                    if (pwb * (chh + 6) > 65535) return fail(SE2GPU_ERR_CAPACITY, "a FAST cell of %dx%d px exceeds the 16-bit patch index", cw, chh);
+                    fsm = std::max(fsm, ((pwb * (chh + 6) + 15) & ~(size_t)15) + ((pwb * (chh + 2) + 15) & ~(size_t)15) + nwords * 8 + (size_t)cw * chh * 2 + 64);
                 }
                 C.push_back(c);
             }
