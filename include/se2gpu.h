@@ -98,6 +98,12 @@ int se2gpu_orb_get_level(se2gpu_orb* h, int frame, int level, int blurred, uint8
 int se2gpu_orb_profile(se2gpu_orb* h, int enable);
 int se2gpu_orb_profile_read(se2gpu_orb* h, double* ms, int* launches);
 
+/* Test hook for the device selection primitive behind KeyPointsFilter::retainBest (ORBextractor.cpp:692, :708):
+ * runs the warp-cooperative std::nth_element on `count` independent lists of packed records (score in bits 31..24)
+ * stored back to back in HOST memory; list k is values[offsets[k] .. offsets[k+1]) and is permuted in place exactly
+ * as std::nth_element(begin, begin + nth[k], end, score-greater) of libstdc++ would. */
+int se2gpu_orb_debug_nth_element(uint32_t* values, const int* offsets, const int* nth, int count, int device);
+
 /* ------------------------------------------------------------------------------------------ matcher */
 /* DescriptorDistance for n pairs of 32-byte descriptors in HOST memory: out[i] = popcount(a_i ^ b_i) */
 int se2gpu_hamming_distance(const uint8_t* a, const uint8_t* b, int n, int* out, int device);

@@ -125,4 +125,93 @@ SE2_HD void kp_nth_element(uint32_t* v, int n, int nth) {
     }
 }
 
+#if defined(__CUDACC__)
+// Warp-cooperative std::nth_element with the SAME resulting permutation as kp_nth_element above; all 32 lanes of a
+// warp call it with identical arguments. The unguarded Hoare partition is the only O(n) part and its outcome is a
+// pure function of the stop positions: with P the pivot score, l_1 < l_2 < ... the positions in (first, last) whose
+// score is <= P ("left stops") and r_1 > r_2 > ... the positions in [first, last) whose score is >= P ("right
+// stops"), the serial loop swaps (l_k, r_k) for k = 1..m, m = the last k with l_k < r_k, and returns
+// cut = min(l_{m+1}, r_m). Here both scans advance 32 elements per ballot, stops are queued in two 64-entry rings
+// (`q`, 128 ints of this warp's shared memory) and up to 32 pairs are swapped per round. Stops found in elements that
+// an earlier round already swapped lie beyond r_m (resp. before l_m), so they can only produce failing pairs and
+// leave m and cut unchanged. Median-of-three, range bookkeeping, the <= 3 element insertion sort and the heap-select
+// fallback are serial on lane 0.
+__device__ __forceinline__ int kp_partition_warp(uint32_t* v, int first, int last, unsigned P, int* q) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int* Lq = q; int* Rq = q + 64;
+    int lc = first + 1, rc = last, nl = 0, nr = 0, lh = 0, rh = 0;
+    int last_r = 0x7fffffff;
+    while (true) {
+        while (nl < 32 && lc < last) {
+            const int p = lc + lane;
+            const bool fl = p < last && (v[p] >> 24) <= P;
+            const unsigned bal = __ballot_sync(0xffffffffu, fl);
+            if (fl) Lq[(lh + nl + __popc(bal & lt)) & 63] = p;
+            nl += __popc(bal); lc += 32;
+        }
+        while (nr < 32 && rc > first) {
+            const int p = rc - 1 - lane;
+            const bool fr = p >= first && (v[p] >> 24) >= P;
+            const unsigned bal = __ballot_sync(0xffffffffu, fr);
+            if (fr) Rq[(rh + nr + __popc(bal & lt)) & 63] = p;
+            nr += __popc(bal); rc -= 32;
+        }
+        __syncwarp();
+        const int np = min(min(nl, nr), 32);
+        if (np == 0) return nl > 0 ? min(Lq[lh & 63], last_r) : last_r;
+        const int l = lane < np ? Lq[(lh + lane) & 63] : 0, r = lane < np ? Rq[(rh + lane) & 63] : 0;
+        const unsigned okb = __ballot_sync(0xffffffffu, lane < np && l < r);
+        const int cnt = min(__ffs(~okb) - 1 < 0 ? 32 : __ffs(~okb) - 1, np);   // leading pairs with l < r
+        if (lane < cnt) { const uint32_t t = v[l]; v[l] = v[r]; v[r] = t; }
+        if (cnt > 0) last_r = __shfl_sync(0xffffffffu, r, cnt - 1);
+        __syncwarp();
+        if (cnt < np) return min(__shfl_sync(0xffffffffu, l, cnt), last_r);
+        lh += np; nl -= np; rh += np; nr -= np;
+    }
+}
+
+__device__ __forceinline__ void kp_nth_element_warp(uint32_t* v, int n, int nth, int* q) {
+    const int lane = threadIdx.x & 31;
+    if (n <= 0 || nth >= n) return;
+    int first = 0, last = n;
+    int depth = 0;
+    for (int t = n; t > 1; t >>= 1) ++depth;
+    depth *= 2;
+    while (last - first > 3) {
+        if (depth == 0) {
+            if (lane == 0) { kp_heap_select(v, first, nth + 1, last); kp_swap(v, first, nth); }
+            __syncwarp();
+            return;
+        }
+        --depth;
+        if (lane == 0) {
+            const int a = first + 1, b = first + (last - first) / 2, c = last - 1;
+            const unsigned sa = v[a] >> 24, sb = v[b] >> 24, sc = v[c] >> 24;
+            int m;
+            if (sa > sb) m = (sb > sc) ? b : (sa > sc) ? c : a;
+            else m = (sa > sc) ? a : (sb > sc) ? c : b;
+            kp_swap(v, first, m);
+        }
+        __syncwarp();
+        const int cut = kp_partition_warp(v, first, last, v[first] >> 24, q);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    if (lane == 0 && first != last) {
+        for (int i = first + 1; i != last; ++i) {
+            const uint32_t val = v[i];
+            if (kp_greater(val, v[first])) {
+                for (int k = i; k > first; --k) v[k] = v[k - 1];
+                v[first] = val;
+            } else {
+                int k = i;
+                while (kp_greater(val, v[k - 1])) { v[k] = v[k - 1]; --k; }
+                v[k] = val;
+            }
+        }
+    }
+    __syncwarp();
+}
+#endif
+
 }  // namespace se2gpu

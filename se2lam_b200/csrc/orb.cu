@@ -88,62 +88,131 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101); 4 output pixels per thread, one word store
-__global__ void orb_pyr0(OrbDev d, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride) {
-    const LevelGeo& L = d.levels[0];
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101). One thread = 16 output bytes x PYR0_ROWS rows;
+// the border is 16 px wide, so interior vectors are aligned 16-byte copies when the caller's rows are 16 B aligned
+// (`aligned`); the border/pad vectors and unaligned inputs take the bytewise reflect path. The level geometry comes
+// in as a kernel parameter (constant bank), not through a dependent global load.
+constexpr int PYR0_ROWS = 4;
+__global__ void __launch_bounds__(256) orb_pyr0(OrbDev d, LevelGeo L, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride, int aligned) {
+    const int x16 = (blockIdx.x * 64 + threadIdx.x) * 16;
+    const int y0 = (blockIdx.y * 4 + threadIdx.y) * PYR0_ROWS;
     const int f = blockIdx.z + d.frame0;
-    if (x4 >= L.pitch) return;
-    const int sy = reflect101(y - EDGE, L.h);
-    const uint8_t* row = imgs + f * frame_stride + (size_t)sy * stride;
-    uint32_t word = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int x = x4 + q;
-        const uint32_t v = (x < L.w + 2 * EDGE) ? row[reflect101(x - EDGE, L.w)] : 0u;
-        word |= v << (8 * q);
-    }
+    if (x16 >= L.pitch) return;
+    const uint8_t* img = imgs + f * frame_stride;
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
+    const bool interior = aligned && x16 >= EDGE && x16 + 16 <= EDGE + L.w;
+    uint4 v[PYR0_ROWS];
+#pragma unroll
+    for (int k = 0; k < PYR0_ROWS; ++k) {
+        const int y = y0 + k;
+        if (y >= L.h + 2 * EDGE) break;
+        const uint8_t* row = img + (size_t)reflect101(y - EDGE, L.h) * stride;
+        if (interior) {
+            v[k] = __ldg(reinterpret_cast<const uint4*>(row + x16 - EDGE));
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                w[j] = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = x16 + 4 * j + q;
+                    const uint32_t px = (x < L.w + 2 * EDGE) ? row[reflect101(x - EDGE, L.w)] : 0u;
+                    w[j] |= px << (8 * q);
+                }
+            }
+            v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PYR0_ROWS; ++k) {
+        const int y = y0 + k;
+        if (y >= L.h + 2 * EDGE) break;
+        *reinterpret_cast<uint4*>(plane + (size_t)y * L.pitch + x16) = v[k];
+    }
 }
 
-// level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass;
-// 4 output pixels per thread (row-dependent terms computed once), one word store
-__global__ void orb_resize(OrbDev d, int level) {
-    const LevelGeo& L = d.levels[level];
-    const LevelGeo& S = d.levels[level - 1];
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+// level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass, cv::resize's
+// fixed-point arithmetic (11-bit coefficients, horizontal pass kept at full precision, vertical pass >>4, >>16, +2 >>2).
+// One thread = 4 adjacent output columns x RESIZE_ROWS consecutive rows: the column terms (xofs, alpha) are loaded
+// once, and the horizontal pass of a source row is reused by the next output row (consecutive output rows share a
+// source row 5 times out of 6 at scale 1.2). A warp covers one row segment, so the reuse test is warp-uniform.
+constexpr int RESIZE_ROWS = 8;
+__global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo S) {
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y0 = (blockIdx.y * 8 + threadIdx.y) * RESIZE_ROWS;
     const int f = blockIdx.z + d.frame0;
-    if (x4 >= L.pitch) return;
-    const int dy = reflect101(y - EDGE, L.h);
+    if (x4 >= L.pitch || y0 >= L.h + 2 * EDGE) return;
     const int* xofs = d.itab + L.tab_off;
     const int* yofs = xofs + L.w;
     const short2* ialpha = reinterpret_cast<const short2*>(d.stab + 2 * (size_t)L.tab_off);
     const short2* ibeta = ialpha + L.w;
-    const int sy = yofs[dy];
-    const int sy0 = min(max(sy, 0), S.h - 1), sy1 = min(max(sy + 1, 0), S.h - 1);
-    const short2 bb = ibeta[dy];
-    const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
-    const uint8_t* r0p = src + (size_t)sy0 * S.pitch;
-    const uint8_t* r1p = src + (size_t)sy1 * S.pitch;
-    uint32_t word = 0;
+    int sx0[4], sx1[4], a0[4], a1[4];
+    bool valid[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int x = x4 + q;
-        uint32_t o = 0;
-        if (x < L.w + 2 * EDGE) {
-            const int dx = reflect101(x - EDGE, L.w);
-            const int sx = xofs[dx], sx1 = min(sx + 1, S.w - 1);
-            const short2 aa = ialpha[dx];
-            const int r0 = r0p[sx] * aa.x + r0p[sx1] * aa.y;
-            const int r1 = r1p[sx] * aa.x + r1p[sx1] * aa.y;
-            const int v = (((bb.x * (r0 >> 4)) >> 16) + ((bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
-            o = (uint32_t)min(max(v, 0), 255);
-        }
-        word |= o << (8 * q);
+        valid[q] = x < L.w + 2 * EDGE;
+        const int dx = valid[q] ? reflect101(x - EDGE, L.w) : 0;
+        sx0[q] = __ldg(xofs + dx);
+        sx1[q] = min(sx0[q] + 1, S.w - 1);
+        const short2 aa = __ldg(ialpha + dx);
+        a0[q] = aa.x; a1[q] = aa.y;
     }
+    int sy0[RESIZE_ROWS], sy1[RESIZE_ROWS], b0[RESIZE_ROWS], b1[RESIZE_ROWS];
+#pragma unroll
+    for (int r = 0; r < RESIZE_ROWS; ++r) {
+        const int dy = reflect101(min(y0 + r, L.h + 2 * EDGE - 1) - EDGE, L.h);
+        const int sy = __ldg(yofs + dy);
+        sy0[r] = min(max(sy, 0), S.h - 1); sy1[r] = min(max(sy + 1, 0), S.h - 1);
+        const short2 bb = __ldg(ibeta + dy);
+        b0[r] = bb.x; b1[r] = bb.y;
+    }
+    const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
+    int cs0 = -1, cs1 = -1;
+    int h0[4], h1[4];
+#pragma unroll
+    for (int r = 0; r < RESIZE_ROWS; ++r) {
+        const int y = y0 + r;
+        if (y >= L.h + 2 * EDGE) break;
+        int A[4], B[4];
+        if (sy0[r] == cs0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) A[q] = h0[q];
+        } else if (sy0[r] == cs1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) A[q] = h1[q];
+        } else {
+            const uint8_t* rp = src + (size_t)sy0[r] * S.pitch;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) A[q] = __ldg(rp + sx0[q]) * a0[q] + __ldg(rp + sx1[q]) * a1[q];
+        }
+        if (sy1[r] == cs1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) B[q] = h1[q];
+        } else if (sy1[r] == cs0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) B[q] = h0[q];
+        } else if (sy1[r] == sy0[r]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) B[q] = A[q];
+        } else {
+            const uint8_t* rp = src + (size_t)sy1[r] * S.pitch;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) B[q] = __ldg(rp + sx0[q]) * a0[q] + __ldg(rp + sx1[q]) * a1[q];
+        }
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int v = (((b0[r] * (A[q] >> 4)) >> 16) + ((b1[r] * (B[q] >> 4)) >> 16) + 2) >> 2;
+            const uint32_t o = valid[q] ? (uint32_t)min(max(v, 0), 255) : 0u;
+            word |= o << (8 * q);
+            h0[q] = A[q]; h1[q] = B[q];
+        }
+        cs0 = sy0[r]; cs1 = sy1[r];
+        *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
+    }
 }
 
 // FAST-9-16 on packed ring differences. For centre v and ring pixel p the s16x2 word
@@ -298,11 +367,16 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
 }
 
 // one CTA per (level, frame): quota redistribution, retainBest per cell and per level. The cells' candidate lists
-// are staged in shared memory when the level's total fits (SEL_STAGE entries), so the serial introselect of each
-// cell (one thread per cell) runs at shared-memory latency; otherwise it runs in place in global memory.
+// are staged in shared memory when the level's total fits (SEL_STAGE entries), otherwise they are processed in place
+// in global memory. retainBest is std::nth_element; one warp per cell runs the warp-cooperative introselect of
+// introselect.h (same permutation as libstdc++'s, 32 elements per step), cells round-robin over the CTA's warps.
 constexpr int SEL_STAGE = 12288;
-__global__ void __launch_bounds__(128) orb_select(OrbDev d) {
+constexpr int SEL_THREADS = 512;
+__global__ void __launch_bounds__(SEL_THREADS) orb_select(OrbDev d) {
     extern __shared__ uint32_t sbuf[];   // [cap] level list | [4*nCells] ints | [SEL_STAGE] staged candidates
+    __shared__ int wq[SEL_THREADS / 32][128];
+    constexpr int NW = SEL_THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int level = blockIdx.x, f = blockIdx.y + d.frame0;
     const LevelGeo& L = d.levels[level];
     const int nCells = L.nCells;
@@ -316,7 +390,7 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
     __shared__ int s_total, s_staged;
     const CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + L.cell_base;
     uint32_t* cand = d.cand + (size_t)f * d.cand_total;
-    for (int c = threadIdx.x; c < nCells; c += blockDim.x) nTotal[c] = d.cells[L.cell_base + c].skipped ? 0 : hdr[c].n_base;
+    for (int c = threadIdx.x; c < nCells; c += SEL_THREADS) nTotal[c] = d.cells[L.cell_base + c].skipped ? 0 : hdr[c].n_base;
     __syncthreads();
     if (threadIdx.x == 0) {
         // :625-679 (skipped cells never enter the first pass: nToRetain/nTotal stay 0, bNoMore stays false)
@@ -345,18 +419,17 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
     }
     __syncthreads();
     const bool staged = s_staged;
-    if (staged) {
-        for (int c = 0; c < nCells; ++c) {
-            const uint32_t* v = cand + d.cells[L.cell_base + c].cand_off;
-            for (int i = threadIdx.x; i < nTotal[c]; i += blockDim.x) stage[kept[c] + i] = v[i];
-        }
-        __syncthreads();
-    }
-    for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
+    for (int c = wid; c < nCells; c += NW) {
         const int n = nToRetain[c], tot = nTotal[c];
-        uint32_t* v = staged ? stage + kept[c] : cand + d.cells[L.cell_base + c].cand_off;
-        koff[c] = (int)(v - (staged ? stage : cand));   // remember where the list lives
-        if (tot > n && n > 0) se2gpu::kp_nth_element(v, tot, n - 1);   // KeyPointsFilter::retainBest + resize (:692-694)
+        uint32_t* g = cand + d.cells[L.cell_base + c].cand_off;
+        uint32_t* v = g;
+        if (staged) {
+            v = stage + kept[c];
+            for (int i = lane; i < tot; i += 32) v[i] = g[i];
+            __syncwarp();
+        }
+        if (lane == 0) koff[c] = (int)(v - (staged ? stage : cand));   // remember where the list lives
+        if (tot > n && n > 0) se2gpu::kp_nth_element_warp(v, tot, n - 1, wq[wid]);   // KeyPointsFilter::retainBest + resize (:692-694)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -366,21 +439,29 @@ __global__ void __launch_bounds__(128) orb_select(OrbDev d) {
         s_total = o;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < nCells; c += blockDim.x) {
+    for (int c = wid; c < nCells; c += NW) {
         const uint32_t* v = (staged ? stage : cand) + koff[c];
         const int o = kept[c];
-        for (int i = 0; i < nTotal[c] && o + i < cap; ++i) lbuf[o + i] = v[i];
+        for (int i = lane; i < nTotal[c] && o + i < cap; i += 32) lbuf[o + i] = v[i];
     }
     __syncthreads();
     int total = s_total;
     if (total > L.nDesired) {  // :706-710
-        if (threadIdx.x == 0) se2gpu::kp_nth_element(lbuf, total, L.nDesired - 1);
+        if (wid == 0) se2gpu::kp_nth_element_warp(lbuf, total, L.nDesired - 1, wq[0]);
         total = L.nDesired;
         __syncthreads();
     }
     uint32_t* out = d.lkp + (size_t)f * d.lkp_total + L.kp_off;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) out[i] = lbuf[i];
+    for (int i = threadIdx.x; i < total; i += SEL_THREADS) out[i] = lbuf[i];
     if (threadIdx.x == 0) d.lcount[f * d.nlevels + level] = total;
+}
+
+// test hook: one warp per list, lists in global memory
+__global__ void __launch_bounds__(128) orb_debug_nth(uint32_t* v, const int* __restrict__ offs, const int* __restrict__ nth, int count) {
+    __shared__ int wq[4][128];
+    const int k = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (k >= count) return;
+    se2gpu::kp_nth_element_warp(v + offs[k], offs[k + 1] - offs[k], nth[k], wq[threadIdx.x >> 5]);
 }
 
 // GaussianBlur 7x7 sigma 2 on the level ROI; the 16 px ring keeps its un-blurred reflect-101 copies.
@@ -729,13 +810,14 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     pr.begin(0, s);
     {
         const LevelGeo& g = h->levels[0];
-        dim3 grid((g.pitch / 4 + 127) / 128, g.h + 2 * EDGE, n);
-        SE2_LAUNCH(orb_pyr0, grid, 128, 0, s, d, d_imgs, stride, frame_stride);
+        const int aligned = (((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_stride) & 15) == 0;
+        dim3 grid((g.pitch / 16 + 63) / 64, (g.h + 2 * EDGE + 4 * PYR0_ROWS - 1) / (4 * PYR0_ROWS), n);
+        SE2_LAUNCH(orb_pyr0, grid, dim3(64, 4), 0, s, d, g, d_imgs, stride, frame_stride, aligned);
     }
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
-        dim3 grid((g.pitch / 4 + 127) / 128, g.h + 2 * EDGE, n);
-        SE2_LAUNCH(orb_resize, grid, 128, 0, s, d, l);
+        dim3 grid((g.pitch / 4 + 31) / 32, (g.h + 2 * EDGE + 8 * RESIZE_ROWS - 1) / (8 * RESIZE_ROWS), n);
+        SE2_LAUNCH(orb_resize, grid, dim3(32, 8), 0, s, d, g, h->levels[l - 1]);
     }
     pr.end(s);
     // the blur only depends on the pyramid: fork it onto the side stream so that it overlaps the (latency-bound)
@@ -752,7 +834,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     pr.end(s);
     pr.begin(2, s);
-    SE2_LAUNCH(orb_select, dim3(h->nlevels, n), 128, h->select_smem, s, d);
+    SE2_LAUNCH(orb_select, dim3(h->nlevels, n), SEL_THREADS, h->select_smem, s, d);
     pr.end(s);
     if (overlap) {
         SE2_CUDA(cudaStreamWaitEvent(s, ev_blur, 0));
@@ -927,6 +1009,25 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     SE2_CUDA(cudaStreamSynchronize(nullptr));
     h->last_n = n;
     if (err) { cudaMemset(h->d.err, 0, sizeof(int)); return fail(SE2GPU_ERR_CAPACITY, "internal candidate buffer overflow (code %d)", err); }
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_debug_nth_element(uint32_t* values, const int* offsets, const int* nth, int count, int device) {
+    if (count <= 0) return SE2GPU_OK;
+    if (!values || !offsets || !nth) return fail(SE2GPU_ERR_INVALID, "null argument");
+    if (se2gpu::select_device(device) != SE2GPU_OK) return SE2GPU_ERR_CUDA;
+    const size_t total = (size_t)offsets[count];
+    uint32_t* dv = nullptr; int* dofs = nullptr; int* dn = nullptr;
+    SE2_CUDA(cudaMalloc((void**)&dv, std::max<size_t>(total, 1) * 4));
+    SE2_CUDA(cudaMalloc((void**)&dofs, sizeof(int) * (count + 1)));
+    SE2_CUDA(cudaMalloc((void**)&dn, sizeof(int) * count));
+    SE2_CUDA(cudaMemcpy(dv, values, total * 4, cudaMemcpyHostToDevice));
+    SE2_CUDA(cudaMemcpy(dofs, offsets, sizeof(int) * (count + 1), cudaMemcpyHostToDevice));
+    SE2_CUDA(cudaMemcpy(dn, nth, sizeof(int) * count, cudaMemcpyHostToDevice));
+    SE2_LAUNCH(orb_debug_nth, (count + 3) / 4, 128, 0, nullptr, dv, dofs, dn, count);
+    SE2_CUDA(cudaGetLastError());
+    SE2_CUDA(cudaMemcpy(values, dv, total * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dv); cudaFree(dofs); cudaFree(dn);
     return SE2GPU_OK;
 }
 

@@ -113,3 +113,39 @@ def test_full_batch_properties():
     for i in (0, 31, 63):
         ko, do_ = o.extract(imgs[i])
         assert_same(k1[i], d1[i], ko, do_, f"frame {i} of 64")
+
+
+def test_warp_nth_element_matches_std_nth_element():
+    """The warp-cooperative introselect must produce libstdc++'s permutation (ties decide which keypoints survive
+    retainBest, ORBextractor.cpp:692/:708): thousands of tie-heavy lists against the oracle's real std::nth_element."""
+    from se2lam_b200 import _capi
+    rng = np.random.default_rng(7)
+    lists, nths = [], []
+    for case in range(1500):
+        kind = case % 5
+        n = int(rng.integers(1, 40)) if kind == 0 else int(rng.integers(40, 3000))
+        if kind == 1:
+            sc = rng.integers(0, 3, n)                    # almost everything tied
+        elif kind == 2:
+            sc = np.sort(rng.integers(0, 256, n))[::-1]   # already ordered
+        elif kind == 3:
+            sc = np.sort(rng.integers(0, 256, n))         # reversed
+        else:
+            sc = rng.integers(0, int(rng.integers(2, 256)), n)
+        lists.append(sc.astype(np.uint32))
+        nths.append(int(rng.integers(0, n)))
+    # organ-pipe / sawtooth lists exercise the depth limit (heap-select fallback)
+    for n in (64, 257, 1024, 2048):
+        half = np.arange(n // 2, dtype=np.uint32) % 251
+        lists.append(np.concatenate([half, half[::-1]])); nths.append(n // 2)
+        lists.append((np.arange(n, dtype=np.uint32) * 37 % 17)); nths.append(n - 2)
+    offs = np.zeros(len(lists) + 1, np.int32)
+    offs[1:] = np.cumsum([len(x) for x in lists])
+    packed = np.concatenate([(sc << 24) | np.arange(len(sc), dtype=np.uint32) for sc in lists]).astype(np.uint32)
+    got = packed.copy()
+    nth = np.asarray(nths, np.int32)
+    _capi.check(_capi.lib().se2gpu_orb_debug_nth_element(got.ctypes.data, offs.ctypes.data, nth.ctypes.data, len(lists), 0), "nth")
+    for k, sc in enumerate(lists):
+        ids = pyoracle.nth_element(sc.astype(np.float32), nths[k])
+        want = packed[offs[k]:offs[k + 1]][ids]
+        assert np.array_equal(got[offs[k]:offs[k + 1]], want), f"list {k} (n={len(sc)}, nth={nths[k]})"
