@@ -32,7 +32,7 @@ constexpr int HALF_PATCH = 15;     // HALF_PATCH_SIZE :82
 constexpr int PATCH = 31;          // PATCH_SIZE :81
 constexpr int MAX_LEVELS = 16;
 constexpr int FAST_THREADS = 256;
-constexpr int BLUR_TW = 64, BLUR_TH = 32;
+constexpr int BLUR_TW = 128, BLUR_TH = 36;   // one warp per tile; BLUR_TH + 6 warm-up rows = 6 turns of the 7-row ring
 
 __device__ const signed char d_pattern[1024] = {
 #include "orb_pattern_31.inc"
@@ -465,69 +465,71 @@ __global__ void __launch_bounds__(128) orb_debug_nth(uint32_t* v, const int* __r
 }
 
 // GaussianBlur 7x7 sigma 2 on the level ROI; the 16 px ring keeps its un-blurred reflect-101 copies.
-// Tile = 64 x 32 outputs. Staging: aligned 32-bit loads (tile origins are multiples of 64, pitch of 32).
-// Row pass: one thread = 4 adjacent outputs from three staged words (12 bytes), stored as one float4.
-// Column pass: one thread = one column x 8 rows with a sliding window (14 loads for 8 outputs, conflict-free).
+// cv::GaussianBlur's float arithmetic: row pass = sequential fmaf over the 7 taps, column pass = centre tap then the
+// three symmetric pairs, round-to-nearest-even, saturate. No shared memory: a tile is one warp = 128 columns x
+// BLUR_TH output rows; a thread owns 4 adjacent columns (one output word) and walks down its strip with the last 7
+// row-pass results in a register ring, so every source word is loaded once per row (3 coalesced words per thread:
+// its own and both neighbours, the latter L1 hits) and every output row costs one 32-bit store.
 __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
-    constexpr int PWW = (BLUR_TW + 8) / 4, PW = BLUR_TW + 8;   // staged columns: x0-4 .. x0+67
-    __shared__ uint32_t patchw[(BLUR_TH + 6) * PWW];
-    __shared__ __align__(16) float rowp[(BLUR_TH + 6) * BLUR_TW];
-    const uint8_t* patch = reinterpret_cast<const uint8_t*>(patchw);
-    const TileGeo t = d.tiles[blockIdx.x];
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= d.n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const TileGeo t = d.tiles[tile];
     const int f = blockIdx.y + d.frame0;
     const LevelGeo& L = d.levels[t.level];
-    const uint8_t* src = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    uint8_t* dst = d.blurred + f * d.frame_plane_bytes + L.plane_off;
-    const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * PWW; i += 256) {
-        const int py = i / PWW, pxw = i - py * PWW;
-        const int gy = min(max(t.y0 - 3 + py, 0), H - 1), gx = t.x0 - 4 + 4 * pxw;
-        // words left of the plane or beyond the pitch are never consumed by an interior pixel
-        patchw[i] = (gx >= 0 && gx + 4 <= L.pitch) ? *reinterpret_cast<const uint32_t*>(src + (size_t)gy * L.pitch + gx) : 0u;
-    }
-    __syncthreads();
+    const int pitch = L.pitch, H = L.h + 2 * EDGE;
+    const int x4 = t.x0 + 4 * lane;
+    if (x4 >= pitch) return;
+    const uint8_t* src = d.plain + f * d.frame_plane_bytes + L.plane_off + x4;
+    uint8_t* dst = d.blurred + f * d.frame_plane_bytes + L.plane_off + x4;
+    const bool has_l = x4 >= 4, has_r = x4 + 8 <= pitch;
+    bool colin[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) colin[q] = x4 + q >= EDGE && x4 + q < EDGE + L.w;
     const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3], g4 = c_gauss[4], g5 = c_gauss[5], g6 = c_gauss[6];
-    for (int i = threadIdx.x; i < (BLUR_TH + 6) * (BLUR_TW / 4); i += 256) {
-        const int py = i / (BLUR_TW / 4), pg = i - py * (BLUR_TW / 4);
-        const uint32_t* wp = patchw + py * PWW + pg;           // bytes 4*pg .. 4*pg+11 of the staged row
-        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-        float b[12];
+    float hr[7][4];      // row-pass results of the last 7 source rows
+    uint32_t cw[7];      // their centre words (ring pixels are copied through)
+    for (int i0 = 0; i0 < BLUR_TH + 6; i0 += 7) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { b[k] = (float)((w0 >> (8 * k)) & 255u); b[4 + k] = (float)((w1 >> (8 * k)) & 255u); b[8 + k] = (float)((w2 >> (8 * k)) & 255u); }
-        float4 o;
-        float* op = &o.x;
+        for (int k = 0; k < 7; ++k) {
+            const int i = i0 + k;                       // source row t.y0 - 3 + i, kept in ring slot k
+            const int sr = min(max(t.y0 - 3 + i, 0), H - 1);   // rows outside the plane only feed ring outputs (copies)
+            const uint8_t* rp = src + (size_t)sr * pitch;
+            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(rp));
+            const uint32_t w0 = has_l ? __ldg(reinterpret_cast<const uint32_t*>(rp - 4)) : 0u;
+            const uint32_t w2 = has_r ? __ldg(reinterpret_cast<const uint32_t*>(rp + 4)) : 0u;
+            float b[10];                                // bytes x4-3 .. x4+6
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {        // output column 4*pg+qd <- staged bytes (4*pg+qd+1 .. +7)
-            float s = __fmul_rn(g0, b[qd + 1]);
-            s = __fmaf_rn(g1, b[qd + 2], s); s = __fmaf_rn(g2, b[qd + 3], s); s = __fmaf_rn(g3, b[qd + 4], s);
-            s = __fmaf_rn(g4, b[qd + 5], s); s = __fmaf_rn(g5, b[qd + 6], s); s = __fmaf_rn(g6, b[qd + 7], s);
-            op[qd] = s;
-        }
-        *reinterpret_cast<float4*>(rowp + py * BLUR_TW + 4 * pg) = o;
-    }
-    __syncthreads();
-    {
-        const int px = threadIdx.x & (BLUR_TW - 1), rg = threadIdx.x / BLUR_TW;      // 64 columns x 4 row groups of 8
-        const int gx = t.x0 + px;
-        float win[14];
+            for (int j = 0; j < 3; ++j) b[j] = (float)((w0 >> (8 * (j + 1))) & 255u);
 #pragma unroll
-        for (int k = 0; k < 14; ++k) win[k] = rowp[(rg * 8 + k) * BLUR_TW + px];
-        const bool colin = gx >= EDGE && gx < EDGE + L.w;
+            for (int j = 0; j < 4; ++j) b[3 + j] = (float)((w1 >> (8 * j)) & 255u);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int py = rg * 8 + r, gy = t.y0 + py;
-            if (gy >= H || gx >= L.pitch) continue;
-            uint8_t o;
-            if (colin && gy >= EDGE && gy < EDGE + L.h) {
-                float s = __fmul_rn(g3, win[r + 3]);
-                s = __fmaf_rn(g4, __fadd_rn(win[r + 4], win[r + 2]), s);
-                s = __fmaf_rn(g5, __fadd_rn(win[r + 5], win[r + 1]), s);
-                s = __fmaf_rn(g6, __fadd_rn(win[r + 6], win[r]), s);
-                o = (uint8_t)min(max(__float2int_rn(s), 0), 255);
-            } else {
-                o = patch[(py + 3) * PW + px + 4];
+            for (int j = 0; j < 3; ++j) b[7 + j] = (float)((w2 >> (8 * j)) & 255u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float s = __fmul_rn(g0, b[q]);
+                s = __fmaf_rn(g1, b[q + 1], s); s = __fmaf_rn(g2, b[q + 2], s); s = __fmaf_rn(g3, b[q + 3], s);
+                s = __fmaf_rn(g4, b[q + 4], s); s = __fmaf_rn(g5, b[q + 5], s); s = __fmaf_rn(g6, b[q + 6], s);
+                hr[k][q] = s;
             }
-            dst[(size_t)gy * L.pitch + gx] = o;
+            cw[k] = w1;
+            const int gy = t.y0 + i - 6;                // output row whose 7-row window ends at source row i
+            if (i >= 6 && gy < H && gy < t.y0 + BLUR_TH) {
+                const bool rowin = gy >= EDGE && gy < EDGE + L.h;
+                const uint32_t centre = cw[(k + 4) % 7];          // source row i-3
+                uint32_t word = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float sacc = __fmul_rn(g3, hr[(k + 4) % 7][q]);
+                    sacc = __fmaf_rn(g4, __fadd_rn(hr[(k + 5) % 7][q], hr[(k + 3) % 7][q]), sacc);
+                    sacc = __fmaf_rn(g5, __fadd_rn(hr[(k + 6) % 7][q], hr[(k + 2) % 7][q]), sacc);
+                    sacc = __fmaf_rn(g6, __fadd_rn(hr[k][q], hr[(k + 1) % 7][q]), sacc);
+                    const uint32_t blurred = (uint32_t)min(max(__float2int_rn(sacc), 0), 255);
+                    const uint32_t o = (rowin && colin[q]) ? blurred : ((centre >> (8 * q)) & 255u);
+                    word |= o << (8 * q);
+                }
+                *reinterpret_cast<uint32_t*>(dst + (size_t)gy * pitch) = word;
+            }
         }
     }
 }
@@ -827,7 +829,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     if (overlap) {
         SE2_CUDA(cudaEventRecord(ev_pyr, s));
         SE2_CUDA(cudaStreamWaitEvent(side, ev_pyr, 0));
-        SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, side, d);
+        SE2_LAUNCH(orb_blur, dim3((d.n_tiles + 7) / 8, n), 256, 0, side, d);
         SE2_CUDA(cudaEventRecord(ev_blur, side));
     }
     pr.begin(1, s);
@@ -840,7 +842,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         SE2_CUDA(cudaStreamWaitEvent(s, ev_blur, 0));
     } else {
         pr.begin(3, s);
-        SE2_LAUNCH(orb_blur, dim3(d.n_tiles, n), 256, 0, s, d);
+        SE2_LAUNCH(orb_blur, dim3((d.n_tiles + 7) / 8, n), 256, 0, s, d);
         pr.end(s);
     }
     const int warps = 8;
