@@ -476,28 +476,39 @@ __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
     const int lane = threadIdx.x & 31;
     const TileGeo t = d.tiles[tile];
     const int f = blockIdx.y + d.frame0;
-    const LevelGeo& L = d.levels[t.level];
-    const int pitch = L.pitch, H = L.h + 2 * EDGE;
+    const int pitch = d.levels[t.level].pitch, Lw = d.levels[t.level].w, Lh = d.levels[t.level].h, H = Lh + 2 * EDGE;
     const int x4 = t.x0 + 4 * lane;
     if (x4 >= pitch) return;
-    const uint8_t* src = d.plain + f * d.frame_plane_bytes + L.plane_off + x4;
-    uint8_t* dst = d.blurred + f * d.frame_plane_bytes + L.plane_off + x4;
+    const size_t plane_off = f * d.frame_plane_bytes + d.levels[t.level].plane_off + x4;
+    const uint8_t* __restrict__ src = d.plain + plane_off;
+    uint8_t* __restrict__ dst = d.blurred + plane_off;
     const bool has_l = x4 >= 4, has_r = x4 + 8 <= pitch;
-    bool colin[4];
+    uint32_t colmask = 0;          // 0xFF in the byte lanes of ROI columns
 #pragma unroll
-    for (int q = 0; q < 4; ++q) colin[q] = x4 + q >= EDGE && x4 + q < EDGE + L.w;
+    for (int q = 0; q < 4; ++q) colmask |= (x4 + q >= EDGE && x4 + q < EDGE + Lw) ? (0xFFu << (8 * q)) : 0u;
     const float g0 = c_gauss[0], g1 = c_gauss[1], g2 = c_gauss[2], g3 = c_gauss[3], g4 = c_gauss[4], g5 = c_gauss[5], g6 = c_gauss[6];
     float hr[7][4];      // row-pass results of the last 7 source rows
     uint32_t cw[7];      // their centre words (ring pixels are copied through)
+    // rows outside the plane only feed ring outputs (copies), so the row index is clamped instead of tested
+    auto row_ptr = [&](int i) { return src + (size_t)min(max(t.y0 - 3 + i, 0), H - 1) * pitch; };
+    uint32_t n0, n1, n2;  // words of the next source row (software prefetch, one row ahead)
+    {
+        const uint8_t* rp = row_ptr(0);
+        n1 = __ldg(reinterpret_cast<const uint32_t*>(rp));
+        n0 = has_l ? __ldg(reinterpret_cast<const uint32_t*>(rp - 4)) : 0u;
+        n2 = has_r ? __ldg(reinterpret_cast<const uint32_t*>(rp + 4)) : 0u;
+    }
     for (int i0 = 0; i0 < BLUR_TH + 6; i0 += 7) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int i = i0 + k;                       // source row t.y0 - 3 + i, kept in ring slot k
-            const int sr = min(max(t.y0 - 3 + i, 0), H - 1);   // rows outside the plane only feed ring outputs (copies)
-            const uint8_t* rp = src + (size_t)sr * pitch;
-            const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(rp));
-            const uint32_t w0 = has_l ? __ldg(reinterpret_cast<const uint32_t*>(rp - 4)) : 0u;
-            const uint32_t w2 = has_r ? __ldg(reinterpret_cast<const uint32_t*>(rp + 4)) : 0u;
+            const uint32_t w0 = n0, w1 = n1, w2 = n2;
+            {
+                const uint8_t* rp = row_ptr(i + 1);
+                n1 = __ldg(reinterpret_cast<const uint32_t*>(rp));
+                n0 = has_l ? __ldg(reinterpret_cast<const uint32_t*>(rp - 4)) : 0u;
+                n2 = has_r ? __ldg(reinterpret_cast<const uint32_t*>(rp + 4)) : 0u;
+            }
             float b[10];                                // bytes x4-3 .. x4+6
 #pragma unroll
             for (int j = 0; j < 3; ++j) b[j] = (float)((w0 >> (8 * (j + 1))) & 255u);
@@ -515,8 +526,6 @@ __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
             cw[k] = w1;
             const int gy = t.y0 + i - 6;                // output row whose 7-row window ends at source row i
             if (i >= 6 && gy < H && gy < t.y0 + BLUR_TH) {
-                const bool rowin = gy >= EDGE && gy < EDGE + L.h;
-                const uint32_t centre = cw[(k + 4) % 7];          // source row i-3
                 uint32_t word = 0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -524,11 +533,10 @@ __global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
                     sacc = __fmaf_rn(g4, __fadd_rn(hr[(k + 5) % 7][q], hr[(k + 3) % 7][q]), sacc);
                     sacc = __fmaf_rn(g5, __fadd_rn(hr[(k + 6) % 7][q], hr[(k + 2) % 7][q]), sacc);
                     sacc = __fmaf_rn(g6, __fadd_rn(hr[k][q], hr[(k + 1) % 7][q]), sacc);
-                    const uint32_t blurred = (uint32_t)min(max(__float2int_rn(sacc), 0), 255);
-                    const uint32_t o = (rowin && colin[q]) ? blurred : ((centre >> (8 * q)) & 255u);
-                    word |= o << (8 * q);
+                    word |= (uint32_t)min(max(__float2int_rn(sacc), 0), 255) << (8 * q);
                 }
-                *reinterpret_cast<uint32_t*>(dst + (size_t)gy * pitch) = word;
+                const uint32_t m = (gy >= EDGE && gy < EDGE + Lh) ? colmask : 0u;
+                *reinterpret_cast<uint32_t*>(dst + (size_t)gy * pitch) = (word & m) | (cw[(k + 4) % 7] & ~m);   // centre word = source row i-3
             }
         }
     }
