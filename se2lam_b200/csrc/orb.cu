@@ -88,47 +88,47 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
-// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101). One thread = 16 output bytes x PYR0_ROWS rows;
-// the border is 16 px wide, so interior vectors are aligned 16-byte copies when the caller's rows are 16 B aligned
-// (`aligned`); the border/pad vectors and unaligned inputs take the bytewise reflect path. The level geometry comes
-// in as a kernel parameter (constant bank), not through a dependent global load.
+// level 0: copyMakeBorder(image, temp, 16,16,16,16, BORDER_REFLECT_101). The border is 16 px wide, so when the caller's
+// rows are 16 B aligned the interior is a stream of aligned 16-byte copies: blockIdx.x < gridDim.x-1 does those, one
+// thread = one vector x PYR0_ROWS rows. The last blockIdx.x column fills what is left of each row (the two 16 px
+// borders, a ragged interior tail, the pitch padding — everything when the input is unaligned) one word per thread.
+// The level geometry comes in as a kernel parameter (constant bank), not through a dependent global load.
 constexpr int PYR0_ROWS = 4;
-__global__ void __launch_bounds__(256) orb_pyr0(OrbDev d, LevelGeo L, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride, int aligned) {
-    const int x16 = (blockIdx.x * 64 + threadIdx.x) * 16;
-    const int y0 = (blockIdx.y * 4 + threadIdx.y) * PYR0_ROWS;
+__global__ void __launch_bounds__(256) orb_pyr0(OrbDev d, LevelGeo L, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride, int nvec) {
+    const int tid = threadIdx.y * 64 + threadIdx.x;
     const int f = blockIdx.z + d.frame0;
-    if (x16 >= L.pitch) return;
     const uint8_t* img = imgs + f * frame_stride;
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    const bool interior = aligned && x16 >= EDGE && x16 + 16 <= EDGE + L.w;
-    uint4 v[PYR0_ROWS];
+    const int rows = L.h + 2 * EDGE;
+    if (blockIdx.x + 1 < gridDim.x) {
+        const int vx = blockIdx.x * 64 + threadIdx.x;
+        const int y0 = (blockIdx.y * 4 + threadIdx.y) * PYR0_ROWS;
+        if (vx >= nvec) return;
+        uint4 v[PYR0_ROWS];
 #pragma unroll
-    for (int k = 0; k < PYR0_ROWS; ++k) {
-        const int y = y0 + k;
-        if (y >= L.h + 2 * EDGE) break;
-        const uint8_t* row = img + (size_t)reflect101(y - EDGE, L.h) * stride;
-        if (interior) {
-            v[k] = __ldg(reinterpret_cast<const uint4*>(row + x16 - EDGE));
-        } else {
-            uint32_t w[4];
+        for (int k = 0; k < PYR0_ROWS; ++k)
+            if (y0 + k < rows) v[k] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)reflect101(y0 + k - EDGE, L.h) * stride) + vx);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                w[j] = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int x = x16 + 4 * j + q;
-                    const uint32_t px = (x < L.w + 2 * EDGE) ? row[reflect101(x - EDGE, L.w)] : 0u;
-                    w[j] |= px << (8 * q);
-                }
-            }
-            v[k] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+        for (int k = 0; k < PYR0_ROWS; ++k)
+            if (y0 + k < rows) *reinterpret_cast<uint4*>(plane + (size_t)(y0 + k) * L.pitch + EDGE + 16 * vx) = v[k];
+        return;
     }
+    // remainder words of the rows [16*blockIdx.y, +16): columns [0,16) and [16 + 16*nvec, pitch)
+    const int tail0 = EDGE + 16 * nvec, nw = 4 + (L.pitch - tail0) / 4;
+    for (int item = tid; item < 4 * PYR0_ROWS * nw; item += 256) {
+        const int r = item / nw, wi = item - r * nw;
+        const int y = blockIdx.y * 4 * PYR0_ROWS + r;
+        if (y >= rows) break;
+        const int x0 = wi < 4 ? 4 * wi : tail0 + 4 * (wi - 4);
+        const uint8_t* row = img + (size_t)reflect101(y - EDGE, L.h) * stride;
+        uint32_t word = 0;
 #pragma unroll
-    for (int k = 0; k < PYR0_ROWS; ++k) {
-        const int y = y0 + k;
-        if (y >= L.h + 2 * EDGE) break;
-        *reinterpret_cast<uint4*>(plane + (size_t)y * L.pitch + x16) = v[k];
+        for (int q = 0; q < 4; ++q) {
+            const int x = x0 + q;
+            const uint32_t px = (x < L.w + 2 * EDGE) ? row[reflect101(x - EDGE, L.w)] : 0u;
+            word |= px << (8 * q);
+        }
+        *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x0) = word;
     }
 }
 
@@ -223,18 +223,6 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
 __device__ __forceinline__ unsigned fast_cv(int v) { return (unsigned)(256 + v) | ((unsigned)(256 - v) << 16); }
 __device__ __forceinline__ unsigned fast_q(unsigned p, unsigned cv) { return p * 0xFFFFu + cv; }
 
-// necessary condition for a corner at threshold t: a 9-arc contains one pixel of each opposite pair (k, k+8), so for
-// one polarity all 4 tested pairs must have a member beyond t. Branch-free: min over the pairs of the pair maxima.
-__device__ __forceinline__ bool fast_maybe_corner(const uint8_t* __restrict__ p, int pw, int t) {
-    const unsigned cv = fast_cv(p[0]);
-    const unsigned a = __vmaxs2(fast_q(p[3 * pw], cv), fast_q(p[-3 * pw], cv));
-    const unsigned b = __vmaxs2(fast_q(p[3], cv), fast_q(p[-3], cv));
-    const unsigned c = __vmaxs2(fast_q(p[2 * pw + 2], cv), fast_q(p[-2 * pw - 2], cv));
-    const unsigned e = __vmaxs2(fast_q(p[-2 * pw + 2], cv), fast_q(p[2 * pw - 2], cv));
-    const unsigned m = __vmins2(__vimin3_s16x2(a, b, c), e);
-    return max(m & 0xFFFFu, m >> 16) > (unsigned)(256 + t);
-}
-
 __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int pw) {
     const unsigned cv = fast_cv(p[0]);
     unsigned q[16];
@@ -257,7 +245,9 @@ __device__ __forceinline__ int fast_arc_score(const uint8_t* __restrict__ p, int
 
 // one CTA per (cell, frame): cv::FAST(cell, fastTh, NMS) and, if that yields <= 3 keypoints, cv::FAST(cell, 7, NMS)
 // (ORBextractor.cpp:616-623). The cell and its 3 px apron are staged once in shared memory with aligned 32-bit loads.
-//   A  every pixel: branch-free 4-pair test, survivors compacted into a shared list (warp ballot + one shared atomic)
+//   A  every pixel: necessary condition (a 9-arc contains one pixel of each opposite pair (k, k+8), so for one polarity all 4
+//      tested pairs need a member beyond t), branch-free on two pixels per s16x2 word; survivors are compacted into a
+//      shared list (warp scan + one shared atomic per 128 pixels)
 //   B  list entries, full warps: arc score -> score plane (same pitch as the patch, 1 px apron)
 //   C  list entries: strict 3x3 maximum -> one bit per pixel in a raster-order bitmap
 //   D  one warp: exclusive scan of the bitmap words' popcounts = raster-order output slots
@@ -281,6 +271,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     const int ph = ch + 6;
     const int pww = (shift + cw + 6 + 3) >> 2, pw = pww * 4;
     const int nbits = pw * ch, nwords = (nbits + 31) >> 5;
+    const int gx0 = (3 + shift) >> 2, G = ((3 + shift + cw - 1) >> 2) - gx0 + 1, nitems = ch * G;   // pass A work items
     uint8_t* patch = smem;
     uint8_t* score = smem + ((pw * ph + 15) & ~15);                                       // [(ch+2) x pw], pixel (x,y) at (y+1)*pw + x+1
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(score + ((pw * (ch + 2) + 15) & ~15)); // [nwords], bit y*pw + x
@@ -299,17 +290,61 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
         for (int i = threadIdx.x; i < nwords; i += FAST_THREADS) bitmap[i] = 0u;
         if (threadIdx.x == 0) s_ncand = 0;
         __syncthreads();
-        // A
-        for (int y = wid; y < ch; y += NW) {
-            const uint8_t* row = p0 + y * pw;
-            for (int x = lane; x < cw + lane; x += 32) {      // whole warp iterates together (x - lane < cw)
-                const bool ok = x < cw && fast_maybe_corner(row + x, pw, thr);
-                const unsigned bal = __ballot_sync(0xffffffffu, ok);
-                if (bal) {
+        // A: one thread = the 4 pixels of one patch word (group), items = (row, group) pairs flattened over the warp
+        {
+            const uint32_t* pwords = reinterpret_cast<const uint32_t*>(patch);
+            const unsigned T1 = (unsigned)(0x10000 - (257 + thr)) * 0x10001u;   // D + T1 >= 0 (s16)  <=>  D > 256 + thr
+            const unsigned U1 = (unsigned)(256 - thr) * 0x10001u;               // U1 + ~B >= 0       <=>  B < 256 - thr
+            for (int it0 = wid * 32; it0 < nitems; it0 += NW * 32) {
+                const int item = it0 + lane;
+                unsigned m = 0;
+                int y = 0, col0 = 0;
+                if (item < nitems) {
+                    y = item / G;
+                    const int g = item - y * G + gx0;
+                    col0 = 4 * g - (3 + shift);                    // interior x of the group's first pixel
+                    const uint32_t* c = pwords + (y + 3) * pww + g;
+                    const uint32_t n3 = c[-3 * pww], s3 = c[3 * pww];
+                    const uint32_t n2a = c[-2 * pww - 1], n2b = c[-2 * pww], n2c = c[-2 * pww + 1];
+                    const uint32_t s2a = c[2 * pww - 1], s2b = c[2 * pww], s2c = c[2 * pww + 1];
+                    const uint32_t za = c[-1], zb = c[0], zc = c[1];
+                    // 4-byte spans starting at dx = -3, -2, +2, +3 of the group's first pixel
+                    const uint32_t w_m3 = __byte_perm(za, zb, 0x4321), w_p3 = __byte_perm(zb, zc, 0x6543);
+                    const uint32_t nw_ = __byte_perm(n2a, n2b, 0x5432), ne_ = __byte_perm(n2b, n2c, 0x5432);
+                    const uint32_t sw_ = __byte_perm(s2a, s2b, 0x5432), se_ = __byte_perm(s2b, s2c, 0x5432);
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        const unsigned sel = hlf ? 0x4342u : 0x4140u;      // pixels (0,1) or (2,3) -> the two s16 halves
+                        const unsigned cb = __byte_perm(zb, 0, sel) + 0x01000100u;          // 256 + v
+                        // e = 256 + v - ring (both halves stay in [1,511], so the plain subtraction never borrows)
+                        const unsigned e0 = cb - __byte_perm(s3, 0, sel), e8 = cb - __byte_perm(n3, 0, sel);      // (0,+3) (0,-3)
+                        const unsigned e4 = cb - __byte_perm(w_p3, 0, sel), e12 = cb - __byte_perm(w_m3, 0, sel); // (+3,0) (-3,0)
+                        const unsigned e2 = cb - __byte_perm(se_, 0, sel), e10 = cb - __byte_perm(nw_, 0, sel);   // (+2,+2) (-2,-2)
+                        const unsigned e6 = cb - __byte_perm(ne_, 0, sel), e14 = cb - __byte_perm(sw_, 0, sel);   // (+2,-2) (-2,+2)
+                        const unsigned D = __vmins2(__vimin3_s16x2(__vmaxs2(e0, e8), __vmaxs2(e4, e12), __vmaxs2(e2, e10)), __vmaxs2(e6, e14));
+                        const unsigned B = __vmaxs2(__vimax3_s16x2(__vmins2(e0, e8), __vmins2(e4, e12), __vmins2(e2, e10)), __vmins2(e6, e14));
+                        const unsigned r = __vmaxs2(__vadd2(D, T1), __vadd2(~B, U1));       // >= 0 per half <=> may be a corner
+                        const unsigned ok = ~r & 0x80008000u;
+                        m |= ((ok >> 15) & 1u) << (2 * hlf) | ((ok >> 31) & 1u) << (2 * hlf + 1);
+                    }
+                    // pixels of the group outside the cell interior
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (col0 + j < 0 || col0 + j >= cw) m &= ~(1u << j);
+                }
+                const int cnt = __popc(m);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                if (tot) {
                     int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (ok) list[base + __popc(bal & ((1u << lane) - 1))] = (uint16_t)(y * pw + x);
+                    if (lane == 31) base = atomicAdd(&s_ncand, tot);
+                    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        list[base++] = (uint16_t)(y * pw + col0 + j);
+                    }
                 }
             }
         }
@@ -821,8 +856,9 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     {
         const LevelGeo& g = h->levels[0];
         const int aligned = (((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_stride) & 15) == 0;
-        dim3 grid((g.pitch / 16 + 63) / 64, (g.h + 2 * EDGE + 4 * PYR0_ROWS - 1) / (4 * PYR0_ROWS), n);
-        SE2_LAUNCH(orb_pyr0, grid, dim3(64, 4), 0, s, d, g, d_imgs, stride, frame_stride, aligned);
+        const int nvec = aligned ? g.w / 16 : 0;      // aligned 16-byte interior vectors per row
+        dim3 grid((nvec + 63) / 64 + 1, (g.h + 2 * EDGE + 4 * PYR0_ROWS - 1) / (4 * PYR0_ROWS), n);
+        SE2_LAUNCH(orb_pyr0, grid, dim3(64, 4), 0, s, d, g, d_imgs, stride, frame_stride, nvec);
     }
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
