@@ -32,6 +32,7 @@ constexpr int HALF_PATCH = 15;     // HALF_PATCH_SIZE :82
 constexpr int PATCH = 31;          // PATCH_SIZE :81
 constexpr int MAX_LEVELS = 16;
 constexpr int FAST_THREADS = 256;
+constexpr int ORB_LANES = 4;
 constexpr int BLUR_TW = 128, BLUR_TH = 36;   // one warp per tile; BLUR_TH + 6 warm-up rows = 6 turns of the 7-row ring
 
 __device__ const signed char d_pattern[1024] = {
@@ -701,8 +702,7 @@ struct se2gpu_orb {
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     // host-buffer path: two pipeline lanes (stream + side stream + events) so that the H2D of chunk c+1 and the D2H of
     // chunk c-1 overlap the kernels of chunk c
-    cudaStream_t pipe[2] = {nullptr, nullptr}, pipe_side[2] = {nullptr, nullptr};
-    cudaEvent_t pipe_ev_pyr[2] = {nullptr, nullptr}, pipe_ev_blur[2] = {nullptr, nullptr};
+    cudaStream_t pipe[ORB_LANES] = {};   // host-path pipeline lanes (chunk k runs on lane k % lanes)
     // pinned staging for results when the caller's buffers are pageable (a D2H copy into pageable memory blocks the
     // host and would serialise the pipeline)
     int* pin_counts = nullptr; se2gpu_keypoint* pin_kps = nullptr; uint8_t* pin_desc = nullptr;
@@ -849,8 +849,9 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     if (rc != SE2GPU_OK) return rc;
     OrbDev d = h->d;             // by-value copy carrying this launch group's frame offset
     d.frame0 = frame0;
-    cudaStream_t side = lane < 0 ? h->side : h->pipe_side[lane];
-    cudaEvent_t ev_pyr = lane < 0 ? h->ev_pyr : h->pipe_ev_pyr[lane], ev_blur = lane < 0 ? h->ev_blur : h->pipe_ev_blur[lane];
+    // pipeline lanes get their concurrency from each other, not from a blur side stream
+    cudaStream_t side = lane < 0 ? h->side : nullptr;
+    cudaEvent_t ev_pyr = h->ev_pyr, ev_blur = h->ev_blur;
     se2gpu::Profiler& pr = h->prof;
     pr.begin(0, s);
     {
@@ -950,11 +951,8 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     cudaMemset(d.err, 0, sizeof(int));
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
-    for (int l = 0; l < 2 && h->side; ++l)
-        if (cudaStreamCreateWithFlags(&h->pipe[l], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->pipe_side[l], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&h->pipe_ev_pyr[l], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->pipe_ev_blur[l], cudaEventDisableTiming) != cudaSuccess) {
-            h->pipe[0] = nullptr; cudaGetLastError(); break;
-        }
+    for (int l = 0; l < ORB_LANES && h->side; ++l)
+        if (cudaStreamCreateWithFlags(&h->pipe[l], cudaStreamNonBlocking) != cudaSuccess) { h->pipe[l] = nullptr; cudaGetLastError(); break; }
     cudaMemcpyToSymbol(c_umax, umax, sizeof umax);
     cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
     d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
@@ -973,12 +971,8 @@ void se2gpu_orb_destroy(se2gpu_orb* h) {
     if (h->pin_counts) cudaFreeHost(h->pin_counts);
     if (h->pin_kps) cudaFreeHost(h->pin_kps);
     if (h->pin_desc) cudaFreeHost(h->pin_desc);
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < ORB_LANES; ++l)
         if (h->pipe[l]) cudaStreamDestroy(h->pipe[l]);
-        if (h->pipe_side[l]) cudaStreamDestroy(h->pipe_side[l]);
-        if (h->pipe_ev_pyr[l]) cudaEventDestroy(h->pipe_ev_pyr[l]);
-        if (h->pipe_ev_blur[l]) cudaEventDestroy(h->pipe_ev_blur[l]);
-    }
     delete h;
 }
 
@@ -1005,12 +999,17 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     SE2_CUDA(cudaSetDevice(h->device));
     int rc = set_geometry(h, w, hgt, nullptr);
     if (rc != SE2GPU_OK) return rc;
-    // pipeline shape: `nchunks` chunks, the first one `first_pct` percent of an even share (a short first chunk exposes
-    // less of the initial H2D copy); SE2GPU_ORB_CHUNKS / SE2GPU_ORB_FIRST override, 1 chunk = one synchronous pass
+    // pipeline shape: `nchunks` chunks round-robin over `lanes` streams (H2D copy, kernels and D2H copies of a chunk are
+    // stream-ordered; different lanes overlap), the first chunk `first_pct` percent of an even share so that less of
+    // the initial H2D copy is exposed. SE2GPU_ORB_CHUNKS / _LANES / _FIRST override; 1 chunk = one synchronous pass.
     static const int env_chunks = [] { const char* e = getenv("SE2GPU_ORB_CHUNKS"); return e ? atoi(e) : 0; }();
     static const int env_first = [] { const char* e = getenv("SE2GPU_ORB_FIRST"); return e ? atoi(e) : 0; }();
-    const int nchunks = env_chunks > 0 ? env_chunks : 2;
-    const bool pipelined = h->pipe[0] && h->pipe[1] && !h->prof.on && n > 1 && nchunks > 1;
+    static const int env_lanes = [] { const char* e = getenv("SE2GPU_ORB_LANES"); return e ? atoi(e) : 0; }();
+    int lanes = 0;
+    while (lanes < ORB_LANES && h->pipe[lanes]) ++lanes;
+    if (env_lanes > 0) lanes = std::min(lanes, env_lanes);
+    const int nchunks = env_chunks > 0 ? env_chunks : 4;
+    const bool pipelined = lanes >= 2 && !h->prof.on && n > 1 && nchunks > 1;
     const int chunk = pipelined ? std::max(1, (n + nchunks - 1) / nchunks) : n;
     const int first = pipelined ? std::max(1, std::min(n, chunk * (env_first > 0 ? env_first : 50) / 100)) : n;
     auto is_pinned = [](const void* p) {
@@ -1030,7 +1029,7 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
         }
     }
     int lane = 0;
-    for (int f0 = 0, m = 0; f0 < n; f0 += m, lane ^= 1) {
+    for (int f0 = 0, m = 0; f0 < n; f0 += m, lane = (lane + 1) % std::max(lanes, 1)) {
         m = std::min(f0 == 0 ? first : std::max(chunk, (n - first + nchunks - 2) / std::max(1, nchunks - 1)), n - f0);
         cudaStream_t s = pipelined ? h->pipe[lane] : nullptr;
         // pack rows tightly on the device (pitch = w); frames of different chunks use disjoint device buffers
@@ -1046,7 +1045,7 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
         SE2_CUDA(cudaMemcpyAsync(out_desc + (size_t)32 * f0 * h->nfeatures, h->d_desc + (size_t)32 * f0 * h->nfeatures, (size_t)32 * m * h->nfeatures, cudaMemcpyDeviceToHost, s));
     }
     if (pipelined) {
-        SE2_CUDA(cudaStreamSynchronize(h->pipe[0])); SE2_CUDA(cudaStreamSynchronize(h->pipe[1]));
+        for (int l = 0; l < lanes; ++l) SE2_CUDA(cudaStreamSynchronize(h->pipe[l]));
         memcpy(counts, out_counts, sizeof(int) * n);
         if (out_kps != kps) { memcpy(kps, out_kps, sizeof(se2gpu_keypoint) * (size_t)n * h->nfeatures); memcpy(desc, out_desc, (size_t)32 * n * h->nfeatures); }
     }
