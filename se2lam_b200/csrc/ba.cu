@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <chrono>
 #include <vector>
 #include <algorithm>
 
@@ -1319,7 +1320,33 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
 }  // namespace
 
 // =================================================================================================
+// page-locked bump arena: uploads staged through it are real asynchronous DMA transfers (a cudaMemcpyAsync from a
+// pageable std::vector is staged by the driver and returns only after the host-side copy)
+struct PinnedArena {
+    uint8_t* base = nullptr; size_t cap = 0, used = 0;
+    ~PinnedArena() { if (base) cudaFreeHost(base); }
+    bool reserve(size_t bytes) {
+        used = 0;
+        if (bytes <= cap) return true;
+        if (base) cudaFreeHost(base);
+        base = nullptr; cap = 0;
+        if (cudaMallocHost((void**)&base, bytes + bytes / 4) != cudaSuccess) { cudaGetLastError(); return false; }
+        cap = bytes + bytes / 4;
+        return true;
+    }
+    template <typename T>
+    int up(T* dst, const T* src, size_t count, cudaStream_t s) {
+        if (!count) return SE2GPU_OK;
+        const size_t bytes = count * sizeof(T);
+        const void* from = src;
+        if (base && used + bytes <= cap) { memcpy(base + used, src, bytes); from = base + used; used += (bytes + 63) & ~(size_t)63; }
+        SE2_CUDA(cudaMemcpyAsync(dst, from, bytes, cudaMemcpyHostToDevice, s));
+        return SE2GPU_OK;
+    }
+};
+
 struct se2gpu_ba {
+    PinnedArena* arena = nullptr;   // page-locked staging of set_problem's uploads
     int device = 0;
     int maxP = 0, maxL = 0, maxE = 0, maxO = 0, maxN = 0;
     size_t cap_pairs = 0, cap_blk = 0;
@@ -1374,6 +1401,7 @@ int upload(T* dst, const std::vector<T>& src, cudaStream_t s) {
     SE2_CUDA(cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
     return SE2GPU_OK;
 }
+
 
 int ensure_cap(se2gpu_ba* h, size_t npairs, size_t nblk, size_t nblk_odo) {
     if (npairs > h->cap_pairs) {
@@ -1456,6 +1484,7 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (h->trace_l) cudaFree(h->trace_l);
     if (h->abort_host) cudaFreeHost(h->abort_host);
     if (h->st_host) cudaFreeHost(h->st_host);
+    delete h->arena;
     delete h;
 }
 
@@ -1481,6 +1510,9 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     if (P > h->maxP || L > h->maxL || E > h->maxE || O > h->maxO) return fail(SE2GPU_ERR_CAPACITY, "problem (%d,%d,%d,%d) exceeds capacity (%d,%d,%d,%d)", P, L, E, O, h->maxP, h->maxL, h->maxE, h->maxO);
     SE2_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
+    static const bool dbg = getenv("SE2GPU_BA_DEBUG") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_begin = tnow();
     for (int e = 0; e < E; ++e)
         if (edge_pose[e] < 0 || edge_pose[e] >= P || edge_point[e] < 0 || edge_point[e] >= L) return fail(SE2GPU_ERR_INVALID, "edge %d references a missing vertex", e);
     for (int o = 0; o < O; ++o)
@@ -1521,20 +1553,8 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     { std::vector<int> cur(pose_odo_ptr.begin(), pose_odo_ptr.end() - 1);
       for (int o = 0; o < Ol; ++o) { int a = hidx[odo_i[o]], b = hidx[odo_j[o]]; if (a >= 0) pose_odo[cur[a]++] = 2 * o; if (b >= 0) pose_odo[cur[b]++] = 2 * o + 1; } }
     // --- structure of the reduced system (BlockSolver::buildStructure): blocks (a>=b) touched by co-observation or odometry
-    struct Pair { long long key; int e1, e2; };
-    std::vector<Pair> pairs;
-    pairs.reserve((size_t)El * 4);
-    for (int j = 0; j < L; ++j)
-        for (int k1 = lm_ptr[j]; k1 < lm_ptr[j + 1]; ++k1) {
-            const int a = e_hidx[k1];
-            if (a < 0) continue;
-            for (int k2 = lm_ptr[j]; k2 < lm_ptr[j + 1]; ++k2) {
-                const int b = e_hidx[k2];
-                if (b < 0 || b > a) continue;
-                pairs.push_back({(long long)a * nf + b, k1, k2});
-            }
-        }
-    std::stable_sort(pairs.begin(), pairs.end(), [](const Pair& x, const Pair& y) { return x.key < y.key; });
+    // The (edge, edge) pair list of every block, blocks in key order (a*nf + b), pairs inside a block in landmark
+    // order: a stable counting sort over a dense nf x nf table when that is small, a comparison sort otherwise.
     struct OdoB { long long key; int code; };
     std::vector<OdoB> odob;
     for (int o = 0; o < Ol; ++o) {
@@ -1546,21 +1566,79 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     }
     std::stable_sort(odob.begin(), odob.end(), [](const OdoB& x, const OdoB& y) { return x.key < y.key; });
     std::vector<long long> keys;
-    for (int a = 0; a < nf; ++a) keys.push_back((long long)a * nf + a);
-    for (auto& p : pairs) keys.push_back(p.key);
-    for (auto& p : odob) keys.push_back(p.key);
-    std::sort(keys.begin(), keys.end());
-    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    std::vector<int> pe1, pe2, blk_pair_ptr;
+    size_t npairs = 0;
+    if ((size_t)nf * nf <= ((size_t)1 << 22)) {
+        std::vector<int> cnt((size_t)nf * nf, 0);
+        std::vector<uint8_t> used((size_t)nf * nf, 0);
+        for (int j = 0; j < L; ++j)
+            for (int k1 = lm_ptr[j]; k1 < lm_ptr[j + 1]; ++k1) {
+                const int a = e_hidx[k1];
+                if (a < 0) continue;
+                for (int k2 = lm_ptr[j]; k2 < lm_ptr[j + 1]; ++k2) {
+                    const int b = e_hidx[k2];
+                    if (b >= 0 && b <= a) { cnt[(size_t)a * nf + b]++; ++npairs; }
+                }
+            }
+        for (int a = 0; a < nf; ++a) used[(size_t)a * nf + a] = 1;
+        for (auto& p : odob) used[(size_t)p.key] = 1;
+        size_t run = 0;
+        for (size_t k = 0; k < cnt.size(); ++k) {
+            const int c = cnt[k];
+            if (c || used[k]) { keys.push_back((long long)k); blk_pair_ptr.push_back((int)run); }
+            cnt[k] = (int)run;     // becomes the fill cursor of block k
+            run += c;
+        }
+        blk_pair_ptr.push_back((int)run);
+        pe1.resize(npairs); pe2.resize(npairs);
+        for (int j = 0; j < L; ++j)
+            for (int k1 = lm_ptr[j]; k1 < lm_ptr[j + 1]; ++k1) {
+                const int a = e_hidx[k1];
+                if (a < 0) continue;
+                for (int k2 = lm_ptr[j]; k2 < lm_ptr[j + 1]; ++k2) {
+                    const int b = e_hidx[k2];
+                    if (b >= 0 && b <= a) { const int at = cnt[(size_t)a * nf + b]++; pe1[at] = k1; pe2[at] = k2; }
+                }
+            }
+    } else {
+        struct Pair { long long key; int e1, e2; };
+        std::vector<Pair> pairs;
+        pairs.reserve((size_t)El * 4);
+        for (int j = 0; j < L; ++j)
+            for (int k1 = lm_ptr[j]; k1 < lm_ptr[j + 1]; ++k1) {
+                const int a = e_hidx[k1];
+                if (a < 0) continue;
+                for (int k2 = lm_ptr[j]; k2 < lm_ptr[j + 1]; ++k2) {
+                    const int b = e_hidx[k2];
+                    if (b < 0 || b > a) continue;
+                    pairs.push_back({(long long)a * nf + b, k1, k2});
+                }
+            }
+        std::stable_sort(pairs.begin(), pairs.end(), [](const Pair& x, const Pair& y) { return x.key < y.key; });
+        npairs = pairs.size();
+        for (int a = 0; a < nf; ++a) keys.push_back((long long)a * nf + a);
+        for (auto& p : pairs) keys.push_back(p.key);
+        for (auto& p : odob) keys.push_back(p.key);
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        pe1.resize(npairs); pe2.resize(npairs);
+        blk_pair_ptr.assign(keys.size() + 1, 0);
+        size_t ip = 0;
+        for (size_t b = 0; b < keys.size(); ++b) {
+            blk_pair_ptr[b] = (int)ip;
+            while (ip < npairs && pairs[ip].key == keys[b]) { pe1[ip] = pairs[ip].e1; pe2[ip] = pairs[ip].e2; ++ip; }
+        }
+        blk_pair_ptr[keys.size()] = (int)ip;
+    }
     const int nblk = (int)keys.size();
-    std::vector<int> blk_a(nblk), blk_b(nblk), blk_pair_ptr(nblk + 1, 0), blk_odo_ptr(nblk + 1, 0), pe1(pairs.size()), pe2(pairs.size()), blk_odo(odob.size());
-    { size_t ip = 0, io = 0;
+    std::vector<int> blk_a(nblk), blk_b(nblk), blk_odo_ptr(nblk + 1, 0), blk_odo(odob.size());
+    { size_t io = 0;
       for (int b = 0; b < nblk; ++b) {
           blk_a[b] = (int)(keys[b] / nf); blk_b[b] = (int)(keys[b] % nf);
-          blk_pair_ptr[b] = (int)ip; blk_odo_ptr[b] = (int)io;
-          while (ip < pairs.size() && pairs[ip].key == keys[b]) { pe1[ip] = pairs[ip].e1; pe2[ip] = pairs[ip].e2; ++ip; }
+          blk_odo_ptr[b] = (int)io;
           while (io < odob.size() && odob[io].key == keys[b]) { blk_odo[io] = odob[io].code; ++io; }
       }
-      blk_pair_ptr[nblk] = (int)ip; blk_odo_ptr[nblk] = (int)io; }
+      blk_odo_ptr[nblk] = (int)io; }
     if (odob.size() + 1 > (size_t)2 * (h->maxO ? h->maxO : 1) + 1) return fail(SE2GPU_ERR_CAPACITY, "too many odometry blocks");
     // envelope of the reduced system: last block row touching each block column, made monotone so that the
     // fill-in of an LDL^T without pivoting stays inside it; in sharded mode every rank needs the envelope of the
@@ -1582,7 +1660,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     blk_order.reserve(nblk);
     for (int b = 0; b < nblk; ++b) if (blk_a[b] == blk_b[b]) blk_order.push_back(b);
     for (int b = 0; b < nblk; ++b) if (blk_a[b] != blk_b[b]) blk_order.push_back(b);
-    int rc = ensure_cap(h, pairs.size(), std::max<size_t>(nblk, odob.size()), odob.size());
+    int rc = ensure_cap(h, npairs, std::max<size_t>(nblk, odob.size()), odob.size());
     if (rc != SE2GPU_OK) return rc;
 
     // --- odometry SoA
@@ -1593,14 +1671,25 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
         for (int q = 0; q < 3; ++q) om[q * (size_t)Ol + o] = odo_meas[3 * o + q];
         for (int q = 0; q < 6; ++q) ow[q * (size_t)Ol + o] = odo_info[6 * o + q];
     }
-    // --- upload
-    SE2_CUDA(cudaMemcpyAsync(h->d.xp[0], poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
-    SE2_CUDA(cudaMemcpyAsync(h->d.xp[1], poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
-    SE2_CUDA(cudaMemcpyAsync(h->d.xl[0], points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
-    SE2_CUDA(cudaMemcpyAsync(h->d.xl[1], points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
-    SE2_CUDA(cudaMemcpyAsync(h->xp0, poses, sizeof(double) * 3 * P, cudaMemcpyHostToDevice, s));
-    SE2_CUDA(cudaMemcpyAsync(h->xl0, points, sizeof(double) * 3 * L, cudaMemcpyHostToDevice, s));
-#define UP(dst, src) do { int _r = upload(dst, src, s); if (_r != SE2GPU_OK) return _r; } while (0)
+    auto t_host = tnow();
+    // --- upload (staged through the page-locked arena, one synchronisation at the end)
+    if (!h->arena) h->arena = new PinnedArena;
+    {
+        size_t bytes = sizeof(double) * (3 * (size_t)P + 3 * (size_t)L) + 64 * 40;
+        bytes += sizeof(int) * (e_pose.size() + e_hidx.size() + lm_ptr.size() + hidx.size() + oi.size() + oj.size() + pose_ptr.size() + pose_edges.size() +
+                                pose_odo_ptr.size() + pose_odo.size() + blk_a.size() + blk_b.size() + blk_pair_ptr.size() + pe1.size() + pe2.size() +
+                                blk_odo_ptr.size() + blk_odo.size() + colmax.size() + blk_order.size());
+        bytes += sizeof(double) * (e_u.size() * 5 + om.size() + ow.size());
+        h->arena->reserve(bytes);   // on failure the uploads fall back to pageable copies
+    }
+    PinnedArena& ar = *h->arena;
+#define UPP(dst, ptr, count) do { int _r = ar.up(dst, ptr, (size_t)(count), s); if (_r != SE2GPU_OK) return _r; } while (0)
+#define UP(dst, src) UPP(dst, (src).data(), (src).size())
+    UPP(h->d.xp[0], poses, 3 * (size_t)P); UPP(h->d.xl[0], points, 3 * (size_t)L);
+    SE2_CUDA(cudaMemcpyAsync(h->d.xp[1], h->d.xp[0], sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d.xl[1], h->d.xl[0], sizeof(double) * 3 * L, cudaMemcpyDeviceToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->xp0, h->d.xp[0], sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->xl0, h->d.xl[0], sizeof(double) * 3 * L, cudaMemcpyDeviceToDevice, s));
     UP(h->e_pose, e_pose); UP(h->e_hidx, e_hidx); UP(h->lm_ptr, lm_ptr); UP(h->hidx, hidx);
     UP(h->e_u, e_u); UP(h->e_v, e_v); UP(h->e_w00, w00); UP(h->e_w01, w01); UP(h->e_w11, w11);
     UP(h->o_i, oi); UP(h->o_j, oj); UP(h->o_m, om); UP(h->o_w, ow);
@@ -1608,12 +1697,19 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UP(h->pair_e1, pe1); UP(h->pair_e2, pe2);
     UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax); UP(h->blk_order, blk_order);
 #undef UP
+#undef UPP
     SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
     LMState st0{};
     st0.ni = 2;
     *h->st_host = st0;
     SE2_CUDA(cudaMemcpyAsync(h->d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+    auto t_enq = tnow();
     SE2_CUDA(cudaStreamSynchronize(s));
+    if (dbg) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[se2gpu_ba_set_problem] host structure %.3f ms, stage+enqueue %.3f ms, drain %.3f ms (P %d L %d E %d blocks %d pairs %zu)\n",
+                ms(t_begin, t_host), ms(t_host, t_enq), ms(t_enq, tnow()), P, L, E, nblk, npairs);
+    }
 
     Dev& d = h->d;
     d.P = P; d.L = L; d.E = El; d.O = Ol; d.nf = nf; d.n = n; d.nblk = nblk; d.rank = rank; d.world = world;

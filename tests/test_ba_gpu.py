@@ -218,3 +218,26 @@ def test_reset_and_stop_flag(mode):
     flag[0] = 0
     n4, st4 = g.optimize(3, stop_flag=flag)
     assert n4 == 3 and st4["chi2_before"][0] == st1["chi2_before"][0]
+
+
+def test_scale_config_c5_matches_oracle():
+    """BASELINE config 5 (2000 KF / 50k landmarks / ~300k edges): the reduced system (n = 5997) does not fit one CTA's
+    shared memory, so this exercises the global-memory envelope LDL^T and the multi-launch path at scale."""
+    prob = synth.ba_config("C5")
+    iters = 3
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o, tp_o, tl_o = o.optimize(iters, trace=True)
+    g = LocalBA.from_problem(prob)
+    n_g, st_g, tp_g, tl_g = g.optimize(iters, trace=True)
+    assert n_g == n_o
+    np.testing.assert_array_equal(st_g["trials"], st_o["trials"])
+    np.testing.assert_array_equal(st_g["accepted"], st_o["accepted"])
+    np.testing.assert_allclose(st_g["lambda"], st_o["lambda"], rtol=1e-6)
+    np.testing.assert_allclose(st_g["chi2_after"], st_o["chi2_after"], rtol=1e-8)
+    prev_p, prev_l = prob.poses, prob.points
+    for k in range(n_o):
+        dp_o, dp_g = tp_o[k] - prev_p, tp_g[k] - prev_p
+        dl_o, dl_g = tl_o[k] - prev_l, tl_g[k] - prev_l
+        assert np.abs(dp_g - dp_o).max() <= REL * max(np.abs(dp_o).max(), 1e-12), f"pose step {k}"
+        assert np.abs(dl_g - dl_o).max() <= REL * max(np.abs(dl_o).max(), 1e-12), f"landmark step {k}"
+        prev_p, prev_l = tp_o[k], tl_o[k]
