@@ -251,7 +251,10 @@ def run_ours(args):
             "kernel_share_of_step": single[dom][0] / sum(v[0] for v in single.values()),
             "per_kernel_ms": {g: v[0] / v[1] for g, v in single.items()},
             "per_kernel_note": "second, event-instrumented pass (kernels serialised); the timed pass overlaps orb_blur with orb_fast_cells+orb_select",
-            "whole_path_GBps": step_alg_bytes / (orb_ms / args.steps * 1e-3) / 1e9}
+            "whole_path_GBps": step_alg_bytes / (orb_ms / args.steps * 1e-3) / 1e9,
+            # the path is instruction-issue bound: issue-slot utilisation and lane efficiency of the
+            # dominant kernel from the committed ncu capture of this round
+            "issue": ncu_traffic("issue:" + dom)}
     clocks = clk.summary()
 
     # e2e: host buffers through se2gpu_orb_extract (H2D + D2H inside the timed region)
@@ -275,6 +278,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     orb_e2e_value = sum_over_ranks(float(tot)) / (e2e_ms * 1e-3)
+    # single-frame latency of the same host call (the reference extracts one frame per Frame constructor, Frame.cpp:25)
+    single_ms = None
+    if e2e_steps:
+        one = host_batches[0].numpy()[:1]
+        for _ in range(3):
+            _capi.check(lib.se2gpu_orb_extract(ext.h, one.ctypes.data, 1, W, H, W, W * H, kps_h.ctypes.data, desc_h.ctypes.data, counts_h.ctypes.data), "se2gpu_orb_extract")
+        t0 = time.perf_counter()
+        for _ in range(50):
+            _capi.check(lib.se2gpu_orb_extract(ext.h, one.ctypes.data, 1, W, H, W, W * H, kps_h.ctypes.data, desc_h.ctypes.data, counts_h.ctypes.data), "se2gpu_orb_extract")
+        single_ms = (time.perf_counter() - t0) * 1e3 / 50
 
     # ------------------------------------------------------------------------------------------ BA
     prob = synth.ba_config("C4")
@@ -360,7 +373,8 @@ def run_ours(args):
                        "l2": f"inputs rotate over {NROT} distinct batches = {NROT * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
                        "keypoints_per_frame": kp_per_frame},
             "e2e": {"value": orb_e2e_value, "unit": "keypoints/s", "h2d_bytes_per_step": BATCH * W * H,
-                    "d2h_bytes_per_step": BATCH * NFEAT * 60 + BATCH * 4, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": BATCH * NFEAT * 60 + BATCH * 4, "ms_per_step": e2e_ms / args.steps,
+                    "single_frame_ms": single_ms},
             "gpu_launches": int(orb_launches + ba_launches),
             "roofline": roof, "clocks": clocks,
             "secondary": {
