@@ -498,7 +498,7 @@ struct GmemIO {   // same interface on byte offsets from a global base (reduced 
 
 // Block LDL^T of the reduced system (see the comment above ldlt_smem_bytes for the algorithm).
 //   ADDR = unsigned (shared window) or unsigned long long (global); aA, aY, aW, aC, aT are the byte addresses of
-//   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int)}.
+//   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int), 2 x 3 back-substitution exchange slots}.
 template <class IO, class ADDR>
 __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR aT, int n, const double* bs, double* dxp, LMState* st) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -595,7 +595,33 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
     STAMP(3);
     const int ok = IO::ldi(aOK);
     if (ok) {
-        if (wid == 0) {
+        if (n <= 160 && nt >= 160) {
+            // Back substitution, axpy form on 5 warps: thread c < n owns the accumulator z_c = u_c - sum(a^T x) of column c in
+            // a register. Per block step (descending) the three owners of block kb publish their finished accumulators,
+            // one named barrier later every thread forms x_kb = W_kb z_kb redundantly and subtracts row block kb of the
+            // factor times x_kb from its own column: no reduction tree, ~40 instructions per warp and step. (A single warp
+            // issues one instruction every ~4 cycles, so the dot-product form below - ~200 instructions per step on one
+            // warp - costs ~800 cycles per step whatever the latencies are.)
+            if (tid < 160) {
+                const int c = tid;
+                double z = c < n ? IO::ld(Y_(c)) : 0.0;
+                const int cm = c < n ? IO::ldi(aC + (ADDR)(c * 4)) : -1;
+                for (int kb = nb - 1; kb >= 0; --kb) {
+                    const int k = 3 * kb;
+                    const ADDR xz = aT + (ADDR)(32 + 24 * (kb & 1));        // double-buffered exchange slots
+                    if (c >= k && c < k + 3) IO::st(xz + (ADDR)((c - k) * 8), z);
+                    const bool in = c < k && cm >= k + 2;                  // row block kb inside this column's envelope
+                    const double a0 = in ? IO::ld(A_(k, c)) : 0.0, a1 = in ? IO::ld(A_(k + 1, c)) : 0.0, a2 = in ? IO::ld(A_(k + 2, c)) : 0.0;
+                    const double w00 = IO::ld(W_(kb, 0)), w01 = IO::ld(W_(kb, 1)), w02 = IO::ld(W_(kb, 2)), w11 = IO::ld(W_(kb, 4)), w12 = IO::ld(W_(kb, 5)), w22 = IO::ld(W_(kb, 8));
+                    asm volatile("bar.sync 1, 160;" ::: "memory");
+                    const double z0 = IO::ld(xz), z1 = IO::ld(xz + 8), z2 = IO::ld(xz + 16);
+                    const double x0 = w00 * z0 + w01 * z1 + w02 * z2, x1 = w01 * z0 + w11 * z1 + w12 * z2, x2 = w02 * z0 + w12 * z1 + w22 * z2;
+                    z -= a0 * x0 + a1 * x1 + a2 * x2;
+                    z = (c == k) ? x0 : (c == k + 1) ? x1 : (c == k + 2) ? x2 : z;
+                }
+                if (c < n) IO::st(Y_(c), z);
+            }
+        } else if (wid == 0) {
             // lanes = 3 columns x 8 row slots; each 8-lane group sums its column's dot product with an xor tree
             const int c = lane >> 3, rs = lane & 7;
             for (int kb = nb - 1; kb >= 0; --kb) {
@@ -643,7 +669,7 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
 }
 
 // bytes of dynamic shared memory the SMEM variant needs for n unknowns
-__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16 + 48; }
+__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16 + 96; }
 
 // S (n*n doubles, rounded up to 16 B: the tail lands in y, which is initialised afterwards) and the envelope -> shared
 // memory. One elected thread issues a single bulk copy; everybody waits on the mbarrier phase `parity`.
