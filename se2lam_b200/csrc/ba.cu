@@ -947,14 +947,30 @@ __device__ __forceinline__ double pk_odo(const Dev& d, const double* xp, int o) 
     return e0 * we[0] + e1 * we[1] + e2 * we[2];
 }
 
+// Landmark work of the persistent kernel: lane groups (LPL lanes per landmark) are dealt to the CTAs round-robin, so every
+// SM gets L / gridDim.x landmarks on its first warps instead of the first CTAs running all 16 warps while the rest
+// idle (the phases are FP64-issue bound per SM). Whole warps iterate together (the lane-group shuffles need them): the
+// loop bound is the warp's first landmark; landmarks >= L are skipped inside the bodies.
+struct PKLmIter {
+    int j, sub, step, j_warp;
+    __device__ __forceinline__ PKLmIter() {
+        const int lg = threadIdx.x / LPL;                       // lane group inside the CTA
+        sub = threadIdx.x % LPL;
+        j = lg * gridDim.x + blockIdx.x;
+        j_warp = (threadIdx.x / 32) * (32 / LPL) * gridDim.x + blockIdx.x;
+        step = (blockDim.x / LPL) * gridDim.x;
+    }
+    __device__ __forceinline__ bool more(int L) const { return j_warp < L; }
+    __device__ __forceinline__ void next() { j += step; j_warp += step; }
+};
+
 template <bool JAC>
 __device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double* part, double* sh) {
     const double* xp = d.xp[xi];
     const double* xl = d.xl[xi];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     double chi = 0;
-    const int nwork = ((d.L * LPL + 31) / 32) * 32;   // whole warps iterate together (the lane-group shuffles need them)
-    for (int g = gtid; g < nwork; g += gthreads) chi += pk_landmark<JAC>(d, cam, xp, xl, g / LPL, g % LPL);
+    for (PKLmIter it; it.more(d.L); it.next()) chi += pk_landmark<JAC>(d, cam, xp, xl, it.j, it.sub);
     for (int o = gtid; o < d.O; o += gthreads) chi += pk_odo<JAC>(d, xp, o);
     const double tot = block_sum(chi, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
@@ -1104,8 +1120,9 @@ __device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double
 __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const size_t L = d.L, E = d.E;
-    for (int g = gtid; g < d.L * LPL; g += gthreads) {
-        const int j = g / LPL, sub = g % LPL;
+    for (PKLmIter it; it.more(d.L); it.next()) {
+        const int j = it.j, sub = it.sub;
+        if (j >= d.L) continue;
         const int beg = d.lm_ptr[j], end = d.lm_ptr[j + 1];
         if (end <= beg) continue;
         const double a = d.Hll[j] + lam, b = d.Hll[L + j], c = d.Hll[2 * L + j], e = d.Hll[3 * L + j] + lam, f = d.Hll[4 * L + j], i = d.Hll[5 * L + j] + lam;
@@ -1137,9 +1154,8 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
     double* xlt = d.xl[cur ^ 1];
     const size_t L = d.L, E = d.E;
     double sc = 0;
-    const int nwork = ((d.L * LPL + 31) / 32) * 32;
-    for (int g = gtid; g < nwork; g += gthreads) {
-        const int j = g / LPL, sub = g % LPL;
+    for (PKLmIter it; it.more(d.L); it.next()) {
+        const int j = it.j, sub = it.sub;
         int beg = 0, end = 0;
         if (j < d.L) { beg = d.lm_ptr[j]; end = d.lm_ptr[j + 1]; }
         double c0 = 0, c1 = 0, c2 = 0;
