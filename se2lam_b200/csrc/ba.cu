@@ -1020,9 +1020,12 @@ __device__ void pk_pose_item(const Dev& d, int a, const int* edges, int ne, doub
     }
 }
 
-// block (a >= b) of the reduced system; pairs interleaved (e1,e2) in `pairs` (shared) or null -> global lists at gp0
+// block (a >= b) of the reduced system; pairs interleaved (e1,e2) in `pairs` (shared) or null -> global lists at gp0.
+// A diagonal block also gathers the pose-side sums of its pose in the same sweep over the pose's edge list (Hpp_aa, b_p;
+// the stand-alone pose gather of phase B is only needed at iteration 0, before lambda_0 exists) and stores them for
+// the gain-ratio denominator. Summation order: thread-strided partials, warp xor-tree, per-warp sums in warp order.
 __device__ void pk_schur_item(const Dev& d, double lam, int blk, int a, int b, const int* pairs, int gp0, int np, const int* edges, int ne,
-                              double* sh12 /*[8][12]*/) {
+                              double* shr /*[warps][21]*/) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t O = d.O, n = d.n, nf = d.nf;
     double acc[12];
@@ -1047,33 +1050,68 @@ __device__ void pk_schur_item(const Dev& d, double lam, int blk, int a, int b, c
 #pragma unroll
             for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + o] : d.oAij[(r * 3 + c) * O + o];
     }
-    if (a == b)
+    const bool diag = a == b;      // block-uniform
+    double ph[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) ph[q] = 0;
+    if (diag) {
         for (int k = threadIdx.x; k < ne; k += blockDim.x) {
             const double* yr = d.Y + (size_t)edges[k] * EB;
+            const double* rec = d.PH + (size_t)edges[k] * EB;
             acc[9] -= yr[9]; acc[10] -= yr[10]; acc[11] -= yr[11];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) ph[q] += rec[q];
         }
+        for (int k = d.pose_odo_ptr[a] + threadIdx.x; k < d.pose_odo_ptr[a + 1]; k += blockDim.x) {
+            const int code = d.pose_odo[k], o = code >> 1;
+            const double* H = (code & 1) ? d.oAjj : d.oAii;
+            const double* bb = (code & 1) ? d.obj : d.obi;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) ph[q] += H[q * O + o];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) ph[6 + q] += bb[q * O + o];
+        }
+    }
 #pragma unroll
     for (int q = 0; q < 12; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-    __syncthreads();
-    if (lane == 0)
+    if (diag) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) sh12[wid * 12 + q] = acc[q];
+        for (int q = 0; q < 9; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ph[q] += __shfl_xor_sync(0xffffffffu, ph[q], o);
+    }
     __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) shr[wid * 21 + q] = acc[q];
+        if (diag) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) shr[wid * 21 + 12 + q] = ph[q];
+        }
+    }
+    __syncthreads();
+    const int nwarp = (int)(blockDim.x >> 5);
     if (threadIdx.x < 12) {
         double v = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh12[w * 12 + threadIdx.x];
+        for (int w = 0; w < nwarp; ++w) v += shr[w * 21 + threadIdx.x];
         const int q = threadIdx.x;
         if (q < 9) {
             const int r = q / 3, c = q % 3;
-            if (a == b) {
+            if (diag) {
                 const int u6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-                v += d.Hpp[u6[r][c] * nf + a] + (r == c ? lam : 0.0);
+                double hsum = 0;
+                for (int w = 0; w < nwarp; ++w) hsum += shr[w * 21 + 12 + u6[r][c]];
+                if (c >= r) d.Hpp[u6[r][c] * nf + a] = hsum;
+                v += hsum + (r == c ? lam : 0.0);
             }
             d.S[(3 * a + r) * n + 3 * b + c] = v;
-        } else if (a == b) {
-            d.bs[3 * a + q - 9] = d.bp[3 * a + q - 9] + v;
+        } else if (diag) {
+            double bsum = 0;
+            for (int w = 0; w < nwarp; ++w) bsum += shr[w * 21 + 12 + 6 + (q - 9)];
+            d.bp[3 * a + q - 9] = bsum;
+            d.bs[3 * a + q - 9] = bsum + v;
         }
     }
 }
@@ -1197,7 +1235,7 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
 __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, PKArgs pa) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
-    __shared__ double shv[(PK_THREADS / 32) * 12];
+    __shared__ double shv[(PK_THREADS / 32) * 21];
     __shared__ __align__(8) unsigned long long stage_bar;
     unsigned stage_parity = 0;
     if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
@@ -1258,7 +1296,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         if (*pa.abort_dev) break;
         // ---- B: pose-side gather (+ landmark diagonal maximum for lambda_0); for it > 0 the damping of the first trial is
         // already known, so the damping-dependent per-landmark terms are prepared in the same phase (one barrier less)
-        pk_phase_pose_reduce(d, work, shv);
+        if (it == 0) pk_phase_pose_reduce(d, work, shv);    // lambda_0 needs the pose diagonal; later the Schur phase gathers it
         if (it > 0) pk_phase_lm_prep(d, lambda);
         if (it == 0) {
             double m = 0;
