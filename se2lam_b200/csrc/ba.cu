@@ -848,7 +848,7 @@ __device__ double cta_max(double v, double* sh) {
 
 // one (landmark j, lane sub) slice of the linearisation / chi2 evaluation; all LPL lanes of a group call it together
 template <bool JAC>
-__device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, const double* xp, const double* xl, int j, int sub) {
+__device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, const double* xp, const double* xl, int j, int sub, double lam_fuse) {
     double chi = 0, h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0, b2 = 0;
     int beg = 0, end = 0;
     if (j < d.L) { beg = d.lm_ptr[j]; end = d.lm_ptr[j + 1]; }
@@ -899,6 +899,29 @@ __device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, cons
             const size_t L = d.L;
             d.Hll[j] = h00; d.Hll[L + j] = h01; d.Hll[2 * L + j] = h02; d.Hll[3 * L + j] = h11; d.Hll[4 * L + j] = h12; d.Hll[5 * L + j] = h22;
             d.bl[j] = b0; d.bl[L + j] = b1; d.bl[2 * L + j] = b2;
+        }
+        // When the damping of the coming trial is already known (every iteration but the first) the damping-dependent
+        // landmark terms are formed right here from the sums every lane of the group holds - same arithmetic as
+        // pk_phase_lm_prep - which removes that phase and its grid barrier from the iteration.
+        if (lam_fuse >= 0.0 && end > beg) {
+            const size_t L = d.L;
+            const double a = h00 + lam_fuse, b = h01, c = h02, e = h11 + lam_fuse, f = h12, i = h22 + lam_fuse;
+            const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
+            const double id = 1.0 / (a * c00 + b * c01 + c * c02);
+            const double i00 = c00 * id, i01 = c01 * id, i02 = c02 * id, i11 = (a * i - c * c) * id, i12 = (b * c - a * f) * id, i22 = (a * e - b * b) * id;
+            if (sub == 0) { d.HllInv[j] = i00; d.HllInv[L + j] = i01; d.HllInv[2 * L + j] = i02; d.HllInv[3 * L + j] = i11; d.HllInv[4 * L + j] = i12; d.HllInv[5 * L + j] = i22; }
+            const double db0 = i00 * b0 + i01 * b1 + i02 * b2, db1 = i01 * b0 + i11 * b1 + i12 * b2, db2 = i02 * b0 + i12 * b1 + i22 * b2;
+            for (int k = beg + sub; k < end; k += LPL) {
+                if (d.e_hidx[k] < 0) continue;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double g0 = d.Hpl[(size_t)k * EB + ((r * 3 + 0))], g1 = d.Hpl[(size_t)k * EB + ((r * 3 + 1))], g2 = d.Hpl[(size_t)k * EB + ((r * 3 + 2))];
+                    d.Y[(size_t)k * EB + ((r * 3 + 0))] = g0 * i00 + g1 * i01 + g2 * i02;
+                    d.Y[(size_t)k * EB + ((r * 3 + 1))] = g0 * i01 + g1 * i11 + g2 * i12;
+                    d.Y[(size_t)k * EB + ((r * 3 + 2))] = g0 * i02 + g1 * i12 + g2 * i22;
+                    d.Y[(size_t)k * EB + 9 + (r)] = g0 * db0 + g1 * db1 + g2 * db2;
+                }
+            }
         }
     }
     return chi;
@@ -965,12 +988,12 @@ struct PKLmIter {
 };
 
 template <bool JAC>
-__device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double* part, double* sh) {
+__device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double* part, double* sh, double lam_fuse = -1.0) {
     const double* xp = d.xp[xi];
     const double* xl = d.xl[xi];
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     double chi = 0;
-    for (PKLmIter it; it.more(d.L); it.next()) chi += pk_landmark<JAC>(d, cam, xp, xl, it.j, it.sub);
+    for (PKLmIter it; it.more(d.L); it.next()) chi += pk_landmark<JAC>(d, cam, xp, xl, it.j, it.sub, lam_fuse);
     for (int o = gtid; o < d.O; o += gthreads) chi += pk_odo<JAC>(d, xp, o);
     const double tot = block_sum(chi, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
@@ -1287,28 +1310,27 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
 #define PK_TICK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); tacc[g] += _t - tprev_s; tprev_s = _t; wprev_s = _t; } } while (0)
 #define PK_WORK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); wacc[g] += _t - wprev_s; wprev_s = _t; } } while (0)
     for (int it = 0; it < pa.max_iters && !stop; ++it) {
-        // ---- A: linearise at x_cur (computeActiveErrors + buildSystem)
-        pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh);
+        // ---- A: linearise at x_cur (computeActiveErrors + buildSystem). For it > 0 the damping of the first trial is already
+        // known, so the damping-dependent landmark terms are formed in the same pass (no phase B, one grid barrier less).
+        pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh, it > 0 ? lambda : -1.0);
         if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
         PK_WORK(0);
         grid.sync();
         PK_TICK(0);
         if (*pa.abort_dev) break;
-        // ---- B: pose-side gather (+ landmark diagonal maximum for lambda_0); for it > 0 the damping of the first trial is
-        // already known, so the damping-dependent per-landmark terms are prepared in the same phase (one barrier less)
-        if (it == 0) pk_phase_pose_reduce(d, work, shv);    // lambda_0 needs the pose diagonal; later the Schur phase gathers it
-        if (it > 0) pk_phase_lm_prep(d, lambda);
         if (it == 0) {
+            // ---- B (first iteration only): pose-side gather and landmark diagonal maximum for lambda_0 = 1e-5 max|diag H|
+            pk_phase_pose_reduce(d, work, shv);
             double m = 0;
             const size_t L = d.L;
             for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < d.L; j += gridDim.x * blockDim.x)
                 if (d.lm_ptr[j + 1] > d.lm_ptr[j]) m = fmax(m, fmax(fabs(d.Hll[j]), fmax(fabs(d.Hll[3 * L + j]), fabs(d.Hll[5 * L + j]))));
             m = cta_max(m, sh);
             if (threadIdx.x == 0) pa.part_max[blockIdx.x] = m;
+            PK_WORK(1);
+            grid.sync();
+            PK_TICK(1);
         }
-        PK_WORK(1);
-        grid.sync();
-        PK_TICK(1);
         chi_cur = cta_sum_array(pa.part_chi, nparts, sh);
         const double chi_before = chi_cur;
         if (it == 0) {
@@ -1322,7 +1344,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         int trials = 0, accepted = 0;
         double rho = 0;
         do {
-            // ---- P: damping-dependent per-landmark terms (first trial of it > 0: done in phase B)
+            // ---- P: damping-dependent per-landmark terms (first trial of it > 0: already formed in phase A)
             PK_TICK(6);
             if (it == 0 || trials > 0) {
                 pk_phase_lm_prep(d, lambda);
