@@ -306,6 +306,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
     ba = LocalBA.from_problem(prob, device=local_rank, rank=rank, world=world, allreduce=allreduce if world > 1 else None,
                               stream=sptr)
+    exchange = "none (single GPU)"
+    if world > 1:
+        # reduced system summed inside the solve kernel over NVLink peer mappings (CUDA IPC); NCCL keeps the scalar reductions.
+        # All ranks must agree on the mode: fall back to the NCCL all-reduce everywhere if any rank cannot map its peers.
+        def _gather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        ok = 1
+        try:
+            ba.enable_peer_exchange(_gather)
+        except Exception as e:      # noqa: BLE001 - e.g. IPC not permitted in this container
+            print(f"[bench] rank {rank}: fused peer exchange unavailable ({e}); using the NCCL all-reduce", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            exchange = "fused: solve kernel sums the ranks' partial [S|b] over NVLink peer mappings; NCCL for the [chi2,scale] scalars"
+        else:
+            exchange = "NCCL all-reduce of [S|b] + [chi2,scale] per trial"
+            ba = LocalBA.from_problem(prob, device=local_rank, rank=rank, world=world, allreduce=allreduce, stream=sptr)
     for _ in range(max(args.warmup, 1)):
         ba.reset(); ba.optimize(BA_ITERS)
     barrier()
@@ -382,7 +403,7 @@ def run_ours(args):
                 "scaling": "strong", "ms_per_step": ba_ms / args.steps, "iterations_per_step": iters / args.steps,
                 "lambda_trials_per_step": trials,
                 "config": {"workload": f"local BA {P} KF / {L} landmarks / {E} EdgeSE2XYZ + {O} PreEdgeSE2, Huber, {BA_ITERS} LM iterations",
-                           "parallelism": "single GPU, one persistent cooperative kernel per optimize()" if world == 1 else f"landmark-sharded over {world} GPUs, 1 all-reduce of [S|b] + 1 of [chi2,scale] per trial"},
+                           "parallelism": "single GPU, one persistent cooperative kernel per optimize()" if world == 1 else f"landmark-sharded over {world} GPUs; exchange: {exchange}"},
                 "e2e": {"value": it2 / (ba_e2e_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(ba_launches), "roofline": ba_roof},
         }

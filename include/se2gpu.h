@@ -198,6 +198,15 @@ int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points);
  * sum (op 0) or max (op 1) `count` doubles at device pointer `buf` in place across ranks, ordered on `stream`. */
 typedef int (*se2gpu_allreduce_fn)(void* user, double* buf, size_t count, int op, void* stream);
 int se2gpu_ba_set_shard(se2gpu_ba* h, int rank, int world, se2gpu_allreduce_fn allreduce, void* user);
+/* Optional fused exchange for sharded runs on one NVLink node (one process per GPU): instead of all-reducing the
+ * reduced system [S | b] through the callback, every rank's solve kernel sums the ranks' partial buffers directly
+ * over peer mappings (the exchange is part of the kernel that consumes it; the small [chi2, scale] reductions keep
+ * using the callback). Protocol: after se2gpu_ba_set_shard every rank calls _peer_export, the handles
+ * (SE2GPU_BA_PEER_HANDLE_BYTES each, CUDA IPC) are all-gathered by the caller in rank order and passed to
+ * _peer_import. Used when the reduced system fits one CTA's shared memory; otherwise the callback path remains. */
+#define SE2GPU_BA_PEER_HANDLE_BYTES 128
+int se2gpu_ba_peer_export(se2gpu_ba* h, void* handle_out);
+int se2gpu_ba_peer_import(se2gpu_ba* h, const void* handles, int world);
 /* stream all BA work is enqueued on (cudaStream_t as void*); NULL = default stream */
 int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream);
 

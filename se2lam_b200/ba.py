@@ -64,6 +64,17 @@ class LocalBA:
         self._cb = _capi.ALLREDUCE_FN(_cb)
         check(lib().se2gpu_ba_set_shard(self.h, rank, world, self._cb, None), "se2gpu_ba_set_shard")
 
+    def enable_peer_exchange(self, all_gather):
+        """Fused exchange of the reduced system over NVLink peer mappings (se2gpu_ba_peer_export/_import).
+        all_gather(local: bytes) -> list[bytes] in rank order (e.g. torch.distributed.all_gather_object)."""
+        n = _capi.PEER_HANDLE_BYTES
+        mine = (C.c_uint8 * n)()
+        check(lib().se2gpu_ba_peer_export(self.h, mine), "se2gpu_ba_peer_export")
+        parts = all_gather(bytes(mine))
+        blob = b"".join(parts)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().se2gpu_ba_peer_import(self.h, buf, len(parts)), "se2gpu_ba_peer_import")
+
     def set_problem(self, prob):
         c = np.ascontiguousarray
         a = [c(prob.poses, np.float64), c(prob.fixed, np.uint8), c(prob.points, np.float64), c(prob.edge_pose, np.int32),

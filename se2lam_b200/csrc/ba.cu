@@ -698,6 +698,79 @@ __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_gmem(Dev d, double
     ldlt_block_solve<false>(d.S, ywork, d.n, d.colmax, d.bs, d.dxp, d.st);
 }
 
+// ---- sharded runs, fused exchange: the all-reduce of the reduced system [S | b_s] happens INSIDE the solve kernel.
+// Every rank publishes "my partial system of trial `epoch` is complete" in a flag word of its own memory; the solve
+// kernel of every rank waits for all flags, then stages S into shared memory as the sum over the ranks' partial
+// buffers in rank order (own buffer through the local pointer, the others through peer mappings over NVLink:
+// cudaIpcOpenMemHandle). The sum order is the same on every rank, so the replicated solves stay bit-identical. The
+// buffers may be overwritten again after the trial's [chi2, scale] all-reduce, which orders every rank's next Schur
+// kernel after every rank's solve kernel.
+constexpr int MAX_PEERS = 8;
+struct PeerArgs {
+    const double* red[MAX_PEERS];          // [S (n*n) | bs (n)] partial buffer of rank r (own rank: local pointer)
+    const long long* flag[MAX_PEERS];      // epoch flag of rank r
+    double* bs_sum;                        // local [n]: summed right-hand side (the partial one is being read by the peers)
+    long long epoch;
+    int world, rank;
+};
+
+__global__ void ba_peer_signal(long long* flag, long long epoch) {
+    __threadfence_system();
+    *reinterpret_cast<volatile long long*>(flag) = epoch;
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_peer(Dev d, PeerArgs pa) {
+    extern __shared__ double sm[];
+    const int n = d.n;
+    if (threadIdx.x < pa.world && threadIdx.x != pa.rank) {
+        const volatile long long* f = reinterpret_cast<const volatile long long*>(pa.flag[threadIdx.x]);
+        const long long t0 = clock64();
+        while (*f < pa.epoch)
+            if (clock64() - t0 > 4000000000LL) __trap();       // ~2 s: a peer died or the ranks diverged - fail, do not hang
+        __threadfence_system();
+    }
+    __syncthreads();
+    int* cmax = reinterpret_cast<int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
+    // [S | bs] = n*n + n doubles, fetched as 16-byte vectors, PEER_BATCH independent loads in flight per thread and peer
+    // (an NVLink round trip is ~2 us: a dependent load chain would serialise them)
+    constexpr int PEER_BATCH = 8;
+    const int total = n * n + n, nvec = total / 2;
+    for (int v0 = threadIdx.x; v0 < nvec; v0 += blockDim.x * PEER_BATCH) {
+        double2 acc[PEER_BATCH];
+#pragma unroll
+        for (int u = 0; u < PEER_BATCH; ++u) acc[u] = make_double2(0.0, 0.0);
+        for (int r = 0; r < pa.world; ++r) {
+            const double2* src = reinterpret_cast<const double2*>(pa.red[r]);
+            double2 t[PEER_BATCH];
+#pragma unroll
+            for (int u = 0; u < PEER_BATCH; ++u) {
+                const int v = v0 + u * blockDim.x;
+                t[u] = v < nvec ? ((r == pa.rank) ? src[v] : __ldcv(src + v)) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < PEER_BATCH; ++u) { acc[u].x += t[u].x; acc[u].y += t[u].y; }
+        }
+#pragma unroll
+        for (int u = 0; u < PEER_BATCH; ++u) {
+            const int v = v0 + u * blockDim.x;
+            if (v < nvec) {
+                const int i = 2 * v;
+                if (i < n * n) sm[i] = acc[u].x; else pa.bs_sum[i - n * n] = acc[u].x;
+                if (i + 1 < n * n) sm[i + 1] = acc[u].y; else pa.bs_sum[i + 1 - n * n] = acc[u].y;
+            }
+        }
+    }
+    if ((total & 1) && threadIdx.x == 0) {       // odd tail element
+        double v = 0;
+        for (int r = 0; r < pa.world; ++r) v += (r == pa.rank) ? pa.red[r][total - 1] : __ldcv(pa.red[r] + total - 1);
+        pa.bs_sum[total - 1 - n * n] = v;
+    }
+    __syncthreads();
+    ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, pa.bs_sum, d.dxp, d.st);
+}
+
 // back-substitution + oplus into the trial buffers + partial sums of computeScale()
 __global__ void __launch_bounds__(LM_THREADS) ba_backsub_update(Dev d) {
     __shared__ double sh[32];
@@ -1455,6 +1528,14 @@ struct se2gpu_ba {
     cudaStream_t stream = nullptr;
     int rank = 0, world = 1;
     se2gpu_allreduce_fn allreduce = nullptr;
+    // fused peer exchange (se2gpu_ba_peer_export / _import)
+    long long* peer_flag = nullptr;            // this rank's epoch flag (own cudaMalloc: exported by IPC handle)
+    double* bs_sum = nullptr;
+    void* peer_opened[8] = {};                 // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
+    const double* peer_red[8] = {};
+    const long long* peer_flags[8] = {};
+    bool peer_on = false;
+    long long peer_epoch = 0;
     void* ar_user = nullptr;
     Dev d{};
     Cam cam{};
@@ -1585,9 +1666,52 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (h->trace_p) cudaFree(h->trace_p);
     if (h->trace_l) cudaFree(h->trace_l);
     if (h->abort_host) cudaFreeHost(h->abort_host);
+    for (void* m : h->peer_opened) if (m) cudaIpcCloseMemHandle(m);
+    if (h->peer_flag) cudaFree(h->peer_flag);
+    if (h->bs_sum) cudaFree(h->bs_sum);
     if (h->st_host) cudaFreeHost(h->st_host);
     delete h->arena;
     delete h;
+}
+
+int se2gpu_ba_peer_export(se2gpu_ba* h, void* handle_out) {
+    if (!h || !handle_out) return fail(SE2GPU_ERR_INVALID, "null argument");
+    SE2_CUDA(cudaSetDevice(h->device));
+    if (!h->peer_flag) {
+        SE2_CUDA(cudaMalloc((void**)&h->peer_flag, 256));
+        SE2_CUDA(cudaMemset(h->peer_flag, 0, 256));
+        SE2_CUDA(cudaMalloc((void**)&h->bs_sum, sizeof(double) * (size_t)std::max(h->maxN, 1)));
+    }
+    cudaIpcMemHandle_t hs[2];
+    SE2_CUDA(cudaIpcGetMemHandle(&hs[0], h->red));
+    SE2_CUDA(cudaIpcGetMemHandle(&hs[1], h->peer_flag));
+    static_assert(sizeof(hs) == SE2GPU_BA_PEER_HANDLE_BYTES, "handle size");
+    memcpy(handle_out, hs, sizeof hs);
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_peer_import(se2gpu_ba* h, const void* handles, int world) {
+    if (!h || !handles) return fail(SE2GPU_ERR_INVALID, "null argument");
+    if (world != h->world || world < 2 || world > MAX_PEERS) return fail(SE2GPU_ERR_INVALID, "peer exchange needs 2..%d ranks matching se2gpu_ba_set_shard", MAX_PEERS);
+    if (!h->peer_flag) return fail(SE2GPU_ERR_INVALID, "call se2gpu_ba_peer_export first");
+    SE2_CUDA(cudaSetDevice(h->device));
+    const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == h->rank) continue;
+        void *pr = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&pr, hs[2 * r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pf, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            const cudaError_t e = cudaGetLastError();
+            if (pr) cudaIpcCloseMemHandle(pr);
+            return fail(SE2GPU_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        h->peer_red[r] = static_cast<const double*>(pr); h->peer_flags[r] = static_cast<const long long*>(pf);
+        for (void*& slot : h->peer_opened) if (!slot) { slot = pr; break; }
+        for (void*& slot : h->peer_opened) if (!slot) { slot = pf; break; }
+    }
+    SE2_CUDA(cudaFuncSetAttribute(ba_chol_solve_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N)));
+    h->peer_on = true;
+    return SE2GPU_OK;
 }
 
 int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream) {
@@ -1865,6 +1989,17 @@ int launch_solve(se2gpu_ba* h) {
     h->prof.begin(3, s);
     if (d.nblk > 0) SE2_LAUNCH(ba_schur, d.nblk, SCHUR_THREADS, 0, s, d);
     h->prof.end(s);
+    if (h->world > 1 && h->peer_on && d.n <= SMEM_CHOL_MAX_N) {
+        // fused exchange: publish this rank's partial system, the solve kernel sums all ranks' buffers over NVLink
+        PeerArgs pa{};
+        for (int r = 0; r < h->world; ++r) { pa.red[r] = (r == h->rank) ? h->red : h->peer_red[r]; pa.flag[r] = (r == h->rank) ? h->peer_flag : h->peer_flags[r]; }
+        pa.bs_sum = h->bs_sum; pa.epoch = ++h->peer_epoch; pa.world = h->world; pa.rank = h->rank;
+        h->prof.begin(4, s);
+        SE2_LAUNCH(ba_peer_signal, 1, 1, 0, s, h->peer_flag, pa.epoch);
+        SE2_LAUNCH(ba_chol_solve_peer, 1, CHOL_THREADS, ldlt_smem_bytes(d.n), s, d, pa);
+        h->prof.end(s);
+        return SE2GPU_OK;
+    }
     int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
     if (rc != SE2GPU_OK) return rc;
     h->prof.begin(4, s);

@@ -31,12 +31,22 @@ def main():
             cache[(ptr, count)] = torch.as_tensor(a, device=dev)
         dist.all_reduce(cache[(ptr, count)], op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX)
 
+    def all_gather_bytes(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
     ok = True
-    for cfg in ("C3", "C4"):
+    for cfg, fused in (("C3", False), ("C4", False), ("C3", True), ("C4", True)):
         prob = synth.ba_config(cfg)
         ba = LocalBA.from_problem(prob, device=local, rank=rank, world=world, allreduce=allreduce,
                                   stream=torch.cuda.current_stream().cuda_stream)
+        if fused:   # reduced system summed inside the solve kernel over NVLink peer mappings instead of an NCCL all-reduce
+            ba.enable_peer_exchange(all_gather_bytes)
+        import time
+        torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
         n, st, tp, tl = ba.optimize(10, trace=True)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
         # every rank holds all poses and its own landmarks; gather the landmark estimates
         _, pts = ba.get()
         t = torch.from_numpy(pts).to(dev)
@@ -51,7 +61,7 @@ def main():
             active = np.zeros(prob.L, bool); active[prob.edge_point] = True
             good = (n == n_o and np.array_equal(st["trials"], st_o["trials"]) and np.allclose(st["lambda"], st_o["lambda"], rtol=1e-6)
                     and np.abs(tp[-1] - po).max() < 1e-8 and np.abs(t.cpu().numpy()[active] - lo[active]).max() < 1e-7)
-            print(f"{cfg}: world={world} iters {n}/{n_o} pose err {np.abs(tp[-1] - po).max():.2e} "
+            print(f"{cfg} ({'fused peer exchange' if fused else 'NCCL all-reduce'}, {dt * 1e3:.2f} ms): world={world} iters {n}/{n_o} pose err {np.abs(tp[-1] - po).max():.2e} "
                   f"landmark err {np.abs(t.cpu().numpy()[active] - lo[active]).max():.2e} -> {'OK' if good else 'MISMATCH'}")
             ok &= bool(good)
     flag = torch.tensor([1 if ok else 0], device=dev)
