@@ -39,6 +39,7 @@ __device__ const signed char d_pattern[1024] = {
 #include "orb_pattern_31.inc"
 };
 __constant__ int c_umax[16];
+__constant__ int c_vmax[16];   // c_vmax[|u|] = largest |v| of the patch disc in column u (the disc is stored row-wise as umax[|v|])
 __constant__ float c_gauss[7];
 
 struct LevelGeo {
@@ -603,8 +604,8 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 // one warp per output keypoint slot: orientation on the plain level, descriptor on the blurred level
 __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
                                                            int* __restrict__ counts) {
-    __shared__ signed char pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) pat[i] = d_pattern[i];
+    __shared__ float4 patf[256];     // the 256 point pairs of the rBRIEF pattern as floats (x0, y0, x1, y1); test 8*lane+k at [k][lane]
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) patf[(i & 7) * 32 + (i >> 3)] = make_float4((float)d_pattern[4 * i], (float)d_pattern[4 * i + 1], (float)d_pattern[4 * i + 2], (float)d_pattern[4 * i + 3]);
     __syncthreads();
     const int f = blockIdx.y + d.frame0;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -623,16 +624,18 @@ __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keyp
     const int x = rec & 0xFFF, y = (rec >> 12) & 0xFFF, score = rec >> 24;
     const size_t base = f * d.frame_plane_bytes + L.plane_off + (size_t)(EDGE + y) * L.pitch + (EDGE + x);
     const uint8_t* center = d.plain + base;
-    // IC_Angle: lanes own a column u = lane-15 of the 31x31 patch, rows +-v limited by umax
+    // IC_Angle: lane = column u = lane-15 of the 31x31 patch disc; it walks its rows in +-v pairs up to the column's
+    // half-height (integer moments: any summation order gives the reference's m10, m01)
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const int u = lane - HALF_PATCH, au = abs(u);
-        int colsum = 0;
-        for (int v = -HALF_PATCH; v <= HALF_PATCH; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = center[(ptrdiff_t)v * L.pitch + u];
-                colsum += val; m01 += v * val;
-            }
+        const int u = lane - HALF_PATCH, vm = c_vmax[abs(u)];
+        const uint8_t* col = center + u;
+        const int pitch = L.pitch;
+        int colsum = col[0];
+        for (int v = 1, off = pitch; v <= vm; ++v, off += pitch) {
+            const int p = col[off], m = col[-off];
+            colsum += p + m;
+            m01 += v * (p - m);
         }
         m10 = u * colsum;
     }
@@ -646,11 +649,11 @@ __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keyp
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
     const uint8_t* bc = d.blurred + base;
-    const signed char* pp = pat + lane * 32;
     unsigned val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1], x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
+        const float4 pt = patf[k * 32 + lane];
+        const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
@@ -954,6 +957,11 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     for (int l = 0; l < ORB_LANES && h->side; ++l)
         if (cudaStreamCreateWithFlags(&h->pipe[l], cudaStreamNonBlocking) != cudaSuccess) { h->pipe[l] = nullptr; cudaGetLastError(); break; }
     cudaMemcpyToSymbol(c_umax, umax, sizeof umax);
+    {
+        int vmax[16];
+        for (int u = 0; u <= HALF_PATCH; ++u) { vmax[u] = 0; for (int v = 0; v <= HALF_PATCH; ++v) if (umax[v] >= u) vmax[u] = v; }
+        cudaMemcpyToSymbol(c_vmax, vmax, sizeof vmax);
+    }
     cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
     d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
     d.levels = h->d_levels; d.cells = h->d_cells; d.tiles = h->d_tiles; d.itab = h->d_itab; d.stab = h->d_stab;
