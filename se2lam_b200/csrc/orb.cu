@@ -403,6 +403,155 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
     if (threadIdx.x == 0) { hdr->n_base = s_total; hdr->n_a = s_total; hdr->n_b = s_total; }
 }
 
+// FAST-9-16 arc score M = max over the 16 nine-pixel arcs of min(+-(v - ring)); corner at t <=> M > t,
+// cv::FAST's stored score == M-1 whatever t was. Returns 0 early when the pixel cannot be a corner at t:
+// a 9-arc always contains one pixel of each opposite pair (k, k+8), so all 4 tested pairs must have a
+// member beyond +-t of the centre.
+__device__ __forceinline__ int fast_arc_score_qr(const uint8_t* __restrict__ p, int pw, int t) {
+    const int v = p[0];
+    const int c0 = v - p[3 * pw], c8 = v - p[-3 * pw];
+    bool dk = (c0 > t) | (c8 > t), br = (c0 < -t) | (c8 < -t);
+    if (!(dk | br)) return 0;
+    const int c4 = v - p[3], c12 = v - p[-3];
+    dk &= (c4 > t) | (c12 > t); br &= (c4 < -t) | (c12 < -t);
+    if (!(dk | br)) return 0;
+    const int c2 = v - p[2 * pw + 2], c10 = v - p[-2 * pw - 2];
+    dk &= (c2 > t) | (c10 > t); br &= (c2 < -t) | (c10 < -t);
+    if (!(dk | br)) return 0;
+    const int c6 = v - p[-2 * pw + 2], c14 = v - p[2 * pw - 2];
+    dk &= (c6 > t) | (c14 > t); br &= (c6 < -t) | (c14 < -t);
+    if (!(dk | br)) return 0;
+    // both polarities at once: each ring difference d is packed as the s16x2 pair (d, -d); an arc's score for the
+    // "darker" / "brighter" test is the min over its 9 packed entries, computed with Blackwell's 3-input packed min
+    // (VIMNMX3.S16x2): m3_k = min(q_k,q_k+1,q_k+2), m9_k = min(m3_k, m3_k+3, m3_k+6); M = max over k and both halves.
+#define SE2_PK(dv) ((static_cast<unsigned>(dv) & 0xFFFFu) | (static_cast<unsigned>(-(dv)) << 16))
+    unsigned q[16];
+    q[0] = SE2_PK(c0);   q[1] = SE2_PK(v - p[3 * pw + 1]);    q[2] = SE2_PK(c2);    q[3] = SE2_PK(v - p[pw + 3]);
+    q[4] = SE2_PK(c4);   q[5] = SE2_PK(v - p[-pw + 3]);       q[6] = SE2_PK(c6);    q[7] = SE2_PK(v - p[-3 * pw + 1]);
+    q[8] = SE2_PK(c8);   q[9] = SE2_PK(v - p[-3 * pw - 1]);   q[10] = SE2_PK(c10);  q[11] = SE2_PK(v - p[-pw - 3]);
+    q[12] = SE2_PK(c12); q[13] = SE2_PK(v - p[pw - 3]);       q[14] = SE2_PK(c14);  q[15] = SE2_PK(v - p[3 * pw - 1]);
+#undef SE2_PK
+    unsigned m3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
+    unsigned best = 0x80008000u;   // (-32768, -32768)
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned a9 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const unsigned b9 = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a9, b9);
+    }
+    const int mdark = static_cast<short>(best & 0xFFFFu), mbright = static_cast<short>(best >> 16);
+    return max(mdark, mbright);
+}
+
+// Fallback for frames whose grid cells are too large for orb_fast_cells' shared-memory candidate list (e.g. 1080p with
+// 1000 features: 470 x 150 px cells): one thread per pixel, no compaction, 2.2 bytes of shared memory per pixel.
+// one CTA per (cell, frame): cv::FAST(cell, fastTh, NMS) and, if that yields <= 3 keypoints, cv::FAST(cell, 7, NMS)
+// (ORBextractor.cpp:616-623). The cell and its 3 px apron are staged once in shared memory with aligned 32-bit loads.
+// Work unit = one 32-pixel row segment per warp iteration (no per-pixel division); segments are numbered in raster
+// order, so one exclusive scan over the per-segment survivor counts gives every keypoint its raster-order slot.
+__global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_big(OrbDev d) {
+    extern __shared__ uint8_t smem[];
+    __shared__ int s_total;
+    const CellGeo c = d.cells[blockIdx.x];
+    const int f = blockIdx.y + d.frame0;
+    CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
+    const int cw = c.x1 - c.x0, ch = c.y1 - c.y0;
+    if (c.skipped || cw <= 0 || ch <= 0) {
+        if (threadIdx.x == 0) { hdr->n_base = 0; hdr->n_a = 0; hdr->n_b = 0; }
+        return;
+    }
+    const LevelGeo& L = d.levels[c.level];
+    const uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    // patch columns start at the 4-aligned bordered-plane column ax0 <= x0-3 (plane base and pitch are 32 B aligned)
+    const int bx0 = c.x0 - 3 + EDGE, by0 = c.y0 - 3 + EDGE;
+    const int ax0 = bx0 & ~3, shift = bx0 - ax0;
+    const int ph = ch + 6, sw = cw + 2, sh = ch + 2;
+    const int pww = (shift + cw + 6 + 3) >> 2, pw = pww * 4;
+    uint8_t* patch = smem;
+    uint8_t* score = smem + ((pw * ph + 15) & ~15);
+    const int nseg = (cw + 31) >> 5, nchunk = ch * nseg;
+    int* cnt = reinterpret_cast<int*>(score + ((sw * sh + 15) & ~15));   // [nchunk] survivors per segment -> exclusive offsets
+    for (int i = threadIdx.x; i < pww * ph; i += FAST_THREADS) {
+        const int py = i / pww, pxw = i - py * pww;
+        reinterpret_cast<uint32_t*>(patch)[i] = *reinterpret_cast<const uint32_t*>(plane + (size_t)(by0 + py) * L.pitch + ax0 + 4 * pxw);
+    }
+    constexpr int NW = FAST_THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint8_t* p0 = patch + 3 * pw + 3 + shift;
+    int thr = d.fast_th;
+    unsigned long long keepmask = 0;   // bit t: this lane's pixel of the warp's t-th segment survived NMS (first 64 segments)
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < (sw * sh + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+        __syncthreads();
+        for (int cidx = wid; cidx < nchunk; cidx += NW) {
+            const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
+            if (x < cw) {
+                const int m = fast_arc_score_qr(p0 + y * pw + x, pw, thr);
+                if (m > thr) score[(y + 1) * sw + (x + 1)] = (uint8_t)(m - 1);
+            }
+        }
+        __syncthreads();
+        keepmask = 0;
+        int t = 0;
+        for (int cidx = wid; cidx < nchunk; cidx += NW, ++t) {
+            const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
+            bool keep = false;
+            if (x < cw) {
+                const uint8_t* q = score + (y + 1) * sw + (x + 1);
+                const int s = q[0];
+                if (s) keep = s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) cnt[cidx] = __popc(bal);
+            if (keep && t < 64) keepmask |= 1ull << t;
+        }
+        __syncthreads();
+        if (wid == 0) {   // exclusive scan of the per-segment counts, in raster order
+            int run = 0;
+            for (int b0 = 0; b0 < nchunk; b0 += 32) {
+                const int v = (b0 + lane < nchunk) ? cnt[b0 + lane] : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                if (b0 + lane < nchunk) cnt[b0 + lane] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_total = run;
+        }
+        __syncthreads();
+        if (s_total > 3 || thr == 7) break;
+        thr = 7;                 // cellKeyPoints.size() <= 3: clear and retry with the fixed fallback threshold
+        __syncthreads();
+    }
+    uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
+    int t = 0;
+    for (int cidx = wid; cidx < nchunk; cidx += NW, ++t) {
+        const int y = cidx / nseg, x = (cidx - y * nseg) * 32 + lane;
+        bool keep;
+        int s = 0;
+        if (t < 64) {
+            keep = (keepmask >> t) & 1ull;
+        } else {
+            keep = false;
+            if (x < cw) {
+                const uint8_t* q = score + (y + 1) * sw + (x + 1);
+                s = q[0];
+                if (s) keep = s > q[-sw - 1] && s > q[-sw] && s > q[-sw + 1] && s > q[-1] && s > q[1] && s > q[sw - 1] && s > q[sw] && s > q[sw + 1];
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            s = score[(y + 1) * sw + (x + 1)];
+            const int pos = cnt[cidx] + __popc(bal & ((1u << lane) - 1));
+            if (pos < c.cand_cap) out[pos] = ((uint32_t)s << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
+            else *d.err = 1;
+        }
+    }
+    if (threadIdx.x == 0) { hdr->n_base = s_total; hdr->n_a = s_total; hdr->n_b = s_total; }
+}
+
 // one CTA per (level, frame): quota redistribution, retainBest per cell and per level. The cells' candidate lists
 // are staged in shared memory when the level's total fits (SEL_STAGE entries), otherwise they are processed in place
 // in global memory. retainBest is std::nth_element; one warp per cell runs the warp-cooperative introselect of
@@ -693,6 +842,7 @@ struct se2gpu_orb {
     std::vector<CellGeo> cells;
     std::vector<TileGeo> tiles;
     size_t fast_smem = 0, select_smem = 0;
+    bool fast_big = false;       // cells too large for the compacting FAST kernel: use orb_fast_cells_big
     // capacities (computed for max_w x max_h)
     size_t cap_plane = 0, cap_cand = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0, cap_lkp = 0;
     OrbDev d{};
@@ -716,13 +866,14 @@ namespace {
 // level geometry exactly as ORBextractor::ComputePyramid / ComputeKeyPoints derive it (float32 arithmetic)
 int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes, size_t* cand_total, size_t* n_cells,
                    size_t* n_tiles, size_t* tab_total, size_t* max_fast_smem, size_t* max_select_smem,
-                   std::vector<LevelGeo>* Lv, std::vector<CellGeo>* Cv, std::vector<TileGeo>* Tv) {
+                   std::vector<LevelGeo>* Lv, std::vector<CellGeo>* Cv, std::vector<TileGeo>* Tv, bool* fast_big_out = nullptr) {
     (void)dry;
     const int nl = h->nlevels;
     std::vector<LevelGeo> L(nl);
     std::vector<CellGeo> C;
     std::vector<TileGeo> T;
-    size_t poff = 0, coff = 0, toff = 0, fsm = 0, ssm = 0;
+    size_t poff = 0, coff = 0, toff = 0, fsm = 0, ssm = 0, fsm_big = 0;
+    bool fast_big = false;   // some cell is too large for orb_fast_cells' shared-memory candidate list -> orb_fast_cells_big
     int kp_off = 0;
     const float imageRatio = (float)w / (float)hgt;   // mvImagePyramid[0].cols/rows (:538)
     for (int l = 0; l < nl; ++l) {
@@ -773,8 +924,10 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 if (cw > 0 && chh > 0) {
                     const size_t pwb = (size_t)((cw + 6 + 3 + 3) / 4 + 1) * 4;   // worst-case alignment shift
                     const size_t nwords = (pwb * chh + 31) / 32;
-                    if (pwb * (chh + 6) > 65535) return fail(SE2GPU_ERR_CAPACITY, "a FAST cell of %dx%d px exceeds the 16-bit patch index", cw, chh);
+                    if (pwb * (chh + 6) > 65535) fast_big = true;    // 16-bit patch offsets in the candidate list
                     fsm = std::max(fsm, ((pwb * (chh + 6) + 15) & ~(size_t)15) + ((pwb * (chh + 2) + 15) & ~(size_t)15) + nwords * 8 + (size_t)cw * chh * 2 + 64);
+                    const size_t nchunk = (size_t)chh * ((cw + 31) / 32);
+                    fsm_big = std::max(fsm_big, ((pwb * (chh + 6) + 15) & ~(size_t)15) + (((size_t)(cw + 2) * (chh + 2) + 15) & ~(size_t)15) + nchunk * 4 + 64);
                 }
                 C.push_back(c);
             }
@@ -785,7 +938,9 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
         for (int ty = 0; ty < g.tiles_y; ++ty) for (int tx = 0; tx < g.tiles_x; ++tx) T.push_back(TileGeo{l, tx * BLUR_TW, ty * BLUR_TH});
     }
     *plane_bytes = poff; *cand_total = coff; *n_cells = C.size(); *n_tiles = T.size(); *tab_total = toff;
-    *max_fast_smem = fsm; *max_select_smem = ssm;
+    if (fsm > 227 * 1024) fast_big = true;
+    *max_fast_smem = fast_big ? fsm_big : fsm; *max_select_smem = ssm;
+    if (fast_big_out) *fast_big_out = fast_big;
     if (Lv) *Lv = L;
     if (Cv) *Cv = C;
     if (Tv) *Tv = T;
@@ -795,7 +950,8 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
 int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     if (w == h->cur_w && hgt == h->cur_h) return SE2GPU_OK;
     size_t pb, ct, nc, nt, tt, fsm, ssm;
-    int rc = build_geometry(h, w, hgt, false, &pb, &ct, &nc, &nt, &tt, &fsm, &ssm, &h->levels, &h->cells, &h->tiles);
+    bool big = false;
+    int rc = build_geometry(h, w, hgt, false, &pb, &ct, &nc, &nt, &tt, &fsm, &ssm, &h->levels, &h->cells, &h->tiles, &big);
     if (rc != SE2GPU_OK) return rc;
     if (pb > h->cap_plane || ct > h->cap_cand || nc > h->cap_cells || nt > h->cap_tiles || tt > h->cap_tab)
         return fail(SE2GPU_ERR_CAPACITY, "frame %dx%d exceeds the capacity this extractor was created with (%dx%d)", w, hgt, h->max_w, h->max_h);
@@ -834,7 +990,8 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     SE2_CUDA(cudaMemcpyAsync(h->d_itab, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d_stab, stab.data(), sizeof(short) * stab.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaStreamSynchronize(s));
-    h->fast_smem = fsm; h->select_smem = ssm;
+    h->fast_smem = fsm; h->select_smem = ssm; h->fast_big = big;
+    SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ssm, 1024)));
     OrbDev& d = h->d;
@@ -881,7 +1038,8 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         SE2_CUDA(cudaEventRecord(ev_blur, side));
     }
     pr.begin(1, s);
-    SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
+    if (h->fast_big) SE2_LAUNCH(orb_fast_cells_big, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
+    else SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     pr.end(s);
     pr.begin(2, s);
     SE2_LAUNCH(orb_select, dim3(h->nlevels, n), SEL_THREADS, h->select_smem, s, d);

@@ -149,3 +149,19 @@ def test_warp_nth_element_matches_std_nth_element():
         ids = pyoracle.nth_element(sc.astype(np.float32), nths[k])
         want = packed[offs[k]:offs[k + 1]][ids]
         assert np.array_equal(got[offs[k]:offs[k + 1]], want), f"list {k} (n={len(sc)}, nth={nths[k]})"
+
+
+def test_hd_frame_big_cells():
+    """1920x1080 with 1000 features has 470 x 150 px grid cells: too large for the compacting FAST kernel's shared-memory
+    candidate list, so the one-thread-per-pixel fallback kernel runs; results must still be bit-exact."""
+    img = synth.orb_frame(4242, 1920, 1080)
+    ext = ORBextractor(1000, 1.2, 8, fastTh=20, max_width=1920, max_height=1080, max_batch=1)
+    kg, dg = ext(img)
+    ko, do_ = pyoracle.OrbOracle(1000, 1.2, 8, 20).extract(img)
+    assert_same(kg, dg, ko, do_, "1080p")
+    # and a frame size in between, which still takes the compacting kernel
+    img2 = synth.orb_frame(4243, 1024, 768)
+    ext2 = ORBextractor(1500, 1.2, 8, fastTh=20, max_width=1024, max_height=768, max_batch=1)
+    kg2, dg2 = ext2(img2)
+    ko2, do2 = pyoracle.OrbOracle(1500, 1.2, 8, 20).extract(img2)
+    assert_same(kg2, dg2, ko2, do2, "1024x768")
