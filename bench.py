@@ -35,6 +35,7 @@ ORB_METRIC = "ORB keypoints/sec at 640x480 (8-level pyramid, 1000 kps/frame)"
 BA_METRIC = "LM iterations/sec on 50-KF/5k-point local BA"
 W, H, NFEAT, NLEV, BATCH = 640, 480, 1000, 8, 64
 BA_ITERS = 10
+ORB_WORKLOAD = "ORB extraction 640x480, 8-level pyramid (scale 1.2), FAST 20/7, 1000 kps/frame, batch of 64 frames per GPU"
 
 
 def ncu_traffic(kernel):
@@ -138,12 +139,12 @@ def run_reference(args):
         "impl": "reference", "metric": ORB_METRIC, "value": orb_v, "unit": "keypoints/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "ORB extraction 640x480, 8 levels, 1000 kps/frame", "sample": f"{nframes} frames per step"},
+        "config": {"workload": ORB_WORKLOAD, "sample": f"{nframes} frames per step (bounded sample of the same workload)"},
         "cpu_baseline": {"value": orb_v, "unit": "keypoints/s", "cores": cores, "kind": "port",
                          "sample": f"{nframes} frames/step x {args.steps} steps, one extractor per thread"},
         "e2e": {"value": orb_v, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "secondary": {"metric": BA_METRIC, "value": ba_v, "unit": "LM iterations/s", "higher_is_better": True, "dtype": "f64",
-                      "config": {"workload": f"local BA {prob.P} KF / {prob.L} landmarks / {prob.E} edges, Huber, {BA_ITERS} LM iterations"},
+                      "config": {"workload": f"local BA {prob.P} KF / {prob.L} landmarks / {prob.E} EdgeSE2XYZ + {prob.O} PreEdgeSE2, Huber, {BA_ITERS} LM iterations"},
                       "cpu_baseline": {"value": ba_v, "unit": "LM iterations/s", "cores": 1, "kind": "port",
                                        "sample": f"{args.steps} x optimize({BA_ITERS})"},
                       "e2e": {"value": ba_v, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
@@ -389,7 +390,7 @@ def run_ours(args):
             "metric": ORB_METRIC, "value": orb_value, "unit": "keypoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": orb_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "ORB extraction 640x480, 8-level pyramid (scale 1.2), FAST 20/7, 1000 kps/frame, batch of 64 frames per GPU",
+            "config": {"workload": ORB_WORKLOAD,
                        "frames_per_step_per_gpu": BATCH, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                        "l2": f"inputs rotate over {NROT} distinct batches = {NROT * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
                        "keypoints_per_frame": kp_per_frame},
