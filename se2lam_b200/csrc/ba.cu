@@ -498,7 +498,7 @@ struct GmemIO {   // same interface on byte offsets from a global base (reduced 
 
 // Block LDL^T of the reduced system (see the comment above ldlt_smem_bytes for the algorithm).
 //   ADDR = unsigned (shared window) or unsigned long long (global); aA, aY, aW, aC, aT are the byte addresses of
-//   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int), 2 x 3 back-substitution exchange slots}.
+//   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int), 2 x 3 back-substitution exchange slots, second tb[3]}.
 template <class IO, class ADDR>
 __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR aT, int n, const double* bs, double* dxp, LMState* st) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -529,7 +529,8 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
         if (lane == 0) {
             IO::st(W_(kb, 0), w00); IO::st(W_(kb, 1), w01); IO::st(W_(kb, 2), w02); IO::st(W_(kb, 3), w01); IO::st(W_(kb, 4), w11);
             IO::st(W_(kb, 5), w12); IO::st(W_(kb, 6), w02); IO::st(W_(kb, 7), w12); IO::st(W_(kb, 8), w22);
-            IO::st(aT, w00 * u0 + w01 * u1 + w02 * u2); IO::st(aT + 8, w01 * u0 + w11 * u1 + w12 * u2); IO::st(aT + 16, w02 * u0 + w12 * u1 + w22 * u2);
+            const ADDR tb = aT + (ADDR)((kb & 1) ? 80 : 0);      // W_k u_k, double-buffered by step parity (no barrier between read and next write)
+            IO::st(tb, w00 * u0 + w01 * u1 + w02 * u2); IO::st(tb + 8, w01 * u0 + w11 * u1 + w12 * u2); IO::st(tb + 16, w02 * u0 + w12 * u1 + w22 * u2);
             if (!pd) IO::sti(aOK, 0);
         }
     };
@@ -541,9 +542,9 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
         const int k = 3 * kb;
         if (kb < 8) STAMP(10 + 4 * kb);
         const double w00 = IO::ld(W_(kb, 0)), w01 = IO::ld(W_(kb, 1)), w02 = IO::ld(W_(kb, 2)), w11 = IO::ld(W_(kb, 4)), w12 = IO::ld(W_(kb, 5)), w22 = IO::ld(W_(kb, 8));
-        const double t0 = IO::ld(aT), t1 = IO::ld(aT + 8), t2 = IO::ld(aT + 16);
+        const ADDR tbk = aT + (ADDR)((kb & 1) ? 80 : 0);
+        const double t0 = IO::ld(tbk), t1 = IO::ld(tbk + 8), t2 = IO::ld(tbk + 16);
         const int m = IO::ldi(aC + (ADDR)((k + 2) * 4)) - (k + 2);            // trailing rows/cols k+3 .. k+2+m
-        __syncthreads();                            // everyone holds W_k / t_k in registers: warp 0 may overwrite the scratch
         if (kb < 8) STAMP(11 + 4 * kb);
         if (wid == 0) {
             // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
@@ -669,7 +670,7 @@ __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* col
 }
 
 // bytes of dynamic shared memory the SMEM variant needs for n unknowns
-__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16 + 96; }
+__host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n + n + 3 * (size_t)n + 2) * 8 + (size_t)n * 4 + 16 + 128; }
 
 // S (n*n doubles, rounded up to 16 B: the tail lands in y, which is initialised afterwards) and the envelope -> shared
 // memory. One elected thread issues a single bulk copy; everybody waits on the mbarrier phase `parity`.
@@ -1510,6 +1511,15 @@ struct PinnedArena {
         return true;
     }
     template <typename T>
+    T* alloc(size_t count) {       // page-locked array built in place (nullptr when the arena is exhausted / unavailable)
+        const size_t bytes = (count * sizeof(T) + 63) & ~(size_t)63;
+        if (!base || used + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return p;
+    }
+    bool owns(const void* p) const { return base && p >= (const void*)base && p < (const void*)(base + cap); }
+    template <typename T>
     int up(T* dst, const T* src, size_t count, cudaStream_t s) {
         if (!count) return SE2GPU_OK;
         const size_t bytes = count * sizeof(T);
@@ -1522,6 +1532,7 @@ struct PinnedArena {
 
 struct se2gpu_ba {
     PinnedArena* arena = nullptr;   // page-locked staging of set_problem's uploads
+    PinnedArena* arena2 = nullptr;  // page-locked arrays that set_problem builds in place (per-edge and per-pair lists)
     int device = 0;
     int maxP = 0, maxL = 0, maxE = 0, maxO = 0, maxN = 0;
     size_t cap_pairs = 0, cap_blk = 0;
@@ -1671,6 +1682,7 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (h->bs_sum) cudaFree(h->bs_sum);
     if (h->st_host) cudaFreeHost(h->st_host);
     delete h->arena;
+    delete h->arena2;
     delete h;
 }
 
@@ -1758,8 +1770,17 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     std::vector<int> perm(El), cursor(lm_ptr.begin(), lm_ptr.end() - 1);
     for (int e = 0; e < E; ++e) if (edge_point[e] % world == rank) perm[cursor[edge_point[e]]++] = e;
     const int Ol = (rank == 0) ? O : 0;
-    std::vector<int> e_pose(El), e_hidx(El);
-    std::vector<double> e_u(El), e_v(El), w00(El), w01(El), w11(El);
+    // the per-edge and per-pair arrays are built directly in page-locked memory (no staging copy before the upload)
+    size_t pair_bound = 0;
+    for (int j = 0; j < L; ++j) { const size_t k = (size_t)(lm_ptr[j + 1] - lm_ptr[j]); pair_bound += k * (k + 1) / 2; }
+    if (!h->arena2) h->arena2 = new PinnedArena;
+    h->arena2->reserve((size_t)El * 48 + pair_bound * 8 + 64 * 16);
+    std::vector<int> fb_i[4];
+    std::vector<double> fb_d[5];
+    auto ints = [&](size_t cnt, std::vector<int>& fb) { int* q = h->arena2->alloc<int>(cnt); if (!q) { fb.resize(cnt); q = fb.data(); } return q; };
+    auto dbls = [&](size_t cnt, std::vector<double>& fb) { double* q = h->arena2->alloc<double>(cnt); if (!q) { fb.resize(cnt); q = fb.data(); } return q; };
+    int *e_pose = ints(El, fb_i[0]), *e_hidx = ints(El, fb_i[1]);
+    double *e_u = dbls(El, fb_d[0]), *e_v = dbls(El, fb_d[1]), *w00 = dbls(El, fb_d[2]), *w01 = dbls(El, fb_d[3]), *w11 = dbls(El, fb_d[4]);
     for (int k = 0; k < El; ++k) {
         const int e = perm[k];
         e_pose[k] = edge_pose[e]; e_hidx[k] = hidx[edge_pose[e]];
@@ -1792,7 +1813,8 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     }
     std::stable_sort(odob.begin(), odob.end(), [](const OdoB& x, const OdoB& y) { return x.key < y.key; });
     std::vector<long long> keys;
-    std::vector<int> pe1, pe2, blk_pair_ptr;
+    int *pe1 = nullptr, *pe2 = nullptr;
+    std::vector<int> blk_pair_ptr;
     size_t npairs = 0;
     if ((size_t)nf * nf <= ((size_t)1 << 22)) {
         std::vector<int> cnt((size_t)nf * nf, 0);
@@ -1816,7 +1838,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
             run += c;
         }
         blk_pair_ptr.push_back((int)run);
-        pe1.resize(npairs); pe2.resize(npairs);
+        pe1 = ints(npairs, fb_i[2]); pe2 = ints(npairs, fb_i[3]);
         for (int j = 0; j < L; ++j)
             for (int k1 = lm_ptr[j]; k1 < lm_ptr[j + 1]; ++k1) {
                 const int a = e_hidx[k1];
@@ -1847,7 +1869,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
         for (auto& p : odob) keys.push_back(p.key);
         std::sort(keys.begin(), keys.end());
         keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-        pe1.resize(npairs); pe2.resize(npairs);
+        pe1 = ints(npairs, fb_i[2]); pe2 = ints(npairs, fb_i[3]);
         blk_pair_ptr.assign(keys.size() + 1, 0);
         size_t ip = 0;
         for (size_t b = 0; b < keys.size(); ++b) {
@@ -1902,25 +1924,27 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     if (!h->arena) h->arena = new PinnedArena;
     {
         size_t bytes = sizeof(double) * (3 * (size_t)P + 3 * (size_t)L) + 64 * 40;
-        bytes += sizeof(int) * (e_pose.size() + e_hidx.size() + lm_ptr.size() + hidx.size() + oi.size() + oj.size() + pose_ptr.size() + pose_edges.size() +
-                                pose_odo_ptr.size() + pose_odo.size() + blk_a.size() + blk_b.size() + blk_pair_ptr.size() + pe1.size() + pe2.size() +
+        bytes += sizeof(int) * (lm_ptr.size() + hidx.size() + oi.size() + oj.size() + pose_ptr.size() + pose_edges.size() +
+                                pose_odo_ptr.size() + pose_odo.size() + blk_a.size() + blk_b.size() + blk_pair_ptr.size() +
                                 blk_odo_ptr.size() + blk_odo.size() + colmax.size() + blk_order.size());
-        bytes += sizeof(double) * (e_u.size() * 5 + om.size() + ow.size());
+        bytes += sizeof(double) * (om.size() + ow.size());
+        if (!fb_i[0].empty()) bytes += (size_t)El * 48 + npairs * 8;   // arena2 unavailable: those arrays are staged too
         h->arena->reserve(bytes);   // on failure the uploads fall back to pageable copies
     }
     PinnedArena& ar = *h->arena;
-#define UPP(dst, ptr, count) do { int _r = ar.up(dst, ptr, (size_t)(count), s); if (_r != SE2GPU_OK) return _r; } while (0)
+    // arrays that already live in page-locked memory are uploaded in place, everything else is staged through `ar`
+#define UPP(dst, ptr, count) do { int _r = h->arena2->owns(ptr) ? (((size_t)(count)) ? (cudaMemcpyAsync(dst, ptr, sizeof(*(ptr)) * (size_t)(count), cudaMemcpyHostToDevice, s) == cudaSuccess ? SE2GPU_OK : fail(SE2GPU_ERR_CUDA, "upload failed")) : SE2GPU_OK) : ar.up(dst, ptr, (size_t)(count), s); if (_r != SE2GPU_OK) return _r; } while (0)
 #define UP(dst, src) UPP(dst, (src).data(), (src).size())
     UPP(h->d.xp[0], poses, 3 * (size_t)P); UPP(h->d.xl[0], points, 3 * (size_t)L);
     SE2_CUDA(cudaMemcpyAsync(h->d.xp[1], h->d.xp[0], sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d.xl[1], h->d.xl[0], sizeof(double) * 3 * L, cudaMemcpyDeviceToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->xp0, h->d.xp[0], sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->xl0, h->d.xl[0], sizeof(double) * 3 * L, cudaMemcpyDeviceToDevice, s));
-    UP(h->e_pose, e_pose); UP(h->e_hidx, e_hidx); UP(h->lm_ptr, lm_ptr); UP(h->hidx, hidx);
-    UP(h->e_u, e_u); UP(h->e_v, e_v); UP(h->e_w00, w00); UP(h->e_w01, w01); UP(h->e_w11, w11);
+    UPP(h->e_pose, e_pose, El); UPP(h->e_hidx, e_hidx, El); UP(h->lm_ptr, lm_ptr); UP(h->hidx, hidx);
+    UPP(h->e_u, e_u, El); UPP(h->e_v, e_v, El); UPP(h->e_w00, w00, El); UPP(h->e_w01, w01, El); UPP(h->e_w11, w11, El);
     UP(h->o_i, oi); UP(h->o_j, oj); UP(h->o_m, om); UP(h->o_w, ow);
     UP(h->pose_ptr, pose_ptr); UP(h->pose_edges, pose_edges); UP(h->pose_odo_ptr, pose_odo_ptr); UP(h->pose_odo, pose_odo);
-    UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UP(h->pair_e1, pe1); UP(h->pair_e2, pe2);
+    UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UPP(h->pair_e1, pe1, npairs); UPP(h->pair_e2, pe2, npairs);
     UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax); UP(h->blk_order, blk_order);
 #undef UP
 #undef UPP
