@@ -572,9 +572,14 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
                 invert_and_publish(kb + 1, k + 3);
             }
             if (kb < 8) STAMP(12 + 4 * kb);
-        } else {
-            // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs)
-            for (int ii = 3 + (wid - 1); ii < m; ii += nw - 1) {
+        } else if (m > 63 || (wid & 3) != 0) {
+            // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs).
+            // Warps are dealt to the 4 SM sub-partitions by warp id mod 4, and each sub-partition has one FP64 issue port:
+            // for a narrow envelope (little trailing work) the warps that share the pivot warp's sub-partition sit the
+            // step out, so the pivot chain - the critical path - never waits for an issue slot.
+            const bool quiet = m <= 63;
+            const int rank = quiet ? wid - (wid >> 2) - 1 : wid - 1, nwk = quiet ? nw - ((nw + 3) >> 2) : nw - 1;
+            for (int ii = 3 + rank; ii < m; ii += nwk) {
                 const int i = k + 3 + ii;
                 const double a0 = IO::ld(A_(i, k)), a1 = IO::ld(A_(i, k + 1)), a2 = IO::ld(A_(i, k + 2));
                 for (int jj = lane; jj <= ii + 1; jj += 32) {
