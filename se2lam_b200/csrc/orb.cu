@@ -136,83 +136,106 @@ __global__ void __launch_bounds__(256) orb_pyr0(OrbDev d, LevelGeo L, const uint
 
 // level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass, cv::resize's
 // fixed-point arithmetic (11-bit coefficients, horizontal pass kept at full precision, vertical pass >>4, >>16, +2 >>2).
-// One thread = 4 adjacent output columns x RESIZE_ROWS consecutive rows: the column terms (xofs, alpha) are loaded
-// once, and the horizontal pass of a source row is reused by the next output row (consecutive output rows share a
-// source row 5 times out of 6 at scale 1.2). A warp covers one row segment, so the reuse test is warp-uniform.
-constexpr int RESIZE_ROWS = 8;
-__global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo S) {
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y0 = (blockIdx.y * 8 + threadIdx.y) * RESIZE_ROWS;
+// One CTA = a 128 x RESIZE_TR tile of the bordered output plane, three stages in shared memory:
+//   0  the source rows/columns the tile touches (a contiguous box, also across the reflected border) as 16 B vectors
+//   1  horizontal pass h[s][x] = src[s][sx]*a0 + src[s][sx+1]*a1 for every staged source row s, ONCE per (row, column)
+//      (consecutive output rows share source rows; cv::resize does the same with its row buffers)
+//   2  vertical pass from two h rows per output row, 4 pixels per thread, one 32-bit store
+// Column terms (xofs, ialpha) live in registers of the thread that owns the 4 columns, row terms in a small table.
+constexpr int RESIZE_TR = 32;
+struct ResizeRow { int s0, s1, b0, b1; };
+__global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    __shared__ ResizeRow rowinfo[RESIZE_TR];
+    __shared__ int s_lo[2], s_hi[2];     // [0] source columns, [1] source rows
+    int* hbuf = reinterpret_cast<int*>(rs_smem);                       // [max_rows][128]
+    uint8_t* raw = rs_smem + (size_t)max_rows * 128 * sizeof(int);     // [max_rows][raw_pitch]
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x4 = blockIdx.x * 128 + tx * 4, y0 = blockIdx.y * RESIZE_TR;
     const int f = blockIdx.z + d.frame0;
-    if (x4 >= L.pitch || y0 >= L.h + 2 * EDGE) return;
+    const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
     const int* xofs = d.itab + L.tab_off;
     const int* yofs = xofs + L.w;
     const short2* ialpha = reinterpret_cast<const short2*>(d.stab + 2 * (size_t)L.tab_off);
     const short2* ibeta = ialpha + L.w;
     int sx0[4], sx1[4], a0[4], a1[4];
     bool valid[4];
+    int cmin = 0x7fffffff, cmax = -1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int x = x4 + q;
-        valid[q] = x < L.w + 2 * EDGE;
+        valid[q] = x < W;
         const int dx = valid[q] ? reflect101(x - EDGE, L.w) : 0;
         sx0[q] = __ldg(xofs + dx);
         sx1[q] = min(sx0[q] + 1, S.w - 1);
         const short2 aa = __ldg(ialpha + dx);
         a0[q] = aa.x; a1[q] = aa.y;
+        if (valid[q]) { cmin = min(cmin, sx0[q]); cmax = max(cmax, sx1[q]); }
     }
-    int sy0[RESIZE_ROWS], sy1[RESIZE_ROWS], b0[RESIZE_ROWS], b1[RESIZE_ROWS];
+    if (ty == 0) {   // the tile's source column range (every ty row owns the same columns)
 #pragma unroll
-    for (int r = 0; r < RESIZE_ROWS; ++r) {
-        const int dy = reflect101(min(y0 + r, L.h + 2 * EDGE - 1) - EDGE, L.h);
-        const int sy = __ldg(yofs + dy);
-        sy0[r] = min(max(sy, 0), S.h - 1); sy1[r] = min(max(sy + 1, 0), S.h - 1);
-        const short2 bb = __ldg(ibeta + dy);
-        b0[r] = bb.x; b1[r] = bb.y;
+        for (int o = 16; o > 0; o >>= 1) { cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); }
+        if (tx == 0) { s_lo[0] = cmin; s_hi[0] = cmax; }
+    } else if (ty == 1) {   // row terms of the tile's RESIZE_TR output rows and their source row range
+        const int y = y0 + tx;
+        int rmin = 0x7fffffff, rmax = -1;
+        if (y < H) {
+            const int dy = reflect101(y - EDGE, L.h);
+            const int sy = __ldg(yofs + dy);
+            const short2 bb = __ldg(ibeta + dy);
+            ResizeRow r{min(max(sy, 0), S.h - 1), min(max(sy + 1, 0), S.h - 1), bb.x, bb.y};
+            rowinfo[tx] = r;
+            rmin = r.s0; rmax = r.s1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o)); rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o)); }
+        if (tx == 0) { s_lo[1] = rmin; s_hi[1] = rmax; }
     }
+    __syncthreads();
+    const int c_lo = s_lo[0] & ~15, nvec = s_hi[0] < 0 ? 0 : (s_hi[0] - c_lo) / 16 + 1;
+    const int r_lo = s_lo[1], nsr = s_hi[1] - r_lo + 1;
+    if (nsr > max_rows || nvec * 16 > raw_pitch) { if (tid == 0) *d.err = 3; return; }   // sized on the host from the scale factor
     const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
+    // stage 0
+    for (int i = tid; i < nsr * nvec; i += 256) {
+        const int r = i / nvec, v = i - r * nvec;
+        *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+    }
+    __syncthreads();
+    // stage 1
+    if (x4 < W) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { sx0[q] = valid[q] ? sx0[q] - c_lo : 0; sx1[q] = valid[q] ? sx1[q] - c_lo : 0; }
+        for (int r = ty; r < nsr; r += 8) {
+            const uint8_t* rp = raw + r * raw_pitch;
+            int4 hv;
+            hv.x = rp[sx0[0]] * a0[0] + rp[sx1[0]] * a1[0];
+            hv.y = rp[sx0[1]] * a0[1] + rp[sx1[1]] * a1[1];
+            hv.z = rp[sx0[2]] * a0[2] + rp[sx1[2]] * a1[2];
+            hv.w = rp[sx0[3]] * a0[3] + rp[sx1[3]] * a1[3];
+            *reinterpret_cast<int4*>(hbuf + r * 128 + 4 * tx) = hv;
+        }
+    }
+    __syncthreads();
+    // stage 2
+    if (x4 >= L.pitch) return;
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    int cs0 = -1, cs1 = -1;
-    int h0[4], h1[4];
 #pragma unroll
-    for (int r = 0; r < RESIZE_ROWS; ++r) {
-        const int y = y0 + r;
-        if (y >= L.h + 2 * EDGE) break;
-        int A[4], B[4];
-        if (sy0[r] == cs0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) A[q] = h0[q];
-        } else if (sy0[r] == cs1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) A[q] = h1[q];
-        } else {
-            const uint8_t* rp = src + (size_t)sy0[r] * S.pitch;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) A[q] = __ldg(rp + sx0[q]) * a0[q] + __ldg(rp + sx1[q]) * a1[q];
-        }
-        if (sy1[r] == cs1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) B[q] = h1[q];
-        } else if (sy1[r] == cs0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) B[q] = h0[q];
-        } else if (sy1[r] == sy0[r]) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) B[q] = A[q];
-        } else {
-            const uint8_t* rp = src + (size_t)sy1[r] * S.pitch;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) B[q] = __ldg(rp + sx0[q]) * a0[q] + __ldg(rp + sx1[q]) * a1[q];
-        }
+    for (int k = 0; k < RESIZE_TR / 8; ++k) {
+        const int r = ty + 8 * k, y = y0 + r;
+        if (y >= H) break;
         uint32_t word = 0;
+        if (x4 < W) {
+            const ResizeRow ri = rowinfo[r];
+            const int4 A = *reinterpret_cast<const int4*>(hbuf + (ri.s0 - r_lo) * 128 + 4 * tx);
+            const int4 B = *reinterpret_cast<const int4*>(hbuf + (ri.s1 - r_lo) * 128 + 4 * tx);
+            const int av[4] = {A.x, A.y, A.z, A.w}, bv[4] = {B.x, B.y, B.z, B.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int v = (((b0[r] * (A[q] >> 4)) >> 16) + ((b1[r] * (B[q] >> 4)) >> 16) + 2) >> 2;
-            const uint32_t o = valid[q] ? (uint32_t)min(max(v, 0), 255) : 0u;
-            word |= o << (8 * q);
-            h0[q] = A[q]; h1[q] = B[q];
+            for (int q = 0; q < 4; ++q) {
+                const int v = (((ri.b0 * (av[q] >> 4)) >> 16) + ((ri.b1 * (bv[q] >> 4)) >> 16) + 2) >> 2;
+                word |= (valid[q] ? (uint32_t)min(max(v, 0), 255) : 0u) << (8 * q);
+            }
         }
-        cs0 = sy0[r]; cs1 = sy1[r];
         *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
     }
 }
@@ -841,7 +864,8 @@ struct se2gpu_orb {
     std::vector<LevelGeo> levels;
     std::vector<CellGeo> cells;
     std::vector<TileGeo> tiles;
-    size_t fast_smem = 0, select_smem = 0;
+    size_t fast_smem = 0, select_smem = 0, resize_smem = 0;
+    int resize_rows = 0, resize_raw_pitch = 0;   // shared-memory box of orb_resize, sized from the scale factor
     bool fast_big = false;       // cells too large for the compacting FAST kernel: use orb_fast_cells_big
     // capacities (computed for max_w x max_h)
     size_t cap_plane = 0, cap_cand = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0, cap_lkp = 0;
@@ -991,6 +1015,16 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     SE2_CUDA(cudaMemcpyAsync(h->d_stab, stab.data(), sizeof(short) * stab.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaStreamSynchronize(s));
     h->fast_smem = fsm; h->select_smem = ssm; h->fast_big = big;
+    {   // consecutive pyramid levels differ by mvScaleFactor[1] up to rounding of the level sizes
+        double ratio = 1.0;
+        for (size_t l = 1; l < h->levels.size(); ++l)
+            ratio = std::max(ratio, std::max((double)h->levels[l - 1].w / h->levels[l].w, (double)h->levels[l - 1].h / h->levels[l].h));
+        h->resize_rows = (int)ceil(RESIZE_TR * ratio) + 4;
+        h->resize_raw_pitch = (((int)ceil(128 * ratio) + 4 + 15 + 15) / 16) * 16;
+        h->resize_smem = (size_t)h->resize_rows * (128 * sizeof(int) + h->resize_raw_pitch);
+        if (h->resize_smem > 200 * 1024) return fail(SE2GPU_ERR_CAPACITY, "scale factor %.3f needs %zu B of shared memory in orb_resize", ratio, h->resize_smem);
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+    }
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ssm, 1024)));
@@ -1023,8 +1057,8 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     }
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
-        dim3 grid((g.pitch / 4 + 31) / 32, (g.h + 2 * EDGE + 8 * RESIZE_ROWS - 1) / (8 * RESIZE_ROWS), n);
-        SE2_LAUNCH(orb_resize, grid, dim3(32, 8), 0, s, d, g, h->levels[l - 1]);
+        dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
+        SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
     }
     pr.end(s);
     // the blur only depends on the pyramid: fork it onto the side stream so that it overlaps the (latency-bound)
