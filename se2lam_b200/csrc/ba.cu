@@ -1547,7 +1547,7 @@ struct se2gpu_ba {
     // fused peer exchange (se2gpu_ba_peer_export / _import)
     long long* peer_flag = nullptr;            // this rank's epoch flag (own cudaMalloc: exported by IPC handle)
     double* bs_sum = nullptr;
-    void* peer_opened[8] = {};                 // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
+    void* peer_opened[16] = {};                 // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
     const double* peer_red[8] = {};
     const long long* peer_flags[8] = {};
     bool peer_on = false;
