@@ -1257,6 +1257,109 @@ __device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double
     }
 }
 
+// Concurrent variant of pk_phase_schur: all blocks a CTA owns are processed at once, each by its own group of warps
+// (plan_w0[i] = first warp, plan_nw[i] = number of warps of owned item i, proportional to the item's pair/edge count;
+// built once per launch). One block barrier for the whole phase instead of two per block, and no warp idles while a
+// 40-pair block is reduced. Summation order per block: lane-strided partials over the item's warps, warp xor-tree, the
+// item's warps in rank order - fixed, so runs stay bit-reproducible.
+__device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, const unsigned char* plan_w0, const unsigned char* plan_nw, double* shr /*[warps][21]*/) {
+    if (w.first < 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t O = d.O, n = d.n, nf = d.nf;
+    int it = -1, rk = 0, nwi = 1, w0 = 0;
+    for (int i = 0; i < w.n_own; ++i)
+        if (wid >= plan_w0[i] && wid < plan_w0[i] + plan_nw[i]) { it = i; w0 = plan_w0[i]; rk = wid - w0; nwi = plan_nw[i]; }
+    PKOwn o{};
+    bool diag = false;
+    if (it >= 0) {
+        o = w.own[it];
+        diag = o.a == o.b;
+        double acc[12], ph[9];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) acc[q] = 0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) ph[q] = 0;
+        const int* pairs = w.arena + o.p0;
+        for (int k = rk * 32 + lane; k < o.np; k += nwi * 32) {
+            const double* yr = d.Y + (size_t)pairs[2 * k] * EB;
+            const double* hr = d.Hpl + (size_t)pairs[2 * k + 1] * EB;
+            double y[9], h[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { y[q] = yr[q]; h[q] = hr[q]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
+        }
+        if (rk == 0)
+            for (int k = d.blk_odo_ptr[o.blk] + lane; k < d.blk_odo_ptr[o.blk + 1]; k += 32) {
+                const int code = d.blk_odo[k], oo = code >> 1;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[r * 3 + c] += (code & 1) ? d.oAij[(c * 3 + r) * O + oo] : d.oAij[(r * 3 + c) * O + oo];
+            }
+        if (diag) {
+            const int* edges = w.arena + o.e0;
+            for (int k = rk * 32 + lane; k < o.ne; k += nwi * 32) {
+                const double* yr = d.Y + (size_t)edges[k] * EB;
+                const double* rec = d.PH + (size_t)edges[k] * EB;
+                acc[9] -= yr[9]; acc[10] -= yr[10]; acc[11] -= yr[11];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) ph[q] += rec[q];
+            }
+            if (rk == 0)
+                for (int k = d.pose_odo_ptr[o.a] + lane; k < d.pose_odo_ptr[o.a + 1]; k += 32) {
+                    const int code = d.pose_odo[k], oo = code >> 1;
+                    const double* H = (code & 1) ? d.oAjj : d.oAii;
+                    const double* bb = (code & 1) ? d.obj : d.obi;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) ph[q] += H[q * O + oo];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) ph[6 + q] += bb[q * O + oo];
+                }
+        }
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+#pragma unroll
+            for (int s2 = 16; s2 > 0; s2 >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s2);
+        if (diag) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+#pragma unroll
+                for (int s2 = 16; s2 > 0; s2 >>= 1) ph[q] += __shfl_xor_sync(0xffffffffu, ph[q], s2);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 12; ++q) shr[wid * 21 + q] = acc[q];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) shr[wid * 21 + 12 + q] = ph[q];
+        }
+    }
+    __syncthreads();
+    if (it >= 0 && rk == 0 && lane < 12) {
+        const int q = lane;
+        double v = 0;
+        for (int r = 0; r < nwi; ++r) v += shr[(w0 + r) * 21 + q];
+        if (q < 9) {
+            const int r3 = q / 3, c3 = q % 3;
+            if (diag) {
+                const int u6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+                double hsum = 0;
+                for (int r = 0; r < nwi; ++r) hsum += shr[(w0 + r) * 21 + 12 + u6[r3][c3]];
+                if (c3 >= r3) d.Hpp[u6[r3][c3] * nf + o.a] = hsum;
+                v += hsum + (r3 == c3 ? lam : 0.0);
+            }
+            d.S[(3 * o.a + r3) * n + 3 * o.b + c3] = v;
+        } else if (diag) {
+            double bsum = 0;
+            for (int r = 0; r < nwi; ++r) bsum += shr[(w0 + r) * 21 + 12 + 6 + (q - 9)];
+            d.bp[3 * o.a + q - 9] = bsum;
+            d.bs[3 * o.a + q - 9] = bsum + v;
+        }
+    }
+}
+
 __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const size_t L = d.L, E = d.E;
@@ -1344,7 +1447,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     // ---- static work lists of this CTA -> shared memory (CTA 0 keeps its shared memory for the reduced solve)
     extern __shared__ double sm[];
     __shared__ PKOwn own[PK_MAXOWN];
-    __shared__ int s_nown;
+    __shared__ int s_nown, s_plan_ok;
+    __shared__ unsigned char plan_w0[PK_MAXOWN], plan_nw[PK_MAXOWN];   // warp groups of the concurrent Schur phase
     PKWork work;
     {
         const int G = gridDim.x;
@@ -1367,6 +1471,24 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                     off += 2 * np + ne; ++no;
                 }
             s_nown = no;
+            // concurrent Schur plan: possible when every owned block is cached; one warp per block, the spare warps go
+            // one by one to the block with the most work per warp
+            int total = 0;
+            if (work.first >= 0) for (int pos = work.first; pos < d.nblk; pos += work.stride) ++total;
+            const int nwarp = (int)(blockDim.x >> 5);
+            s_plan_ok = (no == total && no > 0 && no <= nwarp) ? 1 : 0;
+            if (s_plan_ok) {
+                int wt[PK_MAXOWN], nwv[PK_MAXOWN];
+                for (int i2 = 0; i2 < no; ++i2) { wt[i2] = own[i2].np + own[i2].ne + 8; nwv[i2] = 1; }
+                for (int spare = nwarp - no; spare > 0; --spare) {
+                    int best = 0;
+                    for (int i2 = 1; i2 < no; ++i2) if ((long long)wt[i2] * nwv[best] > (long long)wt[best] * nwv[i2]) best = i2;
+                    if (wt[best] <= 32 * nwv[best]) break;      // everybody already has a lane per work unit
+                    ++nwv[best];
+                }
+                int at = 0;
+                for (int i2 = 0; i2 < no; ++i2) { plan_w0[i2] = (unsigned char)at; plan_nw[i2] = (unsigned char)nwv[i2]; at += nwv[i2]; }
+            }
         }
         __syncthreads();
         work.n_own = s_nown;
@@ -1432,7 +1554,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             }
             PK_TICK(2);
             // ---- C: Schur complement gather
-            pk_phase_schur(d, lambda, work, shv);
+            if (s_plan_ok) pk_phase_schur_par(d, lambda, work, plan_w0, plan_nw, shv);
+            else pk_phase_schur(d, lambda, work, shv);
             PK_WORK(3);
             grid.sync();
             PK_TICK(3);

@@ -24,8 +24,8 @@ dt = (time.perf_counter() - t0) / R
 print(json.dumps({"chunks": os.environ.get("SE2GPU_ORB_CHUNKS"), "pinned_out": pinned, "ms": round(dt * 1e3, 4), "kps": int(counts.sum())}))
 '''
 
-for lanes in ("2", "3", "4"):
-    for c, f in (("3", "50"), ("4", "50"), ("4", "100"), ("6", "50"), ("6", "100"), ("8", "50"), ("8", "100"), ("12", "100"), ("16", "100")):
-        env = dict(os.environ, SE2GPU_ORB_CHUNKS=c, SE2GPU_ORB_FIRST=f, SE2GPU_ORB_LANES=lanes, PINNED_OUT="1")
-        r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
-        print("lanes", lanes, "first", f, r.stdout.strip() or r.stderr[-400:], flush=True)
+for lanes, c, f in (("4", "4", "50"), ("4", "3", "50"), ("4", "3", "100"), ("4", "4", "100"), ("4", "5", "50"), ("4", "5", "100"), ("4", "6", "50"), ("4", "6", "100"),
+                    ("3", "3", "50"), ("3", "3", "100"), ("2", "2", "50"), ("4", "4", "35"), ("4", "5", "35")):
+    env = dict(os.environ, SE2GPU_ORB_CHUNKS=c, SE2GPU_ORB_FIRST=f, SE2GPU_ORB_LANES=lanes, PINNED_OUT="1")
+    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    print("lanes", lanes, "first", f, r.stdout.strip() or r.stderr[-400:], flush=True)
