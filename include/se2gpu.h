@@ -98,6 +98,16 @@ int se2gpu_orb_get_level(se2gpu_orb* h, int frame, int level, int blurred, uint8
 int se2gpu_orb_profile(se2gpu_orb* h, int enable);
 int se2gpu_orb_profile_read(se2gpu_orb* h, double* ms, int* launches);
 
+/* Folds the lens undistortion that Frame::Frame applies right before the extractor (reference src/Frame.cpp:22:
+ * cv::undistort(im, img, Config::Kcam, Config::Dcam)) into the pyramid's level 0: after this call the frames handed to
+ * se2gpu_orb_extract / _extract_device are RAW frames and the keypoints/descriptors are those of the undistorted frame,
+ * bit-identical to undistort-then-extract. K: 3x3 row-major float32 camera matrix (Config::Kcam), dist: 0/4/5/8/12
+ * float32 coefficients (k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4]]], Config::Dcam). K == NULL switches it off. */
+int se2gpu_orb_set_undistort(se2gpu_orb* h, const float* K, const float* dist, int ndist);
+/* Test hook (host only, no GPU needed): the fixed-point map se2gpu_orb_set_undistort builds for a w x h frame;
+ * m1 [h*w*2] int16 integer source coordinates (x, y), m2 [h*w] uint16 fraction index (fy*32 + fx). */
+int se2gpu_orb_debug_undistort_map(const float* K, const float* dist, int ndist, int w, int h, int16_t* m1, uint16_t* m2);
+
 /* Test hook for the device selection primitive behind KeyPointsFilter::retainBest (ORBextractor.cpp:692, :708):
  * runs the warp-cooperative std::nth_element on `count` independent lists of packed records (score in bits 31..24)
  * stored back to back in HOST memory; list k is values[offsets[k] .. offsets[k+1]) and is permuted in place exactly

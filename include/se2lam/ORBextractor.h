@@ -74,6 +74,18 @@ public:
         for (int i = 0; i < count; ++i) std::memcpy(d.ptr<unsigned char>(i), &mDesc[(size_t)i * 32], 32);
     }
 
+    // Extension (not in the reference class): fold Frame::Frame's cv::undistort(im, img, Kcam, Dcam) (Frame.cpp:22) into
+    // the pyramid's level 0, so the frame stays on the device. K: Config::Kcam.ptr<float>() (3x3 row-major), dist:
+    // Config::Dcam.ptr<float>() with n = 4, 5, 8 or 12 coefficients. After this call operator() takes the RAW frame.
+    void SetUndistort(const float* K, const float* dist, int n)
+    {
+        for (int i = 0; i < 9; ++i) mUndK[i] = K[i];
+        mUndN = n;
+        for (int i = 0; i < n && i < 14; ++i) mUndD[i] = dist[i];
+        mUndOn = true;
+        if (mHandle) applyUndistort();
+    }
+
     int inline GetLevels(){
         return nlevels;}
 
@@ -91,6 +103,15 @@ protected:
             std::fprintf(stderr, "se2lam::ORBextractor (GPU): %s\n", se2gpu_last_error());
             std::abort();
         }
+        if (mUndOn) applyUndistort();
+    }
+
+    void applyUndistort()
+    {
+        if (se2gpu_orb_set_undistort(mHandle, mUndK, mUndN ? mUndD : 0, mUndN) != SE2GPU_OK) {
+            std::fprintf(stderr, "se2lam::ORBextractor (GPU): %s\n", se2gpu_last_error());
+            std::abort();
+        }
     }
 
     int nfeatures;
@@ -101,6 +122,9 @@ protected:
 
     se2gpu_orb* mHandle;
     int mMaxW, mMaxH;
+    bool mUndOn = false;
+    float mUndK[9], mUndD[14];
+    int mUndN = 0;
     std::vector<cv::KeyPoint> mKps;
     std::vector<unsigned char> mDesc;
 

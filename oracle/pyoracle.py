@@ -21,7 +21,7 @@ BA_STATS_DTYPE = np.dtype([("chi2_before", "f8"), ("chi2_after", "f8"), ("lambda
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("orb_oracle.cpp", "ba_oracle.cpp", "matcher_oracle.cpp")]
+    srcs = [os.path.join(HERE, f) for f in ("orb_oracle.cpp", "ba_oracle.cpp", "matcher_oracle.cpp", "undistort_oracle.cpp")]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -49,6 +49,8 @@ def lib():
         L.orb_oracle_retain_best.argtypes = [vp, i, i, vp]
         L.orb_oracle_nth_element.argtypes = [vp, i, i, vp]
         L.orb_oracle_tables.argtypes = [vp] * 6
+        L.undistort_oracle.argtypes = [vp, i, i, i, vp, vp, i, vp]
+        L.undistort_oracle_map.argtypes = [vp, vp, i, i, i, vp, vp]
         L.ba_oracle_create.restype = vp
         L.ba_oracle_create.argtypes = [i, i, i, i] + [vp] * 11 + [d, d, d, vp, d]
         L.ba_oracle_destroy.argtypes = [vp]
@@ -120,6 +122,28 @@ def nth_element(responses, nth):
     ids = np.zeros(len(r), np.int32)
     lib().orb_oracle_nth_element(_p(r), len(r), nth, _p(ids))
     return ids
+
+
+def undistort(img, K, dist):
+    """cv::undistort(img, K, dist) (reference src/Frame.cpp:22): K 3x3 float32, dist 4/5/8/12 float32 coefficients."""
+    img = np.ascontiguousarray(img, np.uint8)
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    dist = np.ascontiguousarray(dist, np.float32).ravel()
+    out = np.zeros_like(img)
+    rc = lib().undistort_oracle(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(K), _p(dist), len(dist), _p(out))
+    if rc != 0:
+        raise ValueError("singular camera matrix")
+    return out
+
+
+def undistort_map(K, dist, w, h):
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    dist = np.ascontiguousarray(dist, np.float32).ravel()
+    m1 = np.zeros((h, w, 2), np.int16); m2 = np.zeros((h, w), np.uint16)
+    rc = lib().undistort_oracle_map(_p(K), _p(dist), len(dist), w, h, _p(m1), _p(m2))
+    if rc != 0:
+        raise ValueError("singular camera matrix")
+    return m1, m2
 
 
 # ------------------------------------------------------------------------------------------ BA

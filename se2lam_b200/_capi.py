@@ -42,7 +42,7 @@ SYMBOLS = [
     "se2gpu_device_count", "se2gpu_last_error", "se2gpu_launch_count",
     "se2gpu_orb_create", "se2gpu_orb_destroy", "se2gpu_orb_extract", "se2gpu_orb_extract_device",
     "se2gpu_orb_level_dims", "se2gpu_orb_get_level", "se2gpu_orb_profile", "se2gpu_orb_profile_read",
-    "se2gpu_orb_debug_nth_element",
+    "se2gpu_orb_debug_nth_element", "se2gpu_orb_set_undistort", "se2gpu_orb_debug_undistort_map",
     "se2gpu_hamming_distance", "se2gpu_match_by_window", "se2gpu_match_by_projection", "se2gpu_search_by_bow",
     "se2gpu_ba_create", "se2gpu_ba_destroy", "se2gpu_ba_set_problem", "se2gpu_ba_optimize", "se2gpu_ba_get",
     "se2gpu_ba_set_shard", "se2gpu_ba_peer_export", "se2gpu_ba_peer_import", "se2gpu_ba_set_stream", "se2gpu_ba_debug_system", "se2gpu_ba_reset", "se2gpu_ba_profile",
@@ -78,6 +78,8 @@ def lib():
     L.se2gpu_orb_profile.argtypes = [vp, i]
     L.se2gpu_orb_profile_read.argtypes = [vp, vp, vp]
     L.se2gpu_orb_debug_nth_element.argtypes = [vp, vp, vp, i, i]
+    L.se2gpu_orb_set_undistort.argtypes = [vp, vp, vp, i]
+    L.se2gpu_orb_debug_undistort_map.argtypes = [vp, vp, i, i, i, vp, vp]
     L.se2gpu_ba_reset.argtypes = [vp]
     L.se2gpu_ba_peer_export.argtypes = [vp, vp]
     L.se2gpu_ba_peer_import.argtypes = [vp, vp, i]

@@ -134,6 +134,42 @@ __global__ void __launch_bounds__(256) orb_pyr0(OrbDev d, LevelGeo L, const uint
     }
 }
 
+// level 0 with the lens undistortion of Frame::Frame folded in (reference src/Frame.cpp:22: cv::undistort(im, img, Kcam, Dcam)
+// right before the extractor): every pixel of the bordered level-0 plane is
+// remap(INTER_LINEAR, BORDER_CONSTANT 0) of the raw frame through the fixed-point map of the (reflected) pixel - integer
+// source coordinates in m1, 5+5 fraction bits in m2, weights (32-a)(32-b)*32 ... (sum 2^15), (sum + 2^14) >> 15. The map
+// depends on the camera only and is built once per frame size on the host with OpenCV's double arithmetic
+// (build_undistort_map). One thread = 4 output pixels, one word store; the undistorted image is never materialised.
+__global__ void __launch_bounds__(128) orb_pyr0_undistort(OrbDev d, LevelGeo L, const uint8_t* __restrict__ imgs, int stride, size_t frame_stride,
+                                                          const short2* __restrict__ m1, const uint16_t* __restrict__ m2) {
+    const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4, y = blockIdx.y;
+    const int f = blockIdx.z + d.frame0;
+    if (x4 >= L.pitch) return;
+    const uint8_t* img = imgs + f * frame_stride;
+    const int dy = reflect101(y - EDGE, L.h);
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int x = x4 + q;
+        uint32_t o = 0;
+        if (x < L.w + 2 * EDGE) {
+            const int idx = dy * L.w + reflect101(x - EDGE, L.w);
+            const short2 s = __ldg(m1 + idx);
+            const int fr = __ldg(m2 + idx), a = fr & 31, b = fr >> 5;
+            const int sx = s.x, sy = s.y;
+            const bool x0 = (unsigned)sx < (unsigned)L.w, x1 = (unsigned)(sx + 1) < (unsigned)L.w;
+            const bool y0 = (unsigned)sy < (unsigned)L.h, y1 = (unsigned)(sy + 1) < (unsigned)L.h;
+            const uint8_t* p = img + (ptrdiff_t)sy * stride + sx;
+            const int t00 = (x0 && y0) ? p[0] : 0, t01 = (x1 && y0) ? p[1] : 0, t10 = (x0 && y1) ? p[stride] : 0, t11 = (x1 && y1) ? p[stride + 1] : 0;
+            const int val = t00 * ((32 - a) * (32 - b) * 32) + t01 * (a * (32 - b) * 32) + t10 * ((32 - a) * b * 32) + t11 * (a * b * 32);
+            o = (uint32_t)min(max((val + (1 << 14)) >> 15, 0), 255);
+        }
+        word |= o << (8 * q);
+    }
+    uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
+}
+
 // level l>0: resize(level l-1 -> level l, INTER_LINEAR) + copyMakeBorder(REFLECT_101) in one pass, cv::resize's
 // fixed-point arithmetic (11-bit coefficients, horizontal pass kept at full precision, vertical pass >>4, >>16, +2 >>2).
 // One CTA = a 128 x RESIZE_TR tile of the bordered output plane, three stages in shared memory:
@@ -867,6 +903,11 @@ struct se2gpu_orb {
     size_t fast_smem = 0, select_smem = 0, resize_smem = 0;
     int resize_rows = 0, resize_raw_pitch = 0;   // shared-memory box of orb_resize, sized from the scale factor
     bool fast_big = false;       // cells too large for the compacting FAST kernel: use orb_fast_cells_big
+    // optional lens undistortion folded into level 0 (se2gpu_orb_set_undistort)
+    bool und_on = false;
+    float und_K[9] = {}, und_D[14] = {};
+    int und_nd = 0, und_w = 0, und_h = 0;
+    short2* d_und_m1 = nullptr; uint16_t* d_und_m2 = nullptr; size_t und_cap = 0;
     // capacities (computed for max_w x max_h)
     size_t cap_plane = 0, cap_cand = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0, cap_lkp = 0;
     OrbDev d{};
@@ -1037,10 +1078,85 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     return SE2GPU_OK;
 }
 
+// cv::undistort's map for a w x h frame [upstream OpenCV imgproc/undistort]: stripes of max(1, 4096/w) rows, for the stripe at
+// row y0 the new camera matrix is A with cy - y0; ir = its LU inverse; rays accumulated column by column in double;
+// radial/tangential/thin-prism model; CV_16SC2 + CV_16UC1 fixed point with 5 fraction bits (cvRound(u*32)).
+int build_undistort_map(const float* K, const float* dist, int nd, int w, int hgt, std::vector<short2>& m1, std::vector<uint16_t>& m2) {
+    double A[9], D[14] = {0};
+    for (int i = 0; i < 9; ++i) A[i] = K[i];
+    for (int i = 0; i < nd; ++i) D[i] = dist[i];
+    m1.resize((size_t)w * hgt); m2.resize((size_t)w * hgt);
+    const int stripe = std::min(std::max(1, 4096 / std::max(w, 1)), hgt);
+    for (int y0 = 0; y0 < hgt; y0 += stripe) {
+        double M[9], inv[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int i = 0; i < 9; ++i) M[i] = A[i];
+        M[5] = A[5] - y0;
+        for (int c = 0; c < 3; ++c) {                 // LU with partial pivoting, identity carried as right-hand side
+            int piv = c;
+            for (int r = c + 1; r < 3; ++r) if (std::fabs(M[r * 3 + c]) > std::fabs(M[piv * 3 + c])) piv = r;
+            if (std::fabs(M[piv * 3 + c]) < 2.220446049250313e-14) return fail(SE2GPU_ERR_INVALID, "singular camera matrix");
+            if (piv != c) for (int q = 0; q < 3; ++q) { std::swap(M[c * 3 + q], M[piv * 3 + q]); std::swap(inv[c * 3 + q], inv[piv * 3 + q]); }
+            const double dneg = -1 / M[c * 3 + c];
+            for (int r = c + 1; r < 3; ++r) {
+                const double al = M[r * 3 + c] * dneg;
+                for (int q = c + 1; q < 3; ++q) M[r * 3 + q] += al * M[c * 3 + q];
+                for (int q = 0; q < 3; ++q) inv[r * 3 + q] += al * inv[c * 3 + q];
+            }
+        }
+        for (int r = 2; r >= 0; --r)
+            for (int q = 0; q < 3; ++q) {
+                double acc = inv[r * 3 + q];
+                for (int t = r + 1; t < 3; ++t) acc -= M[r * 3 + t] * inv[t * 3 + q];
+                inv[r * 3 + q] = acc / M[r * 3 + r];
+            }
+        const int rows = std::min(stripe, hgt - y0);
+        for (int i = 0; i < rows; ++i) {
+            double X = i * inv[1] + inv[2], Y = i * inv[4] + inv[5], Wc = i * inv[7] + inv[8];
+            short2* o1 = m1.data() + (size_t)(y0 + i) * w;
+            uint16_t* o2 = m2.data() + (size_t)(y0 + i) * w;
+            for (int jx = 0; jx < w; ++jx, X += inv[0], Y += inv[3], Wc += inv[6]) {
+                const double iw = 1. / Wc, x = X * iw, y = Y * iw;
+                const double x2 = x * x, y2 = y * y, r2 = x2 + y2, xy2 = 2 * x * y;
+                const double kr = (1 + ((D[4] * r2 + D[1]) * r2 + D[0]) * r2) / (1 + ((D[7] * r2 + D[6]) * r2 + D[5]) * r2);
+                const double xd = (x * kr + D[2] * xy2 + D[3] * (r2 + 2 * x2) + D[8] * r2 + D[9] * r2 * r2);
+                const double yd = (y * kr + D[2] * (r2 + 2 * y2) + D[3] * xy2 + D[10] * r2 + D[11] * r2 * r2);
+                const double su = (A[0] * xd + A[2]) * 32, sv = (A[4] * yd + A[5]) * 32;
+                const int iu = su >= 2147483647.0 ? 2147483647 : su <= -2147483648.0 ? (int)-2147483648LL : (int)lrint(su);
+                const int iv = sv >= 2147483647.0 ? 2147483647 : sv <= -2147483648.0 ? (int)-2147483648LL : (int)lrint(sv);
+                o1[jx] = make_short2((short)(iu >> 5), (short)(iv >> 5));
+                o2[jx] = (uint16_t)((iv & 31) * 32 + (iu & 31));
+            }
+        }
+    }
+    return SE2GPU_OK;
+}
+
+int ensure_undistort_map(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
+    if (h->und_w == w && h->und_h == hgt) return SE2GPU_OK;
+    std::vector<short2> m1; std::vector<uint16_t> m2;
+    int rc = build_undistort_map(h->und_K, h->und_D, h->und_nd, w, hgt, m1, m2);
+    if (rc != SE2GPU_OK) return rc;
+    const size_t px = (size_t)w * hgt;
+    if (px > h->und_cap) {
+        if (h->d_und_m1) cudaFree(h->d_und_m1);
+        if (h->d_und_m2) cudaFree(h->d_und_m2);
+        h->d_und_m1 = nullptr; h->d_und_m2 = nullptr; h->und_cap = 0;
+        SE2_CUDA(cudaMalloc((void**)&h->d_und_m1, px * sizeof(short2)));
+        SE2_CUDA(cudaMalloc((void**)&h->d_und_m2, px * sizeof(uint16_t)));
+        h->und_cap = px;
+    }
+    SE2_CUDA(cudaMemcpyAsync(h->d_und_m1, m1.data(), px * sizeof(short2), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaMemcpyAsync(h->d_und_m2, m2.data(), px * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    SE2_CUDA(cudaStreamSynchronize(s));      // the host vectors go out of scope
+    h->und_w = w; h->und_h = hgt;
+    return SE2GPU_OK;
+}
+
 int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int stride, size_t frame_stride,
                se2gpu_keypoint* d_kps, uint8_t* d_desc, int* d_counts, cudaStream_t s, int frame0 = 0, int lane = -1) {
     int rc = set_geometry(h, w, hgt, s);
     if (rc != SE2GPU_OK) return rc;
+    if (h->und_on && (rc = ensure_undistort_map(h, w, hgt, s)) != SE2GPU_OK) return rc;
     OrbDev d = h->d;             // by-value copy carrying this launch group's frame offset
     d.frame0 = frame0;
     // pipeline lanes get their concurrency from each other, not from a blur side stream
@@ -1050,10 +1166,15 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     pr.begin(0, s);
     {
         const LevelGeo& g = h->levels[0];
-        const int aligned = (((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_stride) & 15) == 0;
-        const int nvec = aligned ? g.w / 16 : 0;      // aligned 16-byte interior vectors per row
-        dim3 grid((nvec + 63) / 64 + 1, (g.h + 2 * EDGE + 4 * PYR0_ROWS - 1) / (4 * PYR0_ROWS), n);
-        SE2_LAUNCH(orb_pyr0, grid, dim3(64, 4), 0, s, d, g, d_imgs, stride, frame_stride, nvec);
+        if (h->und_on) {
+            dim3 grid((g.pitch / 4 + 127) / 128, g.h + 2 * EDGE, n);
+            SE2_LAUNCH(orb_pyr0_undistort, grid, 128, 0, s, d, g, d_imgs, stride, frame_stride, h->d_und_m1, h->d_und_m2);
+        } else {
+            const int aligned = (((uintptr_t)d_imgs | (uintptr_t)stride | (uintptr_t)frame_stride) & 15) == 0;
+            const int nvec = aligned ? g.w / 16 : 0;      // aligned 16-byte interior vectors per row
+            dim3 grid((nvec + 63) / 64 + 1, (g.h + 2 * EDGE + 4 * PYR0_ROWS - 1) / (4 * PYR0_ROWS), n);
+            SE2_LAUNCH(orb_pyr0, grid, dim3(64, 4), 0, s, d, g, d_imgs, stride, frame_stride, nvec);
+        }
     }
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
@@ -1167,6 +1288,8 @@ void se2gpu_orb_destroy(se2gpu_orb* h) {
     for (void* p : h->bufs) cudaFree(p);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
+    if (h->d_und_m1) cudaFree(h->d_und_m1);
+    if (h->d_und_m2) cudaFree(h->d_und_m2);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
     if (h->pin_counts) cudaFreeHost(h->pin_counts);
     if (h->pin_kps) cudaFreeHost(h->pin_kps);
@@ -1273,6 +1396,29 @@ int se2gpu_orb_debug_nth_element(uint32_t* values, const int* offsets, const int
     SE2_CUDA(cudaGetLastError());
     SE2_CUDA(cudaMemcpy(values, dv, total * 4, cudaMemcpyDeviceToHost));
     cudaFree(dv); cudaFree(dofs); cudaFree(dn);
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_set_undistort(se2gpu_orb* h, const float* K, const float* dist, int ndist) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (!K) { h->und_on = false; return SE2GPU_OK; }
+    if (ndist != 0 && ndist != 4 && ndist != 5 && ndist != 8 && ndist != 12 && ndist != 14) return fail(SE2GPU_ERR_INVALID, "distortion vector must have 0, 4, 5, 8, 12 or 14 coefficients");
+    if (ndist > 0 && !dist) return fail(SE2GPU_ERR_INVALID, "null distortion vector");
+    if (ndist == 14 && (dist[12] != 0.f || dist[13] != 0.f)) return fail(SE2GPU_ERR_INVALID, "tilted-sensor coefficients (tauX, tauY) are not supported");
+    memcpy(h->und_K, K, sizeof h->und_K);
+    memset(h->und_D, 0, sizeof h->und_D);
+    if (ndist > 0) memcpy(h->und_D, dist, sizeof(float) * ndist);
+    h->und_nd = ndist; h->und_w = h->und_h = 0; h->und_on = true;
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_debug_undistort_map(const float* K, const float* dist, int ndist, int w, int hgt, int16_t* m1, uint16_t* m2) {
+    if (!K || !m1 || !m2 || w <= 0 || hgt <= 0 || ndist < 0 || ndist > 14 || (ndist > 0 && !dist)) return fail(SE2GPU_ERR_INVALID, "bad argument");
+    std::vector<short2> a; std::vector<uint16_t> b;
+    int rc = build_undistort_map(K, dist, ndist, w, hgt, a, b);
+    if (rc != SE2GPU_OK) return rc;
+    memcpy(m1, a.data(), a.size() * sizeof(short2));
+    memcpy(m2, b.data(), b.size() * sizeof(uint16_t));
     return SE2GPU_OK;
 }
 

@@ -42,6 +42,16 @@ class ORBextractor:
         except Exception:      # interpreter shutdown: module globals may already be gone
             pass
 
+    def set_undistort(self, K=None, dist=None):
+        """Fold cv::undistort(im, img, K, dist) (reference src/Frame.cpp:22) into level 0: subsequent calls take RAW frames.
+        K 3x3 float32, dist 0/4/5/8/12 float32 coefficients; K=None switches it off."""
+        if K is None:
+            check(lib().se2gpu_orb_set_undistort(self.h, None, None, 0), "se2gpu_orb_set_undistort")
+            return
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        dist = np.zeros(0, np.float32) if dist is None else np.ascontiguousarray(dist, np.float32).ravel()
+        check(lib().se2gpu_orb_set_undistort(self.h, ptr(K), ptr(dist) if dist.size else None, int(dist.size)), "se2gpu_orb_set_undistort")
+
     def GetLevels(self):
         return self.nlevels
 

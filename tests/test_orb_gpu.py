@@ -165,3 +165,37 @@ def test_hd_frame_big_cells():
     kg2, dg2 = ext2(img2)
     ko2, do2 = pyoracle.OrbOracle(1500, 1.2, 8, 20).extract(img2)
     assert_same(kg2, dg2, ko2, do2, "1024x768")
+
+
+def test_undistort_folded_into_level0():
+    """se2gpu_orb_set_undistort: raw frame in, keypoints/descriptors of cv::undistort(frame) out (reference Frame.cpp:22-25),
+    checked against oracle undistort -> oracle extract, and the level-0 plane against copyMakeBorder(undistorted)."""
+    K = np.array([[520.9, 0, 325.1], [0, 521.0, 249.7], [0, 0, 1]], np.float32)
+    D = np.array([0.2312, -0.7849, -0.0033, -0.0001, 0.9172], np.float32)
+    ext = ORBextractor(1000, 1.2, 8, fastTh=20, max_width=640, max_height=480, max_batch=4)
+    orc = pyoracle.OrbOracle(1000, 1.2, 8, 20)
+    raw = synth.orb_frame(1000)
+    ext.set_undistort(K, D)
+    kg, dg = ext(raw)
+    und = pyoracle.undistort(raw, K, D)
+    ko, do_ = orc.extract(und)
+    assert_same(kg, dg, ko, do_, "undistort 640x480")
+    plane, w, h = ext.level(0, 0)
+    assert np.array_equal(plane[16:16 + h, 16:16 + w], und)
+    # batch through the pipelined host path, other coefficient counts and an odd frame size
+    batch = np.stack([synth.orb_frame(1000 + i) for i in range(4)])
+    kps, desc, counts = ext.extract_batch(batch)
+    for i in range(4):
+        ko, do_ = orc.extract(pyoracle.undistort(batch[i], K, D))
+        assert_same(kps[i, :counts[i]], desc[i, :counts[i]], ko, do_, f"undistort batch frame {i}")
+    K2 = np.array([[700.0, 0, 250.5], [0, 701.0, 188.5], [0, 0, 1]], np.float32)
+    D2 = np.array([0.05, 0.0, 0.0, 0.0, 0.0, 0.01, 0.0, 0.0], np.float32)
+    ext.set_undistort(K2, D2)
+    raw2 = synth.orb_frame(6, 501, 377)
+    kg, dg = ext(raw2)
+    ko, do_ = orc.extract(pyoracle.undistort(raw2, K2, D2))
+    assert_same(kg, dg, ko, do_, "undistort 501x377")
+    ext.set_undistort(None)                      # off again: plain extraction
+    kg, dg = ext(raw)
+    ko, do_ = orc.extract(raw)
+    assert_same(kg, dg, ko, do_, "undistort off")
