@@ -715,9 +715,9 @@ __global__ void __launch_bounds__(128) orb_debug_nth(uint32_t* v, const int* __r
 // BLUR_TH output rows; a thread owns 4 adjacent columns (one output word) and walks down its strip with the last 7
 // row-pass results in a register ring, so every source word is loaded once per row (3 coalesced words per thread:
 // its own and both neighbours, the latter L1 hits) and every output row costs one 32-bit store.
-__global__ void __launch_bounds__(256) orb_blur(OrbDev d) {
-    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (tile >= d.n_tiles) return;
+__global__ void __launch_bounds__(256) orb_blur(OrbDev d, int tile0, int tile_end) {
+    const int tile = tile0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= tile_end) return;
     const int lane = threadIdx.x & 31;
     const TileGeo t = d.tiles[tile];
     const int f = blockIdx.y + d.frame0;
@@ -917,7 +917,7 @@ struct se2gpu_orb {
     int last_n = 0;
     se2gpu::Profiler prof;
     cudaStream_t side = nullptr;          // blur runs here, concurrently with FAST + selection
-    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr, ev_l1 = nullptr;
     // host-buffer path: two pipeline lanes (stream + side stream + events) so that the H2D of chunk c+1 and the D2H of
     // chunk c-1 overlap the kernels of chunk c
     cudaStream_t pipe[ORB_LANES] = {};   // host-path pipeline lanes (chunk k runs on lane k % lanes)
@@ -1180,16 +1180,26 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         const LevelGeo& g = h->levels[l];
         dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
         SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
+        if (l == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     }
+    if (h->nlevels == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     pr.end(s);
-    // the blur only depends on the pyramid: fork it onto the side stream so that it overlaps the (latency-bound)
-    // selection kernel; join before the descriptors are sampled. With the profiler on everything stays on one
-    // stream so that the per-kernel event times are not polluted by the overlap.
+    // The blur of a level only needs that level's plane: on the side stream the blur of levels 0-1 (55 % of the pixels,
+    // no shared memory, so it co-resides with the resize CTAs) starts as soon as level 1 exists and hides behind the
+    // tail of the pyramid, a chain of small latency-bound launches; the remaining levels are blurred when the pyramid is
+    // complete, next to FAST and the selection. The main stream joins before the descriptors are sampled. With the
+    // profiler on everything stays on one stream so that the per-kernel event times are not polluted by the overlap.
     const bool overlap = !pr.on && side != nullptr;
+    auto launch_blur = [&](cudaStream_t st, int t0, int t1) {
+        if (t1 > t0) SE2_LAUNCH(orb_blur, dim3((t1 - t0 + 7) / 8, n), 256, 0, st, d, t0, t1);
+    };
     if (overlap) {
+        const int tilesA = h->nlevels > 2 ? h->levels[2].tile_base : d.n_tiles;
+        SE2_CUDA(cudaStreamWaitEvent(side, h->ev_l1, 0));
+        launch_blur(side, 0, tilesA);
         SE2_CUDA(cudaEventRecord(ev_pyr, s));
         SE2_CUDA(cudaStreamWaitEvent(side, ev_pyr, 0));
-        SE2_LAUNCH(orb_blur, dim3((d.n_tiles + 7) / 8, n), 256, 0, side, d);
+        launch_blur(side, tilesA, d.n_tiles);
         SE2_CUDA(cudaEventRecord(ev_blur, side));
     }
     pr.begin(1, s);
@@ -1203,7 +1213,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         SE2_CUDA(cudaStreamWaitEvent(s, ev_blur, 0));
     } else {
         pr.begin(3, s);
-        SE2_LAUNCH(orb_blur, dim3((d.n_tiles + 7) / 8, n), 256, 0, s, d);
+        launch_blur(s, 0, d.n_tiles);
         pr.end(s);
     }
     const int warps = 8;
@@ -1266,7 +1276,7 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     if (!ok) { fail(SE2GPU_ERR_CUDA, "device allocation failed (%s)", cudaGetErrorString(cudaGetLastError())); se2gpu_orb_destroy(h); return nullptr; }
     cudaMemset(d.err, 0, sizeof(int));
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
+        cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_l1, cudaEventDisableTiming) != cudaSuccess) { h->side = nullptr; cudaGetLastError(); }
     for (int l = 0; l < ORB_LANES && h->side; ++l)
         if (cudaStreamCreateWithFlags(&h->pipe[l], cudaStreamNonBlocking) != cudaSuccess) { h->pipe[l] = nullptr; cudaGetLastError(); break; }
     cudaMemcpyToSymbol(c_umax, umax, sizeof umax);
@@ -1291,6 +1301,7 @@ void se2gpu_orb_destroy(se2gpu_orb* h) {
     if (h->d_und_m1) cudaFree(h->d_und_m1);
     if (h->d_und_m2) cudaFree(h->d_und_m2);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    if (h->ev_l1) cudaEventDestroy(h->ev_l1);
     if (h->pin_counts) cudaFreeHost(h->pin_counts);
     if (h->pin_kps) cudaFreeHost(h->pin_kps);
     if (h->pin_desc) cudaFreeHost(h->pin_desc);
