@@ -6,15 +6,19 @@
 // forms, Schur complement onto the pose block, the reduced solve, landmark back-substitution, the
 // additive oplus update and g2o's Levenberg-Marquardt control (restated in SURVEY.md section 8a B6-B10).
 //
-// Design (DESIGN.md section "BA"): every accumulation is a GATHER with a fixed summation order, so a run
-// is bit-reproducible and free of atomics:
-//   ba_linearize   one thread per landmark walks its (contiguous, landmark-sorted) edges: e, J, Huber,
-//                  Hll/bl in registers, per-edge Hpl and pose-side terms to SoA arrays; extra blocks do
-//                  the PreEdgeSE2 odometry edges
-//   ba_pose_reduce one warp per free pose sums the pose-side terms of its edges (CSR) -> Hpp diag, bp
+// Design: every accumulation is a GATHER with a fixed summation order, so a run is
+// bit-reproducible and free of atomics. Two execution modes share the device functions:
+//   * ba_persistent (one GPU, reduced system <= 156 unknowns): the whole optimize() call is ONE cooperative kernel, the
+//     phases below separated by grid barriers, LM control evaluated redundantly by every CTA;
+//   * one kernel per phase (sharded runs, large windows), the reduction of the reduced system either through the
+//     all-reduce callback or fused into the solve kernel over NVLink peer mappings (ba_chol_solve_peer):
+//   ba_linearize   per landmark (contiguous, landmark-sorted edges): e, J, Huber, Hll/bl in registers, per-edge Hpl
+//                  and pose-side terms as 96-byte records; extra blocks do the PreEdgeSE2 odometry edges
+//   ba_pose_reduce one CTA per free pose sums the pose-side terms of its edges (CSR) -> Hpp diag, bp
 //   ba_lm_prep     per landmark (Hll+lambda I)^-1, Y_e = Hpl_e Hll^-1, g_e = Hpl_e Hll^-1 bl
-//   ba_schur       one warp per non-zero 3x3 block of S gathers its (edge,edge) pair list
-//   ba_chol_solve  one CTA: dense Cholesky of S (in shared memory when it fits) + triangular solves
+//   ba_schur       one CTA per non-zero 3x3 block of S gathers its (edge,edge) pair list
+//   ba_chol_solve  one CTA: block LDL^T (3x3 pivots) of S inside its envelope (shared memory when it fits, TMA-staged)
+//                  + back substitution
 //   ba_backsub     per landmark back-substitution, x_trial = x (+) dx, gain-ratio denominator partials
 //   ba_chi2        robust chi2 at x_trial (same code path as ba_linearize without Jacobians)
 //   ba_decide      g2o's rho test / lambda schedule on device; host reads one small struct per trial

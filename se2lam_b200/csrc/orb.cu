@@ -4,12 +4,15 @@
 // primitives underneath it, for batches of frames, bit-exactly (keypoint order included):
 //   orb_pyr0 / orb_resize   ComputePyramid :790-831 (copyMakeBorder REFLECT_101, resize INTER_LINEAR: 11-bit
 //                           fixed point, each level from the previous one)
+//   orb_pyr0_undistort      optional: cv::undistort of Frame.cpp:22 folded into level 0 (se2gpu_orb_set_undistort)
 //   orb_fast_cells          per-cell cv::FAST(…,fastTh)/FAST(…,7) :608-623 — one CTA per grid cell: the cell and
-//                           its 3 px apron are staged in shared memory once, a threshold-free arc score
-//                           M = max over the 16 nine-pixel arcs of min(+-diff) is computed per pixel
-//                           (corner at t <=> M > t, score = M-1), cell-local 3x3 strict NMS, ordered emission
+//                           its 3 px apron are staged in shared memory once; a branch-free necessary condition on
+//                           every pixel, survivors compacted, then the threshold-free arc score
+//                           M = max over the 16 nine-pixel arcs of min(+-diff) (corner at t <=> M > t, score = M-1)
+//                           at full lane occupancy, cell-local 3x3 strict NMS into a bitmap, raster-ordered emission
+//   orb_fast_cells_big      the same result for cells too large for the shared-memory candidate list
 //   orb_select              quota redistribution :631-679 + KeyPointsFilter::retainBest twice :687-710 — the
-//                           libstdc++ introselect permutation is reproduced exactly (introselect.h)
+//                           libstdc++ introselect permutation is reproduced exactly, warp-cooperatively (introselect.h)
 //   orb_blur                GaussianBlur 7x7 sigma 2 :769 (float32 separable, fused multiply-add, RNE to u8)
 //   orb_orient_describe     IC_Angle :130-157 + computeOrbDescriptor :160-200, one warp per keypoint; keypoint
 //                           records are written as 28-byte cv::KeyPoint and 32-byte descriptors
