@@ -251,7 +251,7 @@ def run_ours(args):
             "traffic": ncu_traffic(dom), "algorithmic_bytes_per_launch": alg[dom] * BATCH, "peak_source": peak_src, "kernel_ms": dom_ms,
             "kernel_share_of_step": single[dom][0] / sum(v[0] for v in single.values()),
             "per_kernel_ms": {g: v[0] / v[1] for g, v in single.items()},
-            "per_kernel_note": "second, event-instrumented pass (kernels serialised); the timed pass overlaps orb_blur with orb_fast_cells+orb_select",
+            "per_kernel_note": "second, event-instrumented pass (kernels serialised); the timed pass runs orb_blur on a side stream (levels 0-1 behind the pyramid tail, the rest next to orb_fast_cells+orb_select)",
             "whole_path_GBps": step_alg_bytes / (orb_ms / args.steps * 1e-3) / 1e9,
             # the path is instruction-issue bound: issue-slot utilisation and lane efficiency of the
             # dominant kernel from the committed ncu capture of this round
