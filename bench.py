@@ -29,7 +29,7 @@ _OUT = sys.stdout
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from se2lam_b200 import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 ORB_METRIC = "ORB keypoints/sec at 640x480 (8-level pyramid, 1000 kps/frame)"
 BA_METRIC = "LM iterations/sec on 50-KF/5k-point local BA"

@@ -26,7 +26,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from se2lam_b200 import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 cv2.setNumThreads(1)
 lib = C.CDLL(os.path.join(HERE, "liboracle.so"))

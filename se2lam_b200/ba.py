@@ -175,7 +175,7 @@ class SlamOptimizer:
         pt_ids = sorted(self._vxyz)
         pmap = {vid: k for k, vid in enumerate(pose_ids)}
         lmap = {vid: k for k, vid in enumerate(pt_ids)}
-        from .synth import BAProblem
+        from .problem import BAProblem
         cam = self._cam
         if cam is None:
             raise _capi.Se2GpuError("addCamPara was not called")

@@ -34,17 +34,40 @@ def is_stale() -> bool:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
+    """One object per translation unit (compiled concurrently, re-used while its source and the shared headers are
+    unchanged), then one link step. Objects live in se2lam_b200/lib/obj (git-ignored)."""
     if not force and not is_stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
     env = dict(os.environ)
     env.pop("CXX", None); env.pop("CC", None)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".inc", ".cuh"))] + \
+              [os.path.join(HERE, "..", "include", "se2gpu.h")]
+    hdr_time = max(os.path.getmtime(hh) for hh in headers if os.path.isfile(hh))
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
+            return obj, ""
+        cmd = [_nvcc()] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on " + src + ":\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max(len(SOURCES), 1)) as pool:
+        results = list(pool.map(compile_one, sources()))
     if verbose:
-        print(res.stderr)
+        for _, log in results:
+            print(log)
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC",
+            "-o", LIB_PATH] + [o for o, _ in results]
+    res = subprocess.run(link, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

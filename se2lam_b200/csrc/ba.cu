@@ -48,7 +48,7 @@ struct Cam {
 
 struct LMState {  // device-resident scalars of the LM loop (host mirrors it once per trial)
     double lambda, ni, chi_cur, chi_before, chi_trial, scale, rho, max_diag;
-    int cur, solve_ok, accepted, trials, terminate, retry, iter, pad;
+    int cur, solve_ok, accepted, trials, terminate, retry, iter, stop_all;   // stop_all: abort flag, OR-ed over the ranks of a sharded run
 };
 
 struct Dev {  // all device pointers of one context (passed by value to kernels)
@@ -348,6 +348,18 @@ __global__ void __launch_bounds__(256) ba_iter_begin(Dev d, int iter, int phase 
             s.trials = 0; s.accepted = 0; s.terminate = 0; s.retry = 0; s.iter = iter; s.rho = 0;
         }
     }
+}
+
+// sharded runs, iteration 0: out = max(out, max |diagonal| of the rank-summed pose blocks hpp [6][nf])
+__global__ void __launch_bounds__(256) ba_pose_diag_max(const double* hpp, int nf, double* out) {
+    __shared__ double sh[8];
+    double m = 0;
+    for (int a = threadIdx.x; a < nf; a += blockDim.x) m = fmax(m, fmax(fabs(hpp[a]), fmax(fabs(hpp[3 * (size_t)nf + a]), fabs(hpp[5 * (size_t)nf + a]))));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sh[w]); *out = fmax(*out, m); }
 }
 
 // per landmark: (Hll + lambda I)^-1 (symmetric, closed form), Y_e = Hpl_e Hll^-1, g_e = Hpl_e (Hll^-1 bl)
@@ -832,7 +844,7 @@ __global__ void __launch_bounds__(LM_THREADS) ba_backsub_update(Dev d) {
 
 // g2o's gain-ratio test and lambda schedule (OptimizationAlgorithmLevenberg::solve) for one trial.
 // phase 0 sums the local partials into scal[0..1]; phase 1 (or single GPU) consumes them.
-__global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase, se2gpu_ba_iter_stats* stats_dev) {
+__global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase, se2gpu_ba_iter_stats* stats_dev, int stop_local) {
     __shared__ double sh[32];
     if (phase == 0) {
         double chi = 0, sc = 0;
@@ -840,12 +852,14 @@ __global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase,
         for (int b = threadIdx.x; b < nb_scale; b += blockDim.x) sc += d.part_scale[b];
         chi = block_sum(chi, sh);
         sc = block_sum(sc, sh);
-        if (threadIdx.x == 0) { d.scal[0] = chi; d.scal[1] = sc; }
+        // scal[2]: this rank's view of the abort flag; summed with the other two scalars, so every rank acts on the same value
+        if (threadIdx.x == 0) { d.scal[0] = chi; d.scal[1] = sc; d.scal[2] = stop_local ? 1.0 : 0.0; }
     }
     if (phase == 1 || d.world == 1) {
         __syncthreads();
         if (threadIdx.x == 0) {
             LMState& s = *d.st;
+            s.stop_all = d.scal[2] > 0.0 ? 1 : 0;
             const double tempChi = s.solve_ok ? d.scal[0] : DBL_MAX;
             const double scale = (s.solve_ok ? d.scal[1] : 0.0) + 1e-3;
             const double rho = (s.chi_cur - tempChi) / scale;
@@ -859,7 +873,7 @@ __global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase,
                 s.lambda *= s.ni; s.ni *= 2;
             }
             s.trials += 1;
-            s.retry = (rho < 0 && s.trials < 10) ? 1 : 0;
+            s.retry = (rho < 0 && s.trials < 10 && !s.stop_all) ? 1 : 0;
             if (!s.retry) {
                 s.terminate = (s.trials == 10 || rho == 0) ? 1 : 0;
                 if (stats_dev) {
@@ -889,8 +903,10 @@ struct PKArgs {
     double* trace_p;          // [max_iters][3P] or null
     double* trace_l;          // [max_iters][3L] or null
     const volatile int* abort_host;   // mapped pinned word written by the host watcher
-    int* abort_dev;           // published copy (read by all CTAs after a grid barrier)
-    double* part_chi;         // [gridDim.x]
+    int* abort_dev;           // [2] published copies (slot 0: written in phase A, slot 1: in phase F; read by all CTAs after the
+                              // grid barrier that ends the phase - two slots so that a CTA running ahead into the next phase
+                              // never overwrites a word a slower CTA has yet to read)
+    double* part_chi;         // [2][gridDim.x]: row 0 = phase A (linearisation at x_cur), row 1 = phase F (chi2 at the trial point)
     double* part_scale;       // [gridDim.x]
     double* part_max;         // [gridDim.x]
     long long* phase_cycles;  // [8] SM cycles CTA 0 spent per phase incl. the barrier that ends it (profiling aid)
@@ -1518,11 +1534,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         // ---- A: linearise at x_cur (computeActiveErrors + buildSystem). For it > 0 the damping of the first trial is already
         // known, so the damping-dependent landmark terms are formed in the same pass (no phase B, one grid barrier less).
         pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh, it > 0 ? lambda : -1.0);
-        if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
+        if (blockIdx.x == 0 && threadIdx.x == 0) pa.abort_dev[0] = *pa.abort_host;
         PK_WORK(0);
         grid.sync();
         PK_TICK(0);
-        if (*pa.abort_dev) break;
+        if (pa.abort_dev[0]) break;
         if (it == 0) {
             // ---- B (first iteration only): pose-side gather and landmark diagonal maximum for lambda_0 = 1e-5 max|diag H|
             pk_phase_pose_reduce(d, work, shv);
@@ -1584,13 +1600,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             grid.sync();
             PK_TICK(5);
             // ---- F: robust chi2 at the trial point
-            pk_phase_linearize<false>(d, cam, cur ^ 1, pa.part_chi, sh);
-            if (blockIdx.x == 0 && threadIdx.x == 0) *pa.abort_dev = *pa.abort_host;
+            pk_phase_linearize<false>(d, cam, cur ^ 1, pa.part_chi + nparts, sh);
+            if (blockIdx.x == 0 && threadIdx.x == 0) pa.abort_dev[1] = *pa.abort_host;
             PK_WORK(7);
             grid.sync();
             PK_TICK(0);
             // ---- LM decision (identical in every CTA)
-            const double tempChi = solve_ok ? cta_sum_array(pa.part_chi, nparts, sh) : DBL_MAX;
+            const double tempChi = solve_ok ? cta_sum_array(pa.part_chi + nparts, nparts, sh) : DBL_MAX;
             const double scale = (solve_ok ? cta_sum_array(pa.part_scale, nparts, sh) : 0.0) + 1e-3;
             rho = (chi_cur - tempChi) / scale;
             if (rho > 0 && isfinite(tempChi)) {
@@ -1601,7 +1617,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 lambda *= ni; ni *= 2;
             }
             ++trials;
-            stop = (*pa.abort_dev != 0);
+            stop = (pa.abort_dev[1] != 0);
         } while (rho < 0 && trials < 10 && !stop);
         const int terminate = (trials == 10 || rho == 0) ? 1 : 0;
         if (blockIdx.x == 0 && threadIdx.x == 0 && pa.stats) {
@@ -1777,7 +1793,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
     A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
-    A(&h->pk_part_chi, 1024); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 1); A(&h->phase_cycles, 8); A(&h->cta_work, 1024 * 8);
+    A(&h->pk_part_chi, 2048); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 2); A(&h->phase_cycles, 8); A(&h->cta_work, 1024 * 8);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
         cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N));
@@ -2227,7 +2243,21 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
     }
     int done = 0;
     bool ok = true;
-    for (int it = 0; it < max_iters && !(stop_flag && *stop_flag) && ok; ++it) {
+    // Sharded runs: every rank must take the same abort decision, otherwise one leaves the loop while the others enter the
+    // next collective. The flag each rank sees is therefore summed over the ranks: once at entry, then as a third word of
+    // the per-trial [chi2, scale] all-reduce (LMState::stop_all).
+    bool stop_all = stop_flag && *stop_flag;
+    if (h->world > 1 && stop_flag) {
+        const double mine = stop_all ? 1.0 : 0.0;
+        double all = 0;
+        SE2_CUDA(cudaMemcpyAsync(d.scal + 2, &mine, sizeof(double), cudaMemcpyHostToDevice, s));
+        int rc0 = ar(h, d.scal + 2, 1, 0);
+        if (rc0 != SE2GPU_OK) return rc0;
+        SE2_CUDA(cudaMemcpyAsync(&all, d.scal + 2, sizeof(double), cudaMemcpyDeviceToHost, s));
+        SE2_CUDA(cudaStreamSynchronize(s));
+        stop_all = all > 0.0;
+    }
+    for (int it = 0; it < max_iters && !stop_all && ok; ++it) {
         int rc = launch_linearize(h);
         if (rc != SE2GPU_OK) return rc;
         h->prof.begin(6, s);
@@ -2238,19 +2268,12 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
             if ((rc = ar(h, d.scal, 1, 0)) != SE2GPU_OK) return rc;
             if (it == 0) {
                 if ((rc = ar(h, d.scal + 1, 1, 1)) != SE2GPU_OK) return rc;   // max over ranks of the landmark diagonal
-                // pose diagonal: sum the 6 x nf block array across ranks on a scratch copy, take its max on the host
-                std::vector<double> hpp(6 * (size_t)d.nf);
-                double* scratch = d.dxl;  // free at this point; 3L >= 6nf is not guaranteed -> use S as scratch instead
-                scratch = d.S;
+                // pose diagonal: sum the 6 x nf block array across ranks on a scratch copy (S is free here), fold its
+                // diagonal maximum into scal[1] on the device - no host round trip
+                double* scratch = d.S;
                 SE2_CUDA(cudaMemcpyAsync(scratch, d.Hpp, sizeof(double) * 6 * d.nf, cudaMemcpyDeviceToDevice, s));
                 if ((rc = ar(h, scratch, 6 * (size_t)d.nf, 0)) != SE2GPU_OK) return rc;
-                SE2_CUDA(cudaMemcpyAsync(hpp.data(), scratch, sizeof(double) * 6 * d.nf, cudaMemcpyDeviceToHost, s));
-                double lmmax = 0;
-                SE2_CUDA(cudaMemcpyAsync(&lmmax, d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-                SE2_CUDA(cudaStreamSynchronize(s));
-                double m = lmmax;
-                for (int a = 0; a < d.nf; ++a) m = std::max(m, std::max(std::fabs(hpp[a]), std::max(std::fabs(hpp[3 * (size_t)d.nf + a]), std::fabs(hpp[5 * (size_t)d.nf + a]))));
-                SE2_CUDA(cudaMemcpyAsync(d.scal + 1, &m, sizeof(double), cudaMemcpyHostToDevice, s));
+                SE2_LAUNCH(ba_pose_diag_max, 1, 256, 0, s, scratch, d.nf, d.scal + 1);
                 SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * 6 * d.nf, s));
             }
             SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 1);
@@ -2265,15 +2288,16 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
             if (d.nb_lm + d.nb_odo > 0) SE2_LAUNCH(ba_linearize<false>, d.nb_lm + d.nb_odo, LM_THREADS, 0, s, d, h->cam, 1);
             h->prof.end(s);
             h->prof.begin(6, s);
-            SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 0, h->stats_dev);
+            SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 0, h->stats_dev, (stop_flag && *stop_flag) ? 1 : 0);
             h->prof.end(s);
             if (h->world > 1) {
-                if ((rc = ar(h, d.scal, 2, 0)) != SE2GPU_OK) return rc;
-                SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 1, h->stats_dev);
+                if ((rc = ar(h, d.scal, 3, 0)) != SE2GPU_OK) return rc;
+                SE2_LAUNCH(ba_decide, 1, 256, 0, s, d, h->nb_scale, 1, h->stats_dev, 0);
             }
             SE2_CUDA(cudaMemcpyAsync(h->st_host, d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
             SE2_CUDA(cudaStreamSynchronize(s));
-            retry = h->st_host->retry && !(stop_flag && *stop_flag);
+            retry = h->st_host->retry != 0;          // already cleared on the device when any rank raised the abort flag
+            stop_all = h->st_host->stop_all != 0;
         }
         const LMState& st = *h->st_host;
         if (stats) {

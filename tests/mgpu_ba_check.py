@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import pyoracle  # noqa: E402
-from se2lam_b200 import synth  # noqa: E402
+from tools import synth  # noqa: E402
 from se2lam_b200.ba import LocalBA  # noqa: E402
 
 

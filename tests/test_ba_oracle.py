@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import ba_numpy, pyoracle
-from se2lam_b200 import synth
+from tools import synth
 
 
 @pytest.fixture(scope="module")

@@ -7,7 +7,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from se2lam_b200 import build, synth
+from se2lam_b200 import build
+from tools import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle
-from se2lam_b200 import synth
+from tools import synth
 from se2lam_b200.matcher import FrameView, ORBmatcher
 from tests.matcher_cases import GRID, make_bow_case, make_frame_pair, make_projection_case
 

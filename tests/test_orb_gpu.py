@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle
-from se2lam_b200 import synth
+from tools import synth
 from se2lam_b200.orb import ORBextractor
 
 pytestmark = pytest.mark.gpu

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle
-from se2lam_b200 import synth
+from tools import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "orb_golden.npz"))

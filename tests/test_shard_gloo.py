@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from se2lam_b200 import shard, synth
+from tools import shard, synth
 
 
 def _free_port():

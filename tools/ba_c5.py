@@ -1,8 +1,9 @@
 """Scale test (BASELINE config 5: 2000 KF / 50k landmarks / ~300k edges): GPU LM vs the CPU oracle, timing both."""
-import sys, time
+import os, sys, time
 import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import pyoracle
-from se2lam_b200 import synth
+from tools import synth
 from se2lam_b200.ba import LocalBA
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 5

@@ -4,7 +4,10 @@ import os, subprocess, sys, json
 
 CHILD = r'''
 import os, time, json, numpy as np, torch
-from se2lam_b200 import synth, _capi
+from se2lam_b200 import _capi
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools import synth
 from se2lam_b200.orb import ORBextractor
 n, NF, W, H = 64, 1000, 640, 480
 ex = ORBextractor(NF, 1.2, 8, max_batch=n)
