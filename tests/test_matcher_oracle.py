@@ -58,13 +58,114 @@ def test_match_by_window_against_bruteforce():
         assert prev_out[i1, 0] == kp2["x"][m12[i1]] and prev_out[i1, 1] == kp2["y"][m12[i1]]
 
 
-def test_match_by_projection_and_bow_smoke():
-    case = make_projection_case(seed=2)
-    n, m = pyoracle.match_by_projection(**case["args"])
-    assert n == int((m >= 0).sum()) and n > 20
-    assert not np.any(case["args"]["kf_observed"][m >= 0] if False else case["args"]["kf_observed"].astype(bool) & (m >= 0))
-    k1, k2 = make_bow_case(seed=3)
-    n, m = pyoracle.search_by_bow(k1, k2, True, 0.6, True)
-    assert n == int((m >= 0).sum()) and n > 20
+def _popcount(a, b):
+    return int(np.unpackbits(a ^ b).sum())
+
+
+def _keep_top3_bins(hist):
+    """ComputeThreeMaxima (ORBmatcher.cpp:64-105): three fullest bins, earlier bin wins ties, 10 % rule."""
+    sizes = [len(h) for h in hist]
+    order = sorted(range(len(hist)), key=lambda i: (-sizes[i], i))
+    top = [order[0]] if sizes[order[0]] > 0 else []
+    if top and sizes[order[1]] > 0 and not (sizes[order[1]] < np.float32(0.1) * np.float32(sizes[order[0]])):
+        top.append(order[1])
+        if sizes[order[2]] > 0 and not (sizes[order[2]] < np.float32(0.1) * np.float32(sizes[order[0]])):
+            top.append(order[2])
+    return top
+
+
+@pytest.mark.parametrize("seed", [2, 7, 11])
+def test_match_by_projection_against_bruteforce(seed):
+    """Independent numpy restatement of ORBmatcher::MatchByProjection (ORBmatcher.cpp:383-454): explicit grid walk for
+    GetFeaturesInArea, window = mMainOctave * winSize (0 px for octave 0), same-level ratio rule, TH_HIGH, steal."""
+    a = make_projection_case(seed=seed)["args"]
+    n, m = pyoracle.match_by_projection(**a)
+    kp, desc = a["kfkp"], a["kfdesc"]
+    ratio = np.float32(a["nnratio"])
+    INT_MAX = np.iinfo(np.int32).max
+    vdist = np.full(len(kp), INT_MAX, np.int64)
+    out = -np.ones(len(kp), int)
+    nm = 0
+    for i in range(len(a["mp_valid"])):
+        if not a["mp_valid"][i]:
+            continue
+        pl = int(a["mp_octave"][i])
+        lo = a["level_offset"]
+        cand = brute_candidates(kp, a["mp_uv"][i, 0], a["mp_uv"][i, 1], float(pl * a["win_size"]), pl - lo if pl > lo else 0, pl + lo)
+        if not cand:
+            continue
+        best = best2 = INT_MAX
+        lvl = lvl2 = bi = -1
+        for idx in cand:
+            if a["kf_observed"][idx]:
+                continue
+            dist = _popcount(a["mp_desc"][i], desc[idx])
+            if vdist[idx] <= dist:
+                continue
+            if dist < best:
+                best2, lvl2 = best, lvl
+                best, lvl, bi = dist, int(kp["octave"][idx]), idx
+            elif dist < best2:
+                best2, lvl2 = dist, int(kp["octave"][idx])
+        if best <= 100:
+            if lvl == lvl2 and np.float32(best) > ratio * np.float32(best2):
+                continue
+            if out[bi] >= 0:
+                out[bi] = -1; nm -= 1
+            out[bi] = i; vdist[bi] = best; nm += 1
+    assert n == nm and n > 20
+    np.testing.assert_array_equal(m, out)
+    assert not np.any(a["kf_observed"].astype(bool) & (m >= 0))
+
+
+@pytest.mark.parametrize("seed,mp_only,ori", [(3, True, True), (8, False, True), (9, True, False), (12, False, False)])
+def test_search_by_bow_against_bruteforce(seed, mp_only, ori):
+    """Independent numpy restatement of ORBmatcher::SearchByBoW (ORBmatcher.cpp:128-276) over dict feature vectors."""
+    k1, k2 = make_bow_case(seed=seed)
+    n, m = pyoracle.search_by_bow(k1, k2, mp_only, 0.6, ori)
+    fv1 = {int(nd): k1["feat"][k1["ptr"][i]:k1["ptr"][i + 1]].tolist() for i, nd in enumerate(k1["node"])}
+    fv2 = {int(nd): k2["feat"][k2["ptr"][i]:k2["ptr"][i + 1]].tolist() for i, nd in enumerate(k2["node"])}
+    matched2 = np.zeros(len(k2["desc"]), bool)
+    mm = {}
+    hist = [[] for _ in range(30)]
+    ratio = np.float32(0.6)
+    INT_MAX = np.iinfo(np.int32).max
+    nm = 0
+    for nd in sorted(set(fv1) & set(fv2)):          # the two-iterator walk visits exactly the common node ids, ascending
+        for idx1 in fv1[nd]:
+            if mp_only and not k1["has_mp"][idx1]:
+                continue
+            best = best2 = INT_MAX
+            bi = -1
+            for idx2 in fv2[nd]:
+                if mp_only and not k2["has_mp"][idx2]:
+                    continue
+                if matched2[idx2]:
+                    continue
+                dist = _popcount(k1["desc"][idx1], k2["desc"][idx2])
+                if dist < best:
+                    best2, best, bi = best, dist, idx2
+                elif dist < best2:
+                    best2 = dist
+            if best < 75 and np.float32(best) < ratio * np.float32(best2):
+                mm[idx1] = bi; matched2[bi] = True
+                if ori:
+                    rot = np.float32(k1["angle"][idx1]) - np.float32(k2["angle"][bi])
+                    if rot < 0:
+                        rot = np.float32(rot + np.float32(360))
+                    b = int(np.floor(np.float32(rot * np.float32(30.0 / 360.0)) + 0.5))
+                    hist[0 if b == 30 else b].append(idx1)
+                nm += 1
+    if ori:
+        top = _keep_top3_bins(hist)
+        for b in range(30):
+            if b not in top:
+                for idx1 in hist[b]:
+                    mm.pop(idx1, None); nm -= 1
+    ref = -np.ones(len(k1["desc"]), int)
+    for i1, i2 in mm.items():
+        ref[i1] = i2
+    assert n == nm and n > 20
+    np.testing.assert_array_equal(m, ref)
     got = m[m >= 0]
     assert len(np.unique(got)) == len(got)        # vbMatched2: one-to-one
