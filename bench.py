@@ -35,6 +35,8 @@ ORB_METRIC = "ORB keypoints/sec at 640x480 (8-level pyramid, 1000 kps/frame)"
 BA_METRIC = "LM iterations/sec on 50-KF/5k-point local BA"
 W, H, NFEAT, NLEV, BATCH = 640, 480, 1000, 8, 64
 BA_ITERS = 10
+MATCH_METRIC = "MatchByWindow frame pairs/sec at 1000 x 1000 keypoints (win 20, ratio 0.9)"
+MATCH_PAIRS = 8
 ORB_WORKLOAD = "ORB extraction 640x480, 8-level pyramid (scale 1.2), FAST 20/7, 1000 kps/frame, batch of 64 frames per GPU"
 
 
@@ -95,6 +97,15 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def matcher_frames():
+    """MATCH_PAIRS (frame, shifted frame) pairs of the ORB benchmark texture: what Track hands to MatchByWindow."""
+    imgs = []
+    for k in range(MATCH_PAIRS):
+        a = synth.orb_frame(2000 + k)
+        imgs += [a, np.roll(a, (3 + k % 3, -5 + k % 4), axis=(0, 1))]
+    return np.stack(imgs)
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -135,6 +146,12 @@ def run_reference(args):
         if k >= args.warmup:
             t_ba += time.perf_counter() - t1; it_ba += n
     ba_v = it_ba / t_ba
+    # matcher: oracle restatement of ORBmatcher::MatchByWindow on one core over (frame, shifted frame) pairs
+    from se2lam_b200.matcher import FrameView
+    mimgs = matcher_frames()[:4]
+    ex = [exts[0].extract(im) for im in mimgs]
+    pairs = [(FrameView(*ex[0]), FrameView(*ex[1])), (FrameView(*ex[2]), FrameView(*ex[3]))]
+    match_cpu = cpu_match(pairs)
     line = {
         "impl": "reference", "metric": ORB_METRIC, "value": orb_v, "unit": "keypoints/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -148,6 +165,8 @@ def run_reference(args):
                       "cpu_baseline": {"value": ba_v, "unit": "LM iterations/s", "cores": 1, "kind": "port",
                                        "sample": f"{args.steps} x optimize({BA_ITERS})"},
                       "e2e": {"value": ba_v, "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "matcher": {"metric": MATCH_METRIC, "value": match_cpu["value"], "unit": "frame pairs/s", "higher_is_better": True,
+                    "cpu_baseline": match_cpu, "e2e": {"value": match_cpu["value"], "unit": "frame pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
     }
     _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
 
@@ -290,6 +309,88 @@ def run_ours(args):
             _capi.check(lib.se2gpu_orb_extract(ext.h, one.ctypes.data, 1, W, H, W, W * H, kps_h.ctypes.data, desc_h.ctypes.data, counts_h.ctypes.data), "se2gpu_orb_extract")
         single_ms = (time.perf_counter() - t0) * 1e3 / 50
 
+    # ------------------------------------------------------------------------------------------ matcher
+    from se2lam_b200.matcher import FrameView, ORBmatcher
+    mimgs = matcher_frames()
+    d_mimgs = torch.from_numpy(mimgs).to(dev)
+    NP2 = 2 * MATCH_PAIRS
+    m_kps = torch.zeros(NP2 * NFEAT * 28, dtype=torch.uint8, device=dev)
+    m_desc = torch.zeros(NP2 * NFEAT * 32, dtype=torch.uint8, device=dev)
+    m_counts = torch.zeros(NP2, dtype=torch.int32, device=dev)
+    ext.extract_device(d_mimgs, NP2, H, W, m_kps, m_desc, m_counts, stream=sptr)
+    torch.cuda.synchronize()
+    mt = ORBmatcher(0.9, device=local_rank, max_queries=NFEAT, max_db=NFEAT)
+    m_prev = torch.zeros(2 * NFEAT, dtype=torch.float32, device=dev)
+    m_out = torch.zeros((MATCH_PAIRS, NFEAT), dtype=torch.int32, device=dev)
+    m_nm = torch.zeros(MATCH_PAIRS, dtype=torch.int32, device=dev)
+    mgrid = FrameView(None, None).grid()
+
+    def match_step(k):
+        pi = k % MATCH_PAIRS
+        a, b = 2 * pi, 2 * pi + 1
+        ORBmatcher.KeypointsToPointsDevice(m_kps.data_ptr() + a * NFEAT * 28, NFEAT, m_prev, d_n=m_counts.data_ptr() + 4 * a, stream=sptr)
+        mt.MatchByWindowDevice(m_kps.data_ptr() + a * NFEAT * 28, m_desc.data_ptr() + a * NFEAT * 32, NFEAT,
+                               m_kps.data_ptr() + b * NFEAT * 28, m_desc.data_ptr() + b * NFEAT * 32, NFEAT, m_prev, mgrid, 20,
+                               m_out[pi], m_nm.data_ptr() + 4 * pi, d_n1=m_counts.data_ptr() + 4 * a, d_n2=m_counts.data_ptr() + 4 * b,
+                               stream=sptr)
+    msteps = max(args.steps, 1) * MATCH_PAIRS
+    for k in range(MATCH_PAIRS):
+        match_step(k)
+    barrier()
+    ml0 = lib.se2gpu_launch_count()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record(stream)
+    for k in range(msteps):
+        match_step(k)
+    m1.record(stream)
+    barrier()
+    match_ms = max_over_ranks(m0.elapsed_time(m1))
+    match_launches = lib.se2gpu_launch_count() - ml0
+    match_value = sum_over_ranks(float(msteps)) / (match_ms * 1e-3)
+    mt.profile(True)
+    for k in range(MATCH_PAIRS):
+        match_step(k)
+    torch.cuda.synchronize()
+    mprof = {g: v for g, v in mt.profile_read().items() if v[1] > 0}
+    mt.profile(False)
+    mrounds, mfallback = mt.last_rounds()
+    mdom = max(mprof, key=lambda g: mprof[g][0])
+    mdom_ms = mprof[mdom][0] / mprof[mdom][1]
+    # algorithmic bytes per pair: both keypoint sets and descriptor sets read once (60 B per keypoint), vbPrevMatched in/out,
+    # vnMatches12 out; the candidate table between k_candidates and k_resolve is an implementation detail and not counted
+    match_alg = 2 * NFEAT * 60 + NFEAT * (16 + 4)
+    c_h = m_counts.cpu().numpy()
+    kps_h2 = m_kps.cpu().numpy().view(_capi.KP_DTYPE).reshape(NP2, NFEAT)
+    desc_h2 = m_desc.cpu().numpy().reshape(NP2, NFEAT, 32)
+    # e2e: host buffers through the handle's host entry point (upload of both frames + download of matches / vbPrevMatched)
+    host_pairs = []
+    for pi in range(MATCH_PAIRS):
+        a, b = 2 * pi, 2 * pi + 1
+        host_pairs.append((FrameView(kps_h2[a, :c_h[a]].copy(), desc_h2[a, :c_h[a]].copy()), FrameView(kps_h2[b, :c_h[b]].copy(), desc_h2[b, :c_h[b]].copy())))
+    me2e_steps = 0 if args.quick else msteps
+    nm_tot = 0
+    t0 = time.perf_counter()
+    for k in range(me2e_steps):
+        f1, f2 = host_pairs[k % MATCH_PAIRS]
+        pv = np.stack([f1.keyPointsUn["x"], f1.keyPointsUn["y"]], axis=1).astype(np.float32)
+        n_, _ = mt.MatchByWindow(f1, f2, pv, 20)
+        nm_tot += n_
+    match_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    match_info = {
+        "metric": MATCH_METRIC, "value": match_value, "unit": "frame pairs/s", "higher_is_better": True, "dtype": "u32 popcount",
+        "ms_per_pair": match_ms / msteps, "pairs_timed": msteps, "matches_per_pair": float(m_nm.float().mean().item()),
+        "config": {"workload": f"MatchByWindow on {MATCH_PAIRS} (frame, shifted frame) pairs of the ORB benchmark texture, {NFEAT} keypoints each, "
+                               "device-resident extractor outputs, window 20 px, level offset 1, ratio 0.9",
+                   "l2": "inputs are 120 KB per pair: L2 resident by nature of the workload (latency bound)"},
+        "e2e": {"value": (sum_over_ranks(float(me2e_steps)) / (match_e2e_ms * 1e-3)) if me2e_steps else None, "unit": "frame pairs/s",
+                "h2d_bytes_per_step": 2 * NFEAT * 60 + NFEAT * 8, "d2h_bytes_per_step": NFEAT * 12 + 4},
+        "gpu_launches": int(match_launches), "speculative_rounds": mrounds, "sequential_fallback": bool(mfallback),
+        "roofline": {"bound": "hbm", "kernel": mdom, "achieved": match_alg / (mdom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": match_alg / (mdom_ms * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_traffic(mdom), "algorithmic_bytes_per_launch": match_alg,
+                     "kernel_ms": mdom_ms, "per_kernel_ms": {g: v[0] / v[1] for g, v in mprof.items()},
+                     "note": "120 KB per pair: the ceiling is launch + dependency latency (3 launches, a handful of resolve rounds), not HBM"},
+    }
+
     # ------------------------------------------------------------------------------------------ BA
     prob = synth.ba_config("C4")
     ar_bufs = {}
@@ -408,9 +509,12 @@ def run_ours(args):
                 "e2e": {"value": it2 / (ba_e2e_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(ba_launches), "roofline": ba_roof},
         }
+        line["matcher"] = match_info
+        line["gpu_launches"] = int(orb_launches + ba_launches + match_launches)
         if cpu_orb:
             line["cpu_baseline"] = cpu_orb
             line["secondary"]["cpu_baseline"] = cpu_ba
+            line["matcher"]["cpu_baseline"] = cpu_match(host_pairs)
         _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
@@ -463,6 +567,20 @@ def cpu_baselines():
     cpu_ba = {"value": it_ba / t_ba, "unit": "LM iterations/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
               "sample": f"{reps} x optimize({BA_ITERS}) of the same window, single thread"}
     return cpu_orb, cpu_ba
+
+
+def cpu_match(host_pairs):
+    """The matcher oracle (restatement of ORBmatcher::MatchByWindow + the Frame grid) on one host core, bounded sample."""
+    from oracle import pyoracle
+    from tests.matcher_cases import GRID
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < 2.0:
+        f1, f2 = host_pairs[n % len(host_pairs)]
+        pv = np.stack([f1.keyPointsUn["x"], f1.keyPointsUn["y"]], axis=1).astype(np.float32)
+        pyoracle.match_by_window(f1.keyPointsUn, f1.descriptors, f2.keyPointsUn, f2.descriptors, pv, GRID, 20, 1, 0, 8, 0.9)
+        n += 1
+    return {"value": n / (time.perf_counter() - t0), "unit": "frame pairs/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+            "sample": f"{n} pairs, single thread"}
 
 
 def _reserve_stdout():

@@ -14,10 +14,11 @@
  *                                    (ComputePyramid :790-831, ComputeKeyPoints :531-716,
  *                                     IC_Angle :130-157, computeOrbDescriptor :160-200)
  *   se2gpu_hamming_distance          se2lam::ORBmatcher::DescriptorDistance   src/ORBmatcher.cpp:110-126
- *   se2gpu_match_by_window           se2lam::ORBmatcher::MatchByWindow        src/ORBmatcher.cpp:278-381
+ *   se2gpu_matcher_create            se2lam::ORBmatcher::ORBmatcher           src/ORBmatcher.cpp:49-51
+ *   se2gpu_[matcher_]match_by_window[_device]      ORBmatcher::MatchByWindow  src/ORBmatcher.cpp:278-381
  *                                    (+ Frame grid / GetFeaturesInArea        src/Frame.cpp:64-77, 209-286)
- *   se2gpu_match_by_projection       se2lam::ORBmatcher::MatchByProjection    src/ORBmatcher.cpp:383-454
- *   se2gpu_search_by_bow             se2lam::ORBmatcher::SearchByBoW          src/ORBmatcher.cpp:128-276
+ *   se2gpu_[matcher_]match_by_projection[_device]  ORBmatcher::MatchByProjection  src/ORBmatcher.cpp:383-454
+ *   se2gpu_[matcher_]search_by_bow   se2lam::ORBmatcher::SearchByBoW          src/ORBmatcher.cpp:128-276
  *   se2gpu_ba_set_problem            Map::loadLocalGraph -> addVertexSE2 / addEdgeSE2 / addVertexSBAXYZ /
  *                                    addEdgeSE2XYZ / addCamPara               src/Map.cpp:891-1053, src/optimizer.cpp:17-62,207-215,316-324
  *                                    + SparseOptimizer::initializeOptimization(0)   src/LocalMapper.cpp:259
@@ -123,25 +124,52 @@ typedef struct se2gpu_grid_params {
     float min_x, min_y, inv_w, inv_h;
 } se2gpu_grid_params;
 
-/* MatchByWindow(frame1, frame2, vbPrevMatched, winSize, vnMatches12, levelOffset, minLevel, maxLevel)
- * with nnratio = ORBmatcher::mfNNratio. prev [n1*2] is vbPrevMatched, updated in place. matches12 [n1].
- * Returns the number of matches (>=0) or a negative error. HOST buffers. */
-int se2gpu_match_by_window(const se2gpu_keypoint* kp1, const uint8_t* desc1, int n1, const se2gpu_keypoint* kp2,
-                           const uint8_t* desc2, int n2, float* prev, se2gpu_grid_params grid, int win_size,
-                           int level_offset, int min_level, int max_level, float nnratio, int* matches12, int device);
+/* Matcher context: owns every device buffer the matchers need for up to max_queries query items (frame-1 keypoints / map
+ * points / KF1 features) against up to max_db database keypoints (candidate table max_queries x max_db x 8 bytes), a
+ * stream and page-locked staging for the host entry points. No allocation happens per call. One context per calling
+ * thread (like the reference's stack-allocated ORBmatcher objects, the calls are not re-entrant on one context). */
+typedef struct se2gpu_matcher se2gpu_matcher;
+se2gpu_matcher* se2gpu_matcher_create(int max_queries, int max_db, int device);
+void se2gpu_matcher_destroy(se2gpu_matcher* m);
 
+/* MatchByWindow(frame1, frame2, vbPrevMatched, winSize, vnMatches12, levelOffset, minLevel, maxLevel) with nnratio =
+ * ORBmatcher::mfNNratio on DEVICE buffers, asynchronous on `stream` (cudaStream_t as void*, NULL = default stream): the
+ * keypoint / descriptor buffers are the ones se2gpu_orb_extract_device wrote (reference call chain Track.cpp:129-132 runs
+ * the extractor and MatchByWindow back to back), nothing crosses PCIe. n1 / n2 are capacities; d_n1 / d_n2 (may be NULL)
+ * point to the actual counts in device memory (e.g. the extractor's d_counts entries). d_prev [n1*2] is vbPrevMatched,
+ * updated in place; d_matches12 [n1]; d_nmatches (may be NULL) receives the match count. */
+int se2gpu_match_by_window_device(se2gpu_matcher* m, const se2gpu_keypoint* d_kp1, const uint8_t* d_desc1, int n1, const int* d_n1,
+                                  const se2gpu_keypoint* d_kp2, const uint8_t* d_desc2, int n2, const int* d_n2, float* d_prev,
+                                  se2gpu_grid_params grid, int win_size, int level_offset, int min_level, int max_level,
+                                  float nnratio, int* d_matches12, int* d_nmatches, void* stream);
+/* vbPrevMatched initialisation (Track.cpp:113-116: the reference frame's keypoint positions): d_xy[2i..] = d_kp[i].pt */
+int se2gpu_keypoints_to_points_device(const se2gpu_keypoint* d_kp, int n, const int* d_n, float* d_xy, void* stream);
+
+/* MatchByProjection on DEVICE buffers (same flattening of the object graph as se2gpu_match_by_projection below). */
+int se2gpu_match_by_projection_device(se2gpu_matcher* m, const se2gpu_keypoint* d_kf_kp, const uint8_t* d_kf_desc, int n_kf,
+                                      const int* d_n_kf, const uint8_t* d_kf_observed, const uint8_t* d_mp_valid,
+                                      const float* d_mp_uv, int n_mp, const int* d_mp_octave, const uint8_t* d_mp_desc,
+                                      se2gpu_grid_params grid, int win_size, int level_offset, float nnratio,
+                                      int* d_matches_idx_mp, int* d_nmatches, void* stream);
+
+/* HOST-buffer entry points on an explicit context (synchronous; one stream synchronisation per call).
+ * MatchByWindow: prev [n1*2] is vbPrevMatched, updated in place. matches12 [n1]. Returns the number of matches (>=0)
+ * or a negative error. */
+int se2gpu_matcher_match_by_window(se2gpu_matcher* m, const se2gpu_keypoint* kp1, const uint8_t* desc1, int n1,
+                                   const se2gpu_keypoint* kp2, const uint8_t* desc2, int n2, float* prev,
+                                   se2gpu_grid_params grid, int win_size, int level_offset, int min_level, int max_level,
+                                   float nnratio, int* matches12);
 /* MatchByProjection(pNewKF, localMPs, winSize, levelOffset, vMatchesIdxMP), object graph flattened:
  *   mp_valid[i]  = !isNull && isGoodPrl && !pNewKF->hasObservation(pMP) && inImgBound(predictUV)
  *   mp_uv[i]     = predictUV;  mp_octave[i] = mMainOctave;  mp_desc = mMainDescriptor
  *   kf_observed[k] = pNewKF->hasObservation(k)
- * matches_idx_mp [n_kf]. Returns the number of matches. HOST buffers. */
-int se2gpu_match_by_projection(const se2gpu_keypoint* kf_kp, const uint8_t* kf_desc, int n_kf,
-                               const uint8_t* kf_observed, const uint8_t* mp_valid, const float* mp_uv, int n_mp,
-                               const int* mp_octave, const uint8_t* mp_desc, se2gpu_grid_params grid, int win_size,
-                               int level_offset, float nnratio, int* matches_idx_mp, int device);
-
+ * matches_idx_mp [n_kf]. Returns the number of matches. */
+int se2gpu_matcher_match_by_projection(se2gpu_matcher* m, const se2gpu_keypoint* kf_kp, const uint8_t* kf_desc, int n_kf,
+                                       const uint8_t* kf_observed, const uint8_t* mp_valid, const float* mp_uv, int n_mp,
+                                       const int* mp_octave, const uint8_t* mp_desc, se2gpu_grid_params grid, int win_size,
+                                       int level_offset, float nnratio, int* matches_idx_mp);
 /* SearchByBoW(pKF1, pKF2, mapMatches12, bIfMPOnly); each DBoW2::FeatureVector flattened to ascending node
- * ids + CSR feature lists (ptr has n_node+1 entries). matches12 [n1], -1 = unmatched. HOST buffers. */
+ * ids + CSR feature lists (ptr has n_node+1 entries). matches12 [n1], -1 = unmatched. */
 typedef struct se2gpu_bow_kf {
     const float* angle;     /* keyPointsUn[i].angle */
     const uint8_t* desc;    /* [n*32] */
@@ -152,8 +180,26 @@ typedef struct se2gpu_bow_kf {
     const int* ptr;         /* [n_node+1] */
     const int* feat;        /* feature indices */
 } se2gpu_bow_kf;
+int se2gpu_matcher_search_by_bow(se2gpu_matcher* m, const se2gpu_bow_kf* kf1, const se2gpu_bow_kf* kf2, int mp_only,
+                                 float nnratio, int check_orientation, int* matches12);
+
+/* The same three with a context per device created on first use and kept for the life of the process. */
+int se2gpu_match_by_window(const se2gpu_keypoint* kp1, const uint8_t* desc1, int n1, const se2gpu_keypoint* kp2,
+                           const uint8_t* desc2, int n2, float* prev, se2gpu_grid_params grid, int win_size,
+                           int level_offset, int min_level, int max_level, float nnratio, int* matches12, int device);
+int se2gpu_match_by_projection(const se2gpu_keypoint* kf_kp, const uint8_t* kf_desc, int n_kf,
+                               const uint8_t* kf_observed, const uint8_t* mp_valid, const float* mp_uv, int n_mp,
+                               const int* mp_octave, const uint8_t* mp_desc, se2gpu_grid_params grid, int win_size,
+                               int level_offset, float nnratio, int* matches_idx_mp, int device);
 int se2gpu_search_by_bow(const se2gpu_bow_kf* kf1, const se2gpu_bow_kf* kf2, int mp_only, float nnratio,
                          int check_orientation, int* matches12, int device);
+
+/* per-kernel device timing for bench.py; groups: 0 k_grid_build, 1 k_candidates, 2 k_resolve, 3 k_fallback_* */
+#define SE2GPU_MATCHER_PROFILE_GROUPS 4
+int se2gpu_matcher_profile(se2gpu_matcher* m, int enable);
+int se2gpu_matcher_profile_read(se2gpu_matcher* m, double* ms, int* launches);
+/* diagnostics of the last resolve on this context: speculative rounds it took, and whether the sequential fallback ran */
+int se2gpu_matcher_last_rounds(se2gpu_matcher* m, int* rounds, int* used_fallback);
 
 /* ------------------------------------------------------------------------------------------ local BA */
 typedef struct se2gpu_ba se2gpu_ba;

@@ -17,6 +17,7 @@ enum { CV_8U_ = 0 };
 #endif
 
 struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
+struct Point3f { float x = 0, y = 0, z = 0; Point3f() {} Point3f(float x_, float y_, float z_) : x(x_), y(y_), z(z_) {} };
 
 struct KeyPoint {   // same 28-byte layout as cv::KeyPoint
     Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1;

@@ -320,7 +320,7 @@ def test_sharded_path_on_one_device(cfg, world):
     all-reduce of [S | b_s] and of [chi2, scale, stop] - run with `world` contexts on ONE device (tests/local_shards.py):
     same kernels and host loop as a multi-GPU run. Must follow the single-device oracle trajectory at the strict bar and
     be identical on every rank."""
-    from local_shards import merge_landmarks, run_local_shards
+    from tests.local_shards import merge_landmarks, run_local_shards
     prob = synth.ba_config(cfg)
     o = pyoracle.BAOracle(prob)
     n_o, st_o, tp_o, tl_o = o.optimize(10, trace=True)
@@ -348,7 +348,7 @@ def test_sharded_path_on_one_device(cfg, world):
 def test_sharded_abort_flag_is_collective():
     """Only ONE rank sees the abort flag raised: the decision is OR-ed over the ranks (third word of the per-trial
     all-reduce), so every rank stops after the same iteration instead of one rank leaving the collective sequence."""
-    from local_shards import run_local_shards
+    from tests.local_shards import run_local_shards
     prob = synth.ba_config("C3")
     flags = [np.zeros(1, np.uint8), np.ones(1, np.uint8)]     # rank 1 asks to stop from the start
     res = run_local_shards(prob, 2, 6, stop_flags=flags)

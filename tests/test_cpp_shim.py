@@ -66,3 +66,74 @@ def test_shim_matches_oracle(tmp_path):
     assert done == n_o and aborted == 0
     np.testing.assert_allclose(poses, po, atol=1e-8)
     np.testing.assert_allclose(pts, lo, atol=1e-7)
+
+
+def compile_matcher_demo(tmp_path):
+    build.build_lib()
+    exe = str(tmp_path / "matcher_demo")
+    libdir = os.path.dirname(build.LIB_PATH)
+    cmd = ["g++", "-O1", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "native", "stub"),
+           os.path.join(ROOT, "tests", "native", "matcher_demo.cpp"), "-o", exe, "-L", libdir, "-lse2gpu", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_matcher_shim_compiles_and_links(tmp_path):
+    compile_matcher_demo(tmp_path)
+
+
+@pytest.mark.gpu
+def test_matcher_shim_matches_oracle(tmp_path):
+    """include/se2lam/ORBmatcher.h driven like Track.cpp:129-132, LocalMapper.cpp:117-118 and GlobalMapper.cpp:274-276."""
+    from oracle import pyoracle
+    from tests.matcher_cases import GRID, make_bow_case, make_frame_pair, make_projection_case
+    exe = compile_matcher_demo(tmp_path)
+    f1, f2, prev = make_frame_pair(seed=4)
+    a = make_projection_case(seed=7)["args"]
+    uvc = a["mp_uv"]      # KeyFrame::inImgBound is part of the flattened mp_valid (ORBmatcher.cpp:398-399): apply it to the oracle's input
+    a["mp_valid"] = (a["mp_valid"].astype(bool) & (uvc[:, 0] >= 0) & (uvc[:, 0] <= 640) & (uvc[:, 1] >= 0) & (uvc[:, 1] <= 480)).astype(np.uint8)
+    k1, k2 = make_bow_case(seed=3)
+    fin, fout = str(tmp_path / "m_in.bin"), str(tmp_path / "m_out.bin")
+
+    def put_frame(f, kp, desc):
+        f.write(struct.pack("i", len(kp))); f.write(np.ascontiguousarray(kp).tobytes()); f.write(np.ascontiguousarray(desc, np.uint8).tobytes())
+    with open(fin, "wb") as f:
+        put_frame(f, f1["kp"], f1["desc"]); put_frame(f, f2["kp"], f2["desc"])
+        put_frame(f, a["kfkp"], a["kfdesc"])
+        f.write(np.ascontiguousarray(a["kf_observed"], np.uint8).tobytes())
+        M = len(a["mp_valid"])
+        f.write(struct.pack("i", M)); f.write(np.ascontiguousarray(a["mp_valid"], np.uint8).tobytes())
+        f.write(np.ascontiguousarray(a["mp_uv"], np.float32).tobytes()); f.write(np.ascontiguousarray(a["mp_octave"], np.int32).tobytes())
+        f.write(np.ascontiguousarray(a["mp_desc"], np.uint8).tobytes())
+        for k in (k1, k2):
+            kp = np.zeros(len(k["desc"]), pyoracle.KP_DTYPE); kp["angle"] = k["angle"]
+            put_frame(f, kp, k["desc"])
+            f.write(np.ascontiguousarray(k["has_mp"], np.uint8).tobytes())
+            f.write(struct.pack("i", len(k["node"]))); f.write(k["node"].astype(np.int32).tobytes()); f.write(k["ptr"].astype(np.int32).tobytes())
+            f.write(k["feat"].astype(np.int32).tobytes())
+    res = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    buf = open(fout, "rb").read()
+    off = 0
+    nm, n = struct.unpack_from("ii", buf, off); off += 8
+    m12 = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    pv = np.frombuffer(buf, np.float32, 2 * n, off).reshape(n, 2); off += 8 * n
+    prev0 = np.stack([f1["kp"]["x"], f1["kp"]["y"]], axis=1).astype(np.float32)
+    n_o, m_o, prev_o = pyoracle.match_by_window(f1["kp"], f1["desc"], f2["kp"], f2["desc"], prev0, GRID, 20, 1, 0, 8, 0.9)
+    assert nm == n_o and n == len(m_o)
+    np.testing.assert_array_equal(m12, m_o); np.testing.assert_array_equal(pv, prev_o)
+    nm, n = struct.unpack_from("ii", buf, off); off += 8
+    mp = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    a2 = dict(a); a2["nnratio"] = 0.6
+    n_o, m_o = pyoracle.match_by_projection(**a2)
+    assert nm == n_o
+    np.testing.assert_array_equal(mp, m_o)
+    nm, sz = struct.unpack_from("ii", buf, off); off += 8
+    pairs = np.frombuffer(buf, np.int32, 2 * sz, off).reshape(sz, 2); off += 8 * sz
+    (dd,) = struct.unpack_from("i", buf, off)
+    n_o, m_o = pyoracle.search_by_bow(k1, k2, True, 0.6, True)
+    assert nm == n_o == sz
+    ref = np.flatnonzero(m_o >= 0)
+    np.testing.assert_array_equal(pairs[:, 0], ref); np.testing.assert_array_equal(pairs[:, 1], m_o[ref])
+    assert dd == int(np.unpackbits(k1["desc"][0] ^ k2["desc"][0]).sum())
