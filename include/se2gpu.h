@@ -25,7 +25,11 @@
  *   se2gpu_ba_optimize               SlamOptimizer::optimize(Config::LOCAL_ITER)    src/LocalMapper.cpp:260
  *                                    (EdgeSE2XYZ::computeError/linearizeOplus src/EdgeSE2XYZ.cpp:61-106,
  *                                     PreEdgeSE2 include/se2lam/EdgeSE2XYZ.h:62-102, g2o LM/Schur/Cholesky/Huber [upstream])
- *   se2gpu_ba_get                    estimateVertexSE2 / estimateVertexSBAXYZ src/optimizer.cpp:45-50, 549-554
+ *   se2gpu_ba_get[_f32]              estimateVertexSE2 / estimateVertexSBAXYZ src/optimizer.cpp:45-50, 549-554
+ *                                    (+ the float write-back of Map::optimizeLocalGraph  src/Map.cpp:768-779)
+ *   se2gpu_ba_build_information      per-edge Omega of Map::loadLocalGraph    src/Map.cpp:1024-1049
+ *   se2gpu_voc_create / _transform   DBoW2 TemplatedVocabulary::transform     Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1220-1262
+ *   se2gpu_median_descriptor         MapPoint::updateMainKFandDescriptor      src/MapPoint.cpp:228-272
  */
 #ifndef SE2GPU_H
 #define SE2GPU_H
@@ -201,6 +205,32 @@ int se2gpu_matcher_profile_read(se2gpu_matcher* m, double* ms, int* launches);
 /* diagnostics of the last resolve on this context: speculative rounds it took, and whether the sequential fallback ran */
 int se2gpu_matcher_last_rounds(se2gpu_matcher* m, int* rounds, int* used_fallback);
 
+/* ------------------------------------------------------------------------------------------ bag of words */
+/* DBoW2 vocabulary tree (TemplatedVocabulary<FORB::TDescriptor, FORB>, reference Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h)
+ * flattened: node 0 is the root (m_nodes[0]); node i has the 32-byte descriptor node_desc[32 i], the children
+ * children[child_ptr[i] .. child_ptr[i+1]) in m_nodes[i].children order, and - for a leaf - word_id[i] >= 0 and its weight
+ * (inner nodes: word_id -1). levels = m_L. */
+typedef struct se2gpu_voc se2gpu_voc;
+se2gpu_voc* se2gpu_voc_create(int n_nodes, const uint8_t* node_desc, const int* child_ptr, const int* children,
+                              const int* word_id, const double* weight, int levels, int device);
+void se2gpu_voc_destroy(se2gpu_voc* v);
+/* transform(feature, word_id, weight, &nid, levelsup) (TemplatedVocabulary.h:1220-1262) for n descriptors [n*32]:
+ * word_id [n], weight [n], node_id [n] (may be NULL) = the node at level m_L - levelsup on the feature's path (0 = root
+ * when that level is <= 0; -1 when the leaf is shallower - the reference leaves *nid unset there). The BowVector /
+ * FeatureVector assembly of transform(features, v, fv, levelsup) (:1150-1216: v.addWeight(id, w) in feature order,
+ * fv.addFeature(nid, i), L1 normalisation) is a sorted-map accumulation over these n triples and stays with the caller.
+ * KeyFrame::ComputeBoW (src/KeyFrame.cpp:244-254) uses levelsup = 4. HOST buffers, synchronous. */
+int se2gpu_voc_transform(se2gpu_voc* v, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id);
+/* same on DEVICE buffers (e.g. the extractor's d_desc), asynchronous on `stream` */
+int se2gpu_voc_transform_device(se2gpu_voc* v, const uint8_t* d_desc, int n, int levelsup, int* d_word_id, double* d_weight,
+                                int* d_node_id, void* stream);
+
+/* MapPoint::updateMainKFandDescriptor (reference src/MapPoint.cpp:228-272) for M map points at once: the descriptors of map
+ * point m's observations are desc rows ptr[m] .. ptr[m+1]); best_idx [m] = index (within the point's list) of the descriptor
+ * with the least median Hamming distance to the others - median = element int(0.5*(N-1)) of the sorted distances incl. the
+ * zero self-distance, first index wins ties - and best_median [m] (may be NULL) that median. HOST buffers. */
+int se2gpu_median_descriptor(const uint8_t* desc, const int* ptr, int M, int* best_idx, int* best_median, int device);
+
 /* ------------------------------------------------------------------------------------------ local BA */
 typedef struct se2gpu_ba se2gpu_ba;
 
@@ -248,6 +278,24 @@ int se2gpu_ba_reset(se2gpu_ba* h);
 
 /* current estimates -> host (poses [P*3], points [L*3]) */
 int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points);
+
+/* Map::optimizeLocalGraph's write-back (reference src/Map.cpp:768-779) in the reference's storage type: poses [P*3] as
+ * Se2(float x, float y, float theta) - theta narrowed to float, then normalised like Se2::Se2 (Config.cpp:194-195) - and
+ * points [L*3] as cv::Point3f (toCvPt3f). Narrowed on the device; either pointer may be NULL. */
+int se2gpu_ba_get_f32(se2gpu_ba* h, float* poses, float* points);
+
+/* Map::loadLocalGraph's per-edge information matrix (reference src/Map.cpp:1024-1049), evaluated on the device from the
+ * reference's own float data:
+ *   Omega_e = (sigma_rot J_rotxy J_rotxy^T + sigma_z J_z J_z^T + mvLevelSigma2[octave_e] I)^-1,
+ *   J_pi from view_mp[e] = pKF->mViewMPs[ftrIdx] and fx = Config::fxCam, Rcw = rows of pKF->Tcw(0:3,0:3),
+ *   J_rotxy = (J_pi Rcw skew(lw - (Twb.x, Twb.y, 0)))[:, 0:2], J_z = -(J_pi Rcw)[:, 2],
+ *   sigma_rot = 1/xrot_info, sigma_z = 1/z_info as float (Config::PLANEMOTION_XROT_INFO / _Z_INFO).
+ * kf_Rcw [P*9], kf_twb_xy [P*2], mp_pos [L*3], view_mp [E*3], octave [E], level_sigma2 [nlevels]; info [E*3] receives
+ * (xx, xy, yy) in double - the `info` argument of se2gpu_ba_set_problem. HOST pointers. */
+int se2gpu_ba_build_information(int P, int L, int E, const float* view_mp, const int* edge_pose, const int* edge_point,
+                                const int* octave, const float* kf_Rcw, const float* kf_twb_xy, const float* mp_pos,
+                                const float* level_sigma2, int nlevels, float fx, float xrot_info, float z_info, double* info,
+                                int device);
 
 /* Multi-GPU: this context owns the landmarks j with j % world == rank (call before set_problem); the reduced
  * pose system [S | b | chi2 | scale] is summed over ranks once per LM trial through `allreduce`, which must

@@ -527,6 +527,51 @@ int ba_oracle_schur_solve(void* h, double lam, double* S_dense, double* bs, doub
     if (dx_l) memcpy(dx_l, b->dx_l.data(), sizeof(double) * 3 * b->L);
     return ok ? 1 : 0;
 }
+// Map::loadLocalGraph's per-edge information matrix (reference src/Map.cpp:1024-1049) from the reference's float data,
+// written with generic small-matrix products in the order of the reference's Eigen expressions.
+void ba_oracle_edge_information(int E, const float* view_mp, const int* edge_pose, const int* edge_point, const int* octave,
+                                const float* kf_Rcw, const float* kf_twb_xy, const float* mp_pos, const float* level_sigma2,
+                                float fx_f, float xrot_info, float z_info, double* info) {
+    for (int e = 0; e < E; ++e) {
+        const int p = edge_pose[e], j = edge_point[e];
+        const float Sigma2 = level_sigma2[octave[e]];
+        double Sigma_u[4] = {Sigma2, 0, 0, Sigma2};                                   // Matrix2d::Identity() * Sigma2
+        double lc[3] = {view_mp[3 * e], view_mp[3 * e + 1], view_mp[3 * e + 2]};       // toVector3d(pKF->mViewMPs[ftrIdx])
+        double zc = lc[2], zc_inv = 1. / zc, zc_inv2 = zc_inv * zc_inv;
+        const float& fx = fx_f;
+        double J_pi[6] = {fx * zc_inv, 0, -fx * lc[0] * zc_inv2, 0, fx * zc_inv, -fx * lc[1] * zc_inv2};
+        double Rcw[9];
+        for (int k = 0; k < 9; ++k) Rcw[k] = kf_Rcw[9 * (size_t)p + k];                // toMatrix3d(pKF->Tcw.rowRange(0,3).colRange(0,3))
+        double pi[3] = {kf_twb_xy[2 * (size_t)p], kf_twb_xy[2 * (size_t)p + 1], 0};     // Vector3d pi(pKF->Twb.x, pKF->Twb.y, 0)
+        double lw[3] = {mp_pos[3 * (size_t)j], mp_pos[3 * (size_t)j + 1], mp_pos[3 * (size_t)j + 2]};
+        double J_pi_Rcw[6];
+        for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) { double s = 0; for (int k = 0; k < 3; ++k) s += J_pi[r * 3 + k] * Rcw[k * 3 + c]; J_pi_Rcw[r * 3 + c] = s; }
+        double v[3] = {lw[0] - pi[0], lw[1] - pi[1], lw[2] - pi[2]};
+        double S[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};                 // g2o skew()
+        double MS[6];
+        for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) { double s = 0; for (int k = 0; k < 3; ++k) s += J_pi_Rcw[r * 3 + k] * S[k * 3 + c]; MS[r * 3 + c] = s; }
+        double J_rotxy[4] = {MS[0], MS[1], MS[3], MS[4]};
+        double J_z[2] = {-J_pi_Rcw[2], -J_pi_Rcw[5]};
+        float Sigma_rotxy = 1. / xrot_info;
+        float Sigma_z = 1. / z_info;
+        double A[4], Sigma_all[4];
+        for (int k = 0; k < 4; ++k) A[k] = Sigma_rotxy * J_rotxy[k];                    // (Sigma_rotxy*J_rotxy) * J_rotxy^T
+        for (int r = 0; r < 2; ++r) for (int c = 0; c < 2; ++c)
+            Sigma_all[r * 2 + c] = (A[r * 2] * J_rotxy[c * 2] + A[r * 2 + 1] * J_rotxy[c * 2 + 1]) + (Sigma_z * J_z[r]) * J_z[c] + Sigma_u[r * 2 + c];
+        double det = Sigma_all[0] * Sigma_all[3] - Sigma_all[1] * Sigma_all[2];
+        double inv[4] = {Sigma_all[3] / det, -Sigma_all[1] / det, -Sigma_all[2] / det, Sigma_all[0] / det};
+        info[3 * (size_t)e] = inv[0]; info[3 * (size_t)e + 1] = 0.5 * (inv[1] + inv[2]); info[3 * (size_t)e + 2] = inv[3];
+    }
+}
+// Map::optimizeLocalGraph's narrowing (Map.cpp:768-779): Se2(float, float, float) normalises the float angle (Config.cpp:194-195)
+void ba_oracle_writeback_f32(void* h, float* poses, float* points) {
+    BA* b = (BA*)h;
+    for (int i = 0; i < b->P; ++i) {
+        float x = (float)b->pose[3 * i], y = (float)b->pose[3 * i + 1], th = (float)b->pose[3 * i + 2];
+        poses[3 * i] = x; poses[3 * i + 1] = y; poses[3 * i + 2] = (float)normalize_theta((double)th);
+    }
+    for (int j = 0; j < 3 * b->L; ++j) points[j] = (float)b->point[j];
+}
 // single-edge evaluation for the Jacobian self-check
 void ba_oracle_edge_xyz(void* h, int e, double* err2, double* Ji6, double* Jj6) { ((BA*)h)->xyz_edge(e, err2, Ji6, Jj6); }
 void ba_oracle_edge_odo(void* h, int o, double* err3, double* Ji9, double* Jj9) { ((BA*)h)->odo_edge(o, err3, Ji9, Jj9); }

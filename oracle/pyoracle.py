@@ -21,7 +21,7 @@ BA_STATS_DTYPE = np.dtype([("chi2_before", "f8"), ("chi2_after", "f8"), ("lambda
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, f) for f in ("orb_oracle.cpp", "ba_oracle.cpp", "matcher_oracle.cpp", "undistort_oracle.cpp")]
+    srcs = [os.path.join(HERE, f) for f in ("orb_oracle.cpp", "ba_oracle.cpp", "matcher_oracle.cpp", "undistort_oracle.cpp", "bow_oracle.cpp")]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -65,6 +65,10 @@ def lib():
         L.ba_oracle_schur_solve.argtypes = [vp, d, vp, vp, vp, vp]
         L.ba_oracle_edge_xyz.argtypes = [vp, i, vp, vp, vp]
         L.ba_oracle_edge_odo.argtypes = [vp, i, vp, vp, vp]
+        L.ba_oracle_edge_information.argtypes = [i, vp, vp, vp, vp, vp, vp, vp, vp, f, f, f, vp]
+        L.ba_oracle_writeback_f32.argtypes = [vp, vp, vp]
+        L.voc_oracle_transform.argtypes = [i, vp, vp, vp, vp, vp, i, vp, i, i, vp, vp, vp]
+        L.median_descriptor_oracle.argtypes = [vp, vp, i, vp, vp]
         if hasattr(L, "matcher_oracle_distance"):
             L.matcher_oracle_distance.argtypes = [vp, vp]
             L.matcher_oracle_match_by_window.argtypes = [vp, vp, i, vp, vp, i, vp, f, f, f, f, f, i, i, i, i, f, vp]
@@ -199,6 +203,11 @@ class BAOracle:
         out["ok"] = lib().ba_oracle_schur_solve(self.h, lam, _p(out["S"]), _p(out["bs"]), _p(out["dx_p"]), _p(out["dx_l"]))
         return out
 
+    def writeback_f32(self):
+        poses = np.zeros((self.prob.P, 3), np.float32); pts = np.zeros((self.prob.L, 3), np.float32)
+        lib().ba_oracle_writeback_f32(self.h, _p(poses), _p(pts))
+        return poses, pts
+
     def edge_xyz(self, e):
         err = np.zeros(2); Ji = np.zeros((2, 3)); Jj = np.zeros((2, 3))
         lib().ba_oracle_edge_xyz(self.h, e, _p(err), _p(Ji), _p(Jj))
@@ -252,3 +261,35 @@ def search_by_bow(kf1, kf2, mp_only=True, nnratio=0.6, check_ori=True):
     m = np.zeros(len(k1[0]), np.int32)
     n = lib().matcher_oracle_search_by_bow(*a1, *a2, int(mp_only), nnratio, int(check_ori), _p(m))
     return n, m
+
+
+def edge_information(view_mp, edge_pose, edge_point, octave, kf_Rcw, kf_twb_xy, mp_pos, level_sigma2, fx, xrot_info=1e6, z_info=1.0):
+    """Per-edge information of Map::loadLocalGraph (Map.cpp:1024-1049) from float inputs. Returns [E,3] (xx, xy, yy)."""
+    c = np.ascontiguousarray
+    view_mp = c(view_mp, np.float32); edge_pose = c(edge_pose, np.int32); edge_point = c(edge_point, np.int32); octave = c(octave, np.int32)
+    kf_Rcw = c(kf_Rcw, np.float32); kf_twb_xy = c(kf_twb_xy, np.float32); mp_pos = c(mp_pos, np.float32); level_sigma2 = c(level_sigma2, np.float32)
+    info = np.zeros((len(edge_pose), 3))
+    lib().ba_oracle_edge_information(len(edge_pose), _p(view_mp), _p(edge_pose), _p(edge_point), _p(octave), _p(kf_Rcw), _p(kf_twb_xy),
+                                     _p(mp_pos), _p(level_sigma2), float(fx), float(xrot_info), float(z_info), _p(info))
+    return info
+
+
+# ------------------------------------------------------------------------------------------ bag of words
+def voc_transform(voc, feats, levelsup):
+    """voc = dict(desc [n,32] u8, child_ptr [n+1], children, word_id [n], weight [n] f8, levels). Returns (word, weight, node)."""
+    c = np.ascontiguousarray
+    desc = c(voc["desc"], np.uint8); cp = c(voc["child_ptr"], np.int32); ch = c(voc["children"], np.int32)
+    wid = c(voc["word_id"], np.int32); wt = c(voc["weight"], np.float64); feats = c(feats, np.uint8)
+    n = len(feats)
+    word = np.zeros(n, np.int32); weight = np.zeros(n); node = np.zeros(n, np.int32)
+    lib().voc_oracle_transform(len(desc), _p(desc), _p(cp), _p(ch), _p(wid), _p(wt), int(voc["levels"]), _p(feats), n, int(levelsup),
+                               _p(word), _p(weight), _p(node))
+    return word, weight, node
+
+
+def median_descriptor(desc, ptr):
+    desc = np.ascontiguousarray(desc, np.uint8); ptr = np.ascontiguousarray(ptr, np.int32)
+    M = len(ptr) - 1
+    idx = np.zeros(M, np.int32); med = np.zeros(M, np.int32)
+    lib().median_descriptor_oracle(_p(desc), _p(ptr), M, _p(idx), _p(med))
+    return idx, med

@@ -1641,6 +1641,18 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     }
 }
 
+// Map::optimizeLocalGraph write-back (Map.cpp:768-779): KeyFrame::setPose(Se2(vp(0), vp(1), vp(2))) narrows the pose to float
+// and re-normalises the float angle (Se2::Se2, Config.cpp:194-195); MapPoint::setPos(toCvPt3f(...)) narrows the point.
+__global__ void __launch_bounds__(256) ba_writeback_f32(const double* __restrict__ xp, int P, const double* __restrict__ xl, int L,
+                                                        float* __restrict__ poses, float* __restrict__ points) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P && poses) {
+        poses[3 * i] = (float)xp[3 * i]; poses[3 * i + 1] = (float)xp[3 * i + 1];
+        poses[3 * i + 2] = (float)normalize_theta((double)(float)xp[3 * i + 2]);
+    }
+    if (i < L && points) { points[3 * i] = (float)xl[3 * i]; points[3 * i + 1] = (float)xl[3 * i + 1]; points[3 * i + 2] = (float)xl[3 * i + 2]; }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -2367,6 +2379,25 @@ int se2gpu_ba_get(se2gpu_ba* h, double* poses, double* points) {
     const int cur = h->st_host->cur;
     if (poses) SE2_CUDA(cudaMemcpyAsync(poses, h->d.xp[cur], sizeof(double) * 3 * h->P, cudaMemcpyDeviceToHost, s));
     if (points) SE2_CUDA(cudaMemcpyAsync(points, h->d.xl[cur], sizeof(double) * 3 * h->L, cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_get_f32(se2gpu_ba* h, float* poses, float* points) {
+    if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
+    SE2_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    SE2_CUDA(cudaMemcpyAsync(h->st_host, h->d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
+    SE2_CUDA(cudaStreamSynchronize(s));
+    const int cur = h->st_host->cur;
+    const int n = std::max(h->P, h->L);
+    // narrow on the device into the (free) dxl / Y scratch, then one copy per array
+    float* fp = reinterpret_cast<float*>(h->d.Y);
+    float* fl = fp + 3 * (size_t)h->P + 8;
+    if ((3 * (size_t)h->P + 8 + 3 * (size_t)h->L) * sizeof(float) > sizeof(double) * EB * (size_t)h->maxE) return fail(SE2GPU_ERR_CAPACITY, "scratch too small for the float write-back");
+    SE2_LAUNCH(ba_writeback_f32, (n + 255) / 256, 256, 0, s, h->d.xp[cur], h->P, h->d.xl[cur], h->L, poses ? fp : nullptr, points ? fl : nullptr);
+    if (poses) SE2_CUDA(cudaMemcpyAsync(poses, fp, sizeof(float) * 3 * h->P, cudaMemcpyDeviceToHost, s));
+    if (points) SE2_CUDA(cudaMemcpyAsync(points, fl, sizeof(float) * 3 * h->L, cudaMemcpyDeviceToHost, s));
     SE2_CUDA(cudaStreamSynchronize(s));
     return SE2GPU_OK;
 }
