@@ -35,6 +35,8 @@ ORB_METRIC = "ORB keypoints/sec at 640x480 (8-level pyramid, 1000 kps/frame)"
 BA_METRIC = "LM iterations/sec on 50-KF/5k-point local BA"
 W, H, NFEAT, NLEV, BATCH = 640, 480, 1000, 8, 64
 BA_ITERS = 10
+C5_METRIC = "LM iterations/sec on 2000-KF/50k-point global-scale BA (BASELINE configs[4])"
+C5_ITERS = 5
 MATCH_METRIC = "MatchByWindow frame pairs/sec at 1000 x 1000 keypoints (win 20, ratio 0.9)"
 MATCH_PAIRS = 8
 ORB_WORKLOAD = "ORB extraction 640x480, 8-level pyramid (scale 1.2), FAST 20/7, 1000 kps/frame, batch of 64 frames per GPU"
@@ -485,6 +487,58 @@ def run_ours(args):
     h2d = sum(a.nbytes for a in (prob.poses, prob.points, prob.uv, prob.info, prob.odo_meas, prob.odo_info)) + 4 * (2 * E + 2 * O) + P
     d2h = 8 * 3 * (P + L)
 
+    # ------------------------------------------------------------------------------------------ BA, config 5 (2000 KF / 50k landmarks)
+    c5_info = None
+    if not args.no_c5:
+        prob5 = synth.ba_config("C5")
+        ba5 = LocalBA.from_problem(prob5, device=local_rank, rank=rank, world=world, allreduce=allreduce if world > 1 else None, stream=sptr)
+        ba5.optimize(C5_ITERS)
+        c5_steps = max(2, min(args.steps, 6))
+        barrier()
+        ba5.profile(True)
+        c5l0 = lib.se2gpu_launch_count()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        it5 = 0
+        barrier()
+        c0.record(stream)
+        for _ in range(c5_steps):
+            ba5.reset()
+            n5, st5 = ba5.optimize(C5_ITERS)
+            it5 += n5
+        c1.record(stream)
+        barrier()
+        c5_ms = max_over_ranks(c0.elapsed_time(c1))
+        c5_launches = lib.se2gpu_launch_count() - c5l0
+        c5prof = {g: v for g, v in ba5.profile_read().items() if v[1] > 0}
+        ba5.profile(False)
+        E5, L5, P5, O5 = prob5.E, prob5.L, prob5.P, prob5.O
+        n5u = 3 * (P5 - 1)
+        band5 = n5u * 18                                          # stored doubles of the reduced system: block half-bandwidth 5
+        iter_alg5 = E5 * 424 + L5 * 288 + P5 * 120 + O5 * 112 + band5 * 8
+        c5alg = {"ba_linearize": E5 * (56 + 48 + 72) + L5 * 72, "ba_pose_reduce": P5 * 72 + E5 * 72, "ba_lm_prep": L5 * 72 + E5 * 72,
+                 "ba_schur": E5 * 72 + L5 * 72 + band5 * 8, "ba_chol_solve": band5 * 8 * 2, "ba_backsub_update": E5 * 72 + L5 * (72 + 24) + (P5 + L5) * 48,
+                 "ba_lm_control": 0}
+        c5dom = max(c5prof, key=lambda g: c5prof[g][0])
+        c5dom_ms = c5prof[c5dom][0] / c5prof[c5dom][1]
+        c5ach = c5alg.get(c5dom, 0) / (c5dom_ms * 1e-3) / 1e9 / max(world, 1)
+        t0 = time.perf_counter()
+        ba5.set_problem(prob5); n5e, _ = ba5.optimize(C5_ITERS); ba5.get()
+        c5_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        c5_info = {
+            "metric": C5_METRIC, "value": it5 / (c5_ms * 1e-3), "unit": "LM iterations/s", "higher_is_better": True, "dtype": "f64", "scaling": "strong",
+            "ms_per_iteration": c5_ms / max(it5, 1), "iterations_timed": it5, "lambda_trials_last_optimize": int(st5["trials"].sum()),
+            "config": {"workload": f"BA {P5} KF / {L5} landmarks / {E5} EdgeSE2XYZ + {O5} PreEdgeSE2, Huber, {C5_ITERS} LM iterations per optimize",
+                       "parallelism": ("single GPU" if world == 1 else f"landmark-sharded over {world} GPUs, one NCCL all-reduce of the band-stored reduced system ({band5 * 8 / 1e6:.2f} MB) + one of [chi2, scale, stop] per trial") +
+                                      "; reduced solve = partitioned block-band LDL^T (ba_band.cu)"},
+            "e2e": {"value": n5e / (c5_e2e_ms * 1e-3), "unit": "LM iterations/s", "h2d_bytes_per_step": int(E5 * 48 + (P5 + L5) * 24 + O5 * 80), "d2h_bytes_per_step": int(24 * (P5 + L5)),
+                    "note": "set_problem (host re-index of 297k edges) + optimize + get"},
+            "gpu_launches": int(c5_launches),
+            "roofline": {"bound": "hbm", "kernel": c5dom, "achieved": c5ach, "peak": hbm_peak, "unit": "GB/s", "frac": c5ach / hbm_peak,
+                         "traffic": ncu_traffic("c5:" + c5dom), "algorithmic_bytes_per_launch": c5alg.get(c5dom, 0) / max(world, 1), "kernel_ms": c5dom_ms,
+                         "per_kernel_ms": {g: v[0] / v[1] for g, v in c5prof.items()},
+                         "whole_path_GBps": iter_alg5 / (c5_ms / max(it5, 1) * 1e-3) / 1e9},
+        }
+
     if rank == 0:
         cpu_orb, cpu_ba = cpu_baselines() if (world == 1 and not args.quick) else (None, None)
         line = {
@@ -510,11 +564,19 @@ def run_ours(args):
                 "gpu_launches": int(ba_launches), "roofline": ba_roof},
         }
         line["matcher"] = match_info
+        if c5_info:
+            line["tertiary"] = c5_info
         line["gpu_launches"] = int(orb_launches + ba_launches + match_launches)
         if cpu_orb:
             line["cpu_baseline"] = cpu_orb
             line["secondary"]["cpu_baseline"] = cpu_ba
             line["matcher"]["cpu_baseline"] = cpu_match(host_pairs)
+            if c5_info:
+                from oracle import pyoracle
+                o5 = pyoracle.BAOracle(prob5)
+                t1 = time.perf_counter(); n5c, _ = o5.optimize(3); dt5 = time.perf_counter() - t1
+                line["tertiary"]["cpu_baseline"] = {"value": n5c / dt5, "unit": "LM iterations/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
+                                                    "sample": "1 x optimize(3) of the same window, single thread (skyline Cholesky)"}
         _OUT.write(json.dumps(line) + "\n"); _OUT.flush()
     if world > 1:
         dist.destroy_process_group()
@@ -601,6 +663,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the CPU baseline and the e2e legs")
+    ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] leg (2000 KF / 50k landmarks; ~20 s of host-side synthesis)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

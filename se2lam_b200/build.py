@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libse2gpu.so")
-SOURCES = ["common.cu", "ba.cu", "ba_loader.cu", "orb.cu", "matcher.cu", "bow.cu"]
+SOURCES = ["common.cu", "ba.cu", "ba_band.cu", "ba_loader.cu", "orb.cu", "matcher.cu", "bow.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

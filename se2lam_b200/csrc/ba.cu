@@ -32,6 +32,7 @@
 #include <algorithm>
 
 #include "common.h"
+#include "ba_band.h"
 
 namespace {
 
@@ -54,6 +55,7 @@ struct LMState {  // device-resident scalars of the LM loop (host mirrors it onc
 struct Dev {  // all device pointers of one context (passed by value to kernels)
     int P, L, E, O, nf, n, nblk;
     int rank, world;
+    int sbw;   // 0: S dense [n*n]; > 0: S in band storage, row r holds columns r-sbw..r (large windows, ba_band.cu)
     // state
     double* xp[2];
     double* xl[2];
@@ -82,6 +84,11 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     double *part_chi, *part_scale;
     int nb_lm, nb_odo;
 };
+
+// element (r, c), r >= c, of the reduced system
+__device__ __forceinline__ size_t sidx(const Dev& d, int r, int c) {
+    return d.sbw ? (size_t)r * (d.sbw + 1) + (size_t)(c - r + d.sbw) : (size_t)r * d.n + c;
+}
 
 __device__ __forceinline__ double normalize_theta(double theta) {
     if (theta >= -M_PI && theta < M_PI) return theta;
@@ -436,7 +443,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int q = 0; q < 12; ++q) { double v = 0; for (int w = 0; w < SCHUR_THREADS / 32; ++w) v += sh[w][q]; acc[q] = v; }
-        const size_t n = d.n, nf = d.nf;
+        const size_t nf = d.nf;
         if (a == b) {
             const double lam = (d.rank == 0) ? d.st->lambda : 0.0;   // damping is added once across shards
             const double H[9] = {d.Hpp[a], d.Hpp[nf + a], d.Hpp[2 * nf + a], d.Hpp[nf + a], d.Hpp[3 * nf + a], d.Hpp[4 * nf + a],
@@ -444,14 +451,15 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) d.S[(3 * a + r) * n + 3 * b + c] = acc[r * 3 + c] + H[r * 3 + c] + (r == c ? lam : 0.0);
+                for (int c = 0; c < 3; ++c)
+                    if (c <= r || !d.sbw) d.S[sidx(d, 3 * a + r, 3 * b + c)] = acc[r * 3 + c] + H[r * 3 + c] + (r == c ? lam : 0.0);
                 d.bs[3 * a + r] = d.bp[3 * a + r] + acc[9 + r];
             }
         } else {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) d.S[(3 * a + r) * n + 3 * b + c] = acc[r * 3 + c];
+                for (int c = 0; c < 3; ++c) d.S[sidx(d, 3 * a + r, 3 * b + c)] = acc[r * 3 + c];
         }
     }
 }
@@ -1738,6 +1746,8 @@ struct se2gpu_ba {
     long long* phase_cycles = nullptr;   // device [8]
     long long* cta_work = nullptr;       // device [1024][8]
     int pk_launches = 0, clock_khz = 0;
+    se2band::Plan band;        // partitioned band solver for reduced systems beyond one CTA's shared memory
+    int smem_optin = 0;
 };
 
 namespace {
@@ -1817,6 +1827,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
         cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device);
+        cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         cudaMemset(h->phase_cycles, 0, 8 * sizeof(long long));
         if (coop && cudaFuncSetAttribute(ba_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent, PK_THREADS, smem_max) == cudaSuccess && occ >= 1)
@@ -1837,6 +1848,7 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (h->trace_p) cudaFree(h->trace_p);
     if (h->trace_l) cudaFree(h->trace_l);
     if (h->abort_host) cudaFreeHost(h->abort_host);
+    se2band::release(h->band);
     for (void* m : h->peer_opened) if (m) cudaIpcCloseMemHandle(m);
     if (h->peer_flag) cudaFree(h->peer_flag);
     if (h->bs_sum) cudaFree(h->bs_sum);
@@ -2062,6 +2074,11 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     }
     std::vector<int> colmax(n);
     for (int a = 0; a < nf; ++a) for (int r = 0; r < 3; ++r) colmax[3 * a + r] = 3 * bmax[a] + 2;
+    // windows beyond one CTA's shared memory: partitioned band factorisation when the envelope is narrow (ba_band.cu),
+    // otherwise the single-CTA global-memory envelope factorisation
+    se2band::release(h->band);
+    if (n > SMEM_CHOL_MAX_N && !getenv("SE2GPU_BA_NO_BAND")) se2band::plan(h->band, nf, bmax, h->smem_optin);
+    const size_t S_elems = h->band.active ? h->band.band_elems : (size_t)n * n;
     // serving order of the blocks for the persistent kernel: diagonal blocks (they also carry the pose-side gather) first,
     // so that round-robin assignment gives every worker CTA at most one of them
     std::vector<int> blk_order;
@@ -2108,7 +2125,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax); UP(h->blk_order, blk_order);
 #undef UP
 #undef UPP
-    SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * ((size_t)n * n + n + 8), s));
+    SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * (S_elems + n + 8), s));
     LMState st0{};
     st0.ni = 2;
     *h->st_host = st0;
@@ -2129,7 +2146,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     d.pose_ptr = h->pose_ptr; d.pose_edges = h->pose_edges; d.pose_odo_ptr = h->pose_odo_ptr; d.pose_odo = h->pose_odo;
     d.blk_a = h->blk_a; d.blk_b = h->blk_b; d.blk_pair_ptr = h->blk_pair_ptr; d.pair_e1 = h->pair_e1; d.pair_e2 = h->pair_e2;
     d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax; d.blk_order = h->blk_order;
-    d.S = h->red; d.bs = h->red + (size_t)n * n; d.scal = d.bs + n;
+    d.S = h->red; d.bs = h->red + S_elems; d.scal = d.bs + n; d.sbw = h->band.active ? h->band.bw : 0;
     d.nb_lm = (L + LM_THREADS - 1) / LM_THREADS; d.nb_odo = (Ol + LM_THREADS - 1) / LM_THREADS;
     h->nb_scale = (std::max(L, P) + LM_THREADS - 1) / LM_THREADS;
     h->cam.fx = fx; h->cam.cx = cx; h->cam.cy = cy; h->cam.delta = huber_delta;
@@ -2169,7 +2186,8 @@ int launch_solve(se2gpu_ba* h) {
     if (d.nb_lm > 0) SE2_LAUNCH(ba_lm_prep, d.nb_lm, LM_THREADS, 0, s, d);
     h->prof.end(s);
     // the global-memory Cholesky factorises S in place (fill-in outside the block list): re-zero it
-    if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
+    const size_t S_elems = h->band.active ? h->band.band_elems : (size_t)d.n * d.n;
+    if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * S_elems, s));
     h->prof.begin(3, s);
     if (d.nblk > 0) SE2_LAUNCH(ba_schur, d.nblk, SCHUR_THREADS, 0, s, d);
     h->prof.end(s);
@@ -2184,10 +2202,11 @@ int launch_solve(se2gpu_ba* h) {
         h->prof.end(s);
         return SE2GPU_OK;
     }
-    int rc = ar(h, d.S, (size_t)d.n * d.n + d.n, 0);
+    int rc = ar(h, d.S, S_elems + d.n, 0);     // the message is the stored pattern: dense for small windows, the band for large ones
     if (rc != SE2GPU_OK) return rc;
     h->prof.begin(4, s);
     if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ldlt_smem_bytes(d.n), s, d);   // n == 0: trivially ok
+    else if (h->band.active) { if ((rc = se2band::solve(h->band, d.S, d.bs, d.dxp, &d.st->solve_ok, s)) != SE2GPU_OK) return rc; }
     else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     h->prof.end(s);
     return SE2GPU_OK;
@@ -2420,13 +2439,23 @@ int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hp
     h->st_host->lambda = lambda;
     SE2_CUDA(cudaMemcpyAsync(d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
     if (d.nb_lm > 0) SE2_LAUNCH(ba_lm_prep, d.nb_lm, LM_THREADS, 0, s, d);
-    if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.n * d.n, s));
+    const size_t S_elems = h->band.active ? h->band.band_elems : (size_t)d.n * d.n;
+    if (d.n > SMEM_CHOL_MAX_N) SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * S_elems, s));
     if (d.nblk > 0) SE2_LAUNCH(ba_schur, d.nblk, SCHUR_THREADS, 0, s, d);
     std::vector<double> tmp;
     auto get = [&](const double* dev, size_t cnt) { tmp.resize(cnt); return cudaMemcpyAsync(tmp.data(), dev, cnt * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess; };
-    if (S) { if (!get(d.S, (size_t)n * n)) return fail(SE2GPU_ERR_CUDA, "copy S"); memcpy(S, tmp.data(), tmp.size() * 8); }
+    if (S) {
+        if (!get(d.S, S_elems)) return fail(SE2GPU_ERR_CUDA, "copy S");
+        if (!h->band.active) memcpy(S, tmp.data(), tmp.size() * 8);
+        else {                         // band storage -> dense lower triangle
+            const int bw = h->band.bw;
+            memset(S, 0, sizeof(double) * (size_t)n * n);
+            for (int r = 0; r < n; ++r) for (int c = std::max(0, r - bw); c <= r; ++c) S[(size_t)r * n + c] = tmp[(size_t)r * (bw + 1) + (c - r + bw)];
+        }
+    }
     if (bs) { if (!get(d.bs, n)) return fail(SE2GPU_ERR_CUDA, "copy bs"); memcpy(bs, tmp.data(), tmp.size() * 8); }
     if (d.n <= SMEM_CHOL_MAX_N) SE2_LAUNCH(ba_chol_solve_smem, 1, CHOL_THREADS, ldlt_smem_bytes(d.n), s, d);
+    else if (h->band.active) { if ((rc = se2band::solve(h->band, d.S, d.bs, d.dxp, &d.st->solve_ok, s)) != SE2GPU_OK) return rc; }
     else SE2_LAUNCH(ba_chol_solve_gmem, 1, CHOL_THREADS, 0, s, d, h->ywork);
     SE2_LAUNCH(ba_backsub_update, h->nb_scale, LM_THREADS, 0, s, d);
     if (Hpp) {

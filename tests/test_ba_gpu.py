@@ -356,6 +356,59 @@ def test_sharded_abort_flag_is_collective():
     np.testing.assert_array_equal(res[0][4], prob.poses)
 
 
+def _medium_window():
+    return synth.ba_window(n_kf=120, n_lm=3000, seed=11)         # n = 357 unknowns: beyond one CTA's shared memory
+
+
+@pytest.mark.parametrize("solver", ["band", "envelope"])
+def test_large_window_solvers_match_oracle(solver, monkeypatch):
+    """Reduced systems that do not fit one CTA's shared memory: the partitioned block-band LDL^T (ba_band.cu) and the
+    single-CTA global-memory envelope factorisation it replaces (SE2GPU_BA_NO_BAND=1) both hold the strict per-step bar."""
+    if solver == "envelope":
+        monkeypatch.setenv("SE2GPU_BA_NO_BAND", "1")
+    prob = _medium_window()
+    _assert_strict_trajectory(prob, 6, 0, need_reject=False)
+    o = pyoracle.BAOracle(prob)
+    lin = o.linearize()
+    lam = 1e-5 * max(np.abs(np.diag(lin["Hpp"])).max(), np.abs(lin["Hll"][:, [0, 1, 2], [0, 1, 2]]).max())
+    ss = o.schur_solve(lam)
+    sysm = LocalBA.from_problem(prob).debug_system(lam)
+    n = sysm["n"]
+    tril = np.tril(np.ones((n, n), bool))
+    assert rel_err(sysm["S"][tril], ss["S"][tril]) < 1e-10
+    assert rel_err(sysm["dx_p"], ss["dx_p"]) < REL and rel_err(sysm["dx_l"], ss["dx_l"]) < REL
+
+
+def test_band_solver_rejects_non_pd_and_recovers():
+    """The partitioned factorisation is a symmetric permutation of S: a non-PD pivot block in any partition == S not PD."""
+    prob = _medium_window()
+    prob.poses = prob.poses.copy(); prob.odo_info = prob.odo_info.copy()
+    prob.poses[0, 2] = 0.0
+    lin = pyoracle.BAOracle(prob).linearize()
+    md = max(np.abs(np.diag(lin["Hpp"])).max(), np.abs(lin["Hll"][:, [0, 1, 2], [0, 1, 2]]).max())
+    prob.odo_info[0] = [0.0, 200.0 * md, 0.0, 0.0, 0.0, prob.odo_info[0][5]]
+    st = _assert_strict_trajectory(prob, 4, 0)
+    assert st["trials"][0] == 8
+
+
+def test_sharded_large_window_on_one_device():
+    """Sharded run of a band-mode window: the per-trial all-reduce carries the band-stored reduced system."""
+    from tests.local_shards import merge_landmarks, run_local_shards
+    prob = _medium_window()
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o, tp_o, tl_o = o.optimize(5, trace=True)
+    res = run_local_shards(prob, 2, 5)
+    for r in range(2):
+        n, st, tp, tl, p, l = res[r]
+        assert n == n_o
+        np.testing.assert_array_equal(st["trials"], st_o["trials"])
+        np.testing.assert_allclose(st["lambda"], st_o["lambda"], rtol=1e-6)
+        assert np.abs(tp[-1] - tp_o[-1]).max() < 1e-8
+    pts = merge_landmarks(prob, res, 2)
+    active = np.zeros(prob.L, bool); active[prob.edge_point] = True
+    assert np.abs(pts[active] - o.get()[1][active]).max() < 1e-7
+
+
 def test_scale_config_c5_matches_oracle():
     """BASELINE config 5 (2000 KF / 50k landmarks / ~300k edges): the reduced system (n = 5997) does not fit one CTA's
     shared memory, so this exercises the global-memory envelope LDL^T and the multi-launch path at scale."""
