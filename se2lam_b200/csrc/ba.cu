@@ -79,7 +79,8 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     // reduced system
     const int *blk_a, *blk_b, *blk_pair_ptr, *pair_e1, *pair_e2, *blk_odo_ptr, *blk_odo;
     const int* colmax;                    // [n] envelope of the reduced system (last structurally non-zero row per column)
-    const int* blk_order;                 // [nblk] diagonal blocks first: position p is served by persistent worker p % W
+    const int* blk_order;                 // [nord] serving order of the persistent kernel: position p belongs to worker p % W; -1 = hole
+    int nord;
     double *S, *bs, *scal, *dxp, *dxl;    // S [n*n] | bs [n] | scal [8] contiguous (all-reduce buffer)
     double *part_chi, *part_scale;
     int nb_lm, nb_odo;
@@ -1098,10 +1099,12 @@ template <bool JAC>
 __device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double* part, double* sh, double lam_fuse = -1.0) {
     const double* xp = d.xp[xi];
     const double* xl = d.xl[xi];
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     double chi = 0;
     for (PKLmIter it; it.more(d.L); it.next()) chi += pk_landmark<JAC>(d, cam, xp, xl, it.j, it.sub, lam_fuse);
-    for (int o = gtid; o < d.O; o += gthreads) chi += pk_odo<JAC>(d, xp, o);
+    // PreEdgeSE2 edges: one per CTA on the first lane of the last warp (idle unless a CTA holds > 60 landmarks), so that no CTA
+    // serialises all of them behind its landmark work (they used to sit on CTA 0 and made it the slowest of the phase)
+    if (threadIdx.x == blockDim.x - 32)
+        for (int o = blockIdx.x; o < d.O; o += gridDim.x) chi += pk_odo<JAC>(d, xp, o);
     const double tot = block_sum(chi, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = tot;
 }
@@ -1257,12 +1260,13 @@ struct PKWork {
 __device__ void pk_phase_pose_reduce(const Dev& d, const PKWork& w, double* sh9) {
     if (w.first < 0) return;
     int i = 0;
-    for (int pos = w.first; pos < d.nblk; pos += w.stride, ++i) {
+    for (int pos = w.first; pos < d.nord; pos += w.stride, ++i) {
         if (i < w.n_own) {
             const PKOwn o = w.own[i];
             if (o.a == o.b) pk_pose_item(d, o.a, w.arena + o.e0, o.ne, sh9);
         } else {
             const int blk = d.blk_order[pos];
+            if (blk < 0) break;
             const int a = d.blk_a[blk];
             if (a == d.blk_b[blk]) pk_pose_item(d, a, d.pose_edges + d.pose_ptr[a], d.pose_ptr[a + 1] - d.pose_ptr[a], sh9);
         }
@@ -1272,12 +1276,13 @@ __device__ void pk_phase_pose_reduce(const Dev& d, const PKWork& w, double* sh9)
 __device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double* sh12) {
     if (w.first < 0) return;
     int i = 0;
-    for (int pos = w.first; pos < d.nblk; pos += w.stride, ++i) {
+    for (int pos = w.first; pos < d.nord; pos += w.stride, ++i) {
         if (i < w.n_own) {
             const PKOwn o = w.own[i];
             pk_schur_item(d, lam, o.blk, o.a, o.b, w.arena + o.p0, 0, o.np, w.arena + o.e0, o.ne, sh12);
         } else {
             const int blk = d.blk_order[pos];
+            if (blk < 0) break;
             const int a = d.blk_a[blk], b = d.blk_b[blk];
             pk_schur_item(d, lam, blk, a, b, nullptr, d.blk_pair_ptr[blk], d.blk_pair_ptr[blk + 1] - d.blk_pair_ptr[blk],
                           d.pose_edges + d.pose_ptr[a], a == b ? d.pose_ptr[a + 1] - d.pose_ptr[a] : 0, sh12);
@@ -1418,7 +1423,6 @@ __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
 }
 
 __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const double* xp = d.xp[cur];
     const double* xl = d.xl[cur];
     double* xpt = d.xp[cur ^ 1];
@@ -1451,7 +1455,9 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
             xlt[3 * j] = xl[3 * j] + dl0; xlt[3 * j + 1] = xl[3 * j + 1] + dl1; xlt[3 * j + 2] = xl[3 * j + 2] + dl2;
         }
     }
-    for (int t = gtid; t < d.P; t += gthreads) {
+    // poses: one per CTA on the first lane of the last warp (see pk_phase_linearize)
+    if (threadIdx.x == blockDim.x - 32)
+    for (int t = blockIdx.x; t < d.P; t += gridDim.x) {
         const int a = d.hidx[t];
         if (a >= 0) {
             const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
@@ -1489,8 +1495,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         if (threadIdx.x == 0) {
             int off = 0, no = 0;
             if (work.first >= 0)
-                for (int pos = work.first; pos < d.nblk && no < PK_MAXOWN; pos += work.stride) {
+                for (int pos = work.first; pos < d.nord && no < PK_MAXOWN; pos += work.stride) {
                     const int blk = d.blk_order[pos];
+                    if (blk < 0) break;                     // holes only trail a worker's list
                     const int a = d.blk_a[blk], b = d.blk_b[blk];
                     const int np = d.blk_pair_ptr[blk + 1] - d.blk_pair_ptr[blk];
                     const int ne = (a == b) ? d.pose_ptr[a + 1] - d.pose_ptr[a] : 0;
@@ -1502,7 +1509,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             // concurrent Schur plan: possible when every owned block is cached; one warp per block, the spare warps go
             // one by one to the block with the most work per warp
             int total = 0;
-            if (work.first >= 0) for (int pos = work.first; pos < d.nblk; pos += work.stride) ++total;
+            if (work.first >= 0) for (int pos = work.first; pos < d.nord; pos += work.stride) if (d.blk_order[pos] >= 0) ++total;
             const int nwarp = (int)(blockDim.x >> 5);
             s_plan_ok = (no == total && no > 0 && no <= nwarp) ? 1 : 0;
             if (s_plan_ok) {
@@ -2081,11 +2088,33 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     const size_t S_elems = h->band.active ? h->band.band_elems : (size_t)n * n;
     // serving order of the blocks for the persistent kernel: diagonal blocks (they also carry the pose-side gather) first,
     // so that round-robin assignment gives every worker CTA at most one of them
+    // Longest-processing-time assignment: blocks by decreasing work (pairs + pose-side edges of a diagonal block) to the least
+    // loaded worker, at most 12 blocks per worker (the concurrent Schur phase gives every owned block its own warp group).
+    // Worker w serves positions w, w + W, w + 2W, ...; unused trailing positions are holes (-1).
     std::vector<int> blk_order;
-    blk_order.reserve(nblk);
-    for (int b = 0; b < nblk; ++b) if (blk_a[b] == blk_b[b]) blk_order.push_back(b);
-    for (int b = 0; b < nblk; ++b) if (blk_a[b] != blk_b[b]) blk_order.push_back(b);
-    int rc = ensure_cap(h, npairs, std::max<size_t>(nblk, odob.size()), odob.size());
+    {
+        const int W = h->pk_grid > 1 ? h->pk_grid - 1 : 1;
+        std::vector<std::pair<long long, int>> byw(nblk);
+        for (int b = 0; b < nblk; ++b) {
+            long long wt = blk_pair_ptr[b + 1] - blk_pair_ptr[b] + 8;
+            if (blk_a[b] == blk_b[b]) wt += pose_ptr[blk_a[b] + 1] - pose_ptr[blk_a[b]];
+            byw[b] = {-wt, b};
+        }
+        std::sort(byw.begin(), byw.end());
+        std::vector<std::vector<int>> lists(W);
+        std::vector<long long> load(W, 0);
+        const size_t cap = std::max<size_t>(12, (nblk + W - 1) / W);
+        for (auto& it : byw) {
+            int best = -1;
+            for (int w2 = 0; w2 < W; ++w2) if (lists[w2].size() < cap && (best < 0 || load[w2] < load[best])) best = w2;
+            lists[best].push_back(it.second); load[best] += -it.first;
+        }
+        size_t maxlen = 0;
+        for (auto& l : lists) maxlen = std::max(maxlen, l.size());
+        blk_order.assign((size_t)W * maxlen, -1);
+        for (int w2 = 0; w2 < W; ++w2) for (size_t i = 0; i < lists[w2].size(); ++i) blk_order[i * W + w2] = lists[w2][i];
+    }
+    int rc = ensure_cap(h, npairs, std::max<size_t>(std::max<size_t>(nblk, blk_order.size()), odob.size()), odob.size());
     if (rc != SE2GPU_OK) return rc;
 
     // --- odometry SoA
@@ -2145,7 +2174,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     d.o_i = h->o_i; d.o_j = h->o_j; d.o_m = h->o_m; d.o_w = h->o_w;
     d.pose_ptr = h->pose_ptr; d.pose_edges = h->pose_edges; d.pose_odo_ptr = h->pose_odo_ptr; d.pose_odo = h->pose_odo;
     d.blk_a = h->blk_a; d.blk_b = h->blk_b; d.blk_pair_ptr = h->blk_pair_ptr; d.pair_e1 = h->pair_e1; d.pair_e2 = h->pair_e2;
-    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax; d.blk_order = h->blk_order;
+    d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax; d.blk_order = h->blk_order; d.nord = (int)blk_order.size();
     d.S = h->red; d.bs = h->red + S_elems; d.scal = d.bs + n; d.sbw = h->band.active ? h->band.bw : 0;
     d.nb_lm = (L + LM_THREADS - 1) / LM_THREADS; d.nb_odo = (Ol + LM_THREADS - 1) / LM_THREADS;
     h->nb_scale = (std::max(L, P) + LM_THREADS - 1) / LM_THREADS;
