@@ -272,6 +272,13 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
 int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char* stop_flag,
                        se2gpu_ba_iter_stats* stats, double* trace_poses, double* trace_points);
 
+/* The same for ONE g2o `solve(iteration)`-style slice of an optimisation: runs LM iterations first_iteration ..
+ * first_iteration + max_iters - 1. lambda is initialised (1e-5 max|diag H|) at iteration 0 only; a call with first_iteration > 0
+ * continues the lambda / nu schedule where the previous call on this context stopped, so optimize_from(0, 1), (1, 1), ... (9, 1)
+ * is bit-identical to optimize(10). This is what a g2o::OptimizationAlgorithm subclass needs (option i). */
+int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, const volatile unsigned char* stop_flag,
+                            se2gpu_ba_iter_stats* stats, double* trace_poses, double* trace_points);
+
 /* restore the estimates loaded by the last se2gpu_ba_set_problem (device-side copy; lets a caller re-run
  * optimize on the same window without re-uploading it) */
 int se2gpu_ba_reset(se2gpu_ba* h);
@@ -302,15 +309,22 @@ int se2gpu_ba_build_information(int P, int L, int E, const float* view_mp, const
  * sum (op 0) or max (op 1) `count` doubles at device pointer `buf` in place across ranks, ordered on `stream`. */
 typedef int (*se2gpu_allreduce_fn)(void* user, double* buf, size_t count, int op, void* stream);
 int se2gpu_ba_set_shard(se2gpu_ba* h, int rank, int world, se2gpu_allreduce_fn allreduce, void* user);
-/* Optional fused exchange for sharded runs on one NVLink node (one process per GPU): instead of all-reducing the
- * reduced system [S | b] through the callback, every rank's solve kernel sums the ranks' partial buffers directly
- * over peer mappings (the exchange is part of the kernel that consumes it; the small [chi2, scale] reductions keep
- * using the callback). Protocol: after se2gpu_ba_set_shard every rank calls _peer_export, the handles
- * (SE2GPU_BA_PEER_HANDLE_BYTES each, CUDA IPC) are all-gathered by the caller in rank order and passed to
- * _peer_import. Used when the reduced system fits one CTA's shared memory; otherwise the callback path remains. */
+/* Sharded runs on one NVLink node without any collective library on the data path: when the reduced system fits one CTA's
+ * shared memory (<= 52 free poses) the whole optimize() of every rank is ONE persistent cooperative kernel, and the ranks'
+ * kernels exchange through peer memory - twice per lambda-trial: the partial reduced systems [S | b] (every CTA of every rank
+ * sums the ranks' buffers slice by slice over NVLink) and the scalars [chi2, scale, abort] - with flag words in peer memory
+ * as the only synchronisation. The callback of se2gpu_ba_set_shard is then unused (it stays the path for larger windows).
+ * One process per GPU: after se2gpu_ba_set_shard every rank calls _peer_export, the handles (SE2GPU_BA_PEER_HANDLE_BYTES
+ * each, CUDA IPC) are all-gathered by the caller in rank order and passed to _peer_import. One process driving several
+ * contexts (one per GPU, or several on one GPU for tests): _peer_attach_local on the array of contexts in rank order; every
+ * context then needs its own host thread and stream, since the ranks' optimize() calls must run concurrently.
+ * se2gpu_ba_optimize is a COLLECTIVE call in a sharded run (same arguments on every rank); stop_flag may differ per rank -
+ * the abort decision is OR-ed over the ranks, so all of them stop after the same trial. A rank that does not show up within
+ * SE2GPU_BA_PEER_TIMEOUT_S (default 10 s) makes the others return SE2GPU_ERR_CUDA instead of hanging. */
 #define SE2GPU_BA_PEER_HANDLE_BYTES 128
 int se2gpu_ba_peer_export(se2gpu_ba* h, void* handle_out);
 int se2gpu_ba_peer_import(se2gpu_ba* h, const void* handles, int world);
+int se2gpu_ba_peer_attach_local(se2gpu_ba** contexts, int world);
 /* stream all BA work is enqueued on (cudaStream_t as void*); NULL = default stream */
 int se2gpu_ba_set_stream(se2gpu_ba* h, void* stream);
 

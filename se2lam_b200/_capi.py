@@ -49,7 +49,7 @@ SYMBOLS = [
     "se2gpu_matcher_search_by_bow", "se2gpu_matcher_profile", "se2gpu_matcher_profile_read", "se2gpu_matcher_last_rounds",
     "se2gpu_ba_create", "se2gpu_ba_destroy", "se2gpu_ba_set_problem", "se2gpu_ba_optimize", "se2gpu_ba_get",
     "se2gpu_ba_set_shard", "se2gpu_ba_peer_export", "se2gpu_ba_peer_import", "se2gpu_ba_set_stream", "se2gpu_ba_debug_system", "se2gpu_ba_reset", "se2gpu_ba_profile",
-    "se2gpu_ba_profile_read", "se2gpu_ba_set_mode", "se2gpu_ba_get_f32", "se2gpu_ba_build_information",
+    "se2gpu_ba_profile_read", "se2gpu_ba_set_mode", "se2gpu_ba_get_f32", "se2gpu_ba_build_information", "se2gpu_ba_optimize_from", "se2gpu_ba_peer_attach_local",
     "se2gpu_voc_create", "se2gpu_voc_destroy", "se2gpu_voc_transform", "se2gpu_voc_transform_device", "se2gpu_median_descriptor",
 ]
 
@@ -116,6 +116,8 @@ def lib():
     L.se2gpu_ba_set_stream.argtypes = [vp, vp]
     L.se2gpu_ba_debug_system.argtypes = [vp, d] + [vp] * 10
     L.se2gpu_ba_get_f32.argtypes = [vp, vp, vp]
+    L.se2gpu_ba_optimize_from.argtypes = [vp, i, i, vp, vp, vp, vp]
+    L.se2gpu_ba_peer_attach_local.argtypes = [vp, i]
     L.se2gpu_ba_build_information.argtypes = [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, i, f, f, f, vp, i]
     L.se2gpu_voc_create.restype = vp
     L.se2gpu_voc_create.argtypes = [i, vp, vp, vp, vp, vp, i, i]

@@ -86,12 +86,26 @@ class LocalBA:
                                           float(prob.fx), float(prob.cx), float(prob.cy), ptr(tcb),
                                           float(prob.huber_delta)), "se2gpu_ba_set_problem")
 
-    def optimize(self, iters, trace=False, stop_flag=None):
+    def optimize(self, iters, trace=False, stop_flag=None, first_iteration=0):
+        """first_iteration > 0 continues the lambda / nu schedule of the previous call (g2o's solve(iteration) slices)."""
         st = np.zeros(max(iters, 1), BA_STATS_DTYPE)
         tp = np.zeros((max(iters, 1), self.P, 3)) if trace else None
         tl = np.zeros((max(iters, 1), self.L, 3)) if trace else None
-        n = check(lib().se2gpu_ba_optimize(self.h, iters, ptr(stop_flag), ptr(st), ptr(tp), ptr(tl)), "se2gpu_ba_optimize")
+        n = check(lib().se2gpu_ba_optimize_from(self.h, int(first_iteration), iters, ptr(stop_flag), ptr(st), ptr(tp), ptr(tl)),
+                  "se2gpu_ba_optimize_from")
         return (n, st[:n], tp[:n], tl[:n]) if trace else (n, st[:n])
+
+    @staticmethod
+    def attach_local(bas):
+        """Peer exchange between several contexts of THIS process (one per GPU, or several on one GPU): rank order."""
+        arr = (C.c_void_p * len(bas))(*[b.h for b in bas])
+        check(lib().se2gpu_ba_peer_attach_local(arr, len(bas)), "se2gpu_ba_peer_attach_local")
+
+    def get_f32(self):
+        """Estimates narrowed on the device like Map::optimizeLocalGraph's write-back (Map.cpp:768-779)."""
+        poses = np.zeros((self.P, 3), np.float32); pts = np.zeros((self.L, 3), np.float32)
+        check(lib().se2gpu_ba_get_f32(self.h, ptr(poses), ptr(pts)), "se2gpu_ba_get_f32")
+        return poses, pts
 
     PROFILE_GROUPS = ("ba_linearize", "ba_pose_reduce", "ba_lm_prep", "ba_schur", "ba_chol_solve", "ba_backsub_update", "ba_lm_control",
                       "ba_persistent", "ba_stage_S")

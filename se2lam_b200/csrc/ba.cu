@@ -50,6 +50,8 @@ struct Cam {
 struct LMState {  // device-resident scalars of the LM loop (host mirrors it once per trial)
     double lambda, ni, chi_cur, chi_before, chi_trial, scale, rho, max_diag;
     int cur, solve_ok, accepted, trials, terminate, retry, iter, stop_all;   // stop_all: abort flag, OR-ed over the ranks of a sharded run
+    long long epoch;   // sharded persistent kernel: last exchange epoch used (continues across optimize() calls)
+    int error, pad;    // 1: a peer did not show up within the exchange timeout
 };
 
 struct Dev {  // all device pointers of one context (passed by value to kernels)
@@ -323,14 +325,14 @@ __global__ void __launch_bounds__(POSE_THREADS) ba_pose_reduce(Dev d) {
 // start of an LM iteration: currentChi from the linearisation partials; lambda init at iteration 0
 // (OptimizationAlgorithmLevenberg::computeLambdaInit: 1e-5 * max |diag H| over all free vertices).
 // In sharded mode the host has all-reduced scal[0] (chi) and scal[1] (max diag) before `finish` runs.
-__global__ void __launch_bounds__(256) ba_iter_begin(Dev d, int iter, int phase /*0: local partials -> scal, 1: consume scal*/) {
+__global__ void __launch_bounds__(256) ba_iter_begin(Dev d, int iter, int phase /*0: local partials -> scal, 1: consume scal*/, int itg /*g2o iteration number: lambda is initialised at 0 only*/) {
     __shared__ double sh[32];
     if (phase == 0) {
         double chi = 0;
         for (int b = threadIdx.x; b < d.nb_lm + d.nb_odo; b += blockDim.x) chi += d.part_chi[b];
         chi = block_sum(chi, sh);
         double m = 0;
-        if (iter == 0) {
+        if (itg == 0) {
             const size_t L = d.L, nf = d.nf;
             for (int j = threadIdx.x; j < d.L; j += blockDim.x)
                 if (d.lm_ptr[j + 1] > d.lm_ptr[j]) m = fmax(m, fmax(fabs(d.Hll[j]), fmax(fabs(d.Hll[3 * L + j]), fabs(d.Hll[5 * L + j]))));
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(256) ba_iter_begin(Dev d, int iter, int phase 
         if (threadIdx.x == 0) {
             LMState& s = *d.st;
             s.chi_cur = d.scal[0]; s.chi_before = s.chi_cur;
-            if (iter == 0) { s.max_diag = d.scal[1]; s.lambda = 1e-5 * s.max_diag; s.ni = 2.0; }
+            if (itg == 0) { s.max_diag = d.scal[1]; s.lambda = 1e-5 * s.max_diag; s.ni = 2.0; }
             s.trials = 0; s.accepted = 0; s.terminate = 0; s.retry = 0; s.iter = iter; s.rho = 0;
         }
     }
@@ -704,13 +706,13 @@ __host__ __device__ inline size_t ldlt_smem_bytes(int n) { return ((size_t)n * n
 
 // S (n*n doubles, rounded up to 16 B: the tail lands in y, which is initialised afterwards) and the envelope -> shared
 // memory. One elected thread issues a single bulk copy; everybody waits on the mbarrier phase `parity`.
-__device__ __forceinline__ void ldlt_stage(const Dev& d, unsigned long long* bar, unsigned parity) {
+__device__ __forceinline__ void ldlt_stage(const Dev& d, const double* S, unsigned long long* bar, unsigned parity) {
     extern __shared__ double sm[];
     const int n = d.n;
     int* cmax = reinterpret_cast<int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2);
     const unsigned bytes = (unsigned)(((size_t)n * n * 8 + 15) & ~(size_t)15);
     if (bytes) {
-        if (threadIdx.x == 0) bulk_g2s(sm, d.S, bytes, bar);
+        if (threadIdx.x == 0) bulk_g2s(sm, S, bytes, bar);
         for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
         mbar_wait(bar, parity);
     }
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
     __shared__ __align__(8) unsigned long long bar;
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
-    ldlt_stage(d, &bar, 0);
+    ldlt_stage(d, d.S, &bar, 0);
     ldlt_block_solve<true>(nullptr, nullptr, d.n, nullptr, d.bs, d.dxp, d.st);
 }
 
@@ -729,78 +731,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_gmem(Dev d, double
     ldlt_block_solve<false>(d.S, ywork, d.n, d.colmax, d.bs, d.dxp, d.st);
 }
 
-// ---- sharded runs, fused exchange: the all-reduce of the reduced system [S | b_s] happens INSIDE the solve kernel.
-// Every rank publishes "my partial system of trial `epoch` is complete" in a flag word of its own memory; the solve
-// kernel of every rank waits for all flags, then stages S into shared memory as the sum over the ranks' partial
-// buffers in rank order (own buffer through the local pointer, the others through peer mappings over NVLink:
-// cudaIpcOpenMemHandle). The sum order is the same on every rank, so the replicated solves stay bit-identical. The
-// buffers may be overwritten again after the trial's [chi2, scale] all-reduce, which orders every rank's next Schur
-// kernel after every rank's solve kernel.
 constexpr int MAX_PEERS = 8;
-struct PeerArgs {
-    const double* red[MAX_PEERS];          // [S (n*n) | bs (n)] partial buffer of rank r (own rank: local pointer)
-    const long long* flag[MAX_PEERS];      // epoch flag of rank r
-    double* bs_sum;                        // local [n]: summed right-hand side (the partial one is being read by the peers)
-    long long epoch;
-    int world, rank;
-};
-
-__global__ void ba_peer_signal(long long* flag, long long epoch) {
-    __threadfence_system();
-    *reinterpret_cast<volatile long long*>(flag) = epoch;
-    __threadfence_system();
-}
-
-__global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_peer(Dev d, PeerArgs pa) {
-    extern __shared__ double sm[];
-    const int n = d.n;
-    if (threadIdx.x < pa.world && threadIdx.x != pa.rank) {
-        const volatile long long* f = reinterpret_cast<const volatile long long*>(pa.flag[threadIdx.x]);
-        const long long t0 = clock64();
-        while (*f < pa.epoch)
-            if (clock64() - t0 > 4000000000LL) __trap();       // ~2 s: a peer died or the ranks diverged - fail, do not hang
-        __threadfence_system();
-    }
-    __syncthreads();
-    int* cmax = reinterpret_cast<int*>(sm + (size_t)n * n + n + 3 * (size_t)n + 2);
-    for (int t = threadIdx.x; t < n; t += blockDim.x) cmax[t] = d.colmax[t];
-    // [S | bs] = n*n + n doubles, fetched as 16-byte vectors, PEER_BATCH independent loads in flight per thread and peer
-    // (an NVLink round trip is ~2 us: a dependent load chain would serialise them)
-    constexpr int PEER_BATCH = 8;
-    const int total = n * n + n, nvec = total / 2;
-    for (int v0 = threadIdx.x; v0 < nvec; v0 += blockDim.x * PEER_BATCH) {
-        double2 acc[PEER_BATCH];
-#pragma unroll
-        for (int u = 0; u < PEER_BATCH; ++u) acc[u] = make_double2(0.0, 0.0);
-        for (int r = 0; r < pa.world; ++r) {
-            const double2* src = reinterpret_cast<const double2*>(pa.red[r]);
-            double2 t[PEER_BATCH];
-#pragma unroll
-            for (int u = 0; u < PEER_BATCH; ++u) {
-                const int v = v0 + u * blockDim.x;
-                t[u] = v < nvec ? ((r == pa.rank) ? src[v] : __ldcv(src + v)) : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < PEER_BATCH; ++u) { acc[u].x += t[u].x; acc[u].y += t[u].y; }
-        }
-#pragma unroll
-        for (int u = 0; u < PEER_BATCH; ++u) {
-            const int v = v0 + u * blockDim.x;
-            if (v < nvec) {
-                const int i = 2 * v;
-                if (i < n * n) sm[i] = acc[u].x; else pa.bs_sum[i - n * n] = acc[u].x;
-                if (i + 1 < n * n) sm[i + 1] = acc[u].y; else pa.bs_sum[i + 1 - n * n] = acc[u].y;
-            }
-        }
-    }
-    if ((total & 1) && threadIdx.x == 0) {       // odd tail element
-        double v = 0;
-        for (int r = 0; r < pa.world; ++r) v += (r == pa.rank) ? pa.red[r][total - 1] : __ldcv(pa.red[r] + total - 1);
-        pa.bs_sum[total - 1 - n * n] = v;
-    }
-    __syncthreads();
-    ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, pa.bs_sum, d.dxp, d.st);
-}
 
 // back-substitution + oplus into the trial buffers + partial sums of computeScale()
 __global__ void __launch_bounds__(LM_THREADS) ba_backsub_update(Dev d) {
@@ -908,6 +839,8 @@ constexpr int LPL = 8;
 
 struct PKArgs {
     int max_iters;
+    int first_iter;           // iteration number of the first LM iteration of this call (g2o's solve(iteration): lambda is
+                              // initialised at iteration 0 only; > 0 continues the lambda / nu schedule of the previous call)
     se2gpu_ba_iter_stats* stats;
     double* trace_p;          // [max_iters][3P] or null
     double* trace_l;          // [max_iters][3L] or null
@@ -922,6 +855,84 @@ struct PKArgs {
     int dyn_smem_bytes;       // dynamic shared memory of the launch (arena size of the non-zero CTAs)
     long long* cta_work;      // [gridDim.x][8] per-CTA busy cycles per phase (debug aid, null = off)
 };
+
+// Multi-GPU hooks of the persistent kernel (sharded runs on one NVLink node, se2gpu_ba_peer_import / _peer_attach_local): every
+// rank runs the same cooperative kernel on its own landmarks; twice per lambda-trial the ranks exchange through peer memory
+//   (1) the partial reduced systems [S | b_s]: after its Schur phase a rank publishes "epoch e complete" in a flag word of its
+//       exchange block; when all flags are in, ALL CTAs of every rank sum the ranks' buffers slice by slice in rank order (own
+//       buffer through the local pointer, the others over NVLink, every peer's load in flight at once: one round trip) into a
+//       local buffer that the solve then stages - identical sums on every rank, so the replicated solves stay bit-identical;
+//   (2) the scalars [chi2, scale, abort] (+ at iteration 0 the landmark-diagonal maximum and the pose diagonal for lambda_0):
+//       same flags, a few doubles per rank.
+// Only CTA 0 polls the peers (bounded spin); it hands the verdict to the other CTAs through a local word, so a missing peer
+// makes every CTA of the rank leave the kernel with an error instead of hanging or trapping.
+struct PKShard {
+    int world, rank;
+    const double* red[MAX_PEERS];      // partial [S | bs] of every rank
+    const double* xch[MAX_PEERS];      // exchange block of every rank
+    double* my_xch;                    // own exchange block
+    double* ssum;                      // local: summed [S | bs]
+    long long* go;                     // local [2]: epoch CTA 0 has seen complete on all peers (S, scalars); -1 = peer timeout
+    long long epoch0, timeout_cycles;
+    int xslot;                         // doubles per scalar slot
+};
+constexpr int XCH_HDR = 16;            // doubles: [0] S flag, [1] scalar flag (as long long), rest padding
+
+__device__ __forceinline__ void pk_publish(const PKShard& sh, int which, long long epoch) {     // CTA 0, thread 0, after a grid barrier
+    __threadfence_system();
+    *reinterpret_cast<volatile long long*>(sh.my_xch + which) = epoch;
+    __threadfence_system();
+}
+// all threads of all CTAs; returns false on peer timeout (uniform across the grid)
+__device__ bool pk_wait_peers(const PKShard& sh, int which, long long epoch) {
+    __shared__ long long s_go;
+    if (blockIdx.x == 0) {
+        int ok = 1;
+        if ((int)threadIdx.x < sh.world && (int)threadIdx.x != sh.rank) {
+            const volatile long long* f = reinterpret_cast<const volatile long long*>(sh.xch[threadIdx.x] + which);
+            const long long t0 = clock64();
+            while (*f < epoch)
+                if (clock64() - t0 > sh.timeout_cycles) { ok = 0; break; }
+        }
+        ok = __syncthreads_and(ok);
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile long long*>(sh.go + which) = ok ? epoch : -1;
+            __threadfence();
+        }
+    }
+    if (threadIdx.x == 0) {
+        long long v;
+        do { v = *reinterpret_cast<volatile long long*>(sh.go + which); } while (v >= 0 && v < epoch);
+        __threadfence_system();
+        s_go = v;
+    }
+    __syncthreads();
+    const bool good = s_go >= 0;
+    __syncthreads();
+    return good;
+}
+// every CTA: ssum[slice] = sum over ranks of red[r][slice], rank order
+__device__ void pk_sum_partials(const PKShard& sh, int total) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int nvec = total / 2;
+    for (int v = gtid; v < nvec; v += gthreads) {
+        double2 t[MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < MAX_PEERS; ++r)
+            if (r < sh.world) t[r] = (r == sh.rank) ? reinterpret_cast<const double2*>(sh.red[r])[v] : __ldcv(reinterpret_cast<const double2*>(sh.red[r]) + v);
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < MAX_PEERS; ++r)
+            if (r < sh.world) { acc.x += t[r].x; acc.y += t[r].y; }
+        reinterpret_cast<double2*>(sh.ssum)[v] = acc;
+    }
+    if ((total & 1) && gtid == 0) {
+        double v = 0;
+        for (int r = 0; r < sh.world; ++r) v += (r == sh.rank) ? sh.red[r][total - 1] : __ldcv(sh.red[r] + total - 1);
+        sh.ssum[total - 1] = v;
+    }
+}
 
 __device__ __forceinline__ double group_sum(double v) {   // sum over the LPL-lane group, fixed order
     v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -1422,7 +1433,7 @@ __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
     }
 }
 
-__device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
+__device__ double pk_phase_backsub(const Dev& d, int cur, double lam, double lam_pose) {
     const double* xp = d.xp[cur];
     const double* xl = d.xl[cur];
     double* xpt = d.xp[cur ^ 1];
@@ -1463,7 +1474,7 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
             const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
             xpt[3 * t] = xp[3 * t] + p0; xpt[3 * t + 1] = xp[3 * t + 1] + p1;
             xpt[3 * t + 2] = normalize_theta(xp[3 * t + 2] + p2);
-            sc += p0 * (lam * p0 + d.bp[3 * a]) + p1 * (lam * p1 + d.bp[3 * a + 1]) + p2 * (lam * p2 + d.bp[3 * a + 2]);
+            sc += p0 * (lam_pose * p0 + d.bp[3 * a]) + p1 * (lam_pose * p1 + d.bp[3 * a + 1]) + p2 * (lam_pose * p2 + d.bp[3 * a + 2]);
         } else {
             xpt[3 * t] = xp[3 * t]; xpt[3 * t + 1] = xp[3 * t + 1]; xpt[3 * t + 2] = xp[3 * t + 2];
         }
@@ -1471,7 +1482,7 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam) {
     return sc;
 }
 
-__global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, PKArgs pa) {
+__global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, PKArgs pa, PKShard shd) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh[32];
     __shared__ double shv[(PK_THREADS / 32) * 21];
@@ -1537,24 +1548,32 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     }
     __syncthreads();
     const int n = d.n, nparts = gridDim.x;
-    double lambda = 0, ni = 2, chi_cur = 0;
+    const bool shard = shd.world > 1;
+    const double* Ssrc = shard ? shd.ssum : d.S;                   // what the solve stages: the rank-summed system in sharded runs
+    const double* bsrc = shard ? shd.ssum + (size_t)n * n : d.bs;
+    double lambda = d.st->lambda, ni = d.st->ni, chi_cur = d.st->chi_cur;   // continued from the previous call when first_iter > 0
+    long long epoch = shd.epoch0;
     int cur = d.st->cur, done = 0;
-    bool stop = false;
+    bool stop = false, peer_err = false;
+    // scalar exchange of a sharded run: CTA 0 fills this rank's slot `epoch & 1` with v[0..nv) (+ the pose diagonal when
+    // asked), publishes, everybody waits for the peers and reads all ranks' slots back in rank order
+    auto xslot_of = [&](int r, long long e) { return shd.xch[r] + XCH_HDR + (size_t)(e & 1) * shd.xslot; };
     // phase timers live in shared memory and are touched by thread 0 only (keeps them out of the register budget)
     __shared__ long long tacc[8], wacc[8], tprev_s, wprev_s;
     if (threadIdx.x == 0) { for (int g = 0; g < 8; ++g) { tacc[g] = 0; wacc[g] = 0; } tprev_s = wprev_s = clock64(); }
 #define PK_TICK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); tacc[g] += _t - tprev_s; tprev_s = _t; wprev_s = _t; } } while (0)
 #define PK_WORK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); wacc[g] += _t - wprev_s; wprev_s = _t; } } while (0)
     for (int it = 0; it < pa.max_iters && !stop; ++it) {
-        // ---- A: linearise at x_cur (computeActiveErrors + buildSystem). For it > 0 the damping of the first trial is already
+        const int itg = pa.first_iter + it;                       // g2o's iteration number
+        // ---- A: linearise at x_cur (computeActiveErrors + buildSystem). For itg > 0 the damping of the first trial is already
         // known, so the damping-dependent landmark terms are formed in the same pass (no phase B, one grid barrier less).
-        pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh, it > 0 ? lambda : -1.0);
+        pk_phase_linearize<true>(d, cam, cur, pa.part_chi, sh, itg > 0 ? lambda : -1.0);
         if (blockIdx.x == 0 && threadIdx.x == 0) pa.abort_dev[0] = *pa.abort_host;
         PK_WORK(0);
         grid.sync();
         PK_TICK(0);
-        if (pa.abort_dev[0]) break;
-        if (it == 0) {
+        if (!shard && pa.abort_dev[0]) break;                      // sharded runs take the abort decision collectively (below)
+        if (itg == 0) {
             // ---- B (first iteration only): pose-side gather and landmark diagonal maximum for lambda_0 = 1e-5 max|diag H|
             pk_phase_pose_reduce(d, work, shv);
             double m = 0;
@@ -1567,39 +1586,86 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             grid.sync();
             PK_TICK(1);
         }
-        chi_cur = cta_sum_array(pa.part_chi, nparts, sh);
-        const double chi_before = chi_cur;
-        if (it == 0) {
+        if (!shard || it == 0) chi_cur = cta_sum_array(pa.part_chi, nparts, sh);   // sharded: afterwards the accepted trial's global chi2 is carried
+        if (itg == 0) {
             double m = 0;
             for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = fmax(m, pa.part_max[i]);
             const size_t nf = d.nf;
-            for (int a = threadIdx.x; a < d.nf; a += blockDim.x) m = fmax(m, fmax(fabs(d.Hpp[a]), fmax(fabs(d.Hpp[3 * nf + a]), fabs(d.Hpp[5 * nf + a]))));
-            m = cta_max(m, sh);
+            if (!shard) {
+                for (int a = threadIdx.x; a < d.nf; a += blockDim.x) m = fmax(m, fmax(fabs(d.Hpp[a]), fmax(fabs(d.Hpp[3 * nf + a]), fabs(d.Hpp[5 * nf + a]))));
+                m = cta_max(m, sh);
+            } else {
+                // lambda_0 needs the maximum over ALL landmarks and over the rank-SUMMED pose diagonal; chi2 and the abort flag ride along
+                m = cta_max(m, sh);
+                ++epoch;
+                if (blockIdx.x == 0) {
+                    double* slot = shd.my_xch + XCH_HDR + (size_t)(epoch & 1) * shd.xslot;
+                    if (threadIdx.x == 0) { slot[0] = chi_cur; slot[1] = 0.0; slot[2] = pa.abort_dev[0] ? 1.0 : 0.0; slot[3] = m; }
+                    for (int a = threadIdx.x; a < d.nf; a += blockDim.x) { slot[8 + 3 * a] = d.Hpp[a]; slot[8 + 3 * a + 1] = d.Hpp[3 * nf + a]; slot[8 + 3 * a + 2] = d.Hpp[5 * nf + a]; }
+                    __syncthreads();
+                    if (threadIdx.x == 0) pk_publish(shd, 1, epoch);
+                }
+                if (!pk_wait_peers(shd, 1, epoch)) { peer_err = true; break; }
+                double chi = 0, ab = 0, mm = 0;
+                for (int r = 0; r < shd.world; ++r) { const double* sl = xslot_of(r, epoch); chi += __ldcv(sl); ab += __ldcv(sl + 2); mm = fmax(mm, __ldcv(sl + 3)); }
+                for (int q = threadIdx.x; q < 3 * d.nf; q += blockDim.x) {
+                    double v = 0;
+                    for (int r = 0; r < shd.world; ++r) v += __ldcv(xslot_of(r, epoch) + 8 + q);
+                    mm = fmax(mm, fabs(v));
+                }
+                m = cta_max(mm, sh);
+                chi_cur = chi;
+                if (ab > 0.0) break;
+            }
             lambda = 1e-5 * m; ni = 2;
+        } else if (shard && it == 0) {
+            // continuation call of a sharded run: this rank's chi2 partial -> global (one scalar exchange)
+            ++epoch;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                double* slot = shd.my_xch + XCH_HDR + (size_t)(epoch & 1) * shd.xslot;
+                slot[0] = chi_cur; slot[1] = 0.0; slot[2] = pa.abort_dev[0] ? 1.0 : 0.0; slot[3] = 0.0;
+                pk_publish(shd, 1, epoch);
+            }
+            if (!pk_wait_peers(shd, 1, epoch)) { peer_err = true; break; }
+            double chi = 0, ab = 0;
+            for (int r = 0; r < shd.world; ++r) { const double* sl = xslot_of(r, epoch); chi += __ldcv(sl); ab += __ldcv(sl + 2); }
+            chi_cur = chi;
+            if (ab > 0.0) break;
         }
+        const double chi_before = chi_cur;
+        const double lam_pose_mask = (d.rank == 0) ? 1.0 : 0.0;     // the damping of the pose block is added once across shards
         int trials = 0, accepted = 0;
         double rho = 0;
         do {
-            // ---- P: damping-dependent per-landmark terms (first trial of it > 0: already formed in phase A)
+            // ---- P: damping-dependent per-landmark terms (first trial of itg > 0: already formed in phase A)
             PK_TICK(6);
-            if (it == 0 || trials > 0) {
+            if (itg == 0 || trials > 0) {
                 pk_phase_lm_prep(d, lambda);
                 PK_WORK(2);
                 grid.sync();
             }
             PK_TICK(2);
             // ---- C: Schur complement gather
-            if (s_plan_ok) pk_phase_schur_par(d, lambda, work, plan_w0, plan_nw, shv);
-            else pk_phase_schur(d, lambda, work, shv);
+            if (s_plan_ok) pk_phase_schur_par(d, lambda * lam_pose_mask, work, plan_w0, plan_nw, shv);
+            else pk_phase_schur(d, lambda * lam_pose_mask, work, shv);
             PK_WORK(3);
             grid.sync();
             PK_TICK(3);
+            if (shard) {
+                // ---- X1: the all-reduce of the reduced system, inside the kernel: publish, wait for the peers, sum the ranks' buffers
+                ++epoch;
+                if (blockIdx.x == 0 && threadIdx.x == 0) pk_publish(shd, 0, epoch);
+                if (!pk_wait_peers(shd, 0, epoch)) { peer_err = true; break; }
+                pk_sum_partials(shd, n * n + n);
+                grid.sync();
+                PK_TICK(1);
+            }
             // ---- D: reduced solve (one CTA; S staged into its shared memory)
             if (blockIdx.x == 0) {
-                ldlt_stage(d, &stage_bar, stage_parity);
+                ldlt_stage(d, Ssrc, &stage_bar, stage_parity);
                 stage_parity ^= 1;
                 PK_TICK(7);
-                ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, d.bs, d.dxp, d.st);
+                ldlt_block_solve<true>(nullptr, nullptr, n, nullptr, bsrc, d.dxp, d.st);
             }
             PK_WORK(4);
             grid.sync();
@@ -1607,7 +1673,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             const int solve_ok = d.st->solve_ok;
             // ---- E: back-substitution, oplus into the trial buffers, computeScale partials
             {
-                const double sc = pk_phase_backsub(d, cur, lambda);
+                const double sc = pk_phase_backsub(d, cur, lambda, lambda * lam_pose_mask);
                 const double tot = block_sum(sc, sh);
                 if (threadIdx.x == 0) pa.part_scale[blockIdx.x] = tot;
             }
@@ -1620,9 +1686,24 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             PK_WORK(7);
             grid.sync();
             PK_TICK(0);
-            // ---- LM decision (identical in every CTA)
-            const double tempChi = solve_ok ? cta_sum_array(pa.part_chi + nparts, nparts, sh) : DBL_MAX;
-            const double scale = (solve_ok ? cta_sum_array(pa.part_scale, nparts, sh) : 0.0) + 1e-3;
+            // ---- LM decision (identical in every CTA, and in every rank)
+            double tempChi = cta_sum_array(pa.part_chi + nparts, nparts, sh);
+            double scale = cta_sum_array(pa.part_scale, nparts, sh);
+            double ab = pa.abort_dev[1] ? 1.0 : 0.0;
+            if (shard) {
+                // ---- X2: [chi2, scale, abort] summed over the ranks
+                ++epoch;
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    double* slot = shd.my_xch + XCH_HDR + (size_t)(epoch & 1) * shd.xslot;
+                    slot[0] = tempChi; slot[1] = scale; slot[2] = ab; slot[3] = 0.0;
+                    pk_publish(shd, 1, epoch);
+                }
+                if (!pk_wait_peers(shd, 1, epoch)) { peer_err = true; break; }
+                tempChi = 0; scale = 0; ab = 0;
+                for (int r = 0; r < shd.world; ++r) { const double* sl = xslot_of(r, epoch); tempChi += __ldcv(sl); scale += __ldcv(sl + 1); ab += __ldcv(sl + 2); }
+            }
+            if (!solve_ok) { tempChi = DBL_MAX; scale = 0.0; }
+            scale += 1e-3;
             rho = (chi_cur - tempChi) / scale;
             if (rho > 0 && isfinite(tempChi)) {
                 double alpha = 1. - pow((2 * rho - 1), 3);
@@ -1632,8 +1713,9 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 lambda *= ni; ni *= 2;
             }
             ++trials;
-            stop = (pa.abort_dev[1] != 0);
+            stop = ab > 0.0;
         } while (rho < 0 && trials < 10 && !stop);
+        if (peer_err) break;
         const int terminate = (trials == 10 || rho == 0) ? 1 : 0;
         if (blockIdx.x == 0 && threadIdx.x == 0 && pa.stats) {
             se2gpu_ba_iter_stats& o = pa.stats[it];
@@ -1651,7 +1733,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     if (pa.cta_work && threadIdx.x == 0) for (int g = 0; g < 8; ++g) pa.cta_work[blockIdx.x * 8 + g] = wacc[g];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         LMState& s = *d.st;
-        s.cur = cur; s.lambda = lambda; s.ni = ni; s.chi_cur = chi_cur; s.iter = done;
+        s.cur = cur; s.lambda = lambda; s.ni = ni; s.chi_cur = chi_cur; s.iter = done; s.epoch = epoch; s.error = peer_err ? 1 : 0;
         if (pa.phase_cycles) for (int g = 0; g < 8; ++g) pa.phase_cycles[g] += tacc[g];
     }
 }
@@ -1714,14 +1796,17 @@ struct se2gpu_ba {
     cudaStream_t stream = nullptr;
     int rank = 0, world = 1;
     se2gpu_allreduce_fn allreduce = nullptr;
-    // fused peer exchange (se2gpu_ba_peer_export / _import)
-    long long* peer_flag = nullptr;            // this rank's epoch flag (own cudaMalloc: exported by IPC handle)
-    double* bs_sum = nullptr;
+    // sharded persistent kernel: exchange through peer memory (se2gpu_ba_peer_export / _import / _peer_attach_local)
+    double* xch = nullptr;                      // this rank's exchange block: flags + 2 scalar slots (own cudaMalloc: exported by IPC handle)
+    int xslot = 0;                              // doubles per scalar slot
+    double* ssum = nullptr;                     // rank-summed [S | bs]
+    long long* go = nullptr;                    // [2] local hand-off words of pk_wait_peers
     void* peer_opened[16] = {};                 // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
     const double* peer_red[8] = {};
-    const long long* peer_flags[8] = {};
+    const double* peer_xch[8] = {};
     bool peer_on = false;
     long long peer_epoch = 0;
+    double peer_timeout_s = 10.0;
     void* ar_user = nullptr;
     Dev d{};
     Cam cam{};
@@ -1839,6 +1924,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
         if (coop && cudaFuncSetAttribute(ba_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ba_persistent, PK_THREADS, smem_max) == cudaSuccess && occ >= 1)
             h->pk_grid = std::min(nsm, 1024);
+        if (const char* g = getenv("SE2GPU_BA_PK_GRID")) { const int lim = atoi(g); if (lim >= 2 && lim < h->pk_grid) h->pk_grid = lim; }   // test hook: several contexts on one GPU
         cudaGetLastError();
         if (cudaHostAlloc((void**)&h->abort_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer((void**)&h->abort_host_dev, h->abort_host, 0) != cudaSuccess) { h->pk_grid = 0; cudaGetLastError(); }
@@ -1857,25 +1943,36 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (h->abort_host) cudaFreeHost(h->abort_host);
     se2band::release(h->band);
     for (void* m : h->peer_opened) if (m) cudaIpcCloseMemHandle(m);
-    if (h->peer_flag) cudaFree(h->peer_flag);
-    if (h->bs_sum) cudaFree(h->bs_sum);
+    if (h->xch) cudaFree(h->xch);
+    if (h->ssum) cudaFree(h->ssum);
+    if (h->go) cudaFree(h->go);
     if (h->st_host) cudaFreeHost(h->st_host);
     delete h->arena;
     delete h->arena2;
     delete h;
 }
 
+static int peer_alloc(se2gpu_ba* h) {
+    if (h->xch) return SE2GPU_OK;
+    SE2_CUDA(cudaSetDevice(h->device));
+    h->xslot = (8 + 3 * h->maxP + 7) & ~7;
+    const size_t xd = XCH_HDR + 2 * (size_t)h->xslot;
+    SE2_CUDA(cudaMalloc((void**)&h->xch, sizeof(double) * xd));
+    SE2_CUDA(cudaMemset(h->xch, 0, sizeof(double) * xd));
+    SE2_CUDA(cudaMalloc((void**)&h->ssum, sizeof(double) * ((size_t)SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + SMEM_CHOL_MAX_N + 8)));
+    SE2_CUDA(cudaMalloc((void**)&h->go, 2 * sizeof(long long)));
+    SE2_CUDA(cudaMemset(h->go, 0, 2 * sizeof(long long)));
+    if (const char* t = getenv("SE2GPU_BA_PEER_TIMEOUT_S")) h->peer_timeout_s = atof(t) > 0 ? atof(t) : h->peer_timeout_s;
+    return SE2GPU_OK;
+}
+
 int se2gpu_ba_peer_export(se2gpu_ba* h, void* handle_out) {
     if (!h || !handle_out) return fail(SE2GPU_ERR_INVALID, "null argument");
-    SE2_CUDA(cudaSetDevice(h->device));
-    if (!h->peer_flag) {
-        SE2_CUDA(cudaMalloc((void**)&h->peer_flag, 256));
-        SE2_CUDA(cudaMemset(h->peer_flag, 0, 256));
-        SE2_CUDA(cudaMalloc((void**)&h->bs_sum, sizeof(double) * (size_t)std::max(h->maxN, 1)));
-    }
+    int rc = peer_alloc(h);
+    if (rc != SE2GPU_OK) return rc;
     cudaIpcMemHandle_t hs[2];
     SE2_CUDA(cudaIpcGetMemHandle(&hs[0], h->red));
-    SE2_CUDA(cudaIpcGetMemHandle(&hs[1], h->peer_flag));
+    SE2_CUDA(cudaIpcGetMemHandle(&hs[1], h->xch));
     static_assert(sizeof(hs) == SE2GPU_BA_PEER_HANDLE_BYTES, "handle size");
     memcpy(handle_out, hs, sizeof hs);
     return SE2GPU_OK;
@@ -1884,11 +1981,11 @@ int se2gpu_ba_peer_export(se2gpu_ba* h, void* handle_out) {
 int se2gpu_ba_peer_import(se2gpu_ba* h, const void* handles, int world) {
     if (!h || !handles) return fail(SE2GPU_ERR_INVALID, "null argument");
     if (world != h->world || world < 2 || world > MAX_PEERS) return fail(SE2GPU_ERR_INVALID, "peer exchange needs 2..%d ranks matching se2gpu_ba_set_shard", MAX_PEERS);
-    if (!h->peer_flag) return fail(SE2GPU_ERR_INVALID, "call se2gpu_ba_peer_export first");
+    if (!h->xch) return fail(SE2GPU_ERR_INVALID, "call se2gpu_ba_peer_export first");
     SE2_CUDA(cudaSetDevice(h->device));
     const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(handles);
     for (int r = 0; r < world; ++r) {
-        if (r == h->rank) continue;
+        if (r == h->rank) { h->peer_red[r] = h->red; h->peer_xch[r] = h->xch; continue; }
         void *pr = nullptr, *pf = nullptr;
         if (cudaIpcOpenMemHandle(&pr, hs[2 * r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
             cudaIpcOpenMemHandle(&pf, hs[2 * r + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -1896,12 +1993,35 @@ int se2gpu_ba_peer_import(se2gpu_ba* h, const void* handles, int world) {
             if (pr) cudaIpcCloseMemHandle(pr);
             return fail(SE2GPU_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
         }
-        h->peer_red[r] = static_cast<const double*>(pr); h->peer_flags[r] = static_cast<const long long*>(pf);
+        h->peer_red[r] = static_cast<const double*>(pr); h->peer_xch[r] = static_cast<const double*>(pf);
         for (void*& slot : h->peer_opened) if (!slot) { slot = pr; break; }
         for (void*& slot : h->peer_opened) if (!slot) { slot = pf; break; }
     }
-    SE2_CUDA(cudaFuncSetAttribute(ba_chol_solve_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N)));
     h->peer_on = true;
+    return SE2GPU_OK;
+}
+
+int se2gpu_ba_peer_attach_local(se2gpu_ba** hs, int world) {
+    if (!hs || world < 2 || world > MAX_PEERS) return fail(SE2GPU_ERR_INVALID, "peer exchange needs 2..%d contexts", MAX_PEERS);
+    for (int r = 0; r < world; ++r) {
+        if (!hs[r] || hs[r]->world != world || hs[r]->rank != r) return fail(SE2GPU_ERR_INVALID, "context %d is not rank %d of %d (se2gpu_ba_set_shard)", r, r, world);
+        int rc = peer_alloc(hs[r]);
+        if (rc != SE2GPU_OK) return rc;
+    }
+    for (int r = 0; r < world; ++r)
+        for (int q = 0; q < world; ++q) {
+            if (q != r && hs[q]->device != hs[r]->device) {      // same process, different GPUs: direct peer access
+                SE2_CUDA(cudaSetDevice(hs[r]->device));
+                int can = 0;
+                SE2_CUDA(cudaDeviceCanAccessPeer(&can, hs[r]->device, hs[q]->device));
+                if (!can) return fail(SE2GPU_ERR_CUDA, "device %d cannot access device %d", hs[r]->device, hs[q]->device);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(hs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(SE2GPU_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            hs[r]->peer_red[q] = hs[q]->red; hs[r]->peer_xch[q] = hs[q]->xch;
+        }
+    for (int r = 0; r < world; ++r) hs[r]->peer_on = true;
     return SE2GPU_OK;
 }
 
@@ -2220,17 +2340,6 @@ int launch_solve(se2gpu_ba* h) {
     h->prof.begin(3, s);
     if (d.nblk > 0) SE2_LAUNCH(ba_schur, d.nblk, SCHUR_THREADS, 0, s, d);
     h->prof.end(s);
-    if (h->world > 1 && h->peer_on && d.n <= SMEM_CHOL_MAX_N) {
-        // fused exchange: publish this rank's partial system, the solve kernel sums all ranks' buffers over NVLink
-        PeerArgs pa{};
-        for (int r = 0; r < h->world; ++r) { pa.red[r] = (r == h->rank) ? h->red : h->peer_red[r]; pa.flag[r] = (r == h->rank) ? h->peer_flag : h->peer_flags[r]; }
-        pa.bs_sum = h->bs_sum; pa.epoch = ++h->peer_epoch; pa.world = h->world; pa.rank = h->rank;
-        h->prof.begin(4, s);
-        SE2_LAUNCH(ba_peer_signal, 1, 1, 0, s, h->peer_flag, pa.epoch);
-        SE2_LAUNCH(ba_chol_solve_peer, 1, CHOL_THREADS, ldlt_smem_bytes(d.n), s, d, pa);
-        h->prof.end(s);
-        return SE2GPU_OK;
-    }
     int rc = ar(h, d.S, S_elems + d.n, 0);     // the message is the stored pattern: dense for small windows, the band for large ones
     if (rc != SE2GPU_OK) return rc;
     h->prof.begin(4, s);
@@ -2247,16 +2356,22 @@ extern "C" {
 
 int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char* stop_flag, se2gpu_ba_iter_stats* stats,
                        double* trace_poses, double* trace_points) {
+    return se2gpu_ba_optimize_from(h, 0, max_iters, stop_flag, stats, trace_poses, trace_points);
+}
+
+int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, const volatile unsigned char* stop_flag,
+                            se2gpu_ba_iter_stats* stats, double* trace_poses, double* trace_points) {
     if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
-    if (max_iters < 0) return fail(SE2GPU_ERR_INVALID, "max_iters < 0");
+    if (max_iters < 0 || first_iteration < 0) return fail(SE2GPU_ERR_INVALID, "negative iteration count");
     if (max_iters > h->max_stats) return fail(SE2GPU_ERR_CAPACITY, "max_iters > %d", h->max_stats);
     SE2_CUDA(cudaSetDevice(h->device));
     Dev& d = h->d;
     cudaStream_t s = h->stream;
-    const bool can_persist = h->world == 1 && h->pk_grid > 0 && d.n <= SMEM_CHOL_MAX_N;
-    if (h->mode == 2 && !can_persist) return fail(SE2GPU_ERR_INVALID, "persistent mode unavailable (sharded run, %d unknowns > %d, or no cooperative launch)", d.n, SMEM_CHOL_MAX_N);
+    const bool can_persist = (h->world == 1 || h->peer_on) && h->pk_grid > 0 && d.n <= SMEM_CHOL_MAX_N;
+    if (h->mode == 2 && !can_persist) return fail(SE2GPU_ERR_INVALID, "persistent mode unavailable (sharded run without peer exchange, %d unknowns > %d, or no cooperative launch)", d.n, SMEM_CHOL_MAX_N);
     if (can_persist && h->mode != 1) {
-        if (max_iters == 0 || (stop_flag && *stop_flag)) return 0;
+        if (max_iters == 0) return 0;
+        if (h->world == 1 && stop_flag && *stop_flag) return 0;      // sharded: the kernel takes the decision collectively
         // the whole optimize() is ONE cooperative launch; the host only forwards the abort flag while it runs
         if (trace_poses && h->trace_cap_p < (size_t)max_iters * 3 * h->P) {
             if (h->trace_p) cudaFree(h->trace_p);
@@ -2268,13 +2383,21 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
             h->trace_cap_l = (size_t)max_iters * 3 * h->L;
             SE2_CUDA(cudaMalloc((void**)&h->trace_l, h->trace_cap_l * sizeof(double)));
         }
-        *h->abort_host = 0;
-        PKArgs pa{max_iters, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
+        *h->abort_host = (stop_flag && *stop_flag) ? 1 : 0;
+        PKShard shd{};
+        shd.world = h->world; shd.rank = h->rank;
+        if (h->world > 1) {
+            for (int r = 0; r < h->world; ++r) { shd.red[r] = h->peer_red[r]; shd.xch[r] = h->peer_xch[r]; }
+            shd.my_xch = h->xch; shd.ssum = h->ssum; shd.go = h->go; shd.epoch0 = h->peer_epoch; shd.xslot = h->xslot;
+            shd.timeout_cycles = (long long)(h->peer_timeout_s * 1e3 * (double)(h->clock_khz > 0 ? h->clock_khz : 1965000));
+            SE2_CUDA(cudaMemsetAsync(h->go, 0, 2 * sizeof(long long), s));
+        }
+        PKArgs pa{max_iters, first_iteration, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
                   h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0, getenv("SE2GPU_BA_DEBUG") ? h->cta_work : nullptr};
         if (h->prof.on) h->pk_launches++;
         const size_t smem = std::max(ldlt_smem_bytes(d.n), (size_t)96 * 1024);
         pa.dyn_smem_bytes = (int)smem;
-        void* args[] = {(void*)&d, (void*)&h->cam, (void*)&pa};
+        void* args[] = {(void*)&d, (void*)&h->cam, (void*)&pa, (void*)&shd};
         h->prof.begin(7, s);
         SE2_CUDA(cudaLaunchCooperativeKernel((void*)ba_persistent, dim3(h->pk_grid), dim3(PK_THREADS), args, smem, s));
         se2gpu::g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -2285,6 +2408,10 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         }
         SE2_CUDA(cudaStreamSynchronize(s));
         const int done = h->st_host->iter;
+        if (h->world > 1) {
+            h->peer_epoch = h->st_host->epoch;
+            if (h->st_host->error) return fail(SE2GPU_ERR_CUDA, "sharded BA: a peer rank did not reach the exchange within %.1f s (rank %d of %d)", h->peer_timeout_s, h->rank, h->world);
+        }
         if (pa.cta_work) {   // SE2GPU_BA_DEBUG=1: per-phase busy cycles of every CTA (max / mean / who) to stderr
             std::vector<long long> w((size_t)h->pk_grid * 8);
             cudaMemcpy(w.data(), h->cta_work, w.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -2318,15 +2445,16 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
         stop_all = all > 0.0;
     }
     for (int it = 0; it < max_iters && !stop_all && ok; ++it) {
+        const int itg = first_iteration + it;
         int rc = launch_linearize(h);
         if (rc != SE2GPU_OK) return rc;
         h->prof.begin(6, s);
-        SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 0);
+        SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 0, itg);
         h->prof.end(s);
         if (h->world > 1) {
             // chi2 is summed; lambda_init needs max|diag| over the SUMMED pose diagonal and all landmarks
             if ((rc = ar(h, d.scal, 1, 0)) != SE2GPU_OK) return rc;
-            if (it == 0) {
+            if (itg == 0) {
                 if ((rc = ar(h, d.scal + 1, 1, 1)) != SE2GPU_OK) return rc;   // max over ranks of the landmark diagonal
                 // pose diagonal: sum the 6 x nf block array across ranks on a scratch copy (S is free here), fold its
                 // diagonal maximum into scal[1] on the device - no host round trip
@@ -2336,7 +2464,7 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
                 SE2_LAUNCH(ba_pose_diag_max, 1, 256, 0, s, scratch, d.nf, d.scal + 1);
                 SE2_CUDA(cudaMemsetAsync(d.S, 0, sizeof(double) * 6 * d.nf, s));
             }
-            SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 1);
+            SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, it, 1, itg);
         }
         bool retry = true;
         while (retry) {
@@ -2460,7 +2588,7 @@ int se2gpu_ba_debug_system(se2gpu_ba* h, double lambda, double* chi2, double* Hp
     const int n = d.n, nf = d.nf, L = d.L, E = d.E;
     int rc = launch_linearize(h);
     if (rc != SE2GPU_OK) return rc;
-    SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, 1, 0);   // iter!=0: keeps lambda untouched, sets chi_cur
+    SE2_LAUNCH(ba_iter_begin, 1, 256, 0, s, d, 1, 0, 1);   // itg != 0: keeps lambda untouched, sets chi_cur
     SE2_CUDA(cudaMemcpyAsync(h->st_host, d.st, sizeof(LMState), cudaMemcpyDeviceToHost, s));
     SE2_CUDA(cudaStreamSynchronize(s));
     LMState saved = *h->st_host;

@@ -22,7 +22,7 @@ def _as_tensor(ptr, count, dev):
     return torch.as_tensor(a, device=dev)
 
 
-def run_local_shards(prob, world, iters, device=0, stop_flags=None, setup=None):
+def run_local_shards(prob, world, iters, device=0, stop_flags=None, setup=None, mode=0):
     """Returns per-rank (n, stats, trace_poses, trace_points, poses, points). `stop_flags[r]` (optional) is the abort word
     rank r polls; `setup(bas)` (optional) runs after all contexts exist (e.g. to attach a fused exchange)."""
     dev = torch.device("cuda", device)
@@ -55,6 +55,7 @@ def run_local_shards(prob, world, iters, device=0, stop_flags=None, setup=None):
             with torch.cuda.stream(streams[rank]):
                 ba = LocalBA.from_problem(prob, device=device, rank=rank, world=world, allreduce=make_cb(rank),
                                           stream=streams[rank].cuda_stream)
+                ba.set_mode(mode)
                 bas[rank] = ba
                 barrier.wait()
                 if setup is not None and rank == 0:

@@ -345,6 +345,75 @@ def test_sharded_path_on_one_device(cfg, world):
     np.testing.assert_array_equal(pts[~active], prob.points[~active])
 
 
+@pytest.mark.parametrize("cfg,world", [("C3", 2), ("C4", 2), ("C4", 3)])
+def test_sharded_persistent_kernel_on_one_device(cfg, world, monkeypatch):
+    """The multi-GPU production path for local windows: every rank runs ONE persistent cooperative kernel and the kernels
+    exchange [S | b] and [chi2, scale, abort] through peer memory (no collective library, no host round trip). Here the
+    ranks are contexts of one process on one GPU (se2gpu_ba_peer_attach_local), each limited to a share of the SMs so that
+    the cooperative grids are co-resident. Strict per-step bar against the single-device oracle; all ranks bit-identical."""
+    from tests.local_shards import merge_landmarks, run_local_shards
+    monkeypatch.setenv("SE2GPU_BA_PK_GRID", str(140 // world))
+    monkeypatch.setenv("SE2GPU_BA_PEER_TIMEOUT_S", "20")
+    prob = synth.ba_config(cfg)
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o, tp_o, tl_o = o.optimize(10, trace=True)
+    res = run_local_shards(prob, world, 10, setup=LocalBA.attach_local, mode=2)
+    for r in range(world):
+        n, st, tp, tl, p, l = res[r]
+        assert n == n_o
+        np.testing.assert_array_equal(st["trials"], st_o["trials"])
+        np.testing.assert_array_equal(st["accepted"], st_o["accepted"])
+        np.testing.assert_allclose(st["lambda"], st_o["lambda"], rtol=1e-6)
+        np.testing.assert_allclose(st["chi2_after"], st_o["chi2_after"], rtol=1e-8)
+        assert tp.tobytes() == res[0][2].tobytes(), "replicated pose solves must be bit-identical across ranks"
+        prev_p = prob.poses
+        for k in range(n_o):
+            dp_o, dp_g = tp_o[k] - prev_p, tp[k] - prev_p
+            assert np.abs(dp_g - dp_o).max() <= REL * max(np.abs(dp_o).max(), 1e-12), f"rank {r} pose step {k}"
+            prev_p = tp_o[k]
+    pts = merge_landmarks(prob, res, world)
+    active = np.zeros(prob.L, bool); active[prob.edge_point] = True
+    assert np.abs(pts[active] - o.get()[1][active]).max() <= 1e-7
+
+
+def test_sharded_persistent_rejections_and_abort(monkeypatch):
+    """Step rejections (restore / nu doubling) and the collective abort flag inside the sharded persistent kernel."""
+    from tests.local_shards import run_local_shards
+    monkeypatch.setenv("SE2GPU_BA_PK_GRID", "70")
+    monkeypatch.setenv("SE2GPU_BA_PEER_TIMEOUT_S", "20")
+    prob = _perturbed(10, 600, 9, 1.0, 0.3, 0.0)
+    n_o, st_o, tp_o, tl_o = pyoracle.BAOracle(prob).optimize(12, trace=True)
+    res = run_local_shards(prob, 2, 12, setup=LocalBA.attach_local, mode=2)
+    for r in range(2):
+        assert res[r][0] == n_o
+        np.testing.assert_array_equal(res[r][1]["trials"], st_o["trials"])
+        np.testing.assert_allclose(res[r][1]["lambda"], st_o["lambda"], rtol=1e-6)
+        assert np.abs(res[r][2][-1] - tp_o[-1]).max() < 1e-8
+    flags = [np.zeros(1, np.uint8), np.ones(1, np.uint8)]
+    res = run_local_shards(synth.ba_config("C3"), 2, 6, setup=LocalBA.attach_local, mode=2, stop_flags=flags)
+    assert res[0][0] == res[1][0] == 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_sliced_optimize_continues_the_lambda_schedule(mode):
+    """se2gpu_ba_optimize_from: ten one-iteration slices (what g2o's solve(iteration) hands to an OptimizationAlgorithm)
+    are bit-identical to optimize(10); lambda is initialised at iteration 0 only."""
+    prob = _perturbed(10, 600, 9, 1.0, 0.3, 0.0)        # rejects steps late in the run
+    g = LocalBA.from_problem(prob, mode=mode)
+    n, st, tp, tl = g.optimize(12, trace=True)
+    g2 = LocalBA.from_problem(prob, mode=mode)
+    sts = []
+    for k in range(12):
+        nk, sk = g2.optimize(1, first_iteration=k)
+        assert nk == 1
+        sts.append(sk[0])
+    sts = np.array(sts, dtype=st.dtype)
+    for f in ("trials", "accepted", "terminate", "lambda", "chi2_after", "rho"):
+        np.testing.assert_array_equal(sts[f], st[f], err_msg=f)
+    p1, l1 = g.get(); p2, l2 = g2.get()
+    assert p1.tobytes() == p2.tobytes() and l1.tobytes() == l2.tobytes()
+
+
 def test_sharded_abort_flag_is_collective():
     """Only ONE rank sees the abort flag raised: the decision is OR-ed over the ranks (third word of the per-trial
     all-reduce), so every rank stops after the same iteration instead of one rank leaving the collective sequence."""
