@@ -279,10 +279,16 @@ def run_ours(args):
             "issue": ncu_traffic("issue:" + dom)}
     clocks = clk.summary()
 
-    # e2e: host buffers through se2gpu_orb_extract (H2D + D2H inside the timed region)
-    kps_h = torch.empty(BATCH * NFEAT * 28, dtype=torch.uint8).pin_memory().numpy().view(_capi.KP_DTYPE)
-    desc_h = torch.empty(BATCH * NFEAT * 32, dtype=torch.uint8).pin_memory().numpy()
-    counts_h = np.zeros(BATCH, np.int32)
+    # e2e: host buffers through the C ABI (H2D of the frames + D2H of keypoints / descriptors / counts inside the timed region).
+    #   e2e.value        se2gpu_orb_submit / _wait, two batches in flight: the H2D copy of batch k+1 and the D2H copy of batch
+    #                    k-1 overlap the kernels of batch k (page-locked caller buffers)
+    #   e2e.sync         se2gpu_orb_extract, one synchronous call per batch (page-locked caller buffers)
+    #   e2e.pageable     se2gpu_orb_extract with ordinary pageable caller buffers (what Frame.cpp:25 hands over: a cv::Mat)
+    def pinned_out():
+        return (torch.empty(BATCH * NFEAT * 28, dtype=torch.uint8).pin_memory().numpy().view(_capi.KP_DTYPE),
+                torch.empty(BATCH * NFEAT * 32, dtype=torch.uint8).pin_memory().numpy(), torch.zeros(BATCH, dtype=torch.int32).pin_memory().numpy())
+    outs = [pinned_out(), pinned_out()]
+    kps_h, desc_h, counts_h = outs[0]
 
     def orb_e2e(k):
         hb = host_batches[k % NROT].numpy()
@@ -298,10 +304,48 @@ def run_ours(args):
     for k in range(e2e_steps):
         tot += orb_e2e(k)
     torch.cuda.synchronize()
+    e2e_sync_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    orb_e2e_sync_value = sum_over_ranks(float(tot)) / (e2e_sync_ms * 1e-3) if e2e_steps else None
+    # pipelined
+    def submit(k):
+        hb = host_batches[k % NROT].numpy()
+        o = outs[k & 1]
+        _capi.check(lib.se2gpu_orb_submit(ext.h, hb.ctypes.data, BATCH, W, H, W, W * H, o[0].ctypes.data, o[1].ctypes.data, o[2].ctypes.data),
+                    "se2gpu_orb_submit")
+    def wait(k):
+        _capi.check(lib.se2gpu_orb_wait(ext.h), "se2gpu_orb_wait")
+        return int(outs[k & 1][2].sum())
+    for k in range(0 if args.quick else 2):        # creates the second context, warms both
+        submit(k)
+    for k in range(0 if args.quick else 2):
+        wait(k)
+    barrier()
+    t0 = time.perf_counter()
+    tot = 0
+    for k in range(e2e_steps):
+        submit(k)
+        if k >= 1:
+            tot += wait(k - 1)
+    if e2e_steps:
+        tot += wait(e2e_steps - 1)
+    torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    orb_e2e_value = sum_over_ranks(float(tot)) / (e2e_ms * 1e-3)
+    orb_e2e_value = sum_over_ranks(float(tot)) / (e2e_ms * 1e-3) if e2e_steps else 0.0
+    # pageable caller buffers (input and outputs): staged through the library's page-locked buffers
+    page_in = [np.array(host_batches[r].numpy(), copy=True) for r in range(min(NROT, 3))]
+    kps_p = np.zeros(BATCH * NFEAT, _capi.KP_DTYPE); desc_p = np.zeros(BATCH * NFEAT * 32, np.uint8); counts_p = np.zeros(BATCH, np.int32)
+    pg_steps = min(e2e_steps, 8)
+    t0 = time.perf_counter()
+    totp = 0
+    for k in range(pg_steps):
+        hb = page_in[k % len(page_in)]
+        _capi.check(lib.se2gpu_orb_extract(ext.h, hb.ctypes.data, BATCH, W, H, W, W * H, kps_p.ctypes.data, desc_p.ctypes.data, counts_p.ctypes.data),
+                    "se2gpu_orb_extract")
+        totp += int(counts_p.sum())
+    e2e_page_ms = (time.perf_counter() - t0) * 1e3
+    orb_e2e_page_value = (totp / (e2e_page_ms * 1e-3)) if pg_steps else None
     # single-frame latency of the same host call (the reference extracts one frame per Frame constructor, Frame.cpp:25)
-    single_ms = None
+    single_ms = single_page_ms = None
     if e2e_steps:
         one = host_batches[0].numpy()[:1]
         for _ in range(3):
@@ -310,6 +354,11 @@ def run_ours(args):
         for _ in range(50):
             _capi.check(lib.se2gpu_orb_extract(ext.h, one.ctypes.data, 1, W, H, W, W * H, kps_h.ctypes.data, desc_h.ctypes.data, counts_h.ctypes.data), "se2gpu_orb_extract")
         single_ms = (time.perf_counter() - t0) * 1e3 / 50
+        onep = np.array(one, copy=True)                 # pageable frame + pageable outputs: the reference's call pattern (Frame.cpp:25)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            _capi.check(lib.se2gpu_orb_extract(ext.h, onep.ctypes.data, 1, W, H, W, W * H, kps_p.ctypes.data, desc_p.ctypes.data, counts_p.ctypes.data), "se2gpu_orb_extract")
+        single_page_ms = (time.perf_counter() - t0) * 1e3 / 50
 
     # ------------------------------------------------------------------------------------------ matcher
     from se2lam_b200.matcher import FrameView, ORBmatcher
@@ -550,8 +599,12 @@ def run_ours(args):
                        "l2": f"inputs rotate over {NROT} distinct batches = {NROT * BATCH * W * H / 1e6:.0f} MB > 126 MB L2",
                        "keypoints_per_frame": kp_per_frame},
             "e2e": {"value": orb_e2e_value, "unit": "keypoints/s", "h2d_bytes_per_step": BATCH * W * H,
-                    "d2h_bytes_per_step": BATCH * NFEAT * 60 + BATCH * 4, "ms_per_step": e2e_ms / args.steps,
-                    "single_frame_ms": single_ms},
+                    "d2h_bytes_per_step": BATCH * NFEAT * 60 + BATCH * 4, "ms_per_step": e2e_ms / max(args.steps, 1),
+                    "api": "se2gpu_orb_submit / se2gpu_orb_wait, two 64-frame batches in flight, page-locked caller buffers",
+                    "sync": {"value": orb_e2e_sync_value, "ms_per_step": e2e_sync_ms / max(args.steps, 1), "api": "se2gpu_orb_extract, one synchronous call per batch, page-locked caller buffers"},
+                    "pageable": {"value": orb_e2e_page_value, "ms_per_step": (e2e_page_ms / pg_steps) if pg_steps else None,
+                                 "api": "se2gpu_orb_extract with pageable caller buffers (staged through the library's page-locked buffers)"},
+                    "single_frame_ms": single_ms, "single_frame_pageable_ms": single_page_ms},
             "gpu_launches": int(orb_launches + ba_launches),
             "roofline": roof, "clocks": clocks,
             "secondary": {

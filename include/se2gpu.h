@@ -84,6 +84,15 @@ void se2gpu_orb_destroy(se2gpu_orb* h);
 int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
                        se2gpu_keypoint* kps, uint8_t* desc, int* counts);
 
+/* Asynchronous, two-deep form of se2gpu_orb_extract for streams of batches: _submit enqueues the copies and kernels of one
+ * batch and returns at once; _wait blocks until the OLDEST submitted batch is complete and its results are in the buffers
+ * handed to _submit. Up to two batches may be in flight, so the host->device copy of batch k+1 and the device->host copy of
+ * batch k-1 overlap the kernels of batch k (a second internal context is created on first use). The buffers of a submitted
+ * batch must stay valid and untouched until its _wait returns; page-locked buffers make the copies true DMA transfers. */
+int se2gpu_orb_submit(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+                      se2gpu_keypoint* kps, uint8_t* desc, int* counts);
+int se2gpu_orb_wait(se2gpu_orb* h);
+
 /* Same with DEVICE buffers (frames already resident in HBM, results left in HBM); asynchronous on
  * `stream` (a cudaStream_t passed as void*; NULL = the default stream). */
 int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int stride,

@@ -40,7 +40,7 @@ PEER_HANDLE_BYTES = 128   # SE2GPU_BA_PEER_HANDLE_BYTES
 
 SYMBOLS = [
     "se2gpu_device_count", "se2gpu_last_error", "se2gpu_launch_count",
-    "se2gpu_orb_create", "se2gpu_orb_destroy", "se2gpu_orb_extract", "se2gpu_orb_extract_device",
+    "se2gpu_orb_create", "se2gpu_orb_destroy", "se2gpu_orb_extract", "se2gpu_orb_extract_device", "se2gpu_orb_submit", "se2gpu_orb_wait",
     "se2gpu_orb_level_dims", "se2gpu_orb_get_level", "se2gpu_orb_profile", "se2gpu_orb_profile_read",
     "se2gpu_orb_debug_nth_element", "se2gpu_orb_set_undistort", "se2gpu_orb_debug_undistort_map",
     "se2gpu_hamming_distance", "se2gpu_match_by_window", "se2gpu_match_by_projection", "se2gpu_search_by_bow",
@@ -76,6 +76,8 @@ def lib():
     L.se2gpu_orb_create.argtypes = [i, f, i, i, i, i, i, i]
     L.se2gpu_orb_destroy.argtypes = [vp]
     L.se2gpu_orb_extract.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp]
+    L.se2gpu_orb_submit.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp]
+    L.se2gpu_orb_wait.argtypes = [vp]
     L.se2gpu_orb_extract_device.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp, vp]
     L.se2gpu_orb_level_dims.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.se2gpu_orb_get_level.argtypes = [vp, i, i, i, vp]

@@ -927,6 +927,14 @@ struct se2gpu_orb {
     // pinned staging for results when the caller's buffers are pageable (a D2H copy into pageable memory blocks the
     // host and would serialise the pipeline)
     int* pin_counts = nullptr; se2gpu_keypoint* pin_kps = nullptr; uint8_t* pin_desc = nullptr;
+    // a host-buffer job that has been enqueued but not yet finished (se2gpu_orb_submit / _wait; se2gpu_orb_extract = both)
+    struct Pending { bool on = false; int n = 0, lanes = 0; bool pipelined = false; se2gpu_keypoint* kps = nullptr; uint8_t* desc = nullptr; int* counts = nullptr;
+                     se2gpu_keypoint* out_kps = nullptr; uint8_t* out_desc = nullptr; int* out_counts = nullptr; } pend;
+    // asynchronous two-deep submission: a second, identical context so that two batches can be in flight (the copy engines move
+    // batch k+1 in and batch k-1 out while the SMs work on batch k)
+    se2gpu_orb* twin = nullptr;
+    int submit_next = 0, wait_next = 0, in_flight = 0;
+    int create_args[8] = {};
 };
 
 namespace {
@@ -1239,6 +1247,7 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     se2gpu_orb* h = new se2gpu_orb;
     h->device = device; h->nfeatures = nfeatures; h->nlevels = nlevels; h->fast_th = fast_th;
     h->max_w = max_w; h->max_h = max_h; h->max_batch = max_batch;
+    { int* a = h->create_args; a[0] = nfeatures; memcpy(&a[1], &scale_factor, sizeof(float)); a[2] = nlevels; a[3] = fast_th; a[4] = max_w; a[5] = max_h; a[6] = max_batch; a[7] = device; }
     h->scaleFactor = scale_factor;   // the reference keeps it in a double member (ORBextractor.h:67)
     // ORBextractor::ORBextractor, ORBextractor.cpp:463-520
     h->mvScaleFactor.resize(nlevels); h->mvInvScaleFactor.resize(nlevels); h->mnFeaturesPerLevel.resize(nlevels);
@@ -1297,6 +1306,7 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
 
 void se2gpu_orb_destroy(se2gpu_orb* h) {
     if (!h) return;
+    if (h->twin) { se2gpu_orb_destroy(h->twin); h->twin = nullptr; }
     cudaSetDevice(h->device);
     for (void* p : h->bufs) cudaFree(p);
     if (h->side) cudaStreamDestroy(h->side);
@@ -1325,9 +1335,11 @@ int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w
     return run_device(h, d_imgs, n, w, hgt, stride, frame_stride, d_kps, d_desc, d_counts, s);
 }
 
-int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+// enqueue one host-buffer batch on this context (copies in, kernels, copies out); nothing is waited for
+static int orb_enqueue(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
                        se2gpu_keypoint* kps, uint8_t* desc, int* counts) {
     if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (h->pend.on) return fail(SE2GPU_ERR_INVALID, "a submitted batch is still pending on this context: call se2gpu_orb_wait first");
     if (n < 0 || n > h->max_batch) return fail(SE2GPU_ERR_CAPACITY, "batch %d exceeds max_batch %d", n, h->max_batch);
     if (n == 0) return SE2GPU_OK;
     if (!imgs || w <= 0 || hgt <= 0) { for (int i = 0; i < n; ++i) counts[i] = 0; return SE2GPU_OK; }   // :730-731
@@ -1381,18 +1393,69 @@ int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
         SE2_CUDA(cudaMemcpyAsync(out_kps + (size_t)f0 * h->nfeatures, h->d_kps + (size_t)f0 * h->nfeatures, sizeof(se2gpu_keypoint) * (size_t)m * h->nfeatures, cudaMemcpyDeviceToHost, s));
         SE2_CUDA(cudaMemcpyAsync(out_desc + (size_t)32 * f0 * h->nfeatures, h->d_desc + (size_t)32 * f0 * h->nfeatures, (size_t)32 * m * h->nfeatures, cudaMemcpyDeviceToHost, s));
     }
-    if (pipelined) {
-        for (int l = 0; l < lanes; ++l) SE2_CUDA(cudaStreamSynchronize(h->pipe[l]));
-        memcpy(counts, out_counts, sizeof(int) * n);
-        if (out_kps != kps) { memcpy(kps, out_kps, sizeof(se2gpu_keypoint) * (size_t)n * h->nfeatures); memcpy(desc, out_desc, (size_t)32 * n * h->nfeatures); }
+    h->pend.on = true; h->pend.n = n; h->pend.lanes = lanes; h->pend.pipelined = pipelined;
+    h->pend.kps = kps; h->pend.desc = desc; h->pend.counts = counts; h->pend.out_kps = out_kps; h->pend.out_desc = out_desc; h->pend.out_counts = out_counts;
+    return SE2GPU_OK;
+}
+
+// wait for the batch enqueued by orb_enqueue and hand the results to the caller's buffers
+static int orb_finish(se2gpu_orb* h) {
+    if (!h->pend.on) return SE2GPU_OK;
+    SE2_CUDA(cudaSetDevice(h->device));
+    const se2gpu_orb::Pending p = h->pend;
+    h->pend.on = false;
+    if (p.pipelined) {
+        for (int l = 0; l < p.lanes; ++l) SE2_CUDA(cudaStreamSynchronize(h->pipe[l]));
+        memcpy(p.counts, p.out_counts, sizeof(int) * p.n);
+        if (p.out_kps != p.kps) { memcpy(p.kps, p.out_kps, sizeof(se2gpu_keypoint) * (size_t)p.n * h->nfeatures); memcpy(p.desc, p.out_desc, (size_t)32 * p.n * h->nfeatures); }
     }
     int err = 0;
     SE2_CUDA(cudaMemcpyAsync(&err, h->d.err, sizeof(int), cudaMemcpyDeviceToHost, nullptr));
     SE2_CUDA(cudaStreamSynchronize(nullptr));
-    h->last_n = n;
+    h->last_n = p.n;
     if (err) { cudaMemset(h->d.err, 0, sizeof(int)); return fail(SE2GPU_ERR_CAPACITY, "internal candidate buffer overflow (code %d)", err); }
     return SE2GPU_OK;
 }
+
+int se2gpu_orb_extract(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+                       se2gpu_keypoint* kps, uint8_t* desc, int* counts) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (h->in_flight) return fail(SE2GPU_ERR_INVALID, "se2gpu_orb_extract while submitted batches are in flight: drain them with se2gpu_orb_wait");
+    int rc = orb_enqueue(h, imgs, n, w, hgt, stride, frame_stride, kps, desc, counts);
+    if (rc != SE2GPU_OK) return rc;
+    return orb_finish(h);
+}
+
+int se2gpu_orb_submit(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
+                      se2gpu_keypoint* kps, uint8_t* desc, int* counts) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (h->in_flight >= 2) return fail(SE2GPU_ERR_INVALID, "two batches are already in flight: call se2gpu_orb_wait first");
+    if (!h->twin) {
+        const int* a = h->create_args;
+        float sf; memcpy(&sf, &a[1], sizeof sf);
+        h->twin = se2gpu_orb_create(a[0], sf, a[2], a[3], a[4], a[5], a[6], a[7]);
+        if (!h->twin) return SE2GPU_ERR_CUDA;
+        if (h->und_on && se2gpu_orb_set_undistort(h->twin, h->und_K, h->und_nd ? h->und_D : nullptr, h->und_nd) != SE2GPU_OK) return SE2GPU_ERR_CUDA;
+    }
+    se2gpu_orb* ctx = (h->submit_next & 1) ? h->twin : h;
+    int rc = orb_enqueue(ctx, imgs, n, w, hgt, stride, frame_stride, kps, desc, counts);
+    if (rc != SE2GPU_OK) return rc;
+    if (!ctx->pend.on) {          // empty image / n == 0: finished synchronously (outputs as se2gpu_orb_extract leaves them)
+        return SE2GPU_OK;
+    }
+    h->submit_next ^= 1; h->in_flight++;
+    return SE2GPU_OK;
+}
+
+int se2gpu_orb_wait(se2gpu_orb* h) {
+    if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
+    if (!h->in_flight) return SE2GPU_OK;
+    se2gpu_orb* ctx = (h->wait_next & 1) ? h->twin : h;
+    h->wait_next ^= 1; h->in_flight--;
+    return orb_finish(ctx);
+}
+
+
 
 int se2gpu_orb_debug_nth_element(uint32_t* values, const int* offsets, const int* nth, int count, int device) {
     if (count <= 0) return SE2GPU_OK;

@@ -80,6 +80,16 @@ class ORBextractor:
                                        ptr(counts)), "se2gpu_orb_extract")
         return kps, desc, counts
 
+    def submit(self, images: np.ndarray, kps: np.ndarray, desc: np.ndarray, counts: np.ndarray):
+        """Asynchronous extract_batch into caller-owned buffers (se2gpu_orb_submit); at most two batches in flight."""
+        n, h, w = images.shape
+        check(lib().se2gpu_orb_submit(self.h, ptr(images), n, w, h, images.strides[1], images.strides[0], ptr(kps), ptr(desc), ptr(counts)),
+              "se2gpu_orb_submit")
+
+    def wait(self):
+        """Blocks until the oldest submitted batch is complete (se2gpu_orb_wait)."""
+        check(lib().se2gpu_orb_wait(self.h), "se2gpu_orb_wait")
+
     def extract_device(self, d_images, n, h, w, d_kps, d_desc, d_counts, stream=0, stride=None, frame_stride=None):
         """Device-resident variant: all pointers are CUDA device pointers (ints or torch tensors); asynchronous."""
         stride = w if stride is None else stride

@@ -199,3 +199,27 @@ def test_undistort_folded_into_level0():
     kg, dg = ext(raw)
     ko, do_ = orc.extract(raw)
     assert_same(kg, dg, ko, do_, "undistort off")
+
+
+def test_submit_wait_pipeline_matches_synchronous_extract():
+    """se2gpu_orb_submit / _wait (two batches in flight on twin contexts) returns exactly what se2gpu_orb_extract returns."""
+    n = 6
+    batches = [synth.orb_batch(n, first_seed=3000 + 10 * k) for k in range(5)]
+    e = ORBextractor(1000, 1.2, 8, max_batch=n)
+    ref = [e.extract_batch(b) for b in batches]
+    outs = [(np.zeros((n, 1000), pyoracle.KP_DTYPE), np.zeros((n, 1000, 32), np.uint8), np.zeros(n, np.int32)) for _ in range(2)]
+    got = []
+    for k, b in enumerate(batches):
+        e.submit(b, *outs[k & 1])
+        if k >= 1:
+            e.wait()
+            got.append(tuple(a.copy() for a in outs[(k - 1) & 1]))
+    e.wait()
+    got.append(tuple(a.copy() for a in outs[(len(batches) - 1) & 1]))
+    with pytest.raises(Exception):
+        e.submit(batches[0], *outs[0]); e.submit(batches[1], *outs[1]); e.submit(batches[2], *outs[0])    # a third batch in flight is refused
+    e.wait(); e.wait()
+    for (kr, dr, cr), (kg, dg, cg) in zip(ref, got):
+        np.testing.assert_array_equal(cg, cr)
+        for i in range(n):
+            assert kg[i, :cr[i]].tobytes() == kr[i, :cr[i]].tobytes() and dg[i, :cr[i]].tobytes() == dr[i, :cr[i]].tobytes()
