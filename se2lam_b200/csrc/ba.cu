@@ -1095,12 +1095,15 @@ __device__ __forceinline__ double pk_odo(const Dev& d, const double* xp, int o) 
 // loop bound is the warp's first landmark; landmarks >= L are skipped inside the bodies.
 struct PKLmIter {
     int j, sub, step, j_warp;
-    __device__ __forceinline__ PKLmIter() {
+    // In a sharded run only the landmarks j % world == rank carry work on this rank: the lane groups are dealt over THOSE (the
+    // k-th owned landmark is j = k * world + rank), otherwise the owned landmarks alias onto a subset of the CTAs (world = 2
+    // and an even grid: all of them on the even CTAs) and sharding buys no time per phase.
+    __device__ __forceinline__ PKLmIter(const Dev& d) {
         const int lg = threadIdx.x / LPL;                       // lane group inside the CTA
         sub = threadIdx.x % LPL;
-        j = lg * gridDim.x + blockIdx.x;
-        j_warp = (threadIdx.x / 32) * (32 / LPL) * gridDim.x + blockIdx.x;
-        step = (blockDim.x / LPL) * gridDim.x;
+        j = (lg * gridDim.x + blockIdx.x) * d.world + d.rank;
+        j_warp = ((threadIdx.x / 32) * (32 / LPL) * gridDim.x + blockIdx.x) * d.world + d.rank;
+        step = (blockDim.x / LPL) * gridDim.x * d.world;
     }
     __device__ __forceinline__ bool more(int L) const { return j_warp < L; }
     __device__ __forceinline__ void next() { j += step; j_warp += step; }
@@ -1111,7 +1114,7 @@ __device__ void pk_phase_linearize(const Dev& d, const Cam& cam, int xi, double*
     const double* xp = d.xp[xi];
     const double* xl = d.xl[xi];
     double chi = 0;
-    for (PKLmIter it; it.more(d.L); it.next()) chi += pk_landmark<JAC>(d, cam, xp, xl, it.j, it.sub, lam_fuse);
+    for (PKLmIter it(d); it.more(d.L); it.next()) chi += pk_landmark<JAC>(d, cam, xp, xl, it.j, it.sub, lam_fuse);
     // PreEdgeSE2 edges: one per CTA on the first lane of the last warp (idle unless a CTA holds > 60 landmarks), so that no CTA
     // serialises all of them behind its landmark work (they used to sit on CTA 0 and made it the slowest of the phase)
     if (threadIdx.x == blockDim.x - 32)
@@ -1407,7 +1410,7 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
 __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
     const size_t L = d.L, E = d.E;
-    for (PKLmIter it; it.more(d.L); it.next()) {
+    for (PKLmIter it(d); it.more(d.L); it.next()) {
         const int j = it.j, sub = it.sub;
         if (j >= d.L) continue;
         const int beg = d.lm_ptr[j], end = d.lm_ptr[j + 1];
@@ -1440,7 +1443,7 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam, double lam
     double* xlt = d.xl[cur ^ 1];
     const size_t L = d.L, E = d.E;
     double sc = 0;
-    for (PKLmIter it; it.more(d.L); it.next()) {
+    for (PKLmIter it(d); it.more(d.L); it.next()) {
         const int j = it.j, sub = it.sub;
         int beg = 0, end = 0;
         if (j < d.L) { beg = d.lm_ptr[j]; end = d.lm_ptr[j + 1]; }
@@ -1838,6 +1841,8 @@ struct se2gpu_ba {
     long long* phase_cycles = nullptr;   // device [8]
     long long* cta_work = nullptr;       // device [1024][8]
     int pk_launches = 0, clock_khz = 0;
+    // topology of the loaded window (host copies): a set_problem with the same graph structure only refreshes the values
+    std::vector<int> t_edge_pose, t_edge_point, t_odo_i, t_odo_j; std::vector<uint8_t> t_fixed; int t_rank = -1, t_world = -1;
     se2band::Plan band;        // partitioned band solver for reduced systems beyond one CTA's shared memory
     int smem_optin = 0;
 };
@@ -2044,6 +2049,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
                           const double* odo_info, double fx, double cx, double cy, const double* Tcb, double huber_delta) {
     if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
     if (P <= 0 || L < 0 || E < 0 || O < 0) return fail(SE2GPU_ERR_INVALID, "bad sizes");
+    SE2_NVTX("se2gpu.ba.set_problem");
     if (P > h->maxP || L > h->maxL || E > h->maxE || O > h->maxO) return fail(SE2GPU_ERR_CAPACITY, "problem (%d,%d,%d,%d) exceeds capacity (%d,%d,%d,%d)", P, L, E, O, h->maxP, h->maxL, h->maxE, h->maxO);
     SE2_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
@@ -2054,6 +2060,52 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
         if (edge_pose[e] < 0 || edge_pose[e] >= P || edge_point[e] < 0 || edge_point[e] >= L) return fail(SE2GPU_ERR_INVALID, "edge %d references a missing vertex", e);
     for (int o = 0; o < O; ++o)
         if (odo_i[o] < 0 || odo_i[o] >= P || odo_j[o] < 0 || odo_j[o] >= P) return fail(SE2GPU_ERR_INVALID, "odometry edge %d references a missing vertex", o);
+
+    // --- same graph structure as the loaded window (same vertices, fixed flags, edge endpoints, shard): everything
+    // initializeOptimization / buildStructure derives is still valid on the device - only the values are refreshed
+    if (h->loaded && P == h->P && L == h->L && E == h->E && O == h->O && h->t_rank == h->rank && h->t_world == h->world &&
+        (int)h->t_edge_pose.size() == E && (int)h->t_odo_i.size() == O && (int)h->t_fixed.size() == P &&
+        memcmp(h->t_fixed.data(), fixed, P) == 0 && (E == 0 || (memcmp(h->t_edge_pose.data(), edge_pose, sizeof(int) * E) == 0 && memcmp(h->t_edge_point.data(), edge_point, sizeof(int) * E) == 0)) &&
+        (O == 0 || (memcmp(h->t_odo_i.data(), odo_i, sizeof(int) * O) == 0 && memcmp(h->t_odo_j.data(), odo_j, sizeof(int) * O) == 0))) {
+        const int El = h->d.E, Ol = h->d.O;
+        if (!h->arena2) h->arena2 = new PinnedArena;
+        h->arena2->reserve((size_t)El * 40 + (size_t)Ol * 72 + 64 * 16);
+        if (!h->arena) h->arena = new PinnedArena;
+        h->arena->reserve(sizeof(double) * (3 * (size_t)P + 3 * (size_t)L) + (size_t)El * 40 + (size_t)Ol * 72 + 64 * 16);
+        PinnedArena& ar = *h->arena;
+        std::vector<double> fb[7];
+        auto dbls = [&](size_t cnt, std::vector<double>& f) { double* q = h->arena2->alloc<double>(cnt); if (!q) { f.resize(cnt); q = f.data(); } return q; };
+        double *e_u = dbls(El, fb[0]), *e_v = dbls(El, fb[1]), *w00 = dbls(El, fb[2]), *w01 = dbls(El, fb[3]), *w11 = dbls(El, fb[4]);
+        for (int k = 0; k < El; ++k) {
+            const int e = h->perm[k];
+            e_u[k] = uv[2 * e]; e_v[k] = uv[2 * e + 1];
+            w00[k] = info[3 * e]; w01[k] = info[3 * e + 1]; w11[k] = info[3 * e + 2];
+        }
+        double *om = dbls(3 * (size_t)Ol, fb[5]), *ow = dbls(6 * (size_t)Ol, fb[6]);
+        for (int o = 0; o < Ol; ++o) {
+            for (int q = 0; q < 3; ++q) om[q * (size_t)Ol + o] = odo_meas[3 * o + q];
+            for (int q = 0; q < 6; ++q) ow[q * (size_t)Ol + o] = odo_info[6 * o + q];
+        }
+#define UPV(dst, ptr, count) do { int _r = h->arena2->owns(ptr) ? (((size_t)(count)) ? (cudaMemcpyAsync(dst, ptr, sizeof(*(ptr)) * (size_t)(count), cudaMemcpyHostToDevice, s) == cudaSuccess ? SE2GPU_OK : fail(SE2GPU_ERR_CUDA, "upload failed")) : SE2GPU_OK) : ar.up(dst, ptr, (size_t)(count), s); if (_r != SE2GPU_OK) return _r; } while (0)
+        UPV(h->d.xp[0], poses, 3 * (size_t)P); UPV(h->d.xl[0], points, 3 * (size_t)L);
+        SE2_CUDA(cudaMemcpyAsync(h->d.xp[1], h->d.xp[0], sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, s));
+        SE2_CUDA(cudaMemcpyAsync(h->d.xl[1], h->d.xl[0], sizeof(double) * 3 * L, cudaMemcpyDeviceToDevice, s));
+        SE2_CUDA(cudaMemcpyAsync(h->xp0, h->d.xp[0], sizeof(double) * 3 * P, cudaMemcpyDeviceToDevice, s));
+        SE2_CUDA(cudaMemcpyAsync(h->xl0, h->d.xl[0], sizeof(double) * 3 * L, cudaMemcpyDeviceToDevice, s));
+        UPV(h->e_u, e_u, El); UPV(h->e_v, e_v, El); UPV(h->e_w00, w00, El); UPV(h->e_w01, w01, El); UPV(h->e_w11, w11, El);
+        UPV(h->o_m, om, 3 * (size_t)Ol); UPV(h->o_w, ow, 6 * (size_t)Ol);
+#undef UPV
+        LMState st0{};
+        st0.ni = 2;
+        *h->st_host = st0;
+        SE2_CUDA(cudaMemcpyAsync(h->d.st, h->st_host, sizeof(LMState), cudaMemcpyHostToDevice, s));
+        SE2_CUDA(cudaStreamSynchronize(s));
+        h->cam.fx = fx; h->cam.cx = cx; h->cam.cy = cy; h->cam.delta = huber_delta;
+        memcpy(h->cam.Rcb, Tcb, sizeof(double) * 9); memcpy(h->cam.tcb, Tcb + 9, sizeof(double) * 3);
+        if (dbg) fprintf(stderr, "[se2gpu_ba_set_problem] same topology: values refreshed in %.3f ms\n", std::chrono::duration<double, std::milli>(tnow() - t_begin).count());
+        return SE2GPU_OK;
+    }
+    h->loaded = false;
 
     // --- index mapping (SparseOptimizer::buildIndexMapping): free poses in id order
     std::vector<int> hidx(P, -1);
@@ -2301,6 +2353,8 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     h->cam.fx = fx; h->cam.cx = cx; h->cam.cy = cy; h->cam.delta = huber_delta;
     memcpy(h->cam.Rcb, Tcb, sizeof(double) * 9); memcpy(h->cam.tcb, Tcb + 9, sizeof(double) * 3);
     h->perm = perm; h->P = P; h->L = L; h->E = E; h->O = O;
+    h->t_edge_pose.assign(edge_pose, edge_pose + E); h->t_edge_point.assign(edge_point, edge_point + E); h->t_odo_i.assign(odo_i, odo_i + O);
+    h->t_odo_j.assign(odo_j, odo_j + O); h->t_fixed.assign(fixed, fixed + P); h->t_rank = h->rank; h->t_world = h->world;
     h->loaded = true;
     return SE2GPU_OK;
 }
@@ -2317,6 +2371,7 @@ int ar(se2gpu_ba* h, double* buf, size_t count, int op) {
 }
 
 int launch_linearize(se2gpu_ba* h) {
+    SE2_NVTX("se2gpu.ba.linearize");
     Dev& d = h->d;
     cudaStream_t s = h->stream;
     h->prof.begin(0, s);
@@ -2329,6 +2384,7 @@ int launch_linearize(se2gpu_ba* h) {
 }
 
 int launch_solve(se2gpu_ba* h) {
+    SE2_NVTX("se2gpu.ba.schur_solve");
     Dev& d = h->d;
     cudaStream_t s = h->stream;
     h->prof.begin(2, s);
@@ -2362,6 +2418,7 @@ int se2gpu_ba_optimize(se2gpu_ba* h, int max_iters, const volatile unsigned char
 int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, const volatile unsigned char* stop_flag,
                             se2gpu_ba_iter_stats* stats, double* trace_poses, double* trace_points) {
     if (!h || !h->loaded) return fail(SE2GPU_ERR_INVALID, "no problem loaded");
+    SE2_NVTX("se2gpu.ba.optimize");
     if (max_iters < 0 || first_iteration < 0) return fail(SE2GPU_ERR_INVALID, "negative iteration count");
     if (max_iters > h->max_stats) return fail(SE2GPU_ERR_CAPACITY, "max_iters > %d", h->max_stats);
     SE2_CUDA(cudaSetDevice(h->device));

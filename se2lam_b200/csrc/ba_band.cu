@@ -366,6 +366,7 @@ void release(Plan& pl) {
 }
 
 int solve(const Plan& pl, const double* Sband, const double* bs, double* dxp, int* solve_ok, cudaStream_t s) {
+    SE2_NVTX("se2gpu.ba.band_solve");
     const int BW1 = pl.bw + 1;
     SE2_LAUNCH(band_part_factor, pl.p, THREADS, pl.smem_part, s, pl.d_parts, BW1, Sband, bs, pl.d_work, pl.d_ok);
     SE2_LAUNCH(band_sep_solve, 1, THREADS, pl.smem_sep, s, pl.d_parts, pl.p, BW1, 3 * pl.w, pl.nT, Sband, bs, pl.d_work, pl.d_ok, dxp, pl.n, solve_ok);

@@ -152,6 +152,7 @@ int se2gpu_voc_transform_device(se2gpu_voc* v, const uint8_t* d_desc, int n, int
     if (!v) return fail(SE2GPU_ERR_INVALID, "null vocabulary");
     if (n < 0 || (n && (!d_desc || !d_word_id || !d_weight))) return fail(SE2GPU_ERR_INVALID, "bad arguments");
     if (n == 0) return SE2GPU_OK;
+    SE2_NVTX("se2gpu.voc_transform");
     SE2_CUDA(cudaSetDevice(v->device));
     SE2_LAUNCH(k_voc_transform, (n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream, reinterpret_cast<const uint32_t*>(d_desc), n, v->desc, v->child_ptr,
                v->children, v->word_id, v->weight, v->levels, levelsup, d_word_id, d_weight, d_node_id);

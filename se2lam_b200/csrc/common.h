@@ -1,6 +1,7 @@
 // Shared host-side helpers of libse2gpu (error reporting, launch accounting).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdarg>
@@ -76,6 +77,15 @@ struct Profiler {
     inline void end(cudaStream_t s) { if (on) { cudaEventRecord(ev[nev][1], s); ++nev; } }
     ~Profiler() { if (created) for (int i = 0; i < MAXEV; ++i) { cudaEventDestroy(ev[i][0]); cudaEventDestroy(ev[i][1]); } }
 };
+
+// NVTX ranges around every kernel group and host entry point (visible in Nsight Systems / ncu --nvtx; a no-op when no tool is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define SE2_NVTX_CAT2(a, b) a##b
+#define SE2_NVTX_CAT(a, b) SE2_NVTX_CAT2(a, b)
+#define SE2_NVTX(name) ::se2gpu::NvtxRange SE2_NVTX_CAT(_se2_nvtx_, __LINE__)(name)
 
 template <class T>
 inline cudaError_t dev_alloc(T** p, size_t count) {

@@ -677,6 +677,7 @@ int se2gpu_match_by_window_device(se2gpu_matcher* m, const se2gpu_keypoint* d_kp
     if (!m) return fail(SE2GPU_ERR_INVALID, "null handle");
     if (n1 < 0 || n2 < 0) return fail(SE2GPU_ERR_INVALID, "negative sizes");
     if (n1 > m->max_q || n2 > m->max_db) return fail(SE2GPU_ERR_CAPACITY, "%d x %d exceeds the matcher's capacity %d x %d", n1, n2, m->max_q, m->max_db);
+    SE2_NVTX("se2gpu.match_by_window");
     if (n1 && (!d_kp1 || !d_desc1 || !d_prev || !d_matches12)) return fail(SE2GPU_ERR_INVALID, "null argument");
     if (n2 && (!d_kp2 || !d_desc2)) return fail(SE2GPU_ERR_INVALID, "null argument");
     SE2_CUDA(cudaSetDevice(m->device));
@@ -710,6 +711,7 @@ int se2gpu_match_by_projection_device(se2gpu_matcher* m, const se2gpu_keypoint* 
     if (!m) return fail(SE2GPU_ERR_INVALID, "null handle");
     if (n_kf < 0 || n_mp < 0) return fail(SE2GPU_ERR_INVALID, "negative sizes");
     if (n_mp > m->max_q || n_kf > m->max_db) return fail(SE2GPU_ERR_CAPACITY, "%d x %d exceeds the matcher's capacity %d x %d", n_mp, n_kf, m->max_q, m->max_db);
+    SE2_NVTX("se2gpu.match_by_projection");
     if (n_kf && (!d_kf_kp || !d_kf_desc || !d_kf_observed || !d_matches_idx_mp)) return fail(SE2GPU_ERR_INVALID, "null argument");
     if (n_mp && (!d_mp_valid || !d_mp_uv || !d_mp_octave || !d_mp_desc)) return fail(SE2GPU_ERR_INVALID, "null argument");
     SE2_CUDA(cudaSetDevice(m->device));
@@ -854,6 +856,7 @@ int se2gpu_matcher_search_by_bow(se2gpu_matcher* m, const se2gpu_bow_kf* k1, con
     if (!k1 || !k2 || k1->n < 0 || k2->n < 0 || (k1->n && !matches12)) return fail(SE2GPU_ERR_INVALID, "bad arguments");
     for (int i = 0; i < k1->n; ++i) matches12[i] = -1;
     if (k1->n == 0 || k2->n == 0 || k1->n_node == 0 || k2->n_node == 0) return 0;
+    SE2_NVTX("se2gpu.search_by_bow");
     // the two-iterator walk over the ascending node ids (:160-247) visits the common nodes; the queries are KF1's
     // features of those nodes in walk order, each with the feature range of the same node in KF2
     std::vector<int> qidx, qb0, qb1;

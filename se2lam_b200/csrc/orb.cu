@@ -1174,6 +1174,8 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     cudaStream_t side = lane < 0 ? h->side : nullptr;
     cudaEvent_t ev_pyr = h->ev_pyr, ev_blur = h->ev_blur;
     se2gpu::Profiler& pr = h->prof;
+    SE2_NVTX("se2gpu.orb.run_device");
+    nvtxRangePushA("se2gpu.orb.pyramid");
     pr.begin(0, s);
     {
         const LevelGeo& g = h->levels[0];
@@ -1195,6 +1197,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     }
     if (h->nlevels == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     pr.end(s);
+    nvtxRangePop();
     // The blur of a level only needs that level's plane: on the side stream the blur of levels 0-1 (55 % of the pixels,
     // no shared memory, so it co-resides with the resize CTAs) starts as soon as level 1 exists and hides behind the
     // tail of the pyramid, a chain of small latency-bound launches; the remaining levels are blurred when the pyramid is
@@ -1213,6 +1216,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         launch_blur(side, tilesA, d.n_tiles);
         SE2_CUDA(cudaEventRecord(ev_blur, side));
     }
+    SE2_NVTX("se2gpu.orb.fast_select_blur_describe");
     pr.begin(1, s);
     if (h->fast_big) SE2_LAUNCH(orb_fast_cells_big, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     else SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
@@ -1338,6 +1342,7 @@ int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w
 // enqueue one host-buffer batch on this context (copies in, kernels, copies out); nothing is waited for
 static int orb_enqueue(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
                        se2gpu_keypoint* kps, uint8_t* desc, int* counts) {
+    SE2_NVTX("se2gpu.orb.enqueue");
     if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
     if (h->pend.on) return fail(SE2GPU_ERR_INVALID, "a submitted batch is still pending on this context: call se2gpu_orb_wait first");
     if (n < 0 || n > h->max_batch) return fail(SE2GPU_ERR_CAPACITY, "batch %d exceeds max_batch %d", n, h->max_batch);
@@ -1400,6 +1405,7 @@ static int orb_enqueue(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
 
 // wait for the batch enqueued by orb_enqueue and hand the results to the caller's buffers
 static int orb_finish(se2gpu_orb* h) {
+    SE2_NVTX("se2gpu.orb.finish");
     if (!h->pend.on) return SE2GPU_OK;
     SE2_CUDA(cudaSetDevice(h->device));
     const se2gpu_orb::Pending p = h->pend;

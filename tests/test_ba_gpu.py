@@ -478,6 +478,36 @@ def test_sharded_large_window_on_one_device():
     assert np.abs(pts[active] - o.get()[1][active]).max() < 1e-7
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_same_topology_reload_refreshes_values_only(mode):
+    """set_problem with the graph structure of the loaded window (same vertices / fixed flags / edge endpoints) keeps the
+    device-side structure and refreshes the values: the result must equal a fresh context's, bit for bit; a changed edge
+    list falls back to the full rebuild."""
+    a = synth.ba_config("C3")
+    b = copy.copy(a)
+    rng = np.random.default_rng(3)
+    b.poses = a.poses + rng.normal(0, 0.01, a.poses.shape); b.poses[0] = a.poses[0]
+    b.points = a.points + rng.normal(0, 0.02, a.points.shape)
+    b.uv = a.uv + rng.normal(0, 0.3, a.uv.shape); b.info = a.info * 1.1; b.odo_meas = a.odo_meas + 1e-3; b.odo_info = a.odo_info * 0.9
+    g = LocalBA.from_problem(a, mode=mode)
+    g.optimize(4)
+    g.set_problem(b)                       # same topology: fast path
+    n1, st1 = g.optimize(6)
+    p1, l1 = g.get()
+    f = LocalBA.from_problem(b, mode=mode)
+    n2, st2 = f.optimize(6)
+    p2, l2 = f.get()
+    assert n1 == n2 and p1.tobytes() == p2.tobytes() and l1.tobytes() == l2.tobytes()
+    np.testing.assert_array_equal(st1["chi2_after"], st2["chi2_after"])
+    c = copy.copy(b)
+    keep = np.ones(b.E, bool); keep[::7] = False
+    c.edge_pose, c.edge_point, c.uv, c.info = b.edge_pose[keep], b.edge_point[keep], b.uv[keep], b.info[keep]
+    g.set_problem(c)                       # different edge list: full rebuild
+    g.optimize(5)
+    o = pyoracle.BAOracle(c); o.optimize(5)
+    np.testing.assert_allclose(g.get()[0], o.get()[0], atol=1e-8)
+
+
 def test_scale_config_c5_matches_oracle():
     """BASELINE config 5 (2000 KF / 50k landmarks / ~300k edges): the reduced system (n = 5997) does not fit one CTA's
     shared memory, so this exercises the global-memory envelope LDL^T and the multi-launch path at scale."""
