@@ -14,6 +14,8 @@ enum { CV_8U_ = 0 };
 #ifndef CV_8U
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
 #endif
 
 struct Point2f { float x = 0, y = 0; Point2f() {} Point2f(float x_, float y_) : x(x_), y(y_) {} };
@@ -30,22 +32,26 @@ public:
     size_t step = 0;
     uint8_t* data = nullptr;
     Mat() {}
-    Mat(int r, int c, int /*type*/) { create(r, c, CV_8U); }
-    Mat(int r, int c, int /*type*/, void* ext, size_t step_ = 0) : rows(r), cols(c), step(step_ ? step_ : (size_t)c), data((uint8_t*)ext) {}
-    void create(int r, int c, int /*type*/) {
-        if (r == rows && c == cols && own_) return;
-        own_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c + 1], std::default_delete<uint8_t[]>());
-        rows = r; cols = c; step = (size_t)c; data = own_.get();
+    Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(int r, int c, int type, void* ext, size_t step_ = 0) : rows(r), cols(c), step(step_ ? step_ : (size_t)c * esz(type)), data((uint8_t*)ext), type_(type) {}
+    void create(int r, int c, int type) {
+        if (r == rows && c == cols && type == type_ && own_) return;
+        own_ = std::shared_ptr<uint8_t>(new uint8_t[(size_t)r * c * esz(type) + 1](), std::default_delete<uint8_t[]>());
+        rows = r; cols = c; type_ = type; step = (size_t)c * esz(type); data = own_.get();
     }
+    template <class T> T& at(int r, int c) { return ((T*)(data + (size_t)r * step))[c]; }
+    template <class T> const T& at(int r, int c) const { return ((const T*)(data + (size_t)r * step))[c]; }
     void release() { own_.reset(); data = nullptr; rows = cols = 0; step = 0; }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    int type() const { return CV_8UC1; }
-    bool isContinuous() const { return step == (size_t)cols; }
+    int type() const { return type_; }
+    bool isContinuous() const { return step == (size_t)cols * esz(type_); }
     template <class T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <class T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     Mat getMat() const { return *this; }
 private:
+    static size_t esz(int type) { return type == CV_32F ? 4 : 1; }
     std::shared_ptr<uint8_t> own_;
+    int type_ = CV_8U;
 };
 
 typedef const Mat& InputArray;

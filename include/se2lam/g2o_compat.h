@@ -67,20 +67,78 @@ struct CameraParameters {
 };
 struct RobustKernelHuber { double delta = 1.0; void setDelta(double d) { delta = d; } };
 
-struct Edge { Vertex* v[2] = {nullptr, nullptr}; virtual ~Edge() {} Vertex** vertices() { return v; } };
+struct Edge {
+    Vertex* v[2] = {nullptr, nullptr};
+    virtual ~Edge() {}
+    Vertex** vertices() { return v; }
+    int level() const { return level_; }
+    void setLevel(int l) { level_ = l; }
+    virtual void computeError() = 0;
+    virtual double chi2() const = 0;
+protected:
+    int level_ = 0;
+};
+inline double normalize_theta(double theta) {                // g2o/stuff/misc.h
+    if (theta >= -M_PI && theta < M_PI) return theta;
+    const double multiplier = std::floor(theta / (2 * M_PI));
+    theta = theta - multiplier * 2 * M_PI;
+    if (theta >= M_PI) theta -= 2 * M_PI;
+    if (theta < -M_PI) theta += 2 * M_PI;
+    return theta;
+}
+// g2o::SE2ToSE3 (reference src/EdgeSE2XYZ.cpp:27-33): planar pose -> rotation about z + translation in the plane
+inline SE3Quat SE2ToSE3(const SE2& se2) {
+    SE3Quat T;
+    const double c = std::cos(se2.th_), s = std::sin(se2.th_);
+    T.R(0, 0) = c; T.R(0, 1) = -s; T.R(1, 0) = s; T.R(1, 1) = c; T.R(2, 2) = 1;
+    T.t[0] = se2.x_; T.t[1] = se2.y_; T.t[2] = 0;
+    return T;
+}
 struct EdgeSE2XYZ : Edge {
     Vector2D meas; Matrix2D info; CameraParameters* cam = nullptr; SE3Quat Tbc, Tcb; RobustKernelHuber* rk = nullptr;
     ~EdgeSE2XYZ() { delete rk; }
     void setMeasurement(const Vector2D& m) { meas = m; }
     void setInformation(const Matrix2D& i) { info = i; }
+    const Matrix2D& information() const { return info; }
     void setCameraParameter(CameraParameters* c) { cam = c; }
     void setExtParameter(const SE3Quat& Tbc_) { Tbc = Tbc_; Tcb = Tbc.inverse(); }      // EdgeSE2XYZ.h:52
     void setRobustKernel(RobustKernelHuber* k) { rk = k; }
+    // one edge, on the host, for the per-edge outlier test after a BA (EdgeSE2XYZ.cpp:61-72): e = cam_map(Tcb Tbw lw) - uv
+    void computeError() override {
+        const SE2& p = static_cast<VertexSE2*>(v[0])->estimate();
+        const Vector3D& lw = static_cast<VertexSBAPointXYZ*>(v[1])->estimate();
+        const SE3Quat Tbw = SE2ToSE3(p).inverse();
+        double lb[3], lc[3];
+        for (int r = 0; r < 3; ++r) lb[r] = Tbw.R(r, 0) * lw[0] + Tbw.R(r, 1) * lw[1] + Tbw.R(r, 2) * lw[2] + Tbw.t[r];
+        for (int r = 0; r < 3; ++r) lc[r] = Tcb.R(r, 0) * lb[0] + Tcb.R(r, 1) * lb[1] + Tcb.R(r, 2) * lb[2] + Tcb.t[r];
+        const double f = cam ? cam->focal_length : 1.0, cx = cam ? cam->principle_point[0] : 0.0, cy = cam ? cam->principle_point[1] : 0.0;
+        err[0] = f * lc[0] / lc[2] + cx - meas[0];
+        err[1] = f * lc[1] / lc[2] + cy - meas[1];
+    }
+    const Vector2D& error() const { return err; }
+    double chi2() const override { return err[0] * (info(0, 0) * err[0] + info(0, 1) * err[1]) + err[1] * (info(1, 0) * err[0] + info(1, 1) * err[1]); }
+private:
+    Vector2D err;
 };
 struct PreEdgeSE2 : Edge {
     Vector3D meas; Matrix3D info;
     void setMeasurement(const Vector3D& m) { meas = m; }
     void setInformation(const Matrix3D& i) { info = i; }
+    const Matrix3D& information() const { return info; }
+    void computeError() override {                                                     // EdgeSE2XYZ.h:68-82
+        const SE2& a = static_cast<VertexSE2*>(v[0])->estimate();
+        const SE2& b = static_cast<VertexSE2*>(v[1])->estimate();
+        const double c = std::cos(a.th_), s = std::sin(a.th_), dx = b.x_ - a.x_, dy = b.y_ - a.y_;
+        err[0] = c * dx + s * dy - meas[0]; err[1] = -s * dx + c * dy - meas[1]; err[2] = b.th_ - a.th_ - meas[2];
+    }
+    const Vector3D& error() const { return err; }
+    double chi2() const override {
+        double s = 0;
+        for (int r = 0; r < 3; ++r) for (int c2 = 0; c2 < 3; ++c2) s += err[r] * info(r, c2) * err[c2];
+        return s;
+    }
+private:
+    Vector3D err;
 };
 
 // the solver stack is fixed on the GPU (LM + Schur + Cholesky); these exist so that
@@ -105,7 +163,7 @@ public:
     const std::vector<Edge*>& edges() const { return edges_; }
 
     // builds the SoA problem (poses in id order first, then points: g2o's index mapping) and uploads it
-    bool initializeOptimization(int /*level*/ = 0) {
+    bool initializeOptimization(int level = 0) {
         poses_.clear(); points_.clear();
         std::vector<double> xp, xl, uv, info, om, oinf;
         std::vector<uint8_t> fixed;
@@ -123,8 +181,14 @@ public:
         }
         const EdgeSE2XYZ* first = nullptr;
         for (Edge* e : edges_) {
+            if (e->level() != level) continue;                // only the edges of this level are active (removeOutlierChi2 moves outliers to level 1)
             if (auto* x = dynamic_cast<EdgeSE2XYZ*>(e)) {
                 if (!first) first = x;
+                else if (x->cam != first->cam || std::memcmp(x->Tcb.R.d, first->Tcb.R.d, sizeof first->Tcb.R.d) || std::memcmp(x->Tcb.t.d, first->Tcb.t.d, sizeof first->Tcb.t.d) ||
+                         (x->rk ? x->rk->delta : -1.0) != (first->rk ? first->rk->delta : -1.0)) {
+                    std::fprintf(stderr, "se2gpu: EdgeSE2XYZ edges with different camera / extrinsic / Huber delta are not supported (Map::loadLocalGraph uses one of each)\n");
+                    return false;
+                }
                 ep.push_back(pidx.at(x->v[0]->id)); el.push_back(lidx.at(x->v[1]->id));
                 uv.push_back(x->meas[0]); uv.push_back(x->meas[1]);
                 info.push_back(x->info(0, 0)); info.push_back(0.5 * (x->info(0, 1) + x->info(1, 0))); info.push_back(x->info(1, 1));
@@ -144,8 +208,12 @@ public:
             if (first->rk) delta = first->rk->delta;
         }
         const int P = (int)poses_.size(), L = (int)points_.size(), E = (int)ep.size(), O = (int)oi.size();
-        if (ba_) { se2gpu_ba_destroy(ba_); ba_ = nullptr; }
-        ba_ = se2gpu_ba_create(P, L > 0 ? L : 1, E > 0 ? E : 1, O > 0 ? O : 1, 0);
+        // the device context (all buffers, the occupancy query, pinned staging) is kept across BAs while its capacity suffices
+        if (ba_ && (P > capP_ || L > capL_ || E > capE_ || O > capO_)) { se2gpu_ba_destroy(ba_); ba_ = nullptr; }
+        if (!ba_) {
+            capP_ = P + P / 2 + 8; capL_ = L + L / 2 + 64; capE_ = E + E / 2 + 256; capO_ = O + O / 2 + 8;
+            ba_ = se2gpu_ba_create(capP_, capL_, capE_, capO_, 0);
+        }
         if (!ba_) { std::fprintf(stderr, "se2gpu: %s\n", se2gpu_last_error()); return false; }
         static const double zero3[3] = {0, 0, 0};
         int rc = se2gpu_ba_set_problem(ba_, P, L, E, O, xp.data(), fixed.data(), L ? xl.data() : zero3, ep.data(), el.data(), uv.data(),
@@ -180,6 +248,7 @@ private:
     std::vector<se2gpu_ba_iter_stats> stats_;
     OptimizationAlgorithmGpuLM* alg_ = nullptr;
     se2gpu_ba* ba_ = nullptr;
+    int capP_ = 0, capL_ = 0, capE_ = 0, capO_ = 0;
     bool* stop_ = nullptr;
     bool verbose_ = false, ready_ = false;
 };

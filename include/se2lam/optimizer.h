@@ -8,6 +8,19 @@
 #define OPTIMIZER_H
 
 #include "g2o_compat.h"
+#include "EdgeSE2XYZ.h"
+
+#if defined(__has_include)
+#if __has_include(<opencv2/core/core.hpp>)
+#include <opencv2/core/core.hpp>
+#ifndef SE2LAM_HAVE_OPENCV
+#define SE2LAM_HAVE_OPENCV 1
+#endif
+#endif
+#endif
+#ifndef SE2LAM_HAVE_OPENCV
+#include "cv_compat.h"
+#endif
 
 namespace se2lam{
 
@@ -26,7 +39,7 @@ initOptimizer(SlamOptimizer &opt, bool verbose=false){                         /
     opt.setVerbose(verbose);
 }
 
-// K is the 3x3 float camera matrix, row-major (cv::Mat CV_32F in the reference: K.at<float>(0,0), (0,2), (1,2))
+// K as a raw 3x3 row-major float array (Config::Kcam.ptr<float>()); the cv::Mat overload below is the reference's signature
 inline CamPara*
 addCamPara(SlamOptimizer &opt, const float* K, int id){                        // optimizer.cpp:207-215
     g2o::Vector2D principal_point = g2o::makeVector2D(K[2], K[5]);
@@ -34,6 +47,14 @@ addCamPara(SlamOptimizer &opt, const float* K, int id){                        /
     campr->setId(id);
     opt.addParameter(campr);
     return campr;
+}
+
+// the reference's own signature (optimizer.cpp:207-215): K is Config::Kcam, a 3x3 CV_32F cv::Mat
+inline CamPara*
+addCamPara(SlamOptimizer &opt, const cv::Mat& K, int id){
+    const float Kf[9] = {K.at<float>(0,0), K.at<float>(0,1), K.at<float>(0,2), K.at<float>(1,0), K.at<float>(1,1), K.at<float>(1,2),
+                         K.at<float>(2,0), K.at<float>(2,1), K.at<float>(2,2)};
+    return addCamPara(opt, Kf, id);
 }
 
 inline g2o::VertexSE2*

@@ -1,0 +1,3 @@
+// TEST MOCK: see mock_core.h
+#pragma once
+#include "mock_core.h"

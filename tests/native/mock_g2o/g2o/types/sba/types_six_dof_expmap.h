@@ -1,0 +1,3 @@
+// TEST MOCK: see mock_core.h
+#pragma once
+#include "../../core/mock_core.h"

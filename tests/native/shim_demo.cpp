@@ -63,8 +63,10 @@ int main(int argc, char** argv) {
     bool mbAbortBA = false;
     optimizer.setForceStopFlag(&mbAbortBA);
 
-    const float K[9] = {(float)cam[0], 0, (float)cam[1], 0, (float)cam[0], (float)cam[2], 0, 0, 1};
-    CamPara* campr = addCamPara(optimizer, K, 0);                               // Map.cpp:897
+    cv::Mat Kcam(3, 3, CV_32FC1);                                               // Config::Kcam
+    Kcam.at<float>(0, 0) = (float)cam[0]; Kcam.at<float>(0, 2) = (float)cam[1]; Kcam.at<float>(1, 1) = (float)cam[0]; Kcam.at<float>(1, 2) = (float)cam[2];
+    Kcam.at<float>(2, 2) = 1.f;
+    CamPara* campr = addCamPara(optimizer, Kcam, 0);                            // Map.cpp:897, the reference's own call shape
     for (int i = 0; i < P; ++i)                                                 // Map.cpp:918-932
         addVertexSE2(optimizer, g2o::SE2(poses[3 * i], poses[3 * i + 1], poses[3 * i + 2]), i, fixed[i] != 0);
     for (int o = 0; o < O; ++o) {                                               // Map.cpp:935-956
@@ -89,6 +91,10 @@ int main(int argc, char** argv) {
     wr(fo, &done, 1);
     for (int i = 0; i < P; ++i) { g2o::Vector3D vp = estimateVertexSE2(optimizer, i).toVector(); wr(fo, vp.d, 3); }   // Map.cpp:768
     for (int j = 0; j < L; ++j) { g2o::Vector3D p = estimateVertexSBAXYZ(optimizer, j + maxKFid); wr(fo, p.d, 3); }   // Map.cpp:777
+    // per-edge outlier test after the BA, as LocalMapper::removeOutlierChi2 does it (LocalMapper.cpp:187-213): computeError() + chi2()
+    double chi2_sum = 0; int n_edges = 0;
+    for (g2o::Edge* e : optimizer.edges()) { e->computeError(); chi2_sum += e->chi2(); ++n_edges; }
+    wr(fo, &chi2_sum, 1); wr(fo, &n_edges, 1);
     // an aborted BA performs no iteration (setForceStopFlag, Track.cpp:372)
     mbAbortBA = true;
     int aborted = optimizer.optimize(iters);

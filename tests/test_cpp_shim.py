@@ -59,6 +59,7 @@ def test_shim_matches_oracle(tmp_path):
     (done,) = struct.unpack_from("i", buf, off); off += 4
     poses = np.frombuffer(buf, "f8", 3 * prob.P, off).reshape(-1, 3); off += 24 * prob.P
     pts = np.frombuffer(buf, "f8", 3 * prob.L, off).reshape(-1, 3); off += 24 * prob.L
+    chi2_sum, n_edges = struct.unpack_from("di", buf, off); off += 12
     (aborted,) = struct.unpack_from("i", buf, off)
     o = pyoracle.BAOracle(prob)
     n_o, _ = o.optimize(10)
@@ -66,6 +67,75 @@ def test_shim_matches_oracle(tmp_path):
     assert done == n_o and aborted == 0
     np.testing.assert_allclose(poses, po, atol=1e-8)
     np.testing.assert_allclose(pts, lo, atol=1e-7)
+    # sum of the per-edge NON-robust chi2 (what removeOutlierChi2 thresholds) at the final estimate, against a numpy restatement
+    assert n_edges == prob.E + prob.O
+    Rcb = np.asarray(prob.Tcb[:9]).reshape(3, 3); tcb = np.asarray(prob.Tcb[9:])
+    tot = 0.0
+    for e in range(prob.E):
+        x, y, th = po[prob.edge_pose[e]]
+        c, s = np.cos(th), np.sin(th)
+        lc = Rcb @ (np.array([[c, s, 0], [-s, c, 0], [0, 0, 1.0]]) @ (lo[prob.edge_point[e]] - np.array([x, y, 0.0]))) + tcb
+        err = prob.fx * lc[:2] / lc[2] + np.array([prob.cx, prob.cy]) - prob.uv[e]
+        w = prob.info[e]
+        tot += err @ np.array([[w[0], w[1]], [w[1], w[2]]]) @ err
+    for k in range(prob.O):
+        a, b = po[prob.odo_i[k]], po[prob.odo_j[k]]
+        c, s = np.cos(a[2]), np.sin(a[2])
+        d = b[:2] - a[:2]
+        err = np.array([c * d[0] + s * d[1], -s * d[0] + c * d[1], b[2] - a[2]]) - prob.odo_meas[k]
+        w = prob.odo_info[k]
+        tot += err @ np.array([[w[0], w[1], w[2]], [w[1], w[3], w[4]], [w[2], w[4], w[5]]]) @ err
+    assert abs(chi2_sum - tot) <= 1e-6 * tot
+
+
+def compile_g2o_demo(tmp_path):
+    build.build_lib()
+    exe = str(tmp_path / "g2o_binding_demo")
+    libdir = os.path.dirname(build.LIB_PATH)
+    cmd = ["g++", "-O1", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "native", "mock_g2o"),
+           os.path.join(ROOT, "tests", "native", "g2o_binding_demo.cpp"), "-o", exe, "-L", libdir, "-lse2gpu", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_g2o_binding_compiles_against_the_g2o_api(tmp_path):
+    compile_g2o_demo(tmp_path)
+
+
+@pytest.mark.gpu
+def test_g2o_binding_matches_oracle(tmp_path):
+    """se2gpu::G2oGpuLevenberg (include/se2lam/g2o_gpu_levenberg.h) as g2o's OptimizationAlgorithm: the (mock) SparseOptimizer
+    drives it with solve(0), solve(1), ... exactly like real g2o, one se2gpu_ba_optimize_from slice per call."""
+    from oracle import pyoracle
+    exe = compile_g2o_demo(tmp_path)
+    prob = synth.ba_config("C3")
+    img = synth.orb_frame(1005, 64, 48)
+    Rbc, tbc = synth.default_Tbc()
+    fin, fout = str(tmp_path / "g_in.bin"), str(tmp_path / "g_out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("ii", 64, 48)); f.write(img.tobytes())
+        f.write(struct.pack("iiiii", prob.P, prob.L, prob.E, prob.O, 10))
+        for a, dt in ((prob.poses, "f8"), (prob.fixed, "u1"), (prob.points, "f8"), (prob.edge_pose, "i4"), (prob.edge_point, "i4"),
+                      (prob.uv, "f8"), (prob.info, "f8"), (prob.odo_i, "i4"), (prob.odo_j, "i4"), (prob.odo_meas, "f8"), (prob.odo_info, "f8")):
+            f.write(np.ascontiguousarray(a, dt).tobytes())
+        f.write(np.array([prob.fx, prob.cx, prob.cy], "f8").tobytes())
+        f.write(np.concatenate([Rbc.reshape(-1), tbc]).astype("f8").tobytes())
+        f.write(struct.pack("d", prob.huber_delta))
+    res = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    buf = open(fout, "rb").read()
+    done, on_gpu = struct.unpack_from("ii", buf, 0); off = 8
+    poses = np.frombuffer(buf, "f8", 3 * prob.P, off).reshape(-1, 3); off += 24 * prob.P
+    pts = np.frombuffer(buf, "f8", 3 * prob.L, off).reshape(-1, 3); off += 24 * prob.L
+    lam, trials = struct.unpack_from("di", buf, off)
+    o = pyoracle.BAOracle(prob)
+    n_o, st_o = o.optimize(10)
+    po, lo = o.get()
+    assert on_gpu == 1 and done == n_o
+    np.testing.assert_allclose(poses, po, atol=1e-8)
+    np.testing.assert_allclose(pts, lo, atol=1e-7)
+    assert abs(lam - st_o["lambda"][-1]) <= 1e-6 * st_o["lambda"][-1] and trials == st_o["trials"][-1]
 
 
 def compile_matcher_demo(tmp_path):
