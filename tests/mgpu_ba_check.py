@@ -89,9 +89,9 @@ def main():
             ok &= bool(good)
         del ba
     flag = torch.tensor([1 if ok else 0])
-    dist.broadcast(flag, 0) if shared_gpu else None
     if not shared_gpu:
-        f2 = flag.to(dev); dist.broadcast(f2, 0); flag = f2.cpu()
+        flag = flag.to(dev)
+    dist.broadcast(flag, 0)
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
