@@ -875,6 +875,8 @@ struct PKShard {
     long long* go;                     // local [2]: epoch CTA 0 has seen complete on all peers (S, scalars); -1 = peer timeout
     long long epoch0, timeout_cycles;
     int xslot;                         // doubles per scalar slot
+    const int* env_idx;                // linear indices (into [S | bs]) of the entries inside the envelope of S, then of bs
+    int nenv;
 };
 constexpr int XCH_HDR = 16;            // doubles: [0] S flag, [1] scalar flag (as long long), rest padding
 
@@ -912,25 +914,22 @@ __device__ bool pk_wait_peers(const PKShard& sh, int which, long long epoch) {
     __syncthreads();
     return good;
 }
-// every CTA: ssum[slice] = sum over ranks of red[r][slice], rank order
-__device__ void pk_sum_partials(const PKShard& sh, int total) {
+// every CTA: ssum[e] = sum over ranks of red[r][e], rank order, for the entries e inside the envelope of the reduced system
+// (the lower triangle within colmax[] - everything the Schur phase can write - and the right-hand side): a few percent of the
+// dense n x n array for a local window, so the exchange moves kilobytes, not the whole buffer. ssum stays zero elsewhere.
+__device__ void pk_sum_partials(const PKShard& sh) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-    const int nvec = total / 2;
-    for (int v = gtid; v < nvec; v += gthreads) {
-        double2 t[MAX_PEERS];
+    for (int v = gtid; v < sh.nenv; v += gthreads) {
+        const int e = sh.env_idx[v];
+        double t[MAX_PEERS];
 #pragma unroll
         for (int r = 0; r < MAX_PEERS; ++r)
-            if (r < sh.world) t[r] = (r == sh.rank) ? reinterpret_cast<const double2*>(sh.red[r])[v] : __ldcv(reinterpret_cast<const double2*>(sh.red[r]) + v);
-        double2 acc = make_double2(0.0, 0.0);
+            if (r < sh.world) t[r] = (r == sh.rank) ? sh.red[r][e] : __ldcv(sh.red[r] + e);
+        double acc = 0.0;
 #pragma unroll
         for (int r = 0; r < MAX_PEERS; ++r)
-            if (r < sh.world) { acc.x += t[r].x; acc.y += t[r].y; }
-        reinterpret_cast<double2*>(sh.ssum)[v] = acc;
-    }
-    if ((total & 1) && gtid == 0) {
-        double v = 0;
-        for (int r = 0; r < sh.world; ++r) v += (r == sh.rank) ? sh.red[r][total - 1] : __ldcv(sh.red[r] + total - 1);
-        sh.ssum[total - 1] = v;
+            if (r < sh.world) acc += t[r];
+        sh.ssum[e] = acc;
     }
 }
 
@@ -1659,7 +1658,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 ++epoch;
                 if (blockIdx.x == 0 && threadIdx.x == 0) pk_publish(shd, 0, epoch);
                 if (!pk_wait_peers(shd, 0, epoch)) { peer_err = true; break; }
-                pk_sum_partials(shd, n * n + n);
+                pk_sum_partials(shd);
                 grid.sync();
                 PK_TICK(1);
             }
@@ -1804,6 +1803,7 @@ struct se2gpu_ba {
     int xslot = 0;                              // doubles per scalar slot
     double* ssum = nullptr;                     // rank-summed [S | bs]
     long long* go = nullptr;                    // [2] local hand-off words of pk_wait_peers
+    int* env_idx = nullptr; int nenv = 0; size_t env_cap = 0;   // envelope entries of [S | bs] (what the exchange sums)
     void* peer_opened[16] = {};                 // mappings opened with cudaIpcOpenMemHandle (closed on destroy)
     const double* peer_red[8] = {};
     const double* peer_xch[8] = {};
@@ -1951,6 +1951,7 @@ void se2gpu_ba_destroy(se2gpu_ba* h) {
     if (h->xch) cudaFree(h->xch);
     if (h->ssum) cudaFree(h->ssum);
     if (h->go) cudaFree(h->go);
+    if (h->env_idx) cudaFree(h->env_idx);
     if (h->st_host) cudaFreeHost(h->st_host);
     delete h->arena;
     delete h->arena2;
@@ -1965,6 +1966,7 @@ static int peer_alloc(se2gpu_ba* h) {
     SE2_CUDA(cudaMalloc((void**)&h->xch, sizeof(double) * xd));
     SE2_CUDA(cudaMemset(h->xch, 0, sizeof(double) * xd));
     SE2_CUDA(cudaMalloc((void**)&h->ssum, sizeof(double) * ((size_t)SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + SMEM_CHOL_MAX_N + 8)));
+    SE2_CUDA(cudaMemset(h->ssum, 0, sizeof(double) * ((size_t)SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + SMEM_CHOL_MAX_N + 8)));
     SE2_CUDA(cudaMalloc((void**)&h->go, 2 * sizeof(long long)));
     SE2_CUDA(cudaMemset(h->go, 0, 2 * sizeof(long long)));
     if (const char* t = getenv("SE2GPU_BA_PEER_TIMEOUT_S")) h->peer_timeout_s = atof(t) > 0 ? atof(t) : h->peer_timeout_s;
@@ -2253,6 +2255,21 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     }
     std::vector<int> colmax(n);
     for (int a = 0; a < nf; ++a) for (int r = 0; r < 3; ++r) colmax[3 * a + r] = 3 * bmax[a] + 2;
+    // sharded persistent kernel: the entries of [S | bs] the ranks exchange = lower triangle inside the envelope + right-hand side
+    std::vector<int> env_idx;
+    if (world > 1 && n <= SMEM_CHOL_MAX_N) {
+        for (int c = 0; c < n; ++c) for (int r = c; r <= colmax[c]; ++r) env_idx.push_back(r * n + c);
+        for (int r = 0; r < n; ++r) env_idx.push_back(n * n + r);
+        if (env_idx.size() > h->env_cap) {
+            if (h->env_idx) cudaFree(h->env_idx);
+            h->env_cap = env_idx.size() + env_idx.size() / 4 + 64;
+            if (cudaMalloc((void**)&h->env_idx, sizeof(int) * h->env_cap) != cudaSuccess) return fail(SE2GPU_ERR_CUDA, "envelope list alloc failed");
+        }
+        SE2_CUDA(cudaMemcpyAsync(h->env_idx, env_idx.data(), sizeof(int) * env_idx.size(), cudaMemcpyHostToDevice, s));
+        SE2_CUDA(cudaStreamSynchronize(s));
+    }
+    h->nenv = (int)env_idx.size();
+    if (h->ssum) SE2_CUDA(cudaMemsetAsync(h->ssum, 0, sizeof(double) * ((size_t)SMEM_CHOL_MAX_N * SMEM_CHOL_MAX_N + SMEM_CHOL_MAX_N + 8), s));   // zero outside the (new) envelope
     // windows beyond one CTA's shared memory: partitioned band factorisation when the envelope is narrow (ba_band.cu),
     // otherwise the single-CTA global-memory envelope factorisation
     se2band::release(h->band);
@@ -2446,6 +2463,7 @@ int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, co
         if (h->world > 1) {
             for (int r = 0; r < h->world; ++r) { shd.red[r] = h->peer_red[r]; shd.xch[r] = h->peer_xch[r]; }
             shd.my_xch = h->xch; shd.ssum = h->ssum; shd.go = h->go; shd.epoch0 = h->peer_epoch; shd.xslot = h->xslot;
+            shd.env_idx = h->env_idx; shd.nenv = h->nenv;
             shd.timeout_cycles = (long long)(h->peer_timeout_s * 1e3 * (double)(h->clock_khz > 0 ? h->clock_khz : 1965000));
             SE2_CUDA(cudaMemsetAsync(h->go, 0, 2 * sizeof(long long), s));
         }
