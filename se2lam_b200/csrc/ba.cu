@@ -88,6 +88,19 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     int nb_lm, nb_odo;
 };
 
+// A per-edge record is 96 bytes (three 32-byte sectors), 32-byte aligned: gathers read it with 16-byte loads - the record gathers of the
+// Schur phase are bound by L1 wavefronts (every lane hits a different record), so halving the load instructions per record halves them.
+__device__ __forceinline__ void load_rec10(const double* __restrict__ rec, double* v) {
+    const double2* r2 = reinterpret_cast<const double2*>(rec);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { const double2 t = r2[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+}
+__device__ __forceinline__ void load_rec12(const double* __restrict__ rec, double* v) {
+    const double2* r2 = reinterpret_cast<const double2*>(rec);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { const double2 t = r2[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+}
+
 // element (r, c), r >= c, of the reduced system
 __device__ __forceinline__ size_t sidx(const Dev& d, int r, int c) {
     return d.sbw ? (size_t)r * (d.sbw + 1) + (size_t)(c - r + d.sbw) : (size_t)r * d.n + c;
@@ -415,9 +428,8 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
     for (int q = 0; q < 12; ++q) acc[q] = 0;
     for (int k = d.blk_pair_ptr[blk] + threadIdx.x; k < d.blk_pair_ptr[blk + 1]; k += SCHUR_THREADS) {
         const int e1 = d.pair_e1[k], e2 = d.pair_e2[k];
-        double y[9], h[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) { y[q] = d.Y[(size_t)e1 * EB + (q)]; h[q] = d.Hpl[(size_t)e2 * EB + (q)]; }
+        double y[10], h[10];
+        load_rec10(d.Y + (size_t)e1 * EB, y); load_rec10(d.Hpl + (size_t)e2 * EB, h);
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -837,6 +849,8 @@ namespace cg = cooperative_groups;
 constexpr int PK_THREADS = 512;
 constexpr int LPL = 8;
 
+__device__ unsigned long long g_lane_dbg[64];   // SE2GPU_BA_DEBUG: per-lane worst loop time of warp 0 in the Schur phase (0..31 pair loop, 32..63 incl. edge loop)
+
 struct PKArgs {
     int max_iters;
     int first_iter;           // iteration number of the first LM iteration of this call (g2o's solve(iteration): lambda is
@@ -853,6 +867,7 @@ struct PKArgs {
     double* part_max;         // [gridDim.x]
     long long* phase_cycles;  // [8] SM cycles CTA 0 spent per phase incl. the barrier that ends it (profiling aid)
     int dyn_smem_bytes;       // dynamic shared memory of the launch (arena size of the non-zero CTAs)
+    int dbg_sysfence;         // diagnostic: CTA 0 issues a system-scope fence after every chi2 phase (single-GPU runs)
     long long* cta_work;      // [gridDim.x][8] per-CTA busy cycles per phase (debug aid, null = off)
 };
 
@@ -998,14 +1013,20 @@ __device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, cons
                 h11 += BtW[2] * B[1] + BtW[3] * B[4]; h12 += BtW[2] * B[2] + BtW[3] * B[5]; h22 += BtW[4] * B[2] + BtW[5] * B[5];
                 b0 += B[0] * r0 + B[3] * r1; b1 += B[1] * r0 + B[4] * r1; b2 += B[2] * r0 + B[5] * r1;
                 if (d.e_hidx[e] >= 0) {
+                    double hv[10], pv[10];            // the two 96-byte records, written with 16-byte stores
 #pragma unroll
                     for (int r = 0; r < 3; ++r)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) d.Hpl[(size_t)e * EB + ((r * 3 + c))] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
-                    d.PH[(size_t)e * EB + (0)] = AtW[0] * A[0] + AtW[1] * A[3]; d.PH[(size_t)e * EB + (1)] = AtW[0] * A[1] + AtW[1] * A[4];
-                    d.PH[(size_t)e * EB + (2)] = AtW[0] * A[2] + AtW[1] * A[5]; d.PH[(size_t)e * EB + (3)] = AtW[2] * A[1] + AtW[3] * A[4];
-                    d.PH[(size_t)e * EB + (4)] = AtW[2] * A[2] + AtW[3] * A[5]; d.PH[(size_t)e * EB + (5)] = AtW[4] * A[2] + AtW[5] * A[5];
-                    d.PH[(size_t)e * EB + 6 + (0)] = A[0] * r0 + A[3] * r1; d.PH[(size_t)e * EB + 6 + (1)] = A[1] * r0 + A[4] * r1; d.PH[(size_t)e * EB + 6 + (2)] = A[2] * r0 + A[5] * r1;
+                        for (int c = 0; c < 3; ++c) hv[r * 3 + c] = AtW[r * 2] * B[c] + AtW[r * 2 + 1] * B[3 + c];
+                    hv[9] = 0.0;
+                    pv[0] = AtW[0] * A[0] + AtW[1] * A[3]; pv[1] = AtW[0] * A[1] + AtW[1] * A[4];
+                    pv[2] = AtW[0] * A[2] + AtW[1] * A[5]; pv[3] = AtW[2] * A[1] + AtW[3] * A[4];
+                    pv[4] = AtW[2] * A[2] + AtW[3] * A[5]; pv[5] = AtW[4] * A[2] + AtW[5] * A[5];
+                    pv[6] = A[0] * r0 + A[3] * r1; pv[7] = A[1] * r0 + A[4] * r1; pv[8] = A[2] * r0 + A[5] * r1; pv[9] = 0.0;
+                    double2* h2 = reinterpret_cast<double2*>(d.Hpl + (size_t)e * EB);
+                    double2* p2 = reinterpret_cast<double2*>(d.PH + (size_t)e * EB);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) { h2[q] = make_double2(hv[2 * q], hv[2 * q + 1]); p2[q] = make_double2(pv[2 * q], pv[2 * q + 1]); }
                 }
             }
         }
@@ -1031,14 +1052,19 @@ __device__ __forceinline__ double pk_landmark(const Dev& d, const Cam& cam, cons
             const double db0 = i00 * b0 + i01 * b1 + i02 * b2, db1 = i01 * b0 + i11 * b1 + i12 * b2, db2 = i02 * b0 + i12 * b1 + i22 * b2;
             for (int k = beg + sub; k < end; k += LPL) {
                 if (d.e_hidx[k] < 0) continue;
+                double hp[10], yv[12];
+                load_rec10(d.Hpl + (size_t)k * EB, hp);
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const double g0 = d.Hpl[(size_t)k * EB + ((r * 3 + 0))], g1 = d.Hpl[(size_t)k * EB + ((r * 3 + 1))], g2 = d.Hpl[(size_t)k * EB + ((r * 3 + 2))];
-                    d.Y[(size_t)k * EB + ((r * 3 + 0))] = g0 * i00 + g1 * i01 + g2 * i02;
-                    d.Y[(size_t)k * EB + ((r * 3 + 1))] = g0 * i01 + g1 * i11 + g2 * i12;
-                    d.Y[(size_t)k * EB + ((r * 3 + 2))] = g0 * i02 + g1 * i12 + g2 * i22;
-                    d.Y[(size_t)k * EB + 9 + (r)] = g0 * db0 + g1 * db1 + g2 * db2;
+                    const double g0 = hp[r * 3], g1 = hp[r * 3 + 1], g2 = hp[r * 3 + 2];
+                    yv[r * 3 + 0] = g0 * i00 + g1 * i01 + g2 * i02;
+                    yv[r * 3 + 1] = g0 * i01 + g1 * i11 + g2 * i12;
+                    yv[r * 3 + 2] = g0 * i02 + g1 * i12 + g2 * i22;
+                    yv[9 + r] = g0 * db0 + g1 * db1 + g2 * db2;
                 }
+                double2* y2 = reinterpret_cast<double2*>(d.Y + (size_t)k * EB);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) y2[q] = make_double2(yv[2 * q], yv[2 * q + 1]);
             }
         }
     }
@@ -1136,7 +1162,8 @@ __device__ void pk_pose_item(const Dev& d, int a, const int* edges, int ne, doub
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[q] = 0;
     for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-        const double* rec = d.PH + (size_t)edges[k] * EB;
+        double rec[10];
+        load_rec10(d.PH + (size_t)edges[k] * EB, rec);
 #pragma unroll
         for (int q = 0; q < 9; ++q) acc[q] += rec[q];
     }
@@ -1179,11 +1206,8 @@ __device__ void pk_schur_item(const Dev& d, double lam, int blk, int a, int b, c
     for (int q = 0; q < 12; ++q) acc[q] = 0;
     for (int k = threadIdx.x; k < np; k += blockDim.x) {
         const int e1 = pairs ? pairs[2 * k] : d.pair_e1[gp0 + k], e2 = pairs ? pairs[2 * k + 1] : d.pair_e2[gp0 + k];
-        const double* yr = d.Y + (size_t)e1 * EB;
-        const double* hr = d.Hpl + (size_t)e2 * EB;
-        double y[9], h[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) { y[q] = yr[q]; h[q] = hr[q]; }
+        double y[10], h[10];
+        load_rec10(d.Y + (size_t)e1 * EB, y); load_rec10(d.Hpl + (size_t)e2 * EB, h);
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -1202,9 +1226,11 @@ __device__ void pk_schur_item(const Dev& d, double lam, int blk, int a, int b, c
     for (int q = 0; q < 9; ++q) ph[q] = 0;
     if (diag) {
         for (int k = threadIdx.x; k < ne; k += blockDim.x) {
-            const double* yr = d.Y + (size_t)edges[k] * EB;
-            const double* rec = d.PH + (size_t)edges[k] * EB;
-            acc[9] -= yr[9]; acc[10] -= yr[10]; acc[11] -= yr[11];
+            const double2* yr2 = reinterpret_cast<const double2*>(d.Y + (size_t)edges[k] * EB);
+            const double2 g01 = yr2[4], g2 = yr2[5];        // doubles 8..11 of the record: Y[8], g[0], g[1], g[2]
+            double rec[10];
+            load_rec10(d.PH + (size_t)edges[k] * EB, rec);
+            acc[9] -= g01.y; acc[10] -= g2.x; acc[11] -= g2.y;
 #pragma unroll
             for (int q = 0; q < 9; ++q) ph[q] += rec[q];
         }
@@ -1308,8 +1334,9 @@ __device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double
 // built once per launch). One block barrier for the whole phase instead of two per block, and no warp idles while a
 // 40-pair block is reduced. Summation order per block: lane-strided partials over the item's warps, warp xor-tree, the
 // item's warps in rank order - fixed, so runs stay bit-reproducible.
-__device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, const unsigned char* plan_w0, const unsigned char* plan_nw, double* shr /*[warps][21]*/) {
+__device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, const unsigned char* plan_w0, const unsigned char* plan_nw, double* shr /*[warps][21]*/, long long* tdbg = nullptr) {
     if (w.first < 0) return;
+    const long long t_in = tdbg ? clock64() : 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t O = d.O, n = d.n, nf = d.nf;
     int it = -1, rk = 0, nwi = 1, w0 = 0;
@@ -1327,16 +1354,14 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
         for (int q = 0; q < 9; ++q) ph[q] = 0;
         const int* pairs = w.arena + o.p0;
         for (int k = rk * 32 + lane; k < o.np; k += nwi * 32) {
-            const double* yr = d.Y + (size_t)pairs[2 * k] * EB;
-            const double* hr = d.Hpl + (size_t)pairs[2 * k + 1] * EB;
-            double y[9], h[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) { y[q] = yr[q]; h[q] = hr[q]; }
+            double y[10], h[10];
+            load_rec10(d.Y + (size_t)pairs[2 * k] * EB, y); load_rec10(d.Hpl + (size_t)pairs[2 * k + 1] * EB, h);
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
         }
+        if (tdbg && wid == 0) atomicMax(&g_lane_dbg[lane], (unsigned long long)(clock64() - t_in));
         if (rk == 0)
             for (int k = d.blk_odo_ptr[o.blk] + lane; k < d.blk_odo_ptr[o.blk + 1]; k += 32) {
                 const int code = d.blk_odo[k], oo = code >> 1;
@@ -1348,9 +1373,11 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
         if (diag) {
             const int* edges = w.arena + o.e0;
             for (int k = rk * 32 + lane; k < o.ne; k += nwi * 32) {
-                const double* yr = d.Y + (size_t)edges[k] * EB;
-                const double* rec = d.PH + (size_t)edges[k] * EB;
-                acc[9] -= yr[9]; acc[10] -= yr[10]; acc[11] -= yr[11];
+                const double2* yr2 = reinterpret_cast<const double2*>(d.Y + (size_t)edges[k] * EB);
+                const double2 g01 = yr2[4], g2 = yr2[5];        // doubles 8..11 of the record: Y[8], g[0], g[1], g[2]
+                double rec[10];
+                load_rec10(d.PH + (size_t)edges[k] * EB, rec);
+                acc[9] -= g01.y; acc[10] -= g2.x; acc[11] -= g2.y;
 #pragma unroll
                 for (int q = 0; q < 9; ++q) ph[q] += rec[q];
             }
@@ -1365,6 +1392,8 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
                     for (int q = 0; q < 3; ++q) ph[6 + q] += bb[q * O + oo];
                 }
         }
+        if (tdbg && wid == 0) atomicMax(&g_lane_dbg[32 + lane], (unsigned long long)(clock64() - t_in));
+        if (tdbg && threadIdx.x == 0) tdbg[8] += clock64() - t_in;      // gather loops of warp 0
 #pragma unroll
         for (int q = 0; q < 12; ++q)
 #pragma unroll
@@ -1375,6 +1404,7 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
 #pragma unroll
                 for (int s2 = 16; s2 > 0; s2 >>= 1) ph[q] += __shfl_xor_sync(0xffffffffu, ph[q], s2);
         }
+        if (tdbg && threadIdx.x == 0) tdbg[9] += clock64() - t_in;      // ... + its shuffle reduction
         if (lane == 0) {
 #pragma unroll
             for (int q = 0; q < 12; ++q) shr[wid * 21 + q] = acc[q];
@@ -1451,9 +1481,11 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam, double lam
             const int a = d.e_hidx[k];
             if (a < 0) continue;
             const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
-            c0 -= d.Hpl[(size_t)k * EB + (0)] * p0 + d.Hpl[(size_t)k * EB + (3)] * p1 + d.Hpl[(size_t)k * EB + (6)] * p2;
-            c1 -= d.Hpl[(size_t)k * EB + (1)] * p0 + d.Hpl[(size_t)k * EB + (4)] * p1 + d.Hpl[(size_t)k * EB + (7)] * p2;
-            c2 -= d.Hpl[(size_t)k * EB + (2)] * p0 + d.Hpl[(size_t)k * EB + (5)] * p1 + d.Hpl[(size_t)k * EB + (8)] * p2;
+            double hp[10];
+            load_rec10(d.Hpl + (size_t)k * EB, hp);
+            c0 -= hp[0] * p0 + hp[3] * p1 + hp[6] * p2;
+            c1 -= hp[1] * p0 + hp[4] * p1 + hp[7] * p2;
+            c2 -= hp[2] * p0 + hp[5] * p1 + hp[8] * p2;
         }
         c0 = group_sum(c0); c1 = group_sum(c1); c2 = group_sum(c2);
         if (sub == 0 && j < d.L) {
@@ -1561,8 +1593,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     // asked), publishes, everybody waits for the peers and reads all ranks' slots back in rank order
     auto xslot_of = [&](int r, long long e) { return shd.xch[r] + XCH_HDR + (size_t)(e & 1) * shd.xslot; };
     // phase timers live in shared memory and are touched by thread 0 only (keeps them out of the register budget)
-    __shared__ long long tacc[8], wacc[8], tprev_s, wprev_s;
-    if (threadIdx.x == 0) { for (int g = 0; g < 8; ++g) { tacc[g] = 0; wacc[g] = 0; } tprev_s = wprev_s = clock64(); }
+    __shared__ long long tacc[8], wacc[10], tprev_s, wprev_s;
+    if (threadIdx.x == 0) { for (int g = 0; g < 8; ++g) tacc[g] = 0; for (int g = 0; g < 10; ++g) wacc[g] = 0; tprev_s = wprev_s = clock64(); }
 #define PK_TICK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); tacc[g] += _t - tprev_s; tprev_s = _t; wprev_s = _t; } } while (0)
 #define PK_WORK(g) do { if (threadIdx.x == 0) { const long long _t = clock64(); wacc[g] += _t - wprev_s; wprev_s = _t; } } while (0)
     for (int it = 0; it < pa.max_iters && !stop; ++it) {
@@ -1648,7 +1680,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             }
             PK_TICK(2);
             // ---- C: Schur complement gather
-            if (s_plan_ok) pk_phase_schur_par(d, lambda * lam_pose_mask, work, plan_w0, plan_nw, shv);
+            if (s_plan_ok) pk_phase_schur_par(d, lambda * lam_pose_mask, work, plan_w0, plan_nw, shv, pa.cta_work ? wacc : nullptr);
             else pk_phase_schur(d, lambda * lam_pose_mask, work, shv);
             PK_WORK(3);
             grid.sync();
@@ -1685,6 +1717,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             // ---- F: robust chi2 at the trial point
             pk_phase_linearize<false>(d, cam, cur ^ 1, pa.part_chi + nparts, sh);
             if (blockIdx.x == 0 && threadIdx.x == 0) pa.abort_dev[1] = *pa.abort_host;
+            if (pa.dbg_sysfence && blockIdx.x == 0 && threadIdx.x == 0) __threadfence_system();
             PK_WORK(7);
             grid.sync();
             PK_TICK(0);
@@ -1732,7 +1765,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     PK_TICK(6);
 #undef PK_TICK
 #undef PK_WORK
-    if (pa.cta_work && threadIdx.x == 0) for (int g = 0; g < 8; ++g) pa.cta_work[blockIdx.x * 8 + g] = wacc[g];
+    if (pa.cta_work && threadIdx.x == 0) for (int g = 0; g < 10; ++g) pa.cta_work[blockIdx.x * 10 + g] = wacc[g];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         LMState& s = *d.st;
         s.cur = cur; s.lambda = lambda; s.ni = ni; s.chi_cur = chi_cur; s.iter = done; s.epoch = epoch; s.error = peer_err ? 1 : 0;
@@ -1912,7 +1945,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
     A(&h->xp0, 3 * P); A(&h->xl0, 3 * L);
-    A(&h->pk_part_chi, 2048); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 2); A(&h->phase_cycles, 8); A(&h->cta_work, 1024 * 8);
+    A(&h->pk_part_chi, 2048); A(&h->pk_part_scale, 1024); A(&h->pk_part_max, 1024); A(&h->abort_dev, 2); A(&h->phase_cycles, 8); A(&h->cta_work, 1024 * 10);
     if (rc == SE2GPU_OK && cudaMallocHost((void**)&h->st_host, sizeof(LMState)) != cudaSuccess) rc = fail(SE2GPU_ERR_CUDA, "cudaMallocHost failed");
     if (rc == SE2GPU_OK) {
         cudaFuncSetAttribute(ba_chol_solve_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ldlt_smem_bytes(SMEM_CHOL_MAX_N));
@@ -2468,7 +2501,7 @@ int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, co
             SE2_CUDA(cudaMemsetAsync(h->go, 0, 2 * sizeof(long long), s));
         }
         PKArgs pa{max_iters, first_iteration, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
-                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0, getenv("SE2GPU_BA_DEBUG") ? h->cta_work : nullptr};
+                  h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0, getenv("SE2GPU_BA_DEBUG_SYSFENCE") ? 1 : 0, getenv("SE2GPU_BA_DEBUG") ? h->cta_work : nullptr};
         if (h->prof.on) h->pk_launches++;
         const size_t smem = std::max(ldlt_smem_bytes(d.n), (size_t)96 * 1024);
         pa.dyn_smem_bytes = (int)smem;
@@ -2487,13 +2520,23 @@ int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, co
             h->peer_epoch = h->st_host->epoch;
             if (h->st_host->error) return fail(SE2GPU_ERR_CUDA, "sharded BA: a peer rank did not reach the exchange within %.1f s (rank %d of %d)", h->peer_timeout_s, h->rank, h->world);
         }
+        if (pa.cta_work) {
+            unsigned long long ld[64];
+            cudaMemcpyFromSymbol(ld, g_lane_dbg, sizeof ld);
+            fprintf(stderr, "[se2gpu_ba] schur warp-0 worst per-lane cycles after pair loop:");
+            for (int i = 0; i < 32; ++i) fprintf(stderr, " %llu", ld[i]);
+            fprintf(stderr, "\n[se2gpu_ba] ... after edge loop:");
+            for (int i = 32; i < 64; ++i) fprintf(stderr, " %llu", ld[i]);
+            fprintf(stderr, "\n");
+            unsigned long long z[64] = {}; cudaMemcpyToSymbol(g_lane_dbg, z, sizeof z);
+        }
         if (pa.cta_work) {   // SE2GPU_BA_DEBUG=1: per-phase busy cycles of every CTA (max / mean / who) to stderr
-            std::vector<long long> w((size_t)h->pk_grid * 8);
+            std::vector<long long> w((size_t)h->pk_grid * 10);
             cudaMemcpy(w.data(), h->cta_work, w.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-            const char* names[8] = {"linearize", "pose+prep", "lm_prep", "schur", "solve", "backsub", "-", "chi2"};
-            for (int g = 0; g < 8; ++g) {
+            const char* names[10] = {"linearize", "pose+prep", "lm_prep", "schur", "solve", "backsub", "-", "chi2", "schur:gather", "schur:+shfl"};
+            for (int g = 0; g < 10; ++g) {
                 long long mx = 0, sum = 0; int who = 0;
-                for (int c = 0; c < h->pk_grid; ++c) { const long long v = w[(size_t)c * 8 + g]; sum += v; if (v > mx) { mx = v; who = c; } }
+                for (int c = 0; c < h->pk_grid; ++c) { const long long v = w[(size_t)c * 10 + g]; sum += v; if (v > mx) { mx = v; who = c; } }
                 fprintf(stderr, "[se2gpu_ba] phase %-10s busy cycles: max %lld (CTA %d) mean %lld  (per optimize of %d iters)\n", names[g], mx, who, sum / h->pk_grid, done);
             }
         }
