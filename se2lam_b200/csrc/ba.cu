@@ -538,19 +538,33 @@ struct GmemIO {   // same interface on byte offsets from a global base (reduced 
 // Block LDL^T of the reduced system (see the comment above ldlt_smem_bytes for the algorithm).
 //   ADDR = unsigned (shared window) or unsigned long long (global); aA, aY, aW, aC, aT are the byte addresses of
 //   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int), 2 x 3 back-substitution exchange slots, second tb[3]}.
+// Slices of the block LDL^T for the two-sided ("twisted") solve; the defaults reproduce the plain full solve.
+struct LdltOpt {
+    int ld = 0;                 // leading dimension of A in elements (0: n)
+    int kb0 = 0, kb1 = -1;      // pivot blocks [kb0, kb1) are eliminated by this call (-1: all)
+    bool init = true;           // load y from bs (when given) and reset the positive-definiteness flag
+    bool backsolve = true;      // run the back substitution and write the outputs
+    int npiv = -1;              // back substitution: blocks >= npiv take their solution from xinj (-1: all blocks are pivots)
+    const double* xinj = nullptr;
+};
+
 template <class IO, class ADDR>
-__device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR aT, int n, const double* bs, double* dxp, LMState* st) {
+__device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR aT, int n, const double* bs, double* dxp, LMState* st, const LdltOpt opt = LdltOpt()) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const ADDR aOK = aT + 24;
-#define A_(r, c) (aA + (ADDR)(((r) * n + (c)) * 8))
+    const int ld = opt.ld > 0 ? opt.ld : n;      // leading dimension of A
+#define A_(r, c) (aA + (ADDR)(((r) * ld + (c)) * 8))
 #define Y_(i) (aY + (ADDR)((i) * 8))
 #define W_(kb, q) (aW + (ADDR)((9 * (kb) + (q)) * 8))
     STAMP(0);
-    if (tid == 0) IO::sti(aOK, 1);
-    for (int i = tid; i < n; i += nt) IO::st(Y_(i), bs[i]);
+    if (opt.init) {
+        if (tid == 0) IO::sti(aOK, 1);
+        if (bs) for (int i = tid; i < n; i += nt) IO::st(Y_(i), bs[i]);
+    }
     __syncthreads();
-    const int nb = n / 3;
+    const int nb = n / 3;                                           // blocks of the matrix (rows below the eliminated part are updated too)
+    const int kb0 = opt.kb0, kb1 = opt.kb1 < 0 ? nb : opt.kb1;      // pivot blocks eliminated by this call
     STAMP(1);
     // The FP64 pipe issues one warp instruction every ~2 cycles per SM sub-partition, so the pivot-block inverse must
     // not be recomputed by every warp: warp 0 ("pivot warp") updates the NEXT pivot block + its rhs entries first,
@@ -573,10 +587,10 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
             if (!pd) IO::sti(aOK, 0);
         }
     };
-    if (wid == 0 && nb > 0) invert_and_publish(0, 0);
+    if (wid == 0 && kb0 < kb1 && IO::ldi(aOK)) invert_and_publish(kb0, 3 * kb0);
     __syncthreads();
     STAMP(2);
-    for (int kb = 0; kb < nb; ++kb) {
+    for (int kb = kb0; kb < kb1; ++kb) {
         if (!IO::ldi(aOK)) break;                                // uniform: written before the barrier that precedes this read
         const int k = 3 * kb;
         if (kb < 8) STAMP(10 + 4 * kb);
@@ -606,7 +620,7 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
                     IO::st(dst, val);
                 }
             }
-            if (kb + 1 < nb) {
+            if (kb + 1 < kb1) {
                 __syncwarp();                       // the 6 + 3 freshly updated values are in memory: re-read, invert, publish
                 invert_and_publish(kb + 1, k + 3);
             }
@@ -639,6 +653,8 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
     __syncthreads();
     STAMP(3);
     const int ok = IO::ldi(aOK);
+    if (!opt.backsolve) return;                                    // factorisation slice only (twisted solve: the driver continues)
+    const int npiv = opt.npiv < 0 ? nb : opt.npiv;                 // blocks >= npiv take their solution from opt.xinj
     if (ok) {
         if (n <= 160 && nt >= 160) {
             // Back substitution, axpy form on 5 warps: thread c < n owns the accumulator z_c = u_c - sum(a^T x) of column c in
@@ -660,7 +676,8 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
                     const double w00 = IO::ld(W_(kb, 0)), w01 = IO::ld(W_(kb, 1)), w02 = IO::ld(W_(kb, 2)), w11 = IO::ld(W_(kb, 4)), w12 = IO::ld(W_(kb, 5)), w22 = IO::ld(W_(kb, 8));
                     asm volatile("bar.sync 1, 160;" ::: "memory");
                     const double z0 = IO::ld(xz), z1 = IO::ld(xz + 8), z2 = IO::ld(xz + 16);
-                    const double x0 = w00 * z0 + w01 * z1 + w02 * z2, x1 = w01 * z0 + w11 * z1 + w12 * z2, x2 = w02 * z0 + w12 * z1 + w22 * z2;
+                    double x0 = w00 * z0 + w01 * z1 + w02 * z2, x1 = w01 * z0 + w11 * z1 + w12 * z2, x2 = w02 * z0 + w12 * z1 + w22 * z2;
+                    if (kb >= npiv) { x0 = opt.xinj[3 * (kb - npiv)]; x1 = opt.xinj[3 * (kb - npiv) + 1]; x2 = opt.xinj[3 * (kb - npiv) + 2]; }
                     z -= a0 * x0 + a1 * x1 + a2 * x2;
                     z = (c == k) ? x0 : (c == k + 1) ? x1 : (c == k + 2) ? x2 : z;
                 }
@@ -685,11 +702,11 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
         }
         __syncthreads();
         STAMP(4);
-        for (int i = tid; i < n; i += nt) dxp[i] = IO::ld(Y_(i));
+        if (dxp) for (int i = tid; i < n; i += nt) dxp[i] = IO::ld(Y_(i));
     } else {
-        for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
+        if (dxp) for (int i = tid; i < n; i += nt) dxp[i] = 0.0;
     }
-    if (tid == 0) st->solve_ok = ok;
+    if (tid == 0 && st) st->solve_ok = ok;
     STAMP(5);
 #undef A_
 #undef Y_
@@ -848,8 +865,6 @@ __global__ void __launch_bounds__(256) ba_decide(Dev d, int nb_scale, int phase,
 namespace cg = cooperative_groups;
 constexpr int PK_THREADS = 512;
 constexpr int LPL = 8;
-
-__device__ unsigned long long g_lane_dbg[64];   // SE2GPU_BA_DEBUG: per-lane worst loop time of warp 0 in the Schur phase (0..31 pair loop, 32..63 incl. edge loop)
 
 struct PKArgs {
     int max_iters;
@@ -1334,7 +1349,7 @@ __device__ void pk_phase_schur(const Dev& d, double lam, const PKWork& w, double
 // built once per launch). One block barrier for the whole phase instead of two per block, and no warp idles while a
 // 40-pair block is reduced. Summation order per block: lane-strided partials over the item's warps, warp xor-tree, the
 // item's warps in rank order - fixed, so runs stay bit-reproducible.
-__device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, const unsigned char* plan_w0, const unsigned char* plan_nw, double* shr /*[warps][21]*/, long long* tdbg = nullptr) {
+__device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, const unsigned char* plan_w0, const unsigned char* plan_nw, double* shr /*[warps][21]*/, double* red /*[warps][21][33]*/, long long* tdbg = nullptr) {
     if (w.first < 0) return;
     const long long t_in = tdbg ? clock64() : 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1361,7 +1376,6 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
 #pragma unroll
                 for (int c = 0; c < 3; ++c) acc[r * 3 + c] -= y[r * 3] * h[c * 3] + y[r * 3 + 1] * h[c * 3 + 1] + y[r * 3 + 2] * h[c * 3 + 2];
         }
-        if (tdbg && wid == 0) atomicMax(&g_lane_dbg[lane], (unsigned long long)(clock64() - t_in));
         if (rk == 0)
             for (int k = d.blk_odo_ptr[o.blk] + lane; k < d.blk_odo_ptr[o.blk + 1]; k += 32) {
                 const int code = d.blk_odo[k], oo = code >> 1;
@@ -1392,25 +1406,23 @@ __device__ void pk_phase_schur_par(const Dev& d, double lam, const PKWork& w, co
                     for (int q = 0; q < 3; ++q) ph[6 + q] += bb[q * O + oo];
                 }
         }
-        if (tdbg && wid == 0) atomicMax(&g_lane_dbg[32 + lane], (unsigned long long)(clock64() - t_in));
         if (tdbg && threadIdx.x == 0) tdbg[8] += clock64() - t_in;      // gather loops of warp 0
+        // warp reduction of the 21 partials through shared memory: every lane parks its values in a [21][33] tile (padded rows:
+        // conflict-free), then lanes 0..20 each add one row in lane order - 21 stores + 32 loads per lane instead of 105
+        // double-precision shuffle steps (210 SHFL + 105 DADD)
+        double* sc = red + (size_t)wid * (21 * 33);
 #pragma unroll
-        for (int q = 0; q < 12; ++q)
+        for (int q = 0; q < 12; ++q) sc[q * 33 + lane] = acc[q];
 #pragma unroll
-            for (int s2 = 16; s2 > 0; s2 >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], s2);
-        if (diag) {
-#pragma unroll
-            for (int q = 0; q < 9; ++q)
-#pragma unroll
-                for (int s2 = 16; s2 > 0; s2 >>= 1) ph[q] += __shfl_xor_sync(0xffffffffu, ph[q], s2);
+        for (int q = 0; q < 9; ++q) sc[(12 + q) * 33 + lane] = ph[q];
+        __syncwarp();
+        if (lane < 21) {
+            double v = 0;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) v += sc[lane * 33 + i];
+            shr[wid * 21 + lane] = v;
         }
-        if (tdbg && threadIdx.x == 0) tdbg[9] += clock64() - t_in;      // ... + its shuffle reduction
-        if (lane == 0) {
-#pragma unroll
-            for (int q = 0; q < 12; ++q) shr[wid * 21 + q] = acc[q];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) shr[wid * 21 + 12 + q] = ph[q];
-        }
+        if (tdbg && threadIdx.x == 0) tdbg[9] += clock64() - t_in;      // ... + its reduction
     }
     __syncthreads();
     if (it >= 0 && rk == 0 && lane < 12) {
@@ -1528,6 +1540,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     __shared__ PKOwn own[PK_MAXOWN];
     __shared__ int s_nown, s_plan_ok;
     __shared__ unsigned char plan_w0[PK_MAXOWN], plan_nw[PK_MAXOWN];   // warp groups of the concurrent Schur phase
+    constexpr int RED_SCRATCH_BYTES = (PK_THREADS / 32) * 21 * 33 * 8;
+    double* red_scratch = sm + (pa.dyn_smem_bytes - RED_SCRATCH_BYTES) / 8;      // worker CTAs only (CTA 0 keeps its arena for the solve)
     PKWork work;
     {
         const int G = gridDim.x;
@@ -1536,7 +1550,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
         work.own = own;
         work.arena = reinterpret_cast<const int*>(sm);
         int* arena = reinterpret_cast<int*>(sm);
-        const int arena_ints = (G > 1 && blockIdx.x > 0) ? pa.dyn_smem_bytes / 4 : 0;
+        const int arena_ints = (G > 1 && blockIdx.x > 0) ? (pa.dyn_smem_bytes - RED_SCRATCH_BYTES) / 4 : 0;   // the top of the arena is the reduction scratch
         if (threadIdx.x == 0) {
             int off = 0, no = 0;
             if (work.first >= 0)
@@ -1680,7 +1694,7 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             }
             PK_TICK(2);
             // ---- C: Schur complement gather
-            if (s_plan_ok) pk_phase_schur_par(d, lambda * lam_pose_mask, work, plan_w0, plan_nw, shv, pa.cta_work ? wacc : nullptr);
+            if (s_plan_ok) pk_phase_schur_par(d, lambda * lam_pose_mask, work, plan_w0, plan_nw, shv, red_scratch, pa.cta_work ? wacc : nullptr);
             else pk_phase_schur(d, lambda * lam_pose_mask, work, shv);
             PK_WORK(3);
             grid.sync();
@@ -2503,7 +2517,7 @@ int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, co
         PKArgs pa{max_iters, first_iteration, h->stats_dev, trace_poses ? h->trace_p : nullptr, trace_points ? h->trace_l : nullptr,
                   h->abort_host_dev, h->abort_dev, h->pk_part_chi, h->pk_part_scale, h->pk_part_max, h->prof.on ? h->phase_cycles : nullptr, 0, getenv("SE2GPU_BA_DEBUG_SYSFENCE") ? 1 : 0, getenv("SE2GPU_BA_DEBUG") ? h->cta_work : nullptr};
         if (h->prof.on) h->pk_launches++;
-        const size_t smem = std::max(ldlt_smem_bytes(d.n), (size_t)96 * 1024);
+        const size_t smem = std::max(ldlt_smem_bytes(d.n), (size_t)160 * 1024);      // worker CTAs: pair lists + 87 KB of reduction scratch
         pa.dyn_smem_bytes = (int)smem;
         void* args[] = {(void*)&d, (void*)&h->cam, (void*)&pa, (void*)&shd};
         h->prof.begin(7, s);
@@ -2519,16 +2533,6 @@ int se2gpu_ba_optimize_from(se2gpu_ba* h, int first_iteration, int max_iters, co
         if (h->world > 1) {
             h->peer_epoch = h->st_host->epoch;
             if (h->st_host->error) return fail(SE2GPU_ERR_CUDA, "sharded BA: a peer rank did not reach the exchange within %.1f s (rank %d of %d)", h->peer_timeout_s, h->rank, h->world);
-        }
-        if (pa.cta_work) {
-            unsigned long long ld[64];
-            cudaMemcpyFromSymbol(ld, g_lane_dbg, sizeof ld);
-            fprintf(stderr, "[se2gpu_ba] schur warp-0 worst per-lane cycles after pair loop:");
-            for (int i = 0; i < 32; ++i) fprintf(stderr, " %llu", ld[i]);
-            fprintf(stderr, "\n[se2gpu_ba] ... after edge loop:");
-            for (int i = 32; i < 64; ++i) fprintf(stderr, " %llu", ld[i]);
-            fprintf(stderr, "\n");
-            unsigned long long z[64] = {}; cudaMemcpyToSymbol(g_lane_dbg, z, sizeof z);
         }
         if (pa.cta_work) {   // SE2GPU_BA_DEBUG=1: per-phase busy cycles of every CTA (max / mean / who) to stderr
             std::vector<long long> w((size_t)h->pk_grid * 10);
