@@ -58,6 +58,12 @@ struct Dev {  // all device pointers of one context (passed by value to kernels)
     int P, L, E, O, nf, n, nblk;
     int rank, world;
     int sbw;   // 0: S dense [n*n]; > 0: S in band storage, row r holds columns r-sbw..r (large windows, ba_band.cu)
+    // two-sided ("twisted") reduced solve of the persistent kernel: pose blocks [0, tw_m0) are eliminated top-down by CTA 0,
+    // blocks [tw_m0 + tw_w, nf) bottom-up by CTA 1, the tw_w separator blocks in between last (tw_m0 == 0: off)
+    int tw_m0, tw_w;
+    const int* tw_cmax1;   // [3 (nf - tw_m0)] envelope of the mirrored bottom part
+    double* tw_buf;        // CTA 1 -> CTA 0: separator Schur complement | rhs | ok; CTA 0 -> CTA 1 at TW_XM: separator solution, mirrored
+    unsigned* tw_flag;     // [0] bottom part ready (sequence number), [1] published separator entries (count), [2] (sequence << 1) | ok
     // state
     double* xp[2];
     double* xl[2];
@@ -489,14 +495,29 @@ __global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(Dev d) {
 // SMEM=true indexes the dynamic shared array directly (LDS, no generic-address conversion in the loops);
 // SMEM=false works in place in global memory (reduced systems too large for one CTA's shared memory).
 #ifdef SE2_SOLVE_STAMPS
-__device__ long long g_stamps[64];   // tools/solve_bench.cu: clock64 stamps of thread 0 (plain stores, no read-modify-write)
-#define STAMP(i) do { if (threadIdx.x == 0) g_stamps[i] = clock64(); } while (0)
+__device__ long long g_stamps[128];  // tools/solve_bench.cu: clock64 stamps of thread 0 of CTAs 0 / 1 (plain stores, no read-modify-write)
+#define STAMP(i) do { if (threadIdx.x == 0) g_stamps[(blockIdx.x & 1) * 64 + (i)] = clock64(); } while (0)
 #else
 #define STAMP(i) do { } while (0)
+#endif
+#if defined(SE2_SOLVE_STAMPS) && SE2_SOLVE_STAMPS >= 2
+// per-step stamps of one steady-state step, written by ALL lanes of a warp to one shared word (a thread-0-only stamp makes
+// thread 0 diverge from its warp and distorts what it measures)
+__device__ long long g_wstamps[16 * 16];
+#define WSTAMP_DECL __shared__ long long s_wst[16 * 16];
+#define WSTAMP(kbv, i) do { if ((kbv) == 10) s_wst[(threadIdx.x >> 5) * 16 + (i)] = clock64(); } while (0)
+#define WSTAMP_DUMP do { __syncthreads(); if (threadIdx.x < 256) g_wstamps[threadIdx.x] = s_wst[threadIdx.x]; } while (0)
+#else
+#define WSTAMP_DECL
+#define WSTAMP(kbv, i) do { } while (0)
+#define WSTAMP_DUMP do { } while (0)
 #endif
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: stage the reduced system into shared memory
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// the same address as an opaque register value: nvcc otherwise RE-MATERIALISES the window base at every use inside the solve's
+// loops (S2UR SR_CgaCtaId + ULEA in front of the LDS of every row pass, on the critical path of every pivot step)
+__device__ __forceinline__ unsigned smem_u32_pinned(const void* p) { unsigned a = smem_u32(p); asm volatile("mov.b32 %0, %0;" : "+r"(a)); return a; }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -527,17 +548,27 @@ struct SmemIO {
     static __device__ __forceinline__ void st(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
     static __device__ __forceinline__ int ldi(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
     static __device__ __forceinline__ void sti(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+    // 16-byte / 8-byte pairs (a must be aligned accordingly): one shared-memory instruction instead of two
+    static __device__ __forceinline__ void ld2(unsigned a, double& x, double& y) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
+    static __device__ __forceinline__ void st2(unsigned a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
+    static __device__ __forceinline__ void ldi2(unsigned a, int& x, int& y) { asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
+    static __device__ __forceinline__ void sti2(unsigned a, int x, int y) { asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 };
 struct GmemIO {   // same interface on byte offsets from a global base (reduced systems that do not fit one CTA's shared memory)
     static __device__ __forceinline__ double ld(unsigned long long a) { return *reinterpret_cast<const volatile double*>(a); }
     static __device__ __forceinline__ void st(unsigned long long a, double v) { *reinterpret_cast<volatile double*>(a) = v; }
     static __device__ __forceinline__ int ldi(unsigned long long a) { return *reinterpret_cast<const volatile int*>(a); }
     static __device__ __forceinline__ void sti(unsigned long long a, int v) { *reinterpret_cast<volatile int*>(a) = v; }
+    static __device__ __forceinline__ void ld2(unsigned long long a, double& x, double& y) { x = ld(a); y = ld(a + 8); }
+    static __device__ __forceinline__ void st2(unsigned long long a, double x, double y) { st(a, x); st(a + 8, y); }
+    static __device__ __forceinline__ void ldi2(unsigned long long a, int& x, int& y) { x = ldi(a); y = ldi(a + 4); }
+    static __device__ __forceinline__ void sti2(unsigned long long a, int x, int y) { sti(a, x); sti(a + 4, y); }
 };
 
 // Block LDL^T of the reduced system (see the comment above ldlt_smem_bytes for the algorithm).
 //   ADDR = unsigned (shared window) or unsigned long long (global); aA, aY, aW, aC, aT are the byte addresses of
-//   A [n*n], y [n], W [9 per pose], cmax (int) [n], scratch {tb[3], ok (int), 2 x 3 back-substitution exchange slots, second tb[3]}.
+//   A [n*n], y [n] (= row n of A when the two are adjacent), W records [8 per pose, 16-byte aligned inside a 9-per-pose area],
+//   cmax (int) [n], scratch {3 unused, ok (int), 2 x 3 back-substitution exchange slots}.
 // Slices of the block LDL^T for the two-sided ("twisted") solve; the defaults reproduce the plain full solve.
 struct LdltOpt {
     int ld = 0;                 // leading dimension of A in elements (0: n)
@@ -546,17 +577,32 @@ struct LdltOpt {
     bool backsolve = true;      // run the back substitution and write the outputs
     int npiv = -1;              // back substitution: blocks >= npiv take their solution from xinj (-1: all blocks are pivots)
     const double* xinj = nullptr;
+    // back substitution hook of the twisted solve: once blocks >= pub_kb are solved their owners write x mirrored to pub and count in
+    double* pub = nullptr; unsigned* pub_cnt = nullptr; int pub_kb = 0;
+    unsigned* okword = nullptr; unsigned okval = 0;     // thread 0 writes okval | ok right after the factorisation
 };
+constexpr int TW_MAX_W = 16;                            // separator blocks
+constexpr int TW_XM = 3 * TW_MAX_W * (3 * TW_MAX_W + 1) + 16;
+constexpr int TW_BUF_DOUBLES = TW_XM + 3 * TW_MAX_W + 16;
 
 template <class IO, class ADDR>
 __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR aT, int n, const double* bs, double* dxp, LMState* st, const LdltOpt opt = LdltOpt()) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     const ADDR aOK = aT + 24;
+    WSTAMP_DECL
     const int ld = opt.ld > 0 ? opt.ld : n;      // leading dimension of A
 #define A_(r, c) (aA + (ADDR)(((r) * ld + (c)) * 8))
 #define Y_(i) (aY + (ADDR)((i) * 8))
-#define W_(kb, q) (aW + (ADDR)((9 * (kb) + (q)) * 8))
+    // per-block record, 64 bytes at a 16-byte aligned address: W = D_kb^-1 packed [w00 w01 | w02 w11 | w12 w22] and {pd, m} (ints):
+    // pd = pivot block positive definite, m = trailing rows/cols of the block's envelope. One 8-byte + three 16-byte shared loads
+    // per warp and step: the step is bound by the shared-memory instruction queue (16 warps re-reading the same words), not by
+    // arithmetic.
+    const ADDR aWr = (aW + (ADDR)15) & ~(ADDR)15;
+#define R_(kb) (aWr + (ADDR)((kb) * 64))
+    // the right-hand side is row n of the matrix: y_i -= a_i . (W u_k) = u_k . (W a_i) is the update of entry (n, i) with
+    // a_n = u_k = y[k..k+2], the same formula as every other trailing entry (no separate code path, no published W u)
+    auto rowaddr = [&](int i) -> ADDR { return i == n ? aY : aA + (ADDR)i * (ADDR)(ld * 8); };
     STAMP(0);
     if (opt.init) {
         if (tid == 0) IO::sti(aOK, 1);
@@ -566,94 +612,105 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
     const int nb = n / 3;                                           // blocks of the matrix (rows below the eliminated part are updated too)
     const int kb0 = opt.kb0, kb1 = opt.kb1 < 0 ? nb : opt.kb1;      // pivot blocks eliminated by this call
     STAMP(1);
-    // The FP64 pipe issues one warp instruction every ~2 cycles per SM sub-partition, so the pivot-block inverse must
-    // not be recomputed by every warp: warp 0 ("pivot warp") updates the NEXT pivot block + its rhs entries first,
-    // inverts it and publishes W_{k+1}, W_{k+1} u_{k+1} to shared memory before the step's barrier, while the other
-    // warps update the rest of the trailing envelope (one row per warp). After the barrier everybody just reads W.
-    auto invert_and_publish = [&](int kb, int r) {     // pivot block at rows/cols r..r+2 (already final), rhs y[r..r+2]
+    // The pivot-block inverse is the serial chain of the factorisation: warp 0 ("pivot warp") updates the NEXT pivot block and
+    // its right-hand-side entries first, inverts it and publishes the record of block k+1 before the step's barrier, while the
+    // other warps update the rest of the trailing envelope. After the barrier everybody just reads the record.
+    auto invert_and_publish = [&](int kb, int r) {     // pivot block at rows/cols r..r+2 (already final)
         const double a = IO::ld(A_(r, r)), b = IO::ld(A_(r + 1, r)), c = IO::ld(A_(r + 2, r));
         const double e = IO::ld(A_(r + 1, r + 1)), f = IO::ld(A_(r + 2, r + 1)), i2 = IO::ld(A_(r + 2, r + 2));
-        const double u0 = IO::ld(Y_(r)), u1 = IO::ld(Y_(r + 1)), u2 = IO::ld(Y_(r + 2));
+        const int mnext = IO::ldi(aC + (ADDR)((r + 2) * 4)) - (r + 2);
         const double c00 = e * i2 - f * f, c01 = c * f - b * i2, c02 = b * f - c * e;
         const double det = a * c00 + b * c01 + c * c02, m2 = a * e - b * b;
         const bool pd = (a > 0.0) && (m2 > 0.0) && (det > 0.0) && isfinite(det);   // leading minors: CHOLMOD's "not positive definite"
+        WSTAMP(kb - 1, 4);
         const double id = 1.0 / det;
         const double w00 = c00 * id, w01 = c01 * id, w02 = c02 * id, w11 = (a * i2 - c * c) * id, w12 = (b * c - a * f) * id, w22 = m2 * id;
+        WSTAMP(kb - 1, 5);
         if (lane == 0) {
-            IO::st(W_(kb, 0), w00); IO::st(W_(kb, 1), w01); IO::st(W_(kb, 2), w02); IO::st(W_(kb, 3), w01); IO::st(W_(kb, 4), w11);
-            IO::st(W_(kb, 5), w12); IO::st(W_(kb, 6), w02); IO::st(W_(kb, 7), w12); IO::st(W_(kb, 8), w22);
-            const ADDR tb = aT + (ADDR)((kb & 1) ? 80 : 0);      // W_k u_k, double-buffered by step parity (no barrier between read and next write)
-            IO::st(tb, w00 * u0 + w01 * u1 + w02 * u2); IO::st(tb + 8, w01 * u0 + w11 * u1 + w12 * u2); IO::st(tb + 16, w02 * u0 + w12 * u1 + w22 * u2);
+            const ADDR rec = R_(kb);
+            IO::st2(rec, w00, w01); IO::st2(rec + 16, w02, w11); IO::st2(rec + 32, w12, w22); IO::sti2(rec + 48, pd ? 1 : 0, mnext);
             if (!pd) IO::sti(aOK, 0);
         }
+        WSTAMP(kb - 1, 6);
     };
-    if (wid == 0 && kb0 < kb1 && IO::ldi(aOK)) invert_and_publish(kb0, 3 * kb0);
+    const bool go = IO::ldi(aOK) != 0;                               // a continuation slice of a system already found indefinite does nothing
+    if (wid == 0 && kb0 < kb1 && go) invert_and_publish(kb0, 3 * kb0);
     __syncthreads();
     STAMP(2);
-    for (int kb = kb0; kb < kb1; ++kb) {
-        if (!IO::ldi(aOK)) break;                                // uniform: written before the barrier that precedes this read
+    for (int kb = go ? kb0 : kb1; kb < kb1; ++kb) {
+        WSTAMP(kb, 0);
+        int pdk, m;                                              // m: trailing rows/cols k+3 .. k+2+m
+        IO::ldi2(R_(kb) + 48, pdk, m);
+        if (!pdk) break;                                         // uniform: published before the barrier that precedes this read
         const int k = 3 * kb;
-        if (kb < 8) STAMP(10 + 4 * kb);
-        const double w00 = IO::ld(W_(kb, 0)), w01 = IO::ld(W_(kb, 1)), w02 = IO::ld(W_(kb, 2)), w11 = IO::ld(W_(kb, 4)), w12 = IO::ld(W_(kb, 5)), w22 = IO::ld(W_(kb, 8));
-        const ADDR tbk = aT + (ADDR)((kb & 1) ? 80 : 0);
-        const double t0 = IO::ld(tbk), t1 = IO::ld(tbk + 8), t2 = IO::ld(tbk + 16);
-        const int m = IO::ldi(aC + (ADDR)((k + 2) * 4)) - (k + 2);            // trailing rows/cols k+3 .. k+2+m
-        if (kb < 8) STAMP(11 + 4 * kb);
+        WSTAMP(kb, 1);
         if (wid == 0) {
-            // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii, plus their rhs entries: lanes 0..8
+            double w00, w01, w02, w11, w12, w22;
+            IO::ld2(R_(kb), w00, w01); IO::ld2(R_(kb) + 16, w02, w11); IO::ld2(R_(kb) + 32, w12, w22);
+            // next pivot block: rows k+3..k+5 (ii = 0..2), cols jj <= ii (lanes 0..5), and the right-hand side of those columns
+            // (row n, lanes 6..8)
             if (kb + 1 < nb && lane < 9) {
-                const int q = lane;                 // 0..5: (ii,jj) = (0,0)(1,0)(1,1)(2,0)(2,1)(2,2); 6..8: rhs of row q-6
-                const int ii = q < 1 ? 0 : (q < 3 ? 1 : (q < 6 ? 2 : q - 6));
-                const int jj = q < 1 ? 0 : (q < 3 ? q - 1 : (q < 6 ? q - 3 : 0));
-                const int i = k + 3 + ii, j = k + 3 + jj;
-                if (ii < m) {                       // rows beyond the envelope of this block column are structurally untouched
-                    const ADDR dst = (q < 6) ? A_(i, j) : Y_(i);
-                    double val = IO::ld(dst);
-                    const double a0 = IO::ld(A_(i, k)), a1 = IO::ld(A_(i, k + 1)), a2 = IO::ld(A_(i, k + 2));
-                    if (q < 6) {
-                        const double b0 = IO::ld(A_(j, k)), b1 = IO::ld(A_(j, k + 1)), b2 = IO::ld(A_(j, k + 2));
-                        const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
-                        val -= a0 * v0 + a1 * v1 + a2 * v2;
-                    } else {
-                        val -= a0 * t0 + a1 * t1 + a2 * t2;
-                    }
-                    IO::st(dst, val);
+                const int q = lane;                 // 0..5: (ii,jj) = (0,0)(1,0)(1,1)(2,0)(2,1)(2,2); 6..8: (n, q-6)
+                const bool rhs = q >= 6;
+                const int ii = q < 1 ? 0 : (q < 3 ? 1 : 2);
+                const int jj = q < 1 ? 0 : (q < 3 ? q - 1 : (q < 6 ? q - 3 : q - 6));
+                if ((rhs ? jj : ii) < m) {          // rows / columns beyond the envelope of this block column are structurally untouched
+                    const int j = k + 3 + jj;
+                    const ADDR ra = rowaddr(rhs ? n : k + 3 + ii), dst = ra + (ADDR)(j * 8), rb = A_(j, k);
+                    const double a0 = IO::ld(ra + (ADDR)(k * 8)), a1 = IO::ld(ra + (ADDR)(k * 8 + 8)), a2 = IO::ld(ra + (ADDR)(k * 8 + 16));
+                    const double b0 = IO::ld(rb), b1 = IO::ld(rb + 8), b2 = IO::ld(rb + 16);
+                    const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
+                    IO::st(dst, IO::ld(dst) - (a0 * v0 + a1 * v1 + a2 * v2));
                 }
             }
+            WSTAMP(kb, 2);
             if (kb + 1 < kb1) {
-                __syncwarp();                       // the 6 + 3 freshly updated values are in memory: re-read, invert, publish
+                __syncwarp();                       // the 6 freshly updated values are in memory: re-read, invert, publish
+                WSTAMP(kb, 3);
                 invert_and_publish(kb + 1, k + 3);
             }
-            if (kb < 8) STAMP(12 + 4 * kb);
+            WSTAMP(kb, 7);
         } else if (m > 63 || (wid & 3) != 0) {
-            // rows ii >= 3 of the trailing envelope: one row per warp pass, lanes over the columns (+1 lane for the rhs).
-            // Warps are dealt to the 4 SM sub-partitions by warp id mod 4, and each sub-partition has one FP64 issue port:
-            // for a narrow envelope (little trailing work) the warps that share the pivot warp's sub-partition sit the
-            // step out, so the pivot chain - the critical path - never waits for an issue slot.
+            // rows ii >= 3 of the trailing envelope and the right-hand side (pseudo row ii == m, columns >= 3): lanes over the columns.
+            // A narrow envelope has rows of <= 16 (8) columns: 2 (4) rows share one warp pass, which halves (quarters) the
+            // shared-memory instructions of the step. Warps are dealt to the 4 SM sub-partitions by warp id mod 4: for a narrow
+            // envelope the warps that share the pivot warp's sub-partition sit the step out, so the pivot chain never waits for an
+            // issue slot.
             const bool quiet = m <= 63;
             const int rank = quiet ? wid - (wid >> 2) - 1 : wid - 1, nwk = quiet ? nw - ((nw + 3) >> 2) : nw - 1;
-            for (int ii = 3 + rank; ii < m; ii += nwk) {
-                const int i = k + 3 + ii;
-                const double a0 = IO::ld(A_(i, k)), a1 = IO::ld(A_(i, k + 1)), a2 = IO::ld(A_(i, k + 2));
-                for (int jj = lane; jj <= ii + 1; jj += 32) {
-                    if (jj <= ii) {
+            const int lg = m <= 8 ? 3 : (m <= 16 ? 4 : 5), rpp = 32 >> lg, col = lane & ((1 << lg) - 1), sub = lane >> lg;
+            const int nrows = m - 2;
+            if (rank * rpp < nrows) {
+                double w00, w01, w02, w11, w12, w22;
+                IO::ld2(R_(kb), w00, w01); IO::ld2(R_(kb) + 16, w02, w11); IO::ld2(R_(kb) + 32, w12, w22);
+                for (int s0 = rank * rpp; s0 < nrows; s0 += nwk * rpp) {
+                    const int ii = 3 + s0 + sub;
+                    if (ii > m) continue;
+                    const bool rhs = ii == m;
+                    const ADDR ra = rowaddr(rhs ? n : k + 3 + ii);
+                    const int jlo = rhs ? 3 : 0, jhi = rhs ? m - 1 : ii;
+                    const double a0 = IO::ld(ra + (ADDR)(k * 8)), a1 = IO::ld(ra + (ADDR)(k * 8 + 8)), a2 = IO::ld(ra + (ADDR)(k * 8 + 16));
+                    for (int jj = col; jj <= jhi; jj += 1 << lg) {
+                        if (jj < jlo) continue;
                         const int j = k + 3 + jj;
-                        const double b0 = IO::ld(A_(j, k)), b1 = IO::ld(A_(j, k + 1)), b2 = IO::ld(A_(j, k + 2));
+                        const ADDR dst = ra + (ADDR)(j * 8), rb = A_(j, k);
+                        const double b0 = IO::ld(rb), b1 = IO::ld(rb + 8), b2 = IO::ld(rb + 16);
                         const double v0 = w00 * b0 + w01 * b1 + w02 * b2, v1 = w01 * b0 + w11 * b1 + w12 * b2, v2 = w02 * b0 + w12 * b1 + w22 * b2;
-                        IO::st(A_(i, j), IO::ld(A_(i, j)) - (a0 * v0 + a1 * v1 + a2 * v2));
-                    } else {
-                        IO::st(Y_(i), IO::ld(Y_(i)) - (a0 * t0 + a1 * t1 + a2 * t2));        // the right-hand side as an extra column
+                        IO::st(dst, IO::ld(dst) - (a0 * v0 + a1 * v1 + a2 * v2));
                     }
                 }
             }
+            WSTAMP(kb, 7);
         }
         __syncthreads();
-        if (kb < 8) STAMP(13 + 4 * kb);
+        WSTAMP(kb, 8);
     }
     __syncthreads();
     STAMP(3);
+    WSTAMP_DUMP;
     const int ok = IO::ldi(aOK);
     if (!opt.backsolve) return;                                    // factorisation slice only (twisted solve: the driver continues)
+    if (opt.okword && tid == 0) { *reinterpret_cast<volatile unsigned*>(opt.okword) = opt.okval | (unsigned)ok; __threadfence(); }
     const int npiv = opt.npiv < 0 ? nb : opt.npiv;                 // blocks >= npiv take their solution from opt.xinj
     if (ok) {
         if (n <= 160 && nt >= 160) {
@@ -673,13 +730,15 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
                     if (c >= k && c < k + 3) IO::st(xz + (ADDR)((c - k) * 8), z);
                     const bool in = c < k && cm >= k + 2;                  // row block kb inside this column's envelope
                     const double a0 = in ? IO::ld(A_(k, c)) : 0.0, a1 = in ? IO::ld(A_(k + 1, c)) : 0.0, a2 = in ? IO::ld(A_(k + 2, c)) : 0.0;
-                    const double w00 = IO::ld(W_(kb, 0)), w01 = IO::ld(W_(kb, 1)), w02 = IO::ld(W_(kb, 2)), w11 = IO::ld(W_(kb, 4)), w12 = IO::ld(W_(kb, 5)), w22 = IO::ld(W_(kb, 8));
+                    double w00, w01, w02, w11, w12, w22;
+                    IO::ld2(R_(kb), w00, w01); IO::ld2(R_(kb) + 16, w02, w11); IO::ld2(R_(kb) + 32, w12, w22);
                     asm volatile("bar.sync 1, 160;" ::: "memory");
                     const double z0 = IO::ld(xz), z1 = IO::ld(xz + 8), z2 = IO::ld(xz + 16);
                     double x0 = w00 * z0 + w01 * z1 + w02 * z2, x1 = w01 * z0 + w11 * z1 + w12 * z2, x2 = w02 * z0 + w12 * z1 + w22 * z2;
                     if (kb >= npiv) { x0 = opt.xinj[3 * (kb - npiv)]; x1 = opt.xinj[3 * (kb - npiv) + 1]; x2 = opt.xinj[3 * (kb - npiv) + 2]; }
                     z -= a0 * x0 + a1 * x1 + a2 * x2;
                     z = (c == k) ? x0 : (c == k + 1) ? x1 : (c == k + 2) ? x2 : z;
+                    if (opt.pub && kb == opt.pub_kb && c >= k && c < n) { opt.pub[n - 1 - c] = z; __threadfence(); atomicAdd(opt.pub_cnt, 1u); }
                 }
                 if (c < n) IO::st(Y_(c), z);
             }
@@ -696,7 +755,10 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
                 sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
                 const double rc = (c < 3) ? IO::ld(Y_(k + c)) - sdot : 0.0;
                 const double r0 = __shfl_sync(0xffffffffu, rc, 0), r1 = __shfl_sync(0xffffffffu, rc, 8), r2 = __shfl_sync(0xffffffffu, rc, 16);
-                if (lane < 3) IO::st(Y_(k + lane), IO::ld(W_(kb, 3 * lane)) * r0 + IO::ld(W_(kb, 3 * lane + 1)) * r1 + IO::ld(W_(kb, 3 * lane + 2)) * r2);
+                if (lane < 3) {     // row `lane` of the symmetric W from its packed upper triangle [00 01 02 11 12 22]
+                    const int q0 = lane, q1 = lane == 0 ? 1 : (lane == 1 ? 3 : 4), q2 = lane == 0 ? 2 : (lane == 1 ? 4 : 5);
+                    IO::st(Y_(k + lane), IO::ld(R_(kb) + (ADDR)(q0 * 8)) * r0 + IO::ld(R_(kb) + (ADDR)(q1 * 8)) * r1 + IO::ld(R_(kb) + (ADDR)(q2 * 8)) * r2);
+                }
                 __syncwarp();
             }
         }
@@ -710,15 +772,15 @@ __device__ void ldlt_block_solve_impl(ADDR aA, ADDR aY, ADDR aW, ADDR aC, ADDR a
     STAMP(5);
 #undef A_
 #undef Y_
-#undef W_
+#undef R_
 }
 
 template <bool SMEM>
 __device__ void ldlt_block_solve(double* G, double* ywork, int n, const int* colmax_g, const double* bs, double* dxp, LMState* st) {
     if (SMEM) {
         extern __shared__ double sm[];
-        // layout: A [n*n] | y [n] | W [3n] | pad [2] | cmax (int) [n] | scratch tb[3], ok
-        const unsigned sA = smem_u32(sm);
+        // layout: A [n*n] | y [n] | W records [3n + 2] | cmax (int) [n] | scratch
+        const unsigned sA = smem_u32_pinned(sm);
         const unsigned sY = sA + (unsigned)n * n * 8, sW = sY + (unsigned)n * 8, sC = sW + (unsigned)(3 * n + 2) * 8;
         const unsigned sT = (sC + (unsigned)n * 4 + 15u) & ~15u;
         ldlt_block_solve_impl<SmemIO, unsigned>(sA, sY, sW, sC, sT, n, bs, dxp, st);
@@ -746,6 +808,111 @@ __device__ __forceinline__ void ldlt_stage(const Dev& d, const double* S, unsign
         mbar_wait(bar, parity);
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// Two-sided solve of the reduced system on CTAs 0 and 1 of the persistent kernel (both resident: cooperative launch).
+// The pivot chain - one dependent 3x3 inverse per pose block - is the critical path of the single-CTA solve; the envelope of a
+// local window is a narrow band, so the blocks split into top [0, m0), separator [m0, m0 + w) and bottom [m0 + w, nb) with no
+// top-bottom coupling. CTA 0 eliminates the top blocks of S[0 : 3(m0+w)) in place; CTA 1 eliminates the bottom blocks on the
+// index-reversed copy A1[r'][c'] = S[n-1-c'][n-1-r'] (lower triangle -> lower triangle, same code); its separator update goes to
+// CTA 0 through tw_buf, CTA 0 finishes the separator blocks, back-substitutes and hands the separator solution back as soon as it
+// exists. Chain length max(m0, nb - m0 - w) + w instead of nb. `seq` counts the solves of this launch from 1.
+__device__ void ldlt_twisted_solve(const Dev& d, const double* S, const double* bs, unsigned long long* bar, unsigned parity, unsigned seq) {
+    extern __shared__ double sm[];
+    __shared__ double xs[3 * TW_MAX_W];
+    const int n = d.n, nb = n / 3, m0 = d.tw_m0, w = d.tw_w, m1 = nb - m0 - w, w3 = 3 * w;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* T = d.tw_buf;
+    if (blockIdx.x == 0) {
+        const int n0 = 3 * (m0 + w);
+        // layout: A [n0 rows, leading dimension n] | y [n0] | W [3 n0] | pad [2] | cmax (int) [n0] | scratch
+        double* y = sm + (size_t)n0 * n;
+        int* cm = reinterpret_cast<int*>(y + 4 * (size_t)n0 + 2);
+        const unsigned sA = smem_u32_pinned(sm), sY = sA + (unsigned)n0 * n * 8, sW = sY + (unsigned)n0 * 8, sC = sY + (unsigned)(4 * n0 + 2) * 8, sT = (sC + (unsigned)n0 * 4 + 15u) & ~15u;
+        const unsigned bytes = (unsigned)(((size_t)n0 * n * 8 + 15) & ~(size_t)15);
+        STAMP(50);
+        if (tid == 0) bulk_g2s(sm, S, bytes, bar);
+        for (int t = tid; t < n0; t += nt) cm[t] = min(d.colmax[t], n0 - 1);
+        mbar_wait(bar, parity);
+        __syncthreads();
+        STAMP(51);
+        LdltOpt o;
+        o.ld = n; o.kb0 = 0; o.kb1 = m0; o.backsolve = false;
+        ldlt_block_solve_impl<SmemIO, unsigned>(sA, sY, sW, sC, sT, n0, bs, nullptr, nullptr, o);
+        STAMP(52);
+        if (tid == 0) while (ld_acquire_u32(d.tw_flag) < seq) { }
+        __syncthreads();
+        STAMP(53);
+        for (int q = tid; q < w3 * w3 + w3; q += nt) {
+            if (q < w3 * w3) {
+                const int i = q / w3, j = q - i * w3;
+                if (j <= i) sm[(size_t)(3 * m0 + i) * n + 3 * m0 + j] += __ldcg(T + (w3 - 1 - j) * w3 + (w3 - 1 - i));
+            } else {
+                const int i = q - w3 * w3;
+                y[3 * m0 + i] += __ldcg(T + w3 * w3 + (w3 - 1 - i));
+            }
+        }
+        if (tid == 0 && __ldcg(T + w3 * w3 + w3) == 0.0) SmemIO::sti(sT + 24, 0);
+        __syncthreads();
+        STAMP(54);
+        o.kb0 = m0; o.kb1 = m0 + w; o.init = false; o.backsolve = true;
+        o.pub = T + TW_XM; o.pub_cnt = d.tw_flag + 1; o.pub_kb = m0; o.okword = d.tw_flag + 2; o.okval = seq << 1;
+        ldlt_block_solve_impl<SmemIO, unsigned>(sA, sY, sW, sC, sT, n0, nullptr, d.dxp, d.st, o);
+        if (tid == 0 && !SmemIO::ldi(sT + 24)) atomicAdd(d.tw_flag + 1, (unsigned)w3);      // not positive definite: nothing was published
+        STAMP(55);
+    } else {
+        const int n1 = 3 * (m1 + w);
+        // layout: A1 [n1 * n1] | y [n1] | W [3 n1] | pad [2] | cmax (int) [n1] | scratch
+        double* y = sm + (size_t)n1 * n1;
+        int* cm = reinterpret_cast<int*>(y + 4 * (size_t)n1 + 2);
+        const unsigned sA = smem_u32_pinned(sm), sY = sA + (unsigned)n1 * n1 * 8, sW = sY + (unsigned)n1 * 8, sC = sY + (unsigned)(4 * n1 + 2) * 8, sT = (sC + (unsigned)n1 * 4 + 15u) & ~15u;
+        STAMP(50);
+#pragma unroll 4
+        for (int q = tid; q < n1 * n1; q += nt) {
+            const int c = q / n1, r = q - c * n1;              // r fastest: consecutive threads read consecutive (descending) columns of one row of S
+            if (r >= c && r <= d.tw_cmax1[c]) sm[(size_t)r * n1 + c] = (c >= 3 * m1) ? 0.0 : S[(size_t)(n - 1 - c) * n + (n - 1 - r)];
+        }
+        for (int t = tid; t < n1; t += nt) { cm[t] = d.tw_cmax1[t]; y[t] = t < 3 * m1 ? bs[n - 1 - t] : 0.0; }
+        __syncthreads();
+        STAMP(51);
+        LdltOpt o;
+        o.ld = n1; o.kb0 = 0; o.kb1 = m1; o.backsolve = false;
+        ldlt_block_solve_impl<SmemIO, unsigned>(sA, sY, sW, sC, sT, n1, nullptr, nullptr, nullptr, o);
+        STAMP(52);
+        for (int q = tid; q < w3 * w3 + w3; q += nt) {
+            if (q < w3 * w3) {
+                const int i = q / w3, j = q - i * w3;
+                if (j <= i) T[q] = sm[(size_t)(3 * m1 + i) * n1 + 3 * m1 + j];
+            } else {
+                T[q] = y[3 * m1 + q - w3 * w3];
+            }
+        }
+        if (tid == 0) T[w3 * w3 + w3] = SmemIO::ldi(sT + 24) ? 1.0 : 0.0;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            st_release_u32(d.tw_flag, seq);
+            STAMP(53);
+            while (ld_acquire_u32(d.tw_flag + 1) < seq * (unsigned)w3) { }
+        }
+        __syncthreads();
+        const bool ok = (__ldcg(d.tw_flag + 2) & 1u) != 0;
+        if (tid < w3) xs[tid] = __ldcg(T + TW_XM + tid);
+        __syncthreads();
+        STAMP(54);
+        if (ok) {
+            o.kb0 = m1; o.kb1 = m1; o.init = false; o.backsolve = true; o.npiv = m1; o.xinj = xs;
+            ldlt_block_solve_impl<SmemIO, unsigned>(sA, sY, sW, sC, sT, n1, nullptr, nullptr, nullptr, o);
+            __syncthreads();
+            for (int c = tid; c < 3 * m1; c += nt) d.dxp[n - 1 - c] = y[c];
+        } else {
+            for (int c = tid; c < 3 * m1; c += nt) d.dxp[n - 1 - c] = 0.0;
+        }
+        STAMP(55);
+    }
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS) ba_chol_solve_smem(Dev d) {
@@ -1545,12 +1712,13 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     PKWork work;
     {
         const int G = gridDim.x;
-        work.stride = G > 1 ? G - 1 : 1;
-        work.first = G > 1 ? (int)blockIdx.x - 1 : 0;      // -1 for CTA 0 of a multi-CTA grid
+        const int nsolve = d.tw_m0 > 0 ? 2 : 1;             // CTAs that keep their shared memory for the reduced solve
+        work.stride = G > 1 ? G - nsolve : 1;
+        work.first = G > 1 ? (int)blockIdx.x - nsolve : 0;  // < 0 for the solver CTAs of a multi-CTA grid
         work.own = own;
         work.arena = reinterpret_cast<const int*>(sm);
         int* arena = reinterpret_cast<int*>(sm);
-        const int arena_ints = (G > 1 && blockIdx.x > 0) ? (pa.dyn_smem_bytes - RED_SCRATCH_BYTES) / 4 : 0;   // the top of the arena is the reduction scratch
+        const int arena_ints = (G > 1 && work.first >= 0) ? (pa.dyn_smem_bytes - RED_SCRATCH_BYTES) / 4 : 0;   // the top of the arena is the reduction scratch
         if (threadIdx.x == 0) {
             int off = 0, no = 0;
             if (work.first >= 0)
@@ -1601,6 +1769,8 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
     const double* bsrc = shard ? shd.ssum + (size_t)n * n : d.bs;
     double lambda = d.st->lambda, ni = d.st->ni, chi_cur = d.st->chi_cur;   // continued from the previous call when first_iter > 0
     long long epoch = shd.epoch0;
+    unsigned tw_seq = 0;
+    if (d.tw_m0 > 0 && blockIdx.x == 0 && threadIdx.x == 0) { d.tw_flag[0] = 0; d.tw_flag[1] = 0; d.tw_flag[2] = 0; }   // first use is several grid barriers away
     int cur = d.st->cur, done = 0;
     bool stop = false, peer_err = false;
     // scalar exchange of a sharded run: CTA 0 fills this rank's slot `epoch & 1` with v[0..nv) (+ the pose diagonal when
@@ -1709,7 +1879,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 PK_TICK(1);
             }
             // ---- D: reduced solve (one CTA; S staged into its shared memory)
-            if (blockIdx.x == 0) {
+            if (d.tw_m0 > 0) {
+                ++tw_seq;
+                if (blockIdx.x < 2) ldlt_twisted_solve(d, Ssrc, bsrc, &stage_bar, stage_parity, tw_seq);
+                stage_parity ^= 1;
+            } else if (blockIdx.x == 0) {
                 ldlt_stage(d, Ssrc, &stage_bar, stage_parity);
                 stage_parity ^= 1;
                 PK_TICK(7);
@@ -1869,6 +2043,7 @@ struct se2gpu_ba {
     double* red = nullptr;     // all-reduce buffer [maxN*maxN + maxN + 8]
     double* ywork = nullptr;
     int* colmax = nullptr;
+    int* tw_cmax1 = nullptr; double* tw_buf = nullptr; unsigned* tw_flag = nullptr;   // twisted reduced solve (persistent kernel)
     int* blk_order = nullptr;
     se2gpu_ba_iter_stats* stats_dev = nullptr;
     int max_stats = 64;
@@ -1954,7 +2129,7 @@ se2gpu_ba* se2gpu_ba_create(int max_poses, int max_points, int max_edges, int ma
     A(&d.oAii, 6 * O); A(&d.oAij, 9 * O); A(&d.oAjj, 6 * O); A(&d.obi, 3 * O); A(&d.obj, 3 * O);
     A(&h->pose_ptr, P + 1); A(&h->pose_edges, E); A(&h->pose_odo_ptr, P + 1); A(&h->pose_odo, 2 * O);
     A(&d.Hpp, 6 * P); A(&d.bp, 3 * P);
-    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 4 * maxN + 32); A(&h->colmax, maxN); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
+    A(&h->red, maxN * maxN + maxN + 8); A(&h->ywork, 4 * maxN + 32); A(&h->colmax, maxN); A(&h->tw_cmax1, maxN); A(&h->tw_buf, TW_BUF_DOUBLES); A(&h->tw_flag, 4); A(&d.dxp, maxN); A(&d.dxl, 3 * L);
     const size_t nb = (L + LM_THREADS - 1) / LM_THREADS + (O + LM_THREADS - 1) / LM_THREADS + (P + LM_THREADS - 1) / LM_THREADS + 4;
     A(&d.part_chi, nb); A(&d.part_scale, nb);
     A(&h->stats_dev, h->max_stats);
@@ -2327,9 +2502,35 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     // Longest-processing-time assignment: blocks by decreasing work (pairs + pose-side edges of a diagonal block) to the least
     // loaded worker, at most 12 blocks per worker (the concurrent Schur phase gives every owned block its own warp group).
     // Worker w serves positions w, w + W, w + 2W, ...; unused trailing positions are holes (-1).
+    // two-sided solve plan: split point m0 with separator w = bmax[m0-1] - m0 + 1 blocks (bmax is monotone), chain max(m0, m1) + w
+    int tw_m0 = 0, tw_w = 0;
+    std::vector<int> tw_cmax1;
+    if (n <= SMEM_CHOL_MAX_N && nf >= 16 && h->pk_grid >= 4 && !getenv("SE2GPU_BA_NO_TWIST")) {
+        int best = nf;
+        for (int m0 = 1; m0 < nf; ++m0) {
+            const int w = bmax[m0 - 1] - m0 + 1, m1 = nf - m0 - w;
+            if (w < 1 || w > TW_MAX_W || m1 < 1) continue;
+            const int chain = std::max(m0, m1 + 1) + w;            // + 1: the bottom part is staged element-wise, not by one bulk copy
+            if (chain < best) { best = chain; tw_m0 = m0; tw_w = w; }
+        }
+        if (best * 4 > nf * 3) tw_m0 = tw_w = 0;                  // not worth two hand-overs
+        if (tw_m0 > 0) {
+            // envelope of the index-reversed bottom part: block column b' <-> global block row R = nf-1-b', reaching up to the
+            // first block column whose envelope contains R
+            const int nb1 = nf - tw_m0;
+            std::vector<int> rminb(nf);
+            for (int R = 0, C = 0; R < nf; ++R) { while (bmax[C] < R) ++C; rminb[R] = C; }
+            tw_cmax1.resize(3 * (size_t)nb1);
+            for (int b = 0; b < nb1; ++b) {
+                int cb = std::min(nf - 1 - rminb[nf - 1 - b], nb1 - 1);
+                if (b >= nb1 - tw_w) cb = nb1 - 1;
+                for (int r = 0; r < 3; ++r) tw_cmax1[3 * b + r] = 3 * cb + 2;
+            }
+        }
+    }
     std::vector<int> blk_order;
     {
-        const int W = h->pk_grid > 1 ? h->pk_grid - 1 : 1;
+        const int W = h->pk_grid > 1 ? h->pk_grid - (tw_m0 > 0 ? 2 : 1) : 1;
         std::vector<std::pair<long long, int>> byw(nblk);
         for (int b = 0; b < nblk; ++b) {
             long long wt = blk_pair_ptr[b + 1] - blk_pair_ptr[b] + 8;
@@ -2368,7 +2569,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
         size_t bytes = sizeof(double) * (3 * (size_t)P + 3 * (size_t)L) + 64 * 40;
         bytes += sizeof(int) * (lm_ptr.size() + hidx.size() + oi.size() + oj.size() + pose_ptr.size() + pose_edges.size() +
                                 pose_odo_ptr.size() + pose_odo.size() + blk_a.size() + blk_b.size() + blk_pair_ptr.size() +
-                                blk_odo_ptr.size() + blk_odo.size() + colmax.size() + blk_order.size());
+                                blk_odo_ptr.size() + blk_odo.size() + colmax.size() + tw_cmax1.size() + blk_order.size());
         bytes += sizeof(double) * (om.size() + ow.size());
         if (!fb_i[0].empty()) bytes += (size_t)El * 48 + npairs * 8;   // arena2 unavailable: those arrays are staged too
         h->arena->reserve(bytes);   // on failure the uploads fall back to pageable copies
@@ -2387,7 +2588,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     UP(h->o_i, oi); UP(h->o_j, oj); UP(h->o_m, om); UP(h->o_w, ow);
     UP(h->pose_ptr, pose_ptr); UP(h->pose_edges, pose_edges); UP(h->pose_odo_ptr, pose_odo_ptr); UP(h->pose_odo, pose_odo);
     UP(h->blk_a, blk_a); UP(h->blk_b, blk_b); UP(h->blk_pair_ptr, blk_pair_ptr); UPP(h->pair_e1, pe1, npairs); UPP(h->pair_e2, pe2, npairs);
-    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax); UP(h->blk_order, blk_order);
+    UP(h->blk_odo_ptr, blk_odo_ptr); UP(h->blk_odo, blk_odo); UP(h->colmax, colmax); UP(h->tw_cmax1, tw_cmax1); UP(h->blk_order, blk_order);
 #undef UP
 #undef UPP
     SE2_CUDA(cudaMemsetAsync(h->red, 0, sizeof(double) * (S_elems + n + 8), s));
@@ -2411,6 +2612,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
     d.pose_ptr = h->pose_ptr; d.pose_edges = h->pose_edges; d.pose_odo_ptr = h->pose_odo_ptr; d.pose_odo = h->pose_odo;
     d.blk_a = h->blk_a; d.blk_b = h->blk_b; d.blk_pair_ptr = h->blk_pair_ptr; d.pair_e1 = h->pair_e1; d.pair_e2 = h->pair_e2;
     d.blk_odo_ptr = h->blk_odo_ptr; d.blk_odo = h->blk_odo; d.colmax = h->colmax; d.blk_order = h->blk_order; d.nord = (int)blk_order.size();
+    d.tw_m0 = tw_m0; d.tw_w = tw_w; d.tw_cmax1 = h->tw_cmax1; d.tw_buf = h->tw_buf; d.tw_flag = h->tw_flag;
     d.S = h->red; d.bs = h->red + S_elems; d.scal = d.bs + n; d.sbw = h->band.active ? h->band.bw : 0;
     d.nb_lm = (L + LM_THREADS - 1) / LM_THREADS; d.nb_odo = (Ol + LM_THREADS - 1) / LM_THREADS;
     h->nb_scale = (std::max(L, P) + LM_THREADS - 1) / LM_THREADS;
