@@ -1644,13 +1644,27 @@ __device__ void pk_phase_lm_prep(const Dev& d, double lam) {
     }
 }
 
-__device__ double pk_phase_backsub(const Dev& d, int cur, double lam, double lam_pose) {
+// E + F in one phase: back-substitution, oplus into the trial buffers, computeScale partial (returned) AND the robust chi2 at the
+// trial point (*chi_out), with no grid barrier in between. The chi2 of a landmark's edges needs the landmark's trial point (formed
+// by the same lane group a few instructions earlier) and the trial POSES: every CTA forms all of them itself first (P is a few
+// dozen; all CTAs store identical values, and a CTA reads back only what it stored itself before its block barrier).
+__device__ double pk_phase_backsub(const Dev& d, const Cam& cam, int cur, double lam, double lam_pose, double* chi_out) {
     const double* xp = d.xp[cur];
     const double* xl = d.xl[cur];
     double* xpt = d.xp[cur ^ 1];
     double* xlt = d.xl[cur ^ 1];
     const size_t L = d.L, E = d.E;
-    double sc = 0;
+    double sc = 0, chi = 0;
+    for (int t = threadIdx.x; t < d.P; t += blockDim.x) {
+        const int a = d.hidx[t];
+        if (a >= 0) {
+            xpt[3 * t] = xp[3 * t] + d.dxp[3 * a]; xpt[3 * t + 1] = xp[3 * t + 1] + d.dxp[3 * a + 1];
+            xpt[3 * t + 2] = normalize_theta(xp[3 * t + 2] + d.dxp[3 * a + 2]);
+        } else {
+            xpt[3 * t] = xp[3 * t]; xpt[3 * t + 1] = xp[3 * t + 1]; xpt[3 * t + 2] = xp[3 * t + 2];
+        }
+    }
+    __syncthreads();
     for (PKLmIter it(d); it.more(d.L); it.next()) {
         const int j = it.j, sub = it.sub;
         int beg = 0, end = 0;
@@ -1678,20 +1692,20 @@ __device__ double pk_phase_backsub(const Dev& d, int cur, double lam, double lam
             d.dxl[3 * j] = dl0; d.dxl[3 * j + 1] = dl1; d.dxl[3 * j + 2] = dl2;
             xlt[3 * j] = xl[3 * j] + dl0; xlt[3 * j + 1] = xl[3 * j + 1] + dl1; xlt[3 * j + 2] = xl[3 * j + 2] + dl2;
         }
+        __syncwarp();                                           // the group's other lanes read the trial point back
+        chi += pk_landmark<false>(d, cam, xpt, xlt, j, sub, -1.0);
     }
-    // poses: one per CTA on the first lane of the last warp (see pk_phase_linearize)
-    if (threadIdx.x == blockDim.x - 32)
-    for (int t = blockIdx.x; t < d.P; t += gridDim.x) {
-        const int a = d.hidx[t];
-        if (a >= 0) {
+    // pose terms of computeScale and the PreEdgeSE2 chi2: one item per CTA on the first lane of the last warp (see pk_phase_linearize)
+    if (threadIdx.x == blockDim.x - 32) {
+        for (int t = blockIdx.x; t < d.P; t += gridDim.x) {
+            const int a = d.hidx[t];
+            if (a < 0) continue;
             const double p0 = d.dxp[3 * a], p1 = d.dxp[3 * a + 1], p2 = d.dxp[3 * a + 2];
-            xpt[3 * t] = xp[3 * t] + p0; xpt[3 * t + 1] = xp[3 * t + 1] + p1;
-            xpt[3 * t + 2] = normalize_theta(xp[3 * t + 2] + p2);
             sc += p0 * (lam_pose * p0 + d.bp[3 * a]) + p1 * (lam_pose * p1 + d.bp[3 * a + 1]) + p2 * (lam_pose * p2 + d.bp[3 * a + 2]);
-        } else {
-            xpt[3 * t] = xp[3 * t]; xpt[3 * t + 1] = xp[3 * t + 1]; xpt[3 * t + 2] = xp[3 * t + 2];
         }
+        for (int o = blockIdx.x; o < d.O; o += gridDim.x) chi += pk_odo<false>(d, xpt, o);
     }
+    *chi_out = chi;
     return sc;
 }
 
@@ -1894,16 +1908,17 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
             PK_TICK(4);
             const int solve_ok = d.st->solve_ok;
             // ---- E: back-substitution, oplus into the trial buffers, computeScale partials
+            //      + F: robust chi2 at the trial point (same phase, see pk_phase_backsub)
             {
-                const double sc = pk_phase_backsub(d, cur, lambda, lambda * lam_pose_mask);
+                double chi_part;
+                const double sc = pk_phase_backsub(d, cam, cur, lambda, lambda * lam_pose_mask, &chi_part);
                 const double tot = block_sum(sc, sh);
                 if (threadIdx.x == 0) pa.part_scale[blockIdx.x] = tot;
+                const double totc = block_sum(chi_part, sh);
+                if (threadIdx.x == 0) pa.part_chi[nparts + blockIdx.x] = totc;
             }
             PK_WORK(5);
-            grid.sync();
             PK_TICK(5);
-            // ---- F: robust chi2 at the trial point
-            pk_phase_linearize<false>(d, cam, cur ^ 1, pa.part_chi + nparts, sh);
             if (blockIdx.x == 0 && threadIdx.x == 0) pa.abort_dev[1] = *pa.abort_host;
             if (pa.dbg_sysfence && blockIdx.x == 0 && threadIdx.x == 0) __threadfence_system();
             PK_WORK(7);
@@ -2510,7 +2525,7 @@ int se2gpu_ba_set_problem(se2gpu_ba* h, int P, int L, int E, int O, const double
         for (int m0 = 1; m0 < nf; ++m0) {
             const int w = bmax[m0 - 1] - m0 + 1, m1 = nf - m0 - w;
             if (w < 1 || w > TW_MAX_W || m1 < 1) continue;
-            const int chain = std::max(m0, m1 + 1) + w;            // + 1: the bottom part is staged element-wise, not by one bulk copy
+            const int chain = std::max(m0, m1 + 4) + w;            // + 4: the bottom part is staged element-wise, not by one bulk copy (~4 pivot steps)
             if (chain < best) { best = chain; tw_m0 = m0; tw_w = w; }
         }
         if (best * 4 > nf * 3) tw_m0 = tw_w = 0;                  // not worth two hand-overs
