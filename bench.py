@@ -461,7 +461,8 @@ def run_ours(args):
                               stream=sptr)
     exchange = "none (single GPU)"
     if world > 1:
-        # reduced system summed inside the solve kernel over NVLink peer mappings (CUDA IPC); NCCL keeps the scalar reductions.
+        # one persistent cooperative kernel per rank and optimize(): the kernels sum the envelope of [S|b] and the [chi2, scale, abort]
+        # scalars over NVLink peer mappings (CUDA IPC) themselves, handshaking through epoch flags in peer memory; no NCCL on the path.
         # All ranks must agree on the mode: fall back to the NCCL all-reduce everywhere if any rank cannot map its peers.
         def _gather(b):
             out = [None] * world
@@ -476,7 +477,7 @@ def run_ours(args):
         flag = torch.tensor([ok], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 1:
-            exchange = "fused: solve kernel sums the ranks' partial [S|b] over NVLink peer mappings; NCCL for the [chi2,scale] scalars"
+            exchange = "in-kernel: each rank runs ONE persistent cooperative kernel per optimize(); the kernels sum the envelope of [S|b] and [chi2, scale, abort] over NVLink peer mappings (epoch flags in peer memory), no NCCL call on the path"
         else:
             exchange = "NCCL all-reduce of [S|b] + [chi2,scale] per trial"
             ba = LocalBA.from_problem(prob, device=local_rank, rank=rank, world=world, allreduce=allreduce, stream=sptr)

@@ -1917,13 +1917,11 @@ __global__ void __launch_bounds__(PK_THREADS, 1) ba_persistent(Dev d, Cam cam, P
                 const double totc = block_sum(chi_part, sh);
                 if (threadIdx.x == 0) pa.part_chi[nparts + blockIdx.x] = totc;
             }
-            PK_WORK(5);
-            PK_TICK(5);
             if (blockIdx.x == 0 && threadIdx.x == 0) pa.abort_dev[1] = *pa.abort_host;
             if (pa.dbg_sysfence && blockIdx.x == 0 && threadIdx.x == 0) __threadfence_system();
-            PK_WORK(7);
+            PK_WORK(5);
             grid.sync();
-            PK_TICK(0);
+            PK_TICK(5);
             // ---- LM decision (identical in every CTA, and in every rank)
             double tempChi = cta_sum_array(pa.part_chi + nparts, nparts, sh);
             double scale = cta_sum_array(pa.part_scale, nparts, sh);
