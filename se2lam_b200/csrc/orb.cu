@@ -180,13 +180,16 @@ __global__ void __launch_bounds__(128) orb_pyr0_undistort(OrbDev d, LevelGeo L, 
 //   1  horizontal pass h[s][x] = src[s][sx]*a0 + src[s][sx+1]*a1 for every staged source row s, ONCE per (row, column)
 //      (consecutive output rows share source rows; cv::resize does the same with its row buffers)
 //   2  vertical pass from two h rows per output row, 4 pixels per thread, one 32-bit store
-// Column terms (xofs, ialpha) live in registers of the thread that owns the 4 columns, row terms in a small table.
+// Column terms (xofs, ialpha) and row terms are computed once per tile (one thread per column / row) and shared through small tables.
 constexpr int RESIZE_TR = 32;
 struct ResizeRow { int s0, s1, b0, b1; };
+struct ResizeCol { int sx0, sx1; short a0, a1; int valid; };   // 16 B
 __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
     __shared__ ResizeRow rowinfo[RESIZE_TR];
-    __shared__ int s_lo[2], s_hi[2];     // [0] source columns, [1] source rows
+    __shared__ __align__(16) ResizeCol colinfo[128];
+    __shared__ int s_lo[2], s_hi[2];     // [1] source rows
+    __shared__ int s_cmin[4], s_cmax[4]; // source column range per column warp
     int* hbuf = reinterpret_cast<int*>(rs_smem);                       // [max_rows][128]
     uint8_t* raw = rs_smem + (size_t)max_rows * 128 * sizeof(int);     // [max_rows][raw_pitch]
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
@@ -197,25 +200,25 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
     const int* yofs = xofs + L.w;
     const short2* ialpha = reinterpret_cast<const short2*>(d.stab + 2 * (size_t)L.tab_off);
     const short2* ibeta = ialpha + L.w;
-    int sx0[4], sx1[4], a0[4], a1[4];
-    bool valid[4];
-    int cmin = 0x7fffffff, cmax = -1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int x = x4 + q;
-        valid[q] = x < W;
-        const int dx = valid[q] ? reflect101(x - EDGE, L.w) : 0;
-        sx0[q] = __ldg(xofs + dx);
-        sx1[q] = min(sx0[q] + 1, S.w - 1);
-        const short2 aa = __ldg(ialpha + dx);
-        a0[q] = aa.x; a1[q] = aa.y;
-        if (valid[q]) { cmin = min(cmin, sx0[q]); cmax = max(cmax, sx1[q]); }
-    }
-    if (ty == 0) {   // the tile's source column range (every ty row owns the same columns)
+    // column terms of the tile's 128 output columns: warps 0..3, one column per thread (the 8 thread rows share them through
+    // shared memory instead of each recomputing its 4 columns); row terms: warp 4
+    if (tid < 128) {
+        const int x = blockIdx.x * 128 + tid;
+        ResizeCol c{0, 0, 0, 0, 0};
+        int cmin = 0x7fffffff, cmax = -1;
+        if (x < W) {
+            const int dx = reflect101(x - EDGE, L.w);
+            c.sx0 = __ldg(xofs + dx);
+            c.sx1 = min(c.sx0 + 1, S.w - 1);
+            const short2 aa = __ldg(ialpha + dx);
+            c.a0 = aa.x; c.a1 = aa.y; c.valid = 1;
+            cmin = c.sx0; cmax = c.sx1;
+        }
+        colinfo[tid] = c;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); }
-        if (tx == 0) { s_lo[0] = cmin; s_hi[0] = cmax; }
-    } else if (ty == 1) {   // row terms of the tile's RESIZE_TR output rows and their source row range
+        if (tx == 0) { s_cmin[ty] = cmin; s_cmax[ty] = cmax; }
+    } else if (ty == 4) {   // row terms of the tile's RESIZE_TR output rows and their source row range
         const int y = y0 + tx;
         int rmin = 0x7fffffff, rmax = -1;
         if (y < H) {
@@ -231,32 +234,49 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
         if (tx == 0) { s_lo[1] = rmin; s_hi[1] = rmax; }
     }
     __syncthreads();
-    const int c_lo = s_lo[0] & ~15, nvec = s_hi[0] < 0 ? 0 : (s_hi[0] - c_lo) / 16 + 1;
+    const int c_min = min(min(s_cmin[0], s_cmin[1]), min(s_cmin[2], s_cmin[3])), c_max = max(max(s_cmax[0], s_cmax[1]), max(s_cmax[2], s_cmax[3]));
+    const int c_lo = c_min & ~15, nvec = c_max < 0 ? 0 : (c_max - c_lo) / 16 + 1;
     const int r_lo = s_lo[1], nsr = s_hi[1] - r_lo + 1;
     if (nsr > max_rows || nvec * 16 > raw_pitch) { if (tid == 0) *d.err = 3; return; }   // sized on the host from the scale factor
     const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
-    // stage 0
-    for (int i = tid; i < nsr * nvec; i += 256) {
-        const int r = i / nvec, v = i - r * nvec;
-        *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+    // stage 0: 16 vectors per source row and pass (a 128-column tile at scale <= 1.9 spans <= 16 vectors), no division
+    if (nvec <= 16) {
+        const int v = tid & 15;
+        if (v < nvec)
+            for (int r = tid >> 4; r < nsr; r += 16)
+                *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+    } else {
+        for (int i = tid; i < nsr * nvec; i += 256) {
+            const int r = i / nvec, v = i - r * nvec;
+            *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+        }
+    }
+    // this thread's 4 columns
+    int sx0[4], sx1[4], a0[4], a1[4];
+    unsigned vmask = 0;                       // byte mask of the valid columns
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const ResizeCol c = colinfo[4 * tx + q];
+        sx0[q] = c.valid ? c.sx0 - c_lo : 0; sx1[q] = c.valid ? c.sx1 - c_lo : 0;
+        a0[q] = c.a0; a1[q] = c.a1;
+        vmask |= c.valid ? (0xFFu << (8 * q)) : 0u;
     }
     __syncthreads();
-    // stage 1
+    // stage 1: horizontal pass, stored pre-shifted (the vertical pass uses S >> 4 only)
     if (x4 < W) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { sx0[q] = valid[q] ? sx0[q] - c_lo : 0; sx1[q] = valid[q] ? sx1[q] - c_lo : 0; }
         for (int r = ty; r < nsr; r += 8) {
             const uint8_t* rp = raw + r * raw_pitch;
             int4 hv;
-            hv.x = rp[sx0[0]] * a0[0] + rp[sx1[0]] * a1[0];
-            hv.y = rp[sx0[1]] * a0[1] + rp[sx1[1]] * a1[1];
-            hv.z = rp[sx0[2]] * a0[2] + rp[sx1[2]] * a1[2];
-            hv.w = rp[sx0[3]] * a0[3] + rp[sx1[3]] * a1[3];
+            hv.x = (rp[sx0[0]] * a0[0] + rp[sx1[0]] * a1[0]) >> 4;
+            hv.y = (rp[sx0[1]] * a0[1] + rp[sx1[1]] * a1[1]) >> 4;
+            hv.z = (rp[sx0[2]] * a0[2] + rp[sx1[2]] * a1[2]) >> 4;
+            hv.w = (rp[sx0[3]] * a0[3] + rp[sx1[3]] * a1[3]) >> 4;
             *reinterpret_cast<int4*>(hbuf + r * 128 + 4 * tx) = hv;
         }
     }
     __syncthreads();
-    // stage 2
+    // stage 2: vertical pass. With coefficients in [0, 2048] (pairs summing to 2048 +- 1) and 8-bit pixels the result is in
+    // [0, 255] by construction ((2049 * (255 * 2049 >> 4) >> 16) + 2 >> 2 = 255): cv's saturate_cast never fires, no clamp here.
     if (x4 >= L.pitch) return;
     uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
 #pragma unroll
@@ -268,12 +288,11 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
             const ResizeRow ri = rowinfo[r];
             const int4 A = *reinterpret_cast<const int4*>(hbuf + (ri.s0 - r_lo) * 128 + 4 * tx);
             const int4 B = *reinterpret_cast<const int4*>(hbuf + (ri.s1 - r_lo) * 128 + 4 * tx);
-            const int av[4] = {A.x, A.y, A.z, A.w}, bv[4] = {B.x, B.y, B.z, B.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int v = (((ri.b0 * (av[q] >> 4)) >> 16) + ((ri.b1 * (bv[q] >> 4)) >> 16) + 2) >> 2;
-                word |= (valid[q] ? (uint32_t)min(max(v, 0), 255) : 0u) << (8 * q);
-            }
+            const unsigned v0 = (unsigned)((((ri.b0 * A.x) >> 16) + ((ri.b1 * B.x) >> 16) + 2) >> 2);
+            const unsigned v1 = (unsigned)((((ri.b0 * A.y) >> 16) + ((ri.b1 * B.y) >> 16) + 2) >> 2);
+            const unsigned v2 = (unsigned)((((ri.b0 * A.z) >> 16) + ((ri.b1 * B.z) >> 16) + 2) >> 2);
+            const unsigned v3 = (unsigned)((((ri.b0 * A.w) >> 16) + ((ri.b1 * B.w) >> 16) + 2) >> 2);
+            word = (v0 | (v1 << 8) | (v2 << 16) | (v3 << 24)) & vmask;
         }
         *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
     }
