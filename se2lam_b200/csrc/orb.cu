@@ -18,12 +18,15 @@
 //                           records are written as 28-byte cv::KeyPoint and 32-byte descriptors
 // Data layout in HBM (per frame): every pyramid level is a bordered u8 plane (w+32) x (h+32) with row pitch
 // rounded up to 32 B; two copies (plain, blurred); candidates are packed 32-bit records x:12|y:12|score:8.
+#include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype only: the entry point is resolved at run time (no libcuda link)
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "common.h"
+#include "fast_screen.h"
 #include "introselect.h"
 
 namespace {
@@ -54,6 +57,7 @@ struct LevelGeo {
     float scale, kp_size;
     int tab_off;        // offset of this level's resize tables (xofs | yofs) in the int table
     int tile_base, tiles_x, tiles_y;
+    int fbw, fbh;       // orb_fast_cells_tma: TMA box of this level's FAST cells (bytes per row: multiple of 16; rows)
 };
 
 struct CellGeo {
@@ -443,6 +447,301 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells(OrbDev d) {
         // C
         for (int i = threadIdx.x; i < ncand; i += FAST_THREADS) {
             const int off = list[i];
+            const uint8_t* q = score + off + pw + 1;
+            const int sc = q[0];
+            if (sc && sc > q[-pw - 1] && sc > q[-pw] && sc > q[-pw + 1] && sc > q[-1] && sc > q[1] && sc > q[pw - 1] && sc > q[pw] && sc > q[pw + 1])
+                atomicOr(&bitmap[off >> 5], 1u << (off & 31));
+        }
+        __syncthreads();
+        // D
+        if (wid == 0) {
+            int run = 0;
+            for (int b0 = 0; b0 < nwords; b0 += 32) {
+                const int v = (b0 + lane < nwords) ? __popc(bitmap[b0 + lane]) : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                if (b0 + lane < nwords) woff[b0 + lane] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_total = run;
+        }
+        __syncthreads();
+        if (s_total > 3 || thr == 7) break;
+        thr = 7;                 // cellKeyPoints.size() <= 3: clear and retry with the fixed fallback threshold
+        __syncthreads();
+    }
+    // E
+    uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
+    for (int j = threadIdx.x; j < nwords; j += FAST_THREADS) {
+        uint32_t w = bitmap[j];
+        int pos = woff[j];
+        while (w) {
+            const int off = j * 32 + __ffs(w) - 1;
+            w &= w - 1;
+            const int y = off / pw, x = off - y * pw;
+            if (pos < c.cand_cap) out[pos] = ((uint32_t)score[off + pw + 1] << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
+            else *d.err = 1;
+            ++pos;
+        }
+    }
+    if (threadIdx.x == 0) { hdr->n_base = s_total; hdr->n_a = s_total; hdr->n_b = s_total; }
+}
+
+// ---- TMA (cp.async.bulk.tensor, SASS UTMALDG) + mbarrier helpers
+struct FastMaps { CUtensorMap m[MAX_LEVELS]; };   // one 3-D map (x bytes, rows, frames) per pyramid level, box = that level's cell patch
+__device__ __forceinline__ unsigned orb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void orb_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(orb_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void orb_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ORB_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ORB_MBAR_DONE;\n"
+        "bra ORB_MBAR_WAIT;\n"
+        "ORB_MBAR_DONE:\n"
+        "}\n" ::"r"(orb_smem_u32(bar)), "r"(parity) : "memory");
+}
+// one box of the 3-D tensor (x, y, z) -> shared memory; completion is signalled on `bar` with the box's byte count
+__device__ __forceinline__ void orb_tma_box3(void* dst_smem, const CUtensorMap* map, int x, int y, int z, unsigned bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(orb_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(orb_smem_u32(dst_smem)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(orb_smem_u32(bar)) : "memory");
+}
+
+// orb_fast_cells with the cell staged by the TMA unit: ONE cp.async.bulk.tensor.3d per CTA pulls the cell and its 3 px apron
+// (box fbw x fbh of the level's tensor map, origin at the cell's first apron pixel - tensor coordinates need no alignment, so
+// the patch has no alignment shift and its pitch is the level's constant fbw) while the CTA clears its score plane and bitmap;
+// the 256 threads no longer issue the ~10 address divisions + LDG + STS each of the staging loop. Pass A walks its
+// (row, 4-pixel group) items with an incremental (y, group) pair instead of a division per item, and masks the group's
+// pixels outside the cell with two shifts. Passes B-E are those of orb_fast_cells; results are bit-identical.
+__global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma(OrbDev d, const __grid_constant__ FastMaps maps) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int s_total, s_ncand;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const CellGeo c = d.cells[blockIdx.x];
+    const int f = blockIdx.y + d.frame0;
+    CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
+    const int cw = c.x1 - c.x0, ch = c.y1 - c.y0;
+    if (c.skipped || cw <= 0 || ch <= 0) {
+        if (threadIdx.x == 0) { hdr->n_base = 0; hdr->n_a = 0; hdr->n_b = 0; }
+        return;
+    }
+    const LevelGeo& L = d.levels[c.level];
+    const int pw = L.fbw, pww = pw >> 2, bh = L.fbh;          // patch pitch = box width
+    uint8_t* smem = smem_raw + ((128u - (orb_smem_u32(smem_raw) & 127u)) & 127u);   // TMA destination: 128 B aligned
+    const int nbits = pw * ch, nwords = (nbits + 31) >> 5;
+    const int G = ((cw + 2) >> 2) + 1, nitems = ch * G;       // pass A work items: group g covers interior x = 4g-3 .. 4g
+    uint8_t* patch = smem;                                                                // [bh x pw], pixel (x,y) of the cell at (y+3)*pw + x+3
+    uint8_t* score = smem + ((pw * bh + 15) & ~15);                                       // [(ch+2) x pw], pixel (x,y) at (y+1)*pw + x+1
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(score + ((pw * (ch + 2) + 15) & ~15)); // [nwords], bit y*pw + x
+    uint32_t* woff = bitmap + nwords;                                                     // [nwords] exclusive popcount scan
+    uint16_t* list = reinterpret_cast<uint16_t*>(woff + nwords);                          // [<= cw*ch] entries y*pw + x
+    if (threadIdx.x == 0) orb_mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], c.x0 - 3 + EDGE, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
+    constexpr int NW = FAST_THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint8_t* p0 = patch + 3 * pw + 3;
+    // pass A item walk: item = y*G + g; this thread's items are threadIdx.x, +256, +512, ...
+    const int y_first = (int)threadIdx.x / G, g_first = (int)threadIdx.x - y_first * G;
+    const int dY = FAST_THREADS / G, dG = FAST_THREADS - dY * G;
+    int thr = d.fast_th;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < (pw * (ch + 2) + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+        for (int i = threadIdx.x; i < nwords; i += FAST_THREADS) bitmap[i] = 0u;
+        if (threadIdx.x == 0) s_ncand = 0;
+        if (pass == 0) orb_mbar_wait(&s_bar, 0);      // the patch has landed (async-proxy writes are visible after the wait)
+        __syncthreads();
+        // A: one thread = the 4 pixels of one patch word (group)
+        {
+            const uint32_t* pwords = reinterpret_cast<const uint32_t*>(patch);
+            const unsigned T1 = fastpx::screen_T1(thr), U1 = fastpx::screen_U1(thr);
+            int y = y_first, g = g_first;
+            for (int it0 = wid * 32; it0 < nitems; it0 += NW * 32) {
+                unsigned m = 0;
+                const int col0 = 4 * g - 3;                        // interior x of the group's first pixel
+                if (y < ch) {                                      // <=> it0 + lane < nitems
+                    const uint32_t* c = pwords + (y + 3) * pww + g;
+                    const uint32_t n3 = c[-3 * pww], s3 = c[3 * pww];
+                    const uint32_t n2a = c[-2 * pww - 1], n2b = c[-2 * pww], n2c = c[-2 * pww + 1];
+                    const uint32_t s2a = c[2 * pww - 1], s2b = c[2 * pww], s2c = c[2 * pww + 1];
+                    const uint32_t za = c[-1], zb = c[0], zc = c[1];
+                    // necessary condition (fast_screen.h), then drop the group's pixels outside the cell interior
+                    m = fastpx::screen4(n3, s3, n2a, n2b, n2c, s2a, s2b, s2c, za, zb, zc, T1, U1) & fastpx::inside_mask8(col0, cw) & 0xFu;
+                }
+                const int cnt = __popc(m);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                if (tot) {
+                    int base = 0;
+                    if (lane == 31) base = atomicAdd(&s_ncand, tot);
+                    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+                    const int e0 = y * pw + col0;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        list[base++] = (uint16_t)(e0 + j);
+                    }
+                }
+                g += dG; y += dY;
+                if (g >= G) { g -= G; ++y; }
+            }
+        }
+        __syncthreads();
+        const int ncand = s_ncand;
+        // B
+        for (int i = threadIdx.x; i < ncand; i += FAST_THREADS) {
+            const int off = list[i];
+            const int m = fast_arc_score(p0 + off, pw);
+            if (m > thr) score[off + pw + 1] = (uint8_t)(m - 1);
+        }
+        __syncthreads();
+        // C
+        for (int i = threadIdx.x; i < ncand; i += FAST_THREADS) {
+            const int off = list[i];
+            const uint8_t* q = score + off + pw + 1;
+            const int sc = q[0];
+            if (sc && sc > q[-pw - 1] && sc > q[-pw] && sc > q[-pw + 1] && sc > q[-1] && sc > q[1] && sc > q[pw - 1] && sc > q[pw] && sc > q[pw + 1])
+                atomicOr(&bitmap[off >> 5], 1u << (off & 31));
+        }
+        __syncthreads();
+        // D
+        if (wid == 0) {
+            int run = 0;
+            for (int b0 = 0; b0 < nwords; b0 += 32) {
+                const int v = (b0 + lane < nwords) ? __popc(bitmap[b0 + lane]) : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                if (b0 + lane < nwords) woff[b0 + lane] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) s_total = run;
+        }
+        __syncthreads();
+        if (s_total > 3 || thr == 7) break;
+        thr = 7;                 // cellKeyPoints.size() <= 3: clear and retry with the fixed fallback threshold
+        __syncthreads();
+    }
+    // E
+    uint32_t* out = d.cand + (size_t)f * d.cand_total + c.cand_off;
+    for (int j = threadIdx.x; j < nwords; j += FAST_THREADS) {
+        uint32_t w = bitmap[j];
+        int pos = woff[j];
+        while (w) {
+            const int off = j * 32 + __ffs(w) - 1;
+            w &= w - 1;
+            const int y = off / pw, x = off - y * pw;
+            if (pos < c.cand_cap) out[pos] = ((uint32_t)score[off + pw + 1] << 24) | ((uint32_t)(c.y0 + y) << 12) | (uint32_t)(c.x0 + x);
+            else *d.err = 1;
+            ++pos;
+        }
+    }
+    if (threadIdx.x == 0) { hdr->n_base = s_total; hdr->n_a = s_total; hdr->n_b = s_total; }
+}
+
+// orb_fast_cells_tma with a leaner pass A (fast_screen.h, host-tested):
+//   * one item = 8 pixels (two patch words): the rows y-3 / y+3 come in as one 64-bit shared load each, rows y-2 / y / y+2 as
+//     32+64+32 bits - 11 shared loads per 8 pixels instead of 22 - and the address arithmetic, the survivor scan and the loop
+//     control are paid once per 8 pixels;
+//   * every warp compacts into its OWN segment of the candidate list (segments are sized by the items a warp owns), so the
+//     shared atomic per 128 pixels and its vote/election code are gone; passes B and C walk the warp's own segment (the 32-item
+//     chunks are dealt round-robin over the warps, so the segments are balanced). The list order never reaches the output:
+//     keypoints are emitted in raster order from the bitmap (pass E), so the result is bit-identical to orb_fast_cells.
+__global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma8(OrbDev d, const __grid_constant__ FastMaps maps) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ int s_total;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const CellGeo c = d.cells[blockIdx.x];
+    const int f = blockIdx.y + d.frame0;
+    CellHdr* hdr = d.hdr + (size_t)f * d.n_cells + blockIdx.x;
+    const int cw = c.x1 - c.x0, ch = c.y1 - c.y0;
+    if (c.skipped || cw <= 0 || ch <= 0) {
+        if (threadIdx.x == 0) { hdr->n_base = 0; hdr->n_a = 0; hdr->n_b = 0; }
+        return;
+    }
+    const LevelGeo& L = d.levels[c.level];
+    const int pw = L.fbw, pww = pw >> 2, bh = L.fbh;          // patch pitch = box width (multiple of 16 B: rows are 8 B aligned)
+    uint8_t* smem = smem_raw + ((128u - (orb_smem_u32(smem_raw) & 127u)) & 127u);   // TMA destination: 128 B aligned
+    const int nbits = pw * ch, nwords = (nbits + 31) >> 5;
+    const int G2 = fastpx::pairs_per_row(cw), nitems = ch * G2;
+    uint8_t* patch = smem;                                                                // [bh x pw], pixel (x,y) of the cell at (y+3)*pw + x+3
+    uint8_t* score = smem + ((pw * bh + 15) & ~15);                                       // [(ch+2) x pw], pixel (x,y) at (y+1)*pw + x+1
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(score + ((pw * (ch + 2) + 15) & ~15)); // [nwords], bit y*pw + x
+    uint32_t* woff = bitmap + nwords;                                                     // [nwords] exclusive popcount scan
+    uint16_t* list = reinterpret_cast<uint16_t*>(woff + nwords);                          // [8 * nitems] entries y*pw + x, one segment per warp
+    if (threadIdx.x == 0) orb_mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], c.x0 - 3 + EDGE, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
+    constexpr int NW = FAST_THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint8_t* p0 = patch + 3 * pw + 3;
+    uint16_t* seg = list + fastpx::seg_offset(wid, nitems, NW);
+    fastpx::ItemWalk first;
+    first.init((int)threadIdx.x, FAST_THREADS, G2);
+    int thr = d.fast_th;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < (pw * (ch + 2) + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
+        for (int i = threadIdx.x; i < nwords; i += FAST_THREADS) bitmap[i] = 0u;
+        if (pass == 0) orb_mbar_wait(&s_bar, 0);      // the patch has landed (async-proxy writes are visible after the wait)
+        __syncthreads();
+        // A: one thread = 8 pixels = patch words 2h, 2h+1 of row y
+        int nseg = 0;                                  // candidates in this warp's segment (warp-uniform)
+        {
+            const uint32_t* pwords = reinterpret_cast<const uint32_t*>(patch);
+            const unsigned T1 = fastpx::screen_T1(thr), U1 = fastpx::screen_U1(thr);
+            fastpx::ItemWalk it = first;
+            for (int it0 = wid * 32; it0 < nitems; it0 += NW * 32) {
+                unsigned m = 0;
+                const int x0 = 8 * it.h - 3;                       // interior x of the item's first pixel
+                if (it.y < ch) {                                   // <=> it0 + lane < nitems
+                    const uint32_t* cp = pwords + (it.y + 3) * pww + 2 * it.h;    // even word index: 8 B aligned
+                    const uint2 n3 = *reinterpret_cast<const uint2*>(cp - 3 * pww), s3 = *reinterpret_cast<const uint2*>(cp + 3 * pww);
+                    const uint2 n2 = *reinterpret_cast<const uint2*>(cp - 2 * pww), s2 = *reinterpret_cast<const uint2*>(cp + 2 * pww);
+                    const uint2 z = *reinterpret_cast<const uint2*>(cp);
+                    const uint32_t n2l = cp[-2 * pww - 1], n2r = cp[-2 * pww + 2];
+                    const uint32_t s2l = cp[2 * pww - 1], s2r = cp[2 * pww + 2];
+                    const uint32_t zl = cp[-1], zr = cp[2];
+                    m = fastpx::screen4(n3.x, s3.x, n2l, n2.x, n2.y, s2l, s2.x, s2.y, zl, z.x, z.y, T1, U1) |
+                        fastpx::screen4(n3.y, s3.y, n2.x, n2.y, n2r, s2.x, s2.y, s2r, z.x, z.y, zr, T1, U1) << 4;
+                    m &= fastpx::inside_mask8(x0, cw);             // pixels of the item outside the cell interior
+                }
+                const int cnt = __popc(m);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+                const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                if (tot) {
+                    int base = nseg + inc - cnt;
+                    const int e0 = it.y * pw + x0;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        seg[base++] = (uint16_t)(e0 + j);
+                    }
+                    nseg += tot;
+                }
+                it.next();
+            }
+        }
+        __syncwarp();
+        // B: this warp's segment
+        for (int i = lane; i < nseg; i += 32) {
+            const int off = seg[i];
+            const int m = fast_arc_score(p0 + off, pw);
+            if (m > thr) score[off + pw + 1] = (uint8_t)(m - 1);
+        }
+        __syncthreads();
+        // C
+        for (int i = lane; i < nseg; i += 32) {
+            const int off = seg[i];
             const uint8_t* q = score + off + pw + 1;
             const int sc = q[0];
             if (sc && sc > q[-pw - 1] && sc > q[-pw] && sc > q[-pw + 1] && sc > q[-1] && sc > q[1] && sc > q[pw - 1] && sc > q[pw] && sc > q[pw + 1])
@@ -925,6 +1224,9 @@ struct se2gpu_orb {
     size_t fast_smem = 0, select_smem = 0, resize_smem = 0;
     int resize_rows = 0, resize_raw_pitch = 0;   // shared-memory box of orb_resize, sized from the scale factor
     bool fast_big = false;       // cells too large for the compacting FAST kernel: use orb_fast_cells_big
+    int fast_tma = 0;            // cells staged by the TMA unit: 0 off, 1 orb_fast_cells_tma, 2 orb_fast_cells_tma8 (SE2GPU_ORB_FAST_TMA)
+    size_t fast_tma_smem = 0;
+    FastMaps fast_maps{};        // kernel parameter (__grid_constant__): one tensor map per level over d.plain
     // optional lens undistortion folded into level 0 (se2gpu_orb_set_undistort)
     bool und_on = false;
     float und_K[9] = {}, und_D[14] = {};
@@ -961,14 +1263,16 @@ namespace {
 // level geometry exactly as ORBextractor::ComputePyramid / ComputeKeyPoints derive it (float32 arithmetic)
 int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes, size_t* cand_total, size_t* n_cells,
                    size_t* n_tiles, size_t* tab_total, size_t* max_fast_smem, size_t* max_select_smem,
-                   std::vector<LevelGeo>* Lv, std::vector<CellGeo>* Cv, std::vector<TileGeo>* Tv, bool* fast_big_out = nullptr) {
+                   std::vector<LevelGeo>* Lv, std::vector<CellGeo>* Cv, std::vector<TileGeo>* Tv, bool* fast_big_out = nullptr,
+                   size_t* fast_tma_smem_out = nullptr) {
     (void)dry;
     const int nl = h->nlevels;
     std::vector<LevelGeo> L(nl);
     std::vector<CellGeo> C;
     std::vector<TileGeo> T;
-    size_t poff = 0, coff = 0, toff = 0, fsm = 0, ssm = 0, fsm_big = 0;
+    size_t poff = 0, coff = 0, toff = 0, fsm = 0, ssm = 0, fsm_big = 0, fsm_tma = 0;
     bool fast_big = false;   // some cell is too large for orb_fast_cells' shared-memory candidate list -> orb_fast_cells_big
+    bool tma_ok = true;      // every level's cell patch fits a TMA box (<= 256 x 256) and 16-bit list offsets
     int kp_off = 0;
     const float imageRatio = (float)w / (float)hgt;   // mvImagePyramid[0].cols/rows (:538)
     for (int l = 0; l < nl; ++l) {
@@ -996,6 +1300,8 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
         g.kp_size = (float)(int)(PATCH * h->mvScaleFactor[l]);
         g.tab_off = (int)toff; toff += (size_t)g.w + g.h;
         std::vector<int> iniXCol(g.cols, 0);
+        const size_t first_cell = C.size();
+        int max_cw = 0, max_ch = 0;
         float hY = cellH + 6;
         for (int i = 0; i < g.rows; ++i) {
             const float iniY = minB + i * cellH - 3;
@@ -1017,6 +1323,7 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 c.cand_cap = ((cw + 1) / 2) * ((chh + 1) / 2) + 8;   // strict 3x3 maxima: at most one per 2x2 block
                 coff += c.cand_cap;
                 if (cw > 0 && chh > 0) {
+                    max_cw = std::max(max_cw, cw); max_ch = std::max(max_ch, chh);
                     const size_t pwb = (size_t)((cw + 6 + 3 + 3) / 4 + 1) * 4;   // worst-case alignment shift
                     const size_t nwords = (pwb * chh + 31) / 32;
                     if (pwb * (chh + 6) > 65535) fast_big = true;    // 16-bit patch offsets in the candidate list
@@ -1025,6 +1332,19 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                     fsm_big = std::max(fsm_big, ((pwb * (chh + 6) + 15) & ~(size_t)15) + (((size_t)(cw + 2) * (chh + 2) + 15) & ~(size_t)15) + nchunk * 4 + 64);
                 }
                 C.push_back(c);
+            }
+        }
+        // orb_fast_cells_tma: one TMA box per level = its widest x tallest cell patch (3 px apron), rows a multiple of 16 bytes
+        g.fbw = (max_cw + 6 + 15) & ~15; g.fbh = max_ch + 6;
+        if (max_cw > 0) {
+            if (g.fbw > 256 || g.fbh > 256 || (size_t)g.fbw * g.fbh > 65535) tma_ok = false;
+            for (size_t ci = first_cell; ci < C.size(); ++ci) {
+                const int cw = C[ci].x1 - C[ci].x0, chh = C[ci].y1 - C[ci].y0;
+                if (C[ci].skipped || cw <= 0 || chh <= 0) continue;
+                const size_t pw = (size_t)g.fbw, nwords = (pw * chh + 31) / 32;
+                // candidate list: 8 entries per (row, 8-pixel pair) item of orb_fast_cells_tma8 (>= cw*chh entries of orb_fast_cells_tma)
+                const size_t list_bytes = (size_t)16 * chh * (((cw + 2) >> 3) + 1);
+                fsm_tma = std::max(fsm_tma, (size_t)128 + ((pw * g.fbh + 15) & ~(size_t)15) + ((pw * (chh + 2) + 15) & ~(size_t)15) + nwords * 8 + list_bytes + 64);
             }
         }
         ssm = std::max(ssm, (size_t)(2 * g.nDesired + 4 * g.nCells + 64) * 4 + (size_t)g.nCells * 16 + (size_t)SEL_STAGE * 4);
@@ -1036,17 +1356,57 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
     if (fsm > 227 * 1024) fast_big = true;
     *max_fast_smem = fast_big ? fsm_big : fsm; *max_select_smem = ssm;
     if (fast_big_out) *fast_big_out = fast_big;
+    if (fast_tma_smem_out) *fast_tma_smem_out = (tma_ok && !fast_big && fsm_tma <= 227 * 1024) ? fsm_tma : 0;
     if (Lv) *Lv = L;
     if (Cv) *Cv = C;
     if (Tv) *Tv = T;
     return SE2GPU_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library does not link libcuda, so that it also
+// loads on a box without a driver, e.g. for the symbol check of the CPU test suite)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+constexpr int FAST_TMA_DEFAULT = 0;   // flipped to 2 once the GPU parity run of the TMA kernels is on record (profiles/)
+int fast_tma_variant() {   // SE2GPU_ORB_FAST_TMA = 0: LDG/STS staging (orb_fast_cells), 1: orb_fast_cells_tma, 2: orb_fast_cells_tma8
+    static const int v = [] { const char* e = getenv("SE2GPU_ORB_FAST_TMA"); const int x = e ? atoi(e) : FAST_TMA_DEFAULT; return x < 0 || x > 2 ? FAST_TMA_DEFAULT : x; }();
+    return v;
+}
+
+// one 3-D u8 tensor per level over the batch of bordered planes: x = byte in the row (pitch), y = row, z = frame
+bool encode_fast_maps(se2gpu_orb* h, size_t frame_plane_bytes) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || (frame_plane_bytes & 15)) return false;
+    for (int l = 0; l < h->nlevels; ++l) {
+        const LevelGeo& g = h->levels[l];
+        if (g.fbw <= 6) { memset(&h->fast_maps.m[l], 0, sizeof(CUtensorMap)); continue; }   // no cell on this level ever launches a copy
+        const cuuint64_t gdim[3] = {(cuuint64_t)g.pitch, (cuuint64_t)(g.h + 2 * EDGE), (cuuint64_t)h->max_batch};
+        const cuuint64_t gstr[2] = {(cuuint64_t)g.pitch, (cuuint64_t)frame_plane_bytes};      // bytes, multiples of 16
+        const cuuint32_t box[3] = {(cuuint32_t)g.fbw, (cuuint32_t)g.fbh, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        void* base = h->d.plain + g.plane_off;
+        if (((uintptr_t)base & 15) || (g.pitch & 15)) return false;
+        if (enc(&h->fast_maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
+    return true;
+}
+
 int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     if (w == h->cur_w && hgt == h->cur_h) return SE2GPU_OK;
-    size_t pb, ct, nc, nt, tt, fsm, ssm;
+    size_t pb, ct, nc, nt, tt, fsm, ssm, fsm_tma = 0;
     bool big = false;
-    int rc = build_geometry(h, w, hgt, false, &pb, &ct, &nc, &nt, &tt, &fsm, &ssm, &h->levels, &h->cells, &h->tiles, &big);
+    int rc = build_geometry(h, w, hgt, false, &pb, &ct, &nc, &nt, &tt, &fsm, &ssm, &h->levels, &h->cells, &h->tiles, &big, &fsm_tma);
     if (rc != SE2GPU_OK) return rc;
     if (pb > h->cap_plane || ct > h->cap_cand || nc > h->cap_cells || nt > h->cap_tiles || tt > h->cap_tab)
         return fail(SE2GPU_ERR_CAPACITY, "frame %dx%d exceeds the capacity this extractor was created with (%dx%d)", w, hgt, h->max_w, h->max_h);
@@ -1098,6 +1458,11 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     }
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
+    // TMA-staged cells when every level's patch fits a box and the driver hands out the tensor-map encoder
+    h->fast_tma = (fast_tma_variant() && fsm_tma > 0 && encode_fast_maps(h, pb)) ? fast_tma_variant() : 0;
+    h->fast_tma_smem = fsm_tma;
+    if (h->fast_tma == 1) SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm_tma, 1024)));
+    if (h->fast_tma == 2) SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_tma8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm_tma, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ssm, 1024)));
     OrbDev& d = h->d;
     d.n_cells = (int)h->cells.size(); d.n_tiles = (int)h->tiles.size();
@@ -1238,6 +1603,8 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     SE2_NVTX("se2gpu.orb.fast_select_blur_describe");
     pr.begin(1, s);
     if (h->fast_big) SE2_LAUNCH(orb_fast_cells_big, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
+    else if (h->fast_tma == 2) SE2_LAUNCH(orb_fast_cells_tma8, dim3(d.n_cells, n), FAST_THREADS, h->fast_tma_smem, s, d, h->fast_maps);
+    else if (h->fast_tma == 1) SE2_LAUNCH(orb_fast_cells_tma, dim3(d.n_cells, n), FAST_THREADS, h->fast_tma_smem, s, d, h->fast_maps);
     else SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     pr.end(s);
     pr.begin(2, s);
