@@ -58,6 +58,7 @@ struct LevelGeo {
     int tab_off;        // offset of this level's resize tables (xofs | yofs) in the int table
     int tile_base, tiles_x, tiles_y;
     int fbw, fbh;       // orb_fast_cells_tma: TMA box of this level's FAST cells (bytes per row: multiple of 16; rows)
+    int rz_col, rz_row, rz_tx, rz_ty;   // orb_resize_tab: offsets of this level's column / row / tile-column / tile-row tables
 };
 
 struct CellGeo {
@@ -78,6 +79,9 @@ struct OrbDev {  // passed by value to kernels
     const TileGeo* tiles;
     const int* itab;            // xofs/yofs tables
     const short* stab;          // ialpha/ibeta tables (2 per entry)
+    const struct ResizeCol* rzcol;   // orb_resize_tab: per bordered output column {sx0, sx1, a0, a1, valid}
+    const struct ResizeRow* rzrow;   //                 per bordered output row {s0, s1, b0, b1}
+    const int2* rztile;              //                 per tile column {c_lo, nvec}, per tile row {r_lo, nsr}
     uint8_t* plain;             // [B][frame_plane_bytes]
     uint8_t* blurred;
     size_t frame_plane_bytes;
@@ -188,7 +192,8 @@ __global__ void __launch_bounds__(128) orb_pyr0_undistort(OrbDev d, LevelGeo L, 
 constexpr int RESIZE_TR = 32;
 struct ResizeRow { int s0, s1, b0, b1; };
 struct ResizeCol { int sx0, sx1; short a0, a1; int valid; };   // 16 B
-__global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) orb_resize(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
     __shared__ ResizeRow rowinfo[RESIZE_TR];
     __shared__ __align__(16) ResizeCol colinfo[128];
@@ -296,6 +301,87 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
             const unsigned v1 = (unsigned)((((ri.b0 * A.y) >> 16) + ((ri.b1 * B.y) >> 16) + 2) >> 2);
             const unsigned v2 = (unsigned)((((ri.b0 * A.z) >> 16) + ((ri.b1 * B.z) >> 16) + 2) >> 2);
             const unsigned v3 = (unsigned)((((ri.b0 * A.w) >> 16) + ((ri.b1 * B.w) >> 16) + 2) >> 2);
+            word = (v0 | (v1 << 8) | (v2 << 16) | (v3 << 24)) & vmask;
+        }
+        *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
+    }
+}
+
+// orb_resize with every per-column, per-row and per-tile term read from tables built once per frame size on the host
+// (set_geometry): the reflected source column / coefficient pair of each bordered output column, the source row pair /
+// coefficient pair of each bordered output row, and per tile column / tile row the staged source range. The CTA no longer
+// derives them (128 threads + a warp, two shuffle reductions, a shared table and one block barrier in orb_resize): it goes
+// straight to staging. Stages 0-2 and the arithmetic are those of orb_resize; the planes are bit-identical.
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) orb_resize_tab(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    int* hbuf = reinterpret_cast<int*>(rs_smem);                       // [max_rows][128]
+    uint8_t* raw = rs_smem + (size_t)max_rows * 128 * sizeof(int);     // [max_rows][raw_pitch]
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x4 = blockIdx.x * 128 + tx * 4, y0 = blockIdx.y * RESIZE_TR;
+    const int f = blockIdx.z + d.frame0;
+    const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
+    const int2 tcol = __ldg(d.rztile + L.rz_tx + blockIdx.x), trow = __ldg(d.rztile + L.rz_ty + blockIdx.y);
+    const int c_lo = tcol.x, nvec = tcol.y, r_lo = trow.x, nsr = trow.y;
+    if (nsr > max_rows || nvec * 16 > raw_pitch) { if (tid == 0) *d.err = 3; return; }   // sized on the host from the scale factor
+    const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
+    // stage 0: the box of source rows / columns the tile touches, 16 B vectors
+    if (nvec <= 16) {
+        const int v = tid & 15;
+        if (v < nvec)
+            for (int r = tid >> 4; r < nsr; r += 16)
+                *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+    } else {
+        for (int i = tid; i < nsr * nvec; i += 256) {
+            const int r = i / nvec, v = i - r * nvec;
+            *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+        }
+    }
+    // this thread's 4 columns (16 B table entries; the table covers whole tiles, entries beyond the plane width are invalid)
+    int sx0[4], sx1[4], a0[4], a1[4];
+    unsigned vmask = 0;                       // byte mask of the valid columns
+    {
+        const int4* ct = reinterpret_cast<const int4*>(d.rzcol + L.rz_col + x4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int4 e = __ldg(ct + q);     // {sx0, sx1, a0 | a1 << 16, valid}
+            const bool valid = e.w != 0;
+            sx0[q] = valid ? e.x - c_lo : 0; sx1[q] = valid ? e.y - c_lo : 0;
+            a0[q] = (short)(e.z & 0xFFFF); a1[q] = e.z >> 16;
+            vmask |= valid ? (0xFFu << (8 * q)) : 0u;
+        }
+    }
+    __syncthreads();
+    // stage 1: horizontal pass, stored pre-shifted (the vertical pass uses S >> 4 only)
+    if (x4 < W) {
+        for (int r = ty; r < nsr; r += 8) {
+            const uint8_t* rp = raw + r * raw_pitch;
+            int4 hv;
+            hv.x = (rp[sx0[0]] * a0[0] + rp[sx1[0]] * a1[0]) >> 4;
+            hv.y = (rp[sx0[1]] * a0[1] + rp[sx1[1]] * a1[1]) >> 4;
+            hv.z = (rp[sx0[2]] * a0[2] + rp[sx1[2]] * a1[2]) >> 4;
+            hv.w = (rp[sx0[3]] * a0[3] + rp[sx1[3]] * a1[3]) >> 4;
+            *reinterpret_cast<int4*>(hbuf + r * 128 + 4 * tx) = hv;
+        }
+    }
+    __syncthreads();
+    // stage 2: vertical pass (no clamp: see orb_resize)
+    if (x4 >= L.pitch) return;
+    uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+    const ResizeRow* rt = d.rzrow + L.rz_row + y0;
+#pragma unroll
+    for (int k = 0; k < RESIZE_TR / 8; ++k) {
+        const int r = ty + 8 * k, y = y0 + r;
+        if (y >= H) break;
+        uint32_t word = 0;
+        if (x4 < W) {
+            const int4 rv = __ldg(reinterpret_cast<const int4*>(rt + r));     // {s0, s1, b0, b1}
+            const int4 A = *reinterpret_cast<const int4*>(hbuf + (rv.x - r_lo) * 128 + 4 * tx);
+            const int4 B = *reinterpret_cast<const int4*>(hbuf + (rv.y - r_lo) * 128 + 4 * tx);
+            const unsigned v0 = (unsigned)((((rv.z * A.x) >> 16) + ((rv.w * B.x) >> 16) + 2) >> 2);
+            const unsigned v1 = (unsigned)((((rv.z * A.y) >> 16) + ((rv.w * B.y) >> 16) + 2) >> 2);
+            const unsigned v2 = (unsigned)((((rv.z * A.z) >> 16) + ((rv.w * B.z) >> 16) + 2) >> 2);
+            const unsigned v3 = (unsigned)((((rv.z * A.w) >> 16) + ((rv.w * B.w) >> 16) + 2) >> 2);
             word = (v0 | (v1 << 8) | (v2 << 16) | (v3 << 24)) & vmask;
         }
         *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
@@ -495,16 +581,21 @@ __device__ __forceinline__ void orb_mbar_init(unsigned long long* bar, unsigned 
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(orb_smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void orb_mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "ORB_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra ORB_MBAR_DONE;\n"
-        "bra ORB_MBAR_WAIT;\n"
-        "ORB_MBAR_DONE:\n"
-        "}\n" ::"r"(orb_smem_u32(bar)), "r"(parity) : "memory");
+// waits for the phase with the given parity; gives up after ~0.2 s of SM clocks (a copy that never lands - a broken tensor map -
+// must end in an error code, not in a hung GPU) and returns false
+__device__ __forceinline__ bool orb_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(orb_smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+        if (clock64() - t0 > 400000000LL) return false;
+    }
 }
 // one box of the 3-D tensor (x, y, z) -> shared memory; completion is signalled on `bar` with the box's byte count
 __device__ __forceinline__ void orb_tma_box3(void* dst_smem, const CUtensorMap* map, int x, int y, int z, unsigned bytes, unsigned long long* bar) {
@@ -555,7 +646,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma(OrbDev d, con
         for (int i = threadIdx.x; i < (pw * (ch + 2) + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
         for (int i = threadIdx.x; i < nwords; i += FAST_THREADS) bitmap[i] = 0u;
         if (threadIdx.x == 0) s_ncand = 0;
-        if (pass == 0) orb_mbar_wait(&s_bar, 0);      // the patch has landed (async-proxy writes are visible after the wait)
+        if (pass == 0 && !orb_mbar_wait(&s_bar, 0)) { *d.err = 4; return; }   // the patch has landed (async-proxy writes are visible after the wait)
         __syncthreads();
         // A: one thread = the 4 pixels of one patch word (group)
         {
@@ -690,7 +781,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma8(OrbDev d, co
     for (int pass = 0; pass < 2; ++pass) {
         for (int i = threadIdx.x; i < (pw * (ch + 2) + 3) / 4; i += FAST_THREADS) reinterpret_cast<uint32_t*>(score)[i] = 0u;
         for (int i = threadIdx.x; i < nwords; i += FAST_THREADS) bitmap[i] = 0u;
-        if (pass == 0) orb_mbar_wait(&s_bar, 0);      // the patch has landed (async-proxy writes are visible after the wait)
+        if (pass == 0 && !orb_mbar_wait(&s_bar, 0)) { *d.err = 4; return; }   // the patch has landed (async-proxy writes are visible after the wait)
         __syncthreads();
         // A: one thread = 8 pixels = patch words 2h, 2h+1 of row y
         int nseg = 0;                                  // candidates in this warp's segment (warp-uniform)
@@ -1130,7 +1221,12 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-// one warp per output keypoint slot: orientation on the plain level, descriptor on the blurred level
+// one warp per output keypoint slot: orientation on the plain level, descriptor on the blurred level.
+// BATCH: the disc column of a lane is read in three batches of 5 row pairs with all 10 loads of a batch issued before their
+// sums (predicated off beyond the column's half-height) instead of one dependent +-v pair per loop trip: the kernel is bound by
+// the latency of first-touch sectors (every plane byte comes from DRAM once), so the loads in flight per warp set its speed.
+// Integer moments: any summation order gives the reference's m10, m01.
+template <bool BATCH>
 __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keypoint* __restrict__ kps, uint8_t* __restrict__ desc,
                                                            int* __restrict__ counts) {
     __shared__ float4 patf[256];     // the 256 point pairs of the rBRIEF pattern as floats (x0, y0, x1, y1); test 8*lane+k at [k][lane]
@@ -1161,10 +1257,25 @@ __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keyp
         const uint8_t* col = center + u;
         const int pitch = L.pitch;
         int colsum = col[0];
-        for (int v = 1, off = pitch; v <= vm; ++v, off += pitch) {
-            const int p = col[off], m = col[-off];
-            colsum += p + m;
-            m01 += v * (p - m);
+        if (BATCH) {
+#pragma unroll
+            for (int v0 = 1; v0 <= HALF_PATCH; v0 += 5) {
+                int p[5], m[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {       // rows beyond the half-height re-read row vm (a cache hit) and are dropped below
+                    const int off = min(v0 + k, vm) * pitch;
+                    p[k] = col[off]; m[k] = col[-off];
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (v0 + k <= vm) { colsum += p[k] + m[k]; m01 += (v0 + k) * (p[k] - m[k]); }
+            }
+        } else {
+            for (int v = 1, off = pitch; v <= vm; ++v, off += pitch) {
+                const int p = col[off], m = col[-off];
+                colsum += p + m;
+                m01 += v * (p - m);
+            }
         }
         m10 = u * colsum;
     }
@@ -1179,16 +1290,35 @@ __global__ void __launch_bounds__(256) orb_orient_describe(OrbDev d, se2gpu_keyp
     const float a = (float)cd, b = (float)sd;
     const uint8_t* bc = d.blurred + base;
     unsigned val = 0;
+    if (BATCH) {   // all 16 tap offsets first, then the 16 loads back to back, then the comparisons
+        int o0[8], o1[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float4 pt = patf[k * 32 + lane];
-        const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bc[(ptrdiff_t)r0 * L.pitch + c0], t1 = bc[(ptrdiff_t)r1 * L.pitch + c1];
-        val |= (unsigned)(t0 < t1) << k;
+        for (int k = 0; k < 8; ++k) {
+            const float4 pt = patf[k * 32 + lane];
+            const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            o0[k] = r0 * L.pitch + c0; o1[k] = r1 * L.pitch + c1;
+        }
+        int t0[8], t1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t0[k] = bc[o0[k]]; t1[k] = bc[o1[k]]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) val |= (unsigned)(t0[k] < t1[k]) << k;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float4 pt = patf[k * 32 + lane];
+            const float x0 = pt.x, y0 = pt.y, x1 = pt.z, y1 = pt.w;
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = bc[(ptrdiff_t)r0 * L.pitch + c0], t1 = bc[(ptrdiff_t)r1 * L.pitch + c1];
+            val |= (unsigned)(t0 < t1) << k;
+        }
     }
     // pack 4 bytes per lane group: lane 4q gets bytes 4q..4q+3
     unsigned w = val;
@@ -1236,6 +1366,9 @@ struct se2gpu_orb {
     size_t cap_plane = 0, cap_cand = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0, cap_lkp = 0;
     OrbDev d{};
     LevelGeo* d_levels = nullptr; CellGeo* d_cells = nullptr; TileGeo* d_tiles = nullptr; int* d_itab = nullptr; short* d_stab = nullptr;
+    ResizeCol* d_rzcol = nullptr; ResizeRow* d_rzrow = nullptr; int2* d_rztile = nullptr;   // orb_resize_tab tables
+    size_t cap_rzcol = 0, cap_rzrow = 0, cap_rztile = 0;
+    bool resize_tab = false;
     uint8_t* d_in = nullptr; se2gpu_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_counts = nullptr;
     std::vector<void*> bufs;
     int last_n = 0;
@@ -1377,6 +1510,9 @@ EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
+constexpr bool ORIENT_BATCH_DEFAULT = false;   // same rule
+constexpr bool RESIZE_TAB_DEFAULT = false;     // same rule
+constexpr int RESIZE_OCC_DEFAULT = 4;          // same rule
 constexpr int FAST_TMA_DEFAULT = 0;   // flipped to 2 once the GPU parity run of the TMA kernels is on record (profiles/)
 int fast_tma_variant() {   // SE2GPU_ORB_FAST_TMA = 0: LDG/STS staging (orb_fast_cells), 1: orb_fast_cells_tma, 2: orb_fast_cells_tma8
     static const int v = [] { const char* e = getenv("SE2GPU_ORB_FAST_TMA"); const int x = e ? atoi(e) : FAST_TMA_DEFAULT; return x < 0 || x > 2 ? FAST_TMA_DEFAULT : x; }();
@@ -1439,6 +1575,48 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
             ibeta[2 * dy + 1] = (short)cv_round_f(fy * 2048.f);
         }
     }
+    // orb_resize_tab: per-column / per-row / per-tile terms of every level > 0 (what orb_resize derives per CTA)
+    std::vector<ResizeCol> rzcol; std::vector<ResizeRow> rzrow; std::vector<int2> rztile;
+    for (int l = 1; l < h->nlevels; ++l) {
+        LevelGeo& g = h->levels[l];
+        const LevelGeo& sg = h->levels[l - 1];
+        const int W = g.w + 2 * EDGE, H = g.h + 2 * EDGE;
+        const int tiles_x = (g.pitch + 127) / 128, tiles_y = (H + RESIZE_TR - 1) / RESIZE_TR;
+        const int* xofs = itab.data() + g.tab_off; const int* yofs = xofs + g.w;
+        const short* ialpha = stab.data() + 2 * (size_t)g.tab_off; const short* ibeta = ialpha + 2 * g.w;
+        auto refl = [](int p, int len) { if (len == 1) return 0; while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p; return p; };
+        g.rz_col = (int)rzcol.size(); g.rz_row = (int)rzrow.size();
+        for (int x = 0; x < tiles_x * 128; ++x) {
+            ResizeCol c{0, 0, 0, 0, 0};
+            if (x < W) { const int dx = refl(x - EDGE, g.w); c.sx0 = xofs[dx]; c.sx1 = std::min(c.sx0 + 1, sg.w - 1); c.a0 = ialpha[2 * dx]; c.a1 = ialpha[2 * dx + 1]; c.valid = 1; }
+            rzcol.push_back(c);
+        }
+        for (int y = 0; y < tiles_y * RESIZE_TR; ++y) {
+            ResizeRow r{0, 0, 0, 0};
+            if (y < H) { const int dy = refl(y - EDGE, g.h); const int sy = yofs[dy]; r.s0 = std::min(std::max(sy, 0), sg.h - 1); r.s1 = std::min(std::max(sy + 1, 0), sg.h - 1); r.b0 = ibeta[2 * dy]; r.b1 = ibeta[2 * dy + 1]; }
+            rzrow.push_back(r);
+        }
+        g.rz_tx = (int)rztile.size();
+        for (int t = 0; t < tiles_x; ++t) {
+            int cmin = 0x7fffffff, cmax = -1;
+            for (int x = t * 128; x < t * 128 + 128; ++x) { const ResizeCol& c = rzcol[g.rz_col + x]; if (c.valid) { cmin = std::min(cmin, c.sx0); cmax = std::max(cmax, c.sx1); } }
+            const int c_lo = cmin & ~15;
+            rztile.push_back(make_int2(c_lo, cmax < 0 ? 0 : (cmax - c_lo) / 16 + 1));
+        }
+        g.rz_ty = (int)rztile.size();
+        for (int t = 0; t < tiles_y; ++t) {
+            int rmin = 0x7fffffff, rmax = -1;
+            for (int y = t * RESIZE_TR; y < std::min((t + 1) * RESIZE_TR, H); ++y) { const ResizeRow& r = rzrow[g.rz_row + y]; rmin = std::min(rmin, r.s0); rmax = std::max(rmax, r.s1); }
+            rztile.push_back(make_int2(rmin, rmax - rmin + 1));
+        }
+    }
+    static const bool env_tab = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_TAB"); return e ? atoi(e) != 0 : RESIZE_TAB_DEFAULT; }();
+    h->resize_tab = env_tab && rzcol.size() <= h->cap_rzcol && rzrow.size() <= h->cap_rzrow && rztile.size() <= h->cap_rztile;
+    if (h->resize_tab && !rzcol.empty()) {
+        SE2_CUDA(cudaMemcpyAsync(h->d_rzcol, rzcol.data(), sizeof(ResizeCol) * rzcol.size(), cudaMemcpyHostToDevice, s));
+        SE2_CUDA(cudaMemcpyAsync(h->d_rzrow, rzrow.data(), sizeof(ResizeRow) * rzrow.size(), cudaMemcpyHostToDevice, s));
+        SE2_CUDA(cudaMemcpyAsync(h->d_rztile, rztile.data(), sizeof(int2) * rztile.size(), cudaMemcpyHostToDevice, s));
+    }
     SE2_CUDA(cudaMemcpyAsync(h->d_levels, h->levels.data(), sizeof(LevelGeo) * h->levels.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d_cells, h->cells.data(), sizeof(CellGeo) * h->cells.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d_tiles, h->tiles.data(), sizeof(TileGeo) * h->tiles.size(), cudaMemcpyHostToDevice, s));
@@ -1454,7 +1632,12 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
         h->resize_raw_pitch = (((int)ceil(128 * ratio) + 4 + 15 + 15) / 16) * 16;
         h->resize_smem = (size_t)h->resize_rows * (128 * sizeof(int) + h->resize_raw_pitch);
         if (h->resize_smem > 200 * 1024) return fail(SE2GPU_ERR_CAPACITY, "scale factor %.3f needs %zu B of shared memory in orb_resize", ratio, h->resize_smem);
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize_tab<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize_tab<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize_tab<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
     }
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
@@ -1576,7 +1759,12 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
         dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
-        SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
+        // SE2GPU_ORB_RESIZE_OCC = 5 / 6: ask the compiler for 5 / 6 resident CTAs per SM (register cap 48 / 40) instead of 4
+        static const int occ = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_OCC"); const int v = e ? atoi(e) : RESIZE_OCC_DEFAULT; return v == 5 || v == 6 ? v : 4; }();
+#define SE2_RESIZE(K, M) SE2_LAUNCH(K<M>, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch)
+        if (h->resize_tab) { if (occ == 5) SE2_RESIZE(orb_resize_tab, 5); else if (occ == 6) SE2_RESIZE(orb_resize_tab, 6); else SE2_RESIZE(orb_resize_tab, 4); }
+        else { if (occ == 5) SE2_RESIZE(orb_resize, 5); else if (occ == 6) SE2_RESIZE(orb_resize, 6); else SE2_RESIZE(orb_resize, 4); }
+#undef SE2_RESIZE
         if (l == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     }
     if (h->nlevels == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
@@ -1619,7 +1807,10 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     }
     const int warps = 8;
     pr.begin(4, s);
-    SE2_LAUNCH(orb_orient_describe, dim3((h->nfeatures + warps - 1) / warps, n), warps * 32, 0, s, d, d_kps, d_desc, d_counts);
+    // SE2GPU_ORB_ORIENT_BATCH=0: one dependent +-v load pair per loop trip (round-1 form)
+    static const bool orient_batch = [] { const char* e = getenv("SE2GPU_ORB_ORIENT_BATCH"); return e ? atoi(e) != 0 : ORIENT_BATCH_DEFAULT; }();
+    if (orient_batch) SE2_LAUNCH(orb_orient_describe<true>, dim3((h->nfeatures + warps - 1) / warps, n), warps * 32, 0, s, d, d_kps, d_desc, d_counts);
+    else SE2_LAUNCH(orb_orient_describe<false>, dim3((h->nfeatures + warps - 1) / warps, n), warps * 32, 0, s, d, d_kps, d_desc, d_counts);
     pr.end(s);
     h->last_n = std::max(h->last_n * (frame0 > 0), frame0 + n);
     return SE2GPU_OK;
@@ -1667,11 +1858,15 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     // head-room so that smaller frames (different cell rounding) always fit
     h->cap_plane = pb + 4096; h->cap_cand = ct + ct / 8 + 4096; h->cap_cells = nc + 64; h->cap_tiles = nt + 64; h->cap_tab = tt + 64;
     h->cap_lkp = nfeatures + 64;
+    // orb_resize_tab tables: every level of a smaller frame is no larger than the same level of the largest frame
+    h->cap_rzcol = (size_t)nlevels * ((size_t)max_w + 2 * EDGE + 31 + 256); h->cap_rzrow = (size_t)nlevels * ((size_t)max_h + 2 * EDGE + 2 * RESIZE_TR);
+    h->cap_rztile = (size_t)nlevels * ((max_w + 2 * EDGE + 31) / 128 + (max_h + 2 * EDGE) / RESIZE_TR + 4);
     const size_t B = max_batch;
     bool ok = true;
     auto A = [&](auto** p, size_t c) { if (ok && se2gpu::dev_alloc(p, c) == cudaSuccess) h->bufs.push_back(*p); else ok = false; };
     OrbDev& d = h->d;
     A(&h->d_levels, (size_t)nlevels); A(&h->d_cells, h->cap_cells); A(&h->d_tiles, h->cap_tiles); A(&h->d_itab, h->cap_tab); A(&h->d_stab, 2 * h->cap_tab);
+    A(&h->d_rzcol, h->cap_rzcol); A(&h->d_rzrow, h->cap_rzrow); A(&h->d_rztile, h->cap_rztile);
     A(&d.plain, B * h->cap_plane); A(&d.blurred, B * h->cap_plane);
     A(&d.cand, B * h->cap_cand); A(&d.hdr, B * h->cap_cells); A(&d.lkp, B * h->cap_lkp); A(&d.lcount, B * nlevels); A(&d.err, 1);
     A(&h->d_in, B * (size_t)max_w * max_h); A(&h->d_kps, B * nfeatures); A(&h->d_desc, B * nfeatures * 32); A(&h->d_counts, B);
@@ -1690,6 +1885,7 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
     d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
     d.levels = h->d_levels; d.cells = h->d_cells; d.tiles = h->d_tiles; d.itab = h->d_itab; d.stab = h->d_stab;
+    d.rzcol = h->d_rzcol; d.rzrow = h->d_rzrow; d.rztile = h->d_rztile;
     if (cudaDeviceSynchronize() != cudaSuccess) { fail(SE2GPU_ERR_CUDA, "init failed"); se2gpu_orb_destroy(h); return nullptr; }
     return h;
 }
@@ -1805,7 +2001,11 @@ static int orb_finish(se2gpu_orb* h) {
     SE2_CUDA(cudaMemcpyAsync(&err, h->d.err, sizeof(int), cudaMemcpyDeviceToHost, nullptr));
     SE2_CUDA(cudaStreamSynchronize(nullptr));
     h->last_n = p.n;
-    if (err) { cudaMemset(h->d.err, 0, sizeof(int)); return fail(SE2GPU_ERR_CAPACITY, "internal candidate buffer overflow (code %d)", err); }
+    if (err) {
+        cudaMemset(h->d.err, 0, sizeof(int));
+        if (err == 4) return fail(SE2GPU_ERR_CUDA, "the TMA copy of a FAST cell did not complete (tensor map / driver problem)");
+        return fail(SE2GPU_ERR_CAPACITY, "internal candidate buffer overflow (code %d)", err);
+    }
     return SE2GPU_OK;
 }
 

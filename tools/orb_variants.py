@@ -1,0 +1,104 @@
+"""A/B of the ORB kernel variants the library selects through environment variables (read once per process, so every
+configuration runs in a child process). For each configuration: the device-resident 64-frame benchmark step (CUDA events, 8 rotating
+input batches = 157 MB > L2, like bench.py), the per-kernel times of an event-instrumented pass, and a SHA-256 over the keypoints,
+descriptors and counts of all 8 batches — every variant must reproduce the checksum of the round-1 kernels bit for bit (the first
+configuration), which tests/test_orb_gpu.py pins against the CPU oracle.
+
+    python tools/orb_variants.py [--steps 20] [--out gpurun_out/orb_variants.jsonl]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r'''
+import hashlib, json, os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from tools import synth
+from se2lam_b200.orb import ORBextractor
+steps = %(steps)d
+B, NF, W, H, NROT = 64, 1000, 640, 480, 8
+dev = torch.device("cuda", 0)
+base = synth.orb_batch(B, first_seed=1000)
+batches = [torch.from_numpy(np.ascontiguousarray(np.roll(base, r * 7, axis=2) if r else base)).to(dev) for r in range(NROT)]
+ext = ORBextractor(NF, 1.2, 8, fastTh=20, max_width=W, max_height=H, max_batch=B, device=0)
+d_kps = torch.empty(B * NF * 28, dtype=torch.uint8, device=dev)
+d_desc = torch.empty(B * NF * 32, dtype=torch.uint8, device=dev)
+d_counts = torch.zeros((NROT, B), dtype=torch.int32, device=dev)
+stream = torch.cuda.current_stream()
+sha = hashlib.sha256()
+total = 0
+for r in range(NROT):      # warm-up + checksum pass
+    ext.extract_device(batches[r], B, H, W, d_kps, d_desc, d_counts[r], stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    c = d_counts[r].cpu().numpy()
+    sha.update(c.tobytes()); total += int(c.sum())
+    k = d_kps.cpu().numpy().reshape(B, NF, 28); d = d_desc.cpu().numpy().reshape(B, NF, 32)
+    for i in range(B):
+        sha.update(k[i, :c[i]].tobytes()); sha.update(d[i, :c[i]].tobytes())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record(stream)
+for k in range(steps):
+    ext.extract_device(batches[k %% NROT], B, H, W, d_kps, d_desc, d_counts[k %% NROT], stream=stream.cuda_stream)
+e1.record(stream)
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+ext.profile(True)
+for k in range(steps):
+    ext.extract_device(batches[k %% NROT], B, H, W, d_kps, d_desc, d_counts[k %% NROT], stream=stream.cuda_stream)
+torch.cuda.synchronize()
+prof = ext.profile_read()
+ext.profile(False)
+print(json.dumps({"ms_per_step": round(ms, 4), "mkps": round(total / NROT / ms / 1e3, 2), "keypoints": total, "sha256": sha.hexdigest()[:16],
+                  "per_kernel_ms": {g: round(v[0] / max(v[1], 1), 4) for g, v in prof.items()}}))
+'''
+
+CONFIGS = [
+    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("fast tma (4 px)", {"SE2GPU_ORB_FAST_TMA": "1", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("fast tma8", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("orient batch", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
+    ("resize occ 5", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "5", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("resize tab", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("resize tab occ 5", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "5", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("resize tab occ 6", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "6", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("all new (tma8, tab, occ 5, batch)", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "5", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
+    ("all new, occ 4", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "orb_variants.jsonl"))
+    ap.add_argument("--timeout", type=int, default=120, help="seconds per configuration (a hung kernel must not eat the GPU call)")
+    args = ap.parse_args()
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    ref = None
+    with open(args.out, "w") as out:
+        for name, env in CONFIGS:
+            rec = {"config": name, "env": env}
+            try:
+                r = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT, "steps": args.steps}], env=dict(os.environ, **env),
+                                   capture_output=True, text=True, timeout=args.timeout)
+                line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+                if r.returncode == 0 and line.startswith("{"):
+                    rec.update(json.loads(line))
+                    if ref is None:
+                        ref = rec["sha256"]
+                    rec["bit_identical_to_round1"] = rec["sha256"] == ref
+                else:
+                    rec["error"] = (r.stderr or r.stdout)[-600:]
+            except subprocess.TimeoutExpired:
+                rec["error"] = "timeout"
+            print(json.dumps(rec), flush=True)
+            out.write(json.dumps(rec) + "\n"); out.flush()
+
+
+if __name__ == "__main__":
+    main()
