@@ -121,8 +121,16 @@ SE2_HD unsigned inside_mask8(int x0, int cw) {
 }
 
 // ---- pass A work distribution of orb_fast_cells_tma8 (shared with the host test, which simulates the CTA's threads)
-// item = y * G2 + h: row y of the cell, 8-pixel pair h = patch words 2h, 2h+1 = interior x 8h-3 .. 8h+4
-SE2_HD int pairs_per_row(int cw) { return ((cw + 2) >> 3) + 1; }       // last pair starts at 8(G2-1)-3 <= cw-1
+// The patch row starts `shift` bytes (0..15) left of the cell's first apron pixel (the TMA box start is 16 B aligned), so interior
+// pixel x sits at patch byte x + 3 + shift. An item = row y of the cell x one 8-byte pair of patch words (2p, 2p+1), i.e. interior
+// x = 8p - 3 - shift .. +7; the pairs that touch the interior are p = first_pair .. first_pair + pairs_per_row - 1.
+SE2_HD int first_pair(int shift) { return (shift + 3) >> 3; }
+SE2_HD int pairs_per_row(int cw, int shift) { return ((shift + 2 + cw) >> 3) - first_pair(shift) + 1; }
+SE2_HD int pair_x0(int h, int shift) { return 8 * (h + first_pair(shift)) - 3 - shift; }   // interior x of bit 0 of item (., h): -7 .. cw-1
+// the same for the 4-pixel groups of orb_fast_cells_tma (one patch word per item)
+SE2_HD int first_group(int shift) { return (shift + 3) >> 2; }
+SE2_HD int groups_per_row(int cw, int shift) { return ((shift + 2 + cw) >> 2) - first_group(shift) + 1; }
+SE2_HD int group_x0(int g, int shift) { return 4 * (g + first_group(shift)) - 3 - shift; }   // -3 .. cw-1
 // thread tid visits items tid, tid + nthreads, tid + 2 nthreads, ... without a division per item
 struct ItemWalk {
     int y, h, dY, dH, G2;

@@ -58,7 +58,6 @@ struct LevelGeo {
     int tab_off;        // offset of this level's resize tables (xofs | yofs) in the int table
     int tile_base, tiles_x, tiles_y;
     int fbw, fbh;       // orb_fast_cells_tma: TMA box of this level's FAST cells (bytes per row: multiple of 16; rows)
-    int rz_col, rz_row, rz_tx, rz_ty;   // orb_resize_tab: offsets of this level's column / row / tile-column / tile-row tables
 };
 
 struct CellGeo {
@@ -79,9 +78,6 @@ struct OrbDev {  // passed by value to kernels
     const TileGeo* tiles;
     const int* itab;            // xofs/yofs tables
     const short* stab;          // ialpha/ibeta tables (2 per entry)
-    const struct ResizeCol* rzcol;   // orb_resize_tab: per bordered output column {sx0, sx1, a0, a1, valid}
-    const struct ResizeRow* rzrow;   //                 per bordered output row {s0, s1, b0, b1}
-    const int2* rztile;              //                 per tile column {c_lo, nvec}, per tile row {r_lo, nsr}
     uint8_t* plain;             // [B][frame_plane_bytes]
     uint8_t* blurred;
     size_t frame_plane_bytes;
@@ -192,8 +188,7 @@ __global__ void __launch_bounds__(128) orb_pyr0_undistort(OrbDev d, LevelGeo L, 
 constexpr int RESIZE_TR = 32;
 struct ResizeRow { int s0, s1, b0, b1; };
 struct ResizeCol { int sx0, sx1; short a0, a1; int valid; };   // 16 B
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) orb_resize(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
+__global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
     extern __shared__ __align__(16) uint8_t rs_smem[];
     __shared__ ResizeRow rowinfo[RESIZE_TR];
     __shared__ __align__(16) ResizeCol colinfo[128];
@@ -301,87 +296,6 @@ __global__ void __launch_bounds__(256, MINB) orb_resize(OrbDev d, LevelGeo L, Le
             const unsigned v1 = (unsigned)((((ri.b0 * A.y) >> 16) + ((ri.b1 * B.y) >> 16) + 2) >> 2);
             const unsigned v2 = (unsigned)((((ri.b0 * A.z) >> 16) + ((ri.b1 * B.z) >> 16) + 2) >> 2);
             const unsigned v3 = (unsigned)((((ri.b0 * A.w) >> 16) + ((ri.b1 * B.w) >> 16) + 2) >> 2);
-            word = (v0 | (v1 << 8) | (v2 << 16) | (v3 << 24)) & vmask;
-        }
-        *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
-    }
-}
-
-// orb_resize with every per-column, per-row and per-tile term read from tables built once per frame size on the host
-// (set_geometry): the reflected source column / coefficient pair of each bordered output column, the source row pair /
-// coefficient pair of each bordered output row, and per tile column / tile row the staged source range. The CTA no longer
-// derives them (128 threads + a warp, two shuffle reductions, a shared table and one block barrier in orb_resize): it goes
-// straight to staging. Stages 0-2 and the arithmetic are those of orb_resize; the planes are bit-identical.
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) orb_resize_tab(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
-    extern __shared__ __align__(16) uint8_t rs_smem[];
-    int* hbuf = reinterpret_cast<int*>(rs_smem);                       // [max_rows][128]
-    uint8_t* raw = rs_smem + (size_t)max_rows * 128 * sizeof(int);     // [max_rows][raw_pitch]
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    const int x4 = blockIdx.x * 128 + tx * 4, y0 = blockIdx.y * RESIZE_TR;
-    const int f = blockIdx.z + d.frame0;
-    const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
-    const int2 tcol = __ldg(d.rztile + L.rz_tx + blockIdx.x), trow = __ldg(d.rztile + L.rz_ty + blockIdx.y);
-    const int c_lo = tcol.x, nvec = tcol.y, r_lo = trow.x, nsr = trow.y;
-    if (nsr > max_rows || nvec * 16 > raw_pitch) { if (tid == 0) *d.err = 3; return; }   // sized on the host from the scale factor
-    const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
-    // stage 0: the box of source rows / columns the tile touches, 16 B vectors
-    if (nvec <= 16) {
-        const int v = tid & 15;
-        if (v < nvec)
-            for (int r = tid >> 4; r < nsr; r += 16)
-                *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
-    } else {
-        for (int i = tid; i < nsr * nvec; i += 256) {
-            const int r = i / nvec, v = i - r * nvec;
-            *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
-        }
-    }
-    // this thread's 4 columns (16 B table entries; the table covers whole tiles, entries beyond the plane width are invalid)
-    int sx0[4], sx1[4], a0[4], a1[4];
-    unsigned vmask = 0;                       // byte mask of the valid columns
-    {
-        const int4* ct = reinterpret_cast<const int4*>(d.rzcol + L.rz_col + x4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int4 e = __ldg(ct + q);     // {sx0, sx1, a0 | a1 << 16, valid}
-            const bool valid = e.w != 0;
-            sx0[q] = valid ? e.x - c_lo : 0; sx1[q] = valid ? e.y - c_lo : 0;
-            a0[q] = (short)(e.z & 0xFFFF); a1[q] = e.z >> 16;
-            vmask |= valid ? (0xFFu << (8 * q)) : 0u;
-        }
-    }
-    __syncthreads();
-    // stage 1: horizontal pass, stored pre-shifted (the vertical pass uses S >> 4 only)
-    if (x4 < W) {
-        for (int r = ty; r < nsr; r += 8) {
-            const uint8_t* rp = raw + r * raw_pitch;
-            int4 hv;
-            hv.x = (rp[sx0[0]] * a0[0] + rp[sx1[0]] * a1[0]) >> 4;
-            hv.y = (rp[sx0[1]] * a0[1] + rp[sx1[1]] * a1[1]) >> 4;
-            hv.z = (rp[sx0[2]] * a0[2] + rp[sx1[2]] * a1[2]) >> 4;
-            hv.w = (rp[sx0[3]] * a0[3] + rp[sx1[3]] * a1[3]) >> 4;
-            *reinterpret_cast<int4*>(hbuf + r * 128 + 4 * tx) = hv;
-        }
-    }
-    __syncthreads();
-    // stage 2: vertical pass (no clamp: see orb_resize)
-    if (x4 >= L.pitch) return;
-    uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
-    const ResizeRow* rt = d.rzrow + L.rz_row + y0;
-#pragma unroll
-    for (int k = 0; k < RESIZE_TR / 8; ++k) {
-        const int r = ty + 8 * k, y = y0 + r;
-        if (y >= H) break;
-        uint32_t word = 0;
-        if (x4 < W) {
-            const int4 rv = __ldg(reinterpret_cast<const int4*>(rt + r));     // {s0, s1, b0, b1}
-            const int4 A = *reinterpret_cast<const int4*>(hbuf + (rv.x - r_lo) * 128 + 4 * tx);
-            const int4 B = *reinterpret_cast<const int4*>(hbuf + (rv.y - r_lo) * 128 + 4 * tx);
-            const unsigned v0 = (unsigned)((((rv.z * A.x) >> 16) + ((rv.w * B.x) >> 16) + 2) >> 2);
-            const unsigned v1 = (unsigned)((((rv.z * A.y) >> 16) + ((rv.w * B.y) >> 16) + 2) >> 2);
-            const unsigned v2 = (unsigned)((((rv.z * A.z) >> 16) + ((rv.w * B.z) >> 16) + 2) >> 2);
-            const unsigned v3 = (unsigned)((((rv.z * A.w) >> 16) + ((rv.w * B.w) >> 16) + 2) >> 2);
             word = (v0 | (v1 << 8) | (v2 << 16) | (v3 << 24)) & vmask;
         }
         *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
@@ -605,8 +519,8 @@ __device__ __forceinline__ void orb_tma_box3(void* dst_smem, const CUtensorMap* 
 }
 
 // orb_fast_cells with the cell staged by the TMA unit: ONE cp.async.bulk.tensor.3d per CTA pulls the cell and its 3 px apron
-// (box fbw x fbh of the level's tensor map, origin at the cell's first apron pixel - tensor coordinates need no alignment, so
-// the patch has no alignment shift and its pitch is the level's constant fbw) while the CTA clears its score plane and bitmap;
+// (box fbw x fbh of the level's tensor map, origin at the 16 B aligned column left of the cell's first apron pixel; the patch
+// pitch is the level's constant fbw) while the CTA clears its score plane and bitmap;
 // the 256 threads no longer issue the ~10 address divisions + LDG + STS each of the staging loop. Pass A walks its
 // (row, 4-pixel group) items with an incremental (y, group) pair instead of a division per item, and masks the group's
 // pixels outside the cell with two shifts. Passes B-E are those of orb_fast_cells; results are bit-identical.
@@ -626,7 +540,10 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma(OrbDev d, con
     const int pw = L.fbw, pww = pw >> 2, bh = L.fbh;          // patch pitch = box width
     uint8_t* smem = smem_raw + ((128u - (orb_smem_u32(smem_raw) & 127u)) & 127u);   // TMA destination: 128 B aligned
     const int nbits = pw * ch, nwords = (nbits + 31) >> 5;
-    const int G = ((cw + 2) >> 2) + 1, nitems = ch * G;       // pass A work items: group g covers interior x = 4g-3 .. 4g
+    // the box starts at the 16 B aligned bordered-plane column ax0 <= x0-3 (TMA tile coordinates of 1-byte elements must be 16 B
+    // aligned in the innermost dimension: an unaligned start raises an illegal-instruction fault, tools/tma_probe.cu)
+    const int bx0 = c.x0 - 3 + EDGE, ax0 = bx0 & ~15, shift = bx0 - ax0;
+    const int g0 = fastpx::first_group(shift), G = fastpx::groups_per_row(cw, shift), nitems = ch * G;   // pass A work items
     uint8_t* patch = smem;                                                                // [bh x pw], pixel (x,y) of the cell at (y+3)*pw + x+3
     uint8_t* score = smem + ((pw * bh + 15) & ~15);                                       // [(ch+2) x pw], pixel (x,y) at (y+1)*pw + x+1
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(score + ((pw * (ch + 2) + 15) & ~15)); // [nwords], bit y*pw + x
@@ -634,10 +551,10 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma(OrbDev d, con
     uint16_t* list = reinterpret_cast<uint16_t*>(woff + nwords);                          // [<= cw*ch] entries y*pw + x
     if (threadIdx.x == 0) orb_mbar_init(&s_bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], c.x0 - 3 + EDGE, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
+    if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], ax0, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
     constexpr int NW = FAST_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint8_t* p0 = patch + 3 * pw + 3;
+    const uint8_t* p0 = patch + 3 * pw + 3 + shift;
     // pass A item walk: item = y*G + g; this thread's items are threadIdx.x, +256, +512, ...
     const int y_first = (int)threadIdx.x / G, g_first = (int)threadIdx.x - y_first * G;
     const int dY = FAST_THREADS / G, dG = FAST_THREADS - dY * G;
@@ -655,9 +572,9 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma(OrbDev d, con
             int y = y_first, g = g_first;
             for (int it0 = wid * 32; it0 < nitems; it0 += NW * 32) {
                 unsigned m = 0;
-                const int col0 = 4 * g - 3;                        // interior x of the group's first pixel
+                const int col0 = fastpx::group_x0(g, shift);       // interior x of the group's first pixel
                 if (y < ch) {                                      // <=> it0 + lane < nitems
-                    const uint32_t* c = pwords + (y + 3) * pww + g;
+                    const uint32_t* c = pwords + (y + 3) * pww + g + g0;
                     const uint32_t n3 = c[-3 * pww], s3 = c[3 * pww];
                     const uint32_t n2a = c[-2 * pww - 1], n2b = c[-2 * pww], n2c = c[-2 * pww + 1];
                     const uint32_t s2a = c[2 * pww - 1], s2b = c[2 * pww], s2c = c[2 * pww + 1];
@@ -762,18 +679,21 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma8(OrbDev d, co
     const int pw = L.fbw, pww = pw >> 2, bh = L.fbh;          // patch pitch = box width (multiple of 16 B: rows are 8 B aligned)
     uint8_t* smem = smem_raw + ((128u - (orb_smem_u32(smem_raw) & 127u)) & 127u);   // TMA destination: 128 B aligned
     const int nbits = pw * ch, nwords = (nbits + 31) >> 5;
-    const int G2 = fastpx::pairs_per_row(cw), nitems = ch * G2;
-    uint8_t* patch = smem;                                                                // [bh x pw], pixel (x,y) of the cell at (y+3)*pw + x+3
+    // the box starts at the 16 B aligned bordered-plane column ax0 <= x0-3 (TMA tile coordinates of 1-byte elements must be 16 B
+    // aligned in the innermost dimension: an unaligned start raises an illegal-instruction fault, tools/tma_probe.cu)
+    const int bx0 = c.x0 - 3 + EDGE, ax0 = bx0 & ~15, shift = bx0 - ax0;
+    const int h0 = fastpx::first_pair(shift), G2 = fastpx::pairs_per_row(cw, shift), nitems = ch * G2;
+    uint8_t* patch = smem;                                                                // [bh x pw], pixel (x,y) of the cell at (y+3)*pw + x+3+shift
     uint8_t* score = smem + ((pw * bh + 15) & ~15);                                       // [(ch+2) x pw], pixel (x,y) at (y+1)*pw + x+1
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(score + ((pw * (ch + 2) + 15) & ~15)); // [nwords], bit y*pw + x
     uint32_t* woff = bitmap + nwords;                                                     // [nwords] exclusive popcount scan
     uint16_t* list = reinterpret_cast<uint16_t*>(woff + nwords);                          // [8 * nitems] entries y*pw + x, one segment per warp
     if (threadIdx.x == 0) orb_mbar_init(&s_bar, 1);
     __syncthreads();
-    if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], c.x0 - 3 + EDGE, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
+    if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], ax0, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
     constexpr int NW = FAST_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint8_t* p0 = patch + 3 * pw + 3;
+    const uint8_t* p0 = patch + 3 * pw + 3 + shift;
     uint16_t* seg = list + fastpx::seg_offset(wid, nitems, NW);
     fastpx::ItemWalk first;
     first.init((int)threadIdx.x, FAST_THREADS, G2);
@@ -791,9 +711,9 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma8(OrbDev d, co
             fastpx::ItemWalk it = first;
             for (int it0 = wid * 32; it0 < nitems; it0 += NW * 32) {
                 unsigned m = 0;
-                const int x0 = 8 * it.h - 3;                       // interior x of the item's first pixel
+                const int x0 = fastpx::pair_x0(it.h, shift);       // interior x of the item's first pixel
                 if (it.y < ch) {                                   // <=> it0 + lane < nitems
-                    const uint32_t* cp = pwords + (it.y + 3) * pww + 2 * it.h;    // even word index: 8 B aligned
+                    const uint32_t* cp = pwords + (it.y + 3) * pww + 2 * (it.h + h0);    // even word index: 8 B aligned
                     const uint2 n3 = *reinterpret_cast<const uint2*>(cp - 3 * pww), s3 = *reinterpret_cast<const uint2*>(cp + 3 * pww);
                     const uint2 n2 = *reinterpret_cast<const uint2*>(cp - 2 * pww), s2 = *reinterpret_cast<const uint2*>(cp + 2 * pww);
                     const uint2 z = *reinterpret_cast<const uint2*>(cp);
@@ -1366,9 +1286,7 @@ struct se2gpu_orb {
     size_t cap_plane = 0, cap_cand = 0, cap_cells = 0, cap_tiles = 0, cap_tab = 0, cap_lkp = 0;
     OrbDev d{};
     LevelGeo* d_levels = nullptr; CellGeo* d_cells = nullptr; TileGeo* d_tiles = nullptr; int* d_itab = nullptr; short* d_stab = nullptr;
-    ResizeCol* d_rzcol = nullptr; ResizeRow* d_rzrow = nullptr; int2* d_rztile = nullptr;   // orb_resize_tab tables
-    size_t cap_rzcol = 0, cap_rzrow = 0, cap_rztile = 0;
-    bool resize_tab = false;
+
     uint8_t* d_in = nullptr; se2gpu_keypoint* d_kps = nullptr; uint8_t* d_desc = nullptr; int* d_counts = nullptr;
     std::vector<void*> bufs;
     int last_n = 0;
@@ -1456,7 +1374,7 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 c.cand_cap = ((cw + 1) / 2) * ((chh + 1) / 2) + 8;   // strict 3x3 maxima: at most one per 2x2 block
                 coff += c.cand_cap;
                 if (cw > 0 && chh > 0) {
-                    max_cw = std::max(max_cw, cw); max_ch = std::max(max_ch, chh);
+                    max_cw = std::max(max_cw, ((c.x0 - 3 + EDGE) & 15) + cw); max_ch = std::max(max_ch, chh);   // incl. the TMA alignment shift
                     const size_t pwb = (size_t)((cw + 6 + 3 + 3) / 4 + 1) * 4;   // worst-case alignment shift
                     const size_t nwords = (pwb * chh + 31) / 32;
                     if (pwb * (chh + 6) > 65535) fast_big = true;    // 16-bit patch offsets in the candidate list
@@ -1476,7 +1394,7 @@ int build_geometry(se2gpu_orb* h, int w, int hgt, bool dry, size_t* plane_bytes,
                 if (C[ci].skipped || cw <= 0 || chh <= 0) continue;
                 const size_t pw = (size_t)g.fbw, nwords = (pw * chh + 31) / 32;
                 // candidate list: 8 entries per (row, 8-pixel pair) item of orb_fast_cells_tma8 (>= cw*chh entries of orb_fast_cells_tma)
-                const size_t list_bytes = (size_t)16 * chh * (((cw + 2) >> 3) + 1);
+                const size_t list_bytes = (size_t)16 * chh * fastpx::pairs_per_row(cw, (C[ci].x0 - 3 + EDGE) & 15);
                 fsm_tma = std::max(fsm_tma, (size_t)128 + ((pw * g.fbh + 15) & ~(size_t)15) + ((pw * (chh + 2) + 15) & ~(size_t)15) + nwords * 8 + list_bytes + 64);
             }
         }
@@ -1510,9 +1428,7 @@ EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
-constexpr bool ORIENT_BATCH_DEFAULT = false;   // same rule
-constexpr bool RESIZE_TAB_DEFAULT = false;     // same rule
-constexpr int RESIZE_OCC_DEFAULT = 4;          // same rule
+constexpr bool ORIENT_BATCH_DEFAULT = true;    // measured: 0.0928 -> 0.0897 ms per 64 frames, bit-identical (profiles/r02b_orb_variants.jsonl)
 constexpr int FAST_TMA_DEFAULT = 0;   // flipped to 2 once the GPU parity run of the TMA kernels is on record (profiles/)
 int fast_tma_variant() {   // SE2GPU_ORB_FAST_TMA = 0: LDG/STS staging (orb_fast_cells), 1: orb_fast_cells_tma, 2: orb_fast_cells_tma8
     static const int v = [] { const char* e = getenv("SE2GPU_ORB_FAST_TMA"); const int x = e ? atoi(e) : FAST_TMA_DEFAULT; return x < 0 || x > 2 ? FAST_TMA_DEFAULT : x; }();
@@ -1575,48 +1491,6 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
             ibeta[2 * dy + 1] = (short)cv_round_f(fy * 2048.f);
         }
     }
-    // orb_resize_tab: per-column / per-row / per-tile terms of every level > 0 (what orb_resize derives per CTA)
-    std::vector<ResizeCol> rzcol; std::vector<ResizeRow> rzrow; std::vector<int2> rztile;
-    for (int l = 1; l < h->nlevels; ++l) {
-        LevelGeo& g = h->levels[l];
-        const LevelGeo& sg = h->levels[l - 1];
-        const int W = g.w + 2 * EDGE, H = g.h + 2 * EDGE;
-        const int tiles_x = (g.pitch + 127) / 128, tiles_y = (H + RESIZE_TR - 1) / RESIZE_TR;
-        const int* xofs = itab.data() + g.tab_off; const int* yofs = xofs + g.w;
-        const short* ialpha = stab.data() + 2 * (size_t)g.tab_off; const short* ibeta = ialpha + 2 * g.w;
-        auto refl = [](int p, int len) { if (len == 1) return 0; while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p; return p; };
-        g.rz_col = (int)rzcol.size(); g.rz_row = (int)rzrow.size();
-        for (int x = 0; x < tiles_x * 128; ++x) {
-            ResizeCol c{0, 0, 0, 0, 0};
-            if (x < W) { const int dx = refl(x - EDGE, g.w); c.sx0 = xofs[dx]; c.sx1 = std::min(c.sx0 + 1, sg.w - 1); c.a0 = ialpha[2 * dx]; c.a1 = ialpha[2 * dx + 1]; c.valid = 1; }
-            rzcol.push_back(c);
-        }
-        for (int y = 0; y < tiles_y * RESIZE_TR; ++y) {
-            ResizeRow r{0, 0, 0, 0};
-            if (y < H) { const int dy = refl(y - EDGE, g.h); const int sy = yofs[dy]; r.s0 = std::min(std::max(sy, 0), sg.h - 1); r.s1 = std::min(std::max(sy + 1, 0), sg.h - 1); r.b0 = ibeta[2 * dy]; r.b1 = ibeta[2 * dy + 1]; }
-            rzrow.push_back(r);
-        }
-        g.rz_tx = (int)rztile.size();
-        for (int t = 0; t < tiles_x; ++t) {
-            int cmin = 0x7fffffff, cmax = -1;
-            for (int x = t * 128; x < t * 128 + 128; ++x) { const ResizeCol& c = rzcol[g.rz_col + x]; if (c.valid) { cmin = std::min(cmin, c.sx0); cmax = std::max(cmax, c.sx1); } }
-            const int c_lo = cmin & ~15;
-            rztile.push_back(make_int2(c_lo, cmax < 0 ? 0 : (cmax - c_lo) / 16 + 1));
-        }
-        g.rz_ty = (int)rztile.size();
-        for (int t = 0; t < tiles_y; ++t) {
-            int rmin = 0x7fffffff, rmax = -1;
-            for (int y = t * RESIZE_TR; y < std::min((t + 1) * RESIZE_TR, H); ++y) { const ResizeRow& r = rzrow[g.rz_row + y]; rmin = std::min(rmin, r.s0); rmax = std::max(rmax, r.s1); }
-            rztile.push_back(make_int2(rmin, rmax - rmin + 1));
-        }
-    }
-    static const bool env_tab = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_TAB"); return e ? atoi(e) != 0 : RESIZE_TAB_DEFAULT; }();
-    h->resize_tab = env_tab && rzcol.size() <= h->cap_rzcol && rzrow.size() <= h->cap_rzrow && rztile.size() <= h->cap_rztile;
-    if (h->resize_tab && !rzcol.empty()) {
-        SE2_CUDA(cudaMemcpyAsync(h->d_rzcol, rzcol.data(), sizeof(ResizeCol) * rzcol.size(), cudaMemcpyHostToDevice, s));
-        SE2_CUDA(cudaMemcpyAsync(h->d_rzrow, rzrow.data(), sizeof(ResizeRow) * rzrow.size(), cudaMemcpyHostToDevice, s));
-        SE2_CUDA(cudaMemcpyAsync(h->d_rztile, rztile.data(), sizeof(int2) * rztile.size(), cudaMemcpyHostToDevice, s));
-    }
     SE2_CUDA(cudaMemcpyAsync(h->d_levels, h->levels.data(), sizeof(LevelGeo) * h->levels.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d_cells, h->cells.data(), sizeof(CellGeo) * h->cells.size(), cudaMemcpyHostToDevice, s));
     SE2_CUDA(cudaMemcpyAsync(h->d_tiles, h->tiles.data(), sizeof(TileGeo) * h->tiles.size(), cudaMemcpyHostToDevice, s));
@@ -1632,12 +1506,7 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
         h->resize_raw_pitch = (((int)ceil(128 * ratio) + 4 + 15 + 15) / 16) * 16;
         h->resize_smem = (size_t)h->resize_rows * (128 * sizeof(int) + h->resize_raw_pitch);
         if (h->resize_smem > 200 * 1024) return fail(SE2GPU_ERR_CAPACITY, "scale factor %.3f needs %zu B of shared memory in orb_resize", ratio, h->resize_smem);
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize_tab<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize_tab<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize_tab<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
     }
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
@@ -1759,12 +1628,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
         dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
-        // SE2GPU_ORB_RESIZE_OCC = 5 / 6: ask the compiler for 5 / 6 resident CTAs per SM (register cap 48 / 40) instead of 4
-        static const int occ = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_OCC"); const int v = e ? atoi(e) : RESIZE_OCC_DEFAULT; return v == 5 || v == 6 ? v : 4; }();
-#define SE2_RESIZE(K, M) SE2_LAUNCH(K<M>, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch)
-        if (h->resize_tab) { if (occ == 5) SE2_RESIZE(orb_resize_tab, 5); else if (occ == 6) SE2_RESIZE(orb_resize_tab, 6); else SE2_RESIZE(orb_resize_tab, 4); }
-        else { if (occ == 5) SE2_RESIZE(orb_resize, 5); else if (occ == 6) SE2_RESIZE(orb_resize, 6); else SE2_RESIZE(orb_resize, 4); }
-#undef SE2_RESIZE
+        SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
         if (l == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     }
     if (h->nlevels == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
@@ -1858,15 +1722,11 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     // head-room so that smaller frames (different cell rounding) always fit
     h->cap_plane = pb + 4096; h->cap_cand = ct + ct / 8 + 4096; h->cap_cells = nc + 64; h->cap_tiles = nt + 64; h->cap_tab = tt + 64;
     h->cap_lkp = nfeatures + 64;
-    // orb_resize_tab tables: every level of a smaller frame is no larger than the same level of the largest frame
-    h->cap_rzcol = (size_t)nlevels * ((size_t)max_w + 2 * EDGE + 31 + 256); h->cap_rzrow = (size_t)nlevels * ((size_t)max_h + 2 * EDGE + 2 * RESIZE_TR);
-    h->cap_rztile = (size_t)nlevels * ((max_w + 2 * EDGE + 31) / 128 + (max_h + 2 * EDGE) / RESIZE_TR + 4);
     const size_t B = max_batch;
     bool ok = true;
     auto A = [&](auto** p, size_t c) { if (ok && se2gpu::dev_alloc(p, c) == cudaSuccess) h->bufs.push_back(*p); else ok = false; };
     OrbDev& d = h->d;
     A(&h->d_levels, (size_t)nlevels); A(&h->d_cells, h->cap_cells); A(&h->d_tiles, h->cap_tiles); A(&h->d_itab, h->cap_tab); A(&h->d_stab, 2 * h->cap_tab);
-    A(&h->d_rzcol, h->cap_rzcol); A(&h->d_rzrow, h->cap_rzrow); A(&h->d_rztile, h->cap_rztile);
     A(&d.plain, B * h->cap_plane); A(&d.blurred, B * h->cap_plane);
     A(&d.cand, B * h->cap_cand); A(&d.hdr, B * h->cap_cells); A(&d.lkp, B * h->cap_lkp); A(&d.lcount, B * nlevels); A(&d.err, 1);
     A(&h->d_in, B * (size_t)max_w * max_h); A(&h->d_kps, B * nfeatures); A(&h->d_desc, B * nfeatures * 32); A(&h->d_counts, B);
@@ -1885,7 +1745,6 @@ se2gpu_orb* se2gpu_orb_create(int nfeatures, float scale_factor, int nlevels, in
     cudaMemcpyToSymbol(c_gauss, gk, sizeof gk);
     d.nlevels = nlevels; d.nfeatures = nfeatures; d.fast_th = fast_th; d.t_lo = std::min(fast_th, 7);
     d.levels = h->d_levels; d.cells = h->d_cells; d.tiles = h->d_tiles; d.itab = h->d_itab; d.stab = h->d_stab;
-    d.rzcol = h->d_rzcol; d.rzrow = h->d_rzrow; d.rztile = h->d_rztile;
     if (cudaDeviceSynchronize() != cudaSuccess) { fail(SE2GPU_ERR_CUDA, "init failed"); se2gpu_orb_destroy(h); return nullptr; }
     return h;
 }

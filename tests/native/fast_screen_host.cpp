@@ -72,28 +72,44 @@ int main() {
             ++checks;
         }
     }
-    // ---- inside_mask8, exhaustively over the argument range the kernel produces
-    for (int cw = 1; cw <= 300; ++cw)
-        for (int h = 0; h < fastpx::pairs_per_row(cw); ++h) {
-            const int x0 = 8 * h - 3;
-            if (x0 > cw - 1) FAIL("pair %d of a %d px row starts outside the cell", h, cw);
-            unsigned want = 0;
-            for (int j = 0; j < 8; ++j) if (x0 + j >= 0 && x0 + j < cw) want |= 1u << j;
-            if (fastpx::inside_mask8(x0, cw) != want) FAIL("inside_mask8(%d, %d) = %x, want %x", x0, cw, fastpx::inside_mask8(x0, cw), want);
-            ++checks;
+    // ---- inside_mask8, exhaustively over the argument range the kernels produce (every alignment shift of the TMA box)
+    for (int shift = 0; shift < 16; ++shift)
+        for (int cw = 1; cw <= 300; ++cw) {
+            std::vector<int> seen(cw, 0);
+            for (int h = 0; h < fastpx::pairs_per_row(cw, shift); ++h) {
+                const int x0 = fastpx::pair_x0(h, shift);
+                if (x0 > cw - 1 || x0 < -7) FAIL("pair %d of a %d px row (shift %d) starts at %d", h, cw, shift, x0);
+                unsigned want = 0;
+                for (int j = 0; j < 8; ++j) if (x0 + j >= 0 && x0 + j < cw) { want |= 1u << j; seen[x0 + j]++; }
+                if (fastpx::inside_mask8(x0, cw) != want) FAIL("inside_mask8(%d, %d) = %x, want %x", x0, cw, fastpx::inside_mask8(x0, cw), want);
+                ++checks;
+            }
+            for (int x = 0; x < cw; ++x) if (seen[x] != 1) FAIL("pairs cover pixel %d of %d (shift %d) %d times", x, cw, shift, seen[x]);
+            std::fill(seen.begin(), seen.end(), 0);
+            for (int g = 0; g < fastpx::groups_per_row(cw, shift); ++g) {
+                const int x0 = fastpx::group_x0(g, shift);
+                if (x0 > cw - 1 || x0 < -3) FAIL("group %d of a %d px row (shift %d) starts at %d", g, cw, shift, x0);
+                const unsigned m = fastpx::inside_mask8(x0, cw) & 0xFu;
+                for (int j = 0; j < 4; ++j) { const bool in = x0 + j >= 0 && x0 + j < cw; if ((((m >> j) & 1u) != 0) != in) FAIL("group mask"); if (in) seen[x0 + j]++; }
+            }
+            for (int x = 0; x < cw; ++x) if (seen[x] != 1) FAIL("groups cover pixel %d of %d (shift %d) %d times", x, cw, shift, seen[x]);
         }
     // ---- 3: pass A of one CTA (256 threads = 8 warps), simulated thread by thread exactly as the kernel addresses the patch
     const int NT = 256, NW = 8;
-    const int sizes[][2] = {{122, 75}, {101, 62}, {103, 61}, {85, 50}, {93, 50}, {75, 41}, {61, 33}, {49, 26}, {1, 1}, {5, 3}, {6, 9}, {250, 249}, {7, 200}, {13, 1}, {249, 17}};
+    const int sizes[][2] = {{122, 75}, {101, 62}, {103, 61}, {85, 50}, {93, 50}, {75, 41}, {61, 33}, {49, 26}, {1, 1}, {5, 3}, {6, 9}, {230, 225}, {250, 249}, {7, 200}, {13, 1}, {229, 17}};
+    int cell_no = 0;
     for (const auto& sz : sizes) {
+      for (int rep = 0; rep < 4; ++rep) {
         const int cw = sz[0], ch = sz[1];
-        const int pw = (cw + 6 + 15) & ~15, pww = pw / 4, bh = ch + 6 + (int)(rng() % 3);
+        const int shift = (cell_no++ * 7 + rep * 5) % 16;                       // alignment shift of the TMA box start
+        const int pw = (shift + cw + 6 + 15) & ~15, pww = pw / 4, bh = ch + 6 + (int)(rng() % 3);
+        if ((size_t)pw * bh > 65535 || pw > 256 || bh > 256) continue;   // the library takes such cells to orb_fast_cells / _big (16-bit list entries, box <= 256 x 256)
         std::vector<uint8_t> smem((size_t)pw * bh + 4096, 0xAB);   // bytes behind the patch = the kernel's score plane (garbage to pass A)
         for (int y = 0; y < bh; ++y) for (int x = 0; x < pw; ++x) smem[(size_t)y * pw + x] = (uint8_t)((((x / 5) ^ (y / 4)) & 1) * 60 + 80 + (int)(rng() % 25));
         const uint8_t* patch = smem.data();
-        const uint8_t* p0 = patch + 3 * pw + 3;
+        const uint8_t* p0 = patch + 3 * pw + 3 + shift;
         const int t = 20;
-        const int G2 = fastpx::pairs_per_row(cw), nitems = ch * G2;
+        const int h0 = fastpx::first_pair(shift), G2 = fastpx::pairs_per_row(cw, shift), nitems = ch * G2;
         std::vector<int> visited((size_t)cw * ch, 0), cand((size_t)cw * ch, 0);
         std::vector<int> owner((size_t)8 * nitems, -1);
         std::vector<int> nseg(NW, 0);
@@ -107,8 +123,8 @@ int main() {
                 if (active != (it0 + lane < nitems)) FAIL("activity test differs from the item bound (cw %d ch %d tid %d)", cw, ch, tid);
                 if (active) {
                     if (it.y * G2 + it.h != it0 + lane) FAIL("ItemWalk left its item sequence (cw %d ch %d tid %d)", cw, ch, tid);
-                    const int x0 = 8 * it.h - 3;
-                    const long cp = (long)(it.y + 3) * pww + 2 * it.h;
+                    const int x0 = fastpx::pair_x0(it.h, shift);
+                    const long cp = (long)(it.y + 3) * pww + 2 * (it.h + h0);
                     if (cp & 1) FAIL("odd word index for a 64-bit load");
                     const uint32_t n3x = ldw(patch, cp - 3 * pww), n3y = ldw(patch, cp - 3 * pww + 1), s3x = ldw(patch, cp + 3 * pww), s3y = ldw(patch, cp + 3 * pww + 1);
                     const uint32_t n2x = ldw(patch, cp - 2 * pww), n2y = ldw(patch, cp - 2 * pww + 1), s2x = ldw(patch, cp + 2 * pww), s2y = ldw(patch, cp + 2 * pww + 1);
@@ -146,6 +162,7 @@ int main() {
                 if ((cand[(size_t)y * cw + x] != 0) != want) FAIL("candidate set differs at (%d,%d) of a %dx%d cell", x, y, cw, ch);
                 ++checks;
             }
+      }
     }
     printf("OK %ld\n", checks);
     return 0;

@@ -6,7 +6,7 @@ import sys
 recs = [json.loads(l) for l in open(sys.argv[1]) if l.strip()]
 ok = [r for r in recs if r.get("bit_identical_to_round1") and "per_kernel_ms" in r]
 base = ok[0] if ok and ok[0]["config"] == "round-1 kernels" else None
-env = {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}
+env = {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0"}
 if base:
     def single(r, keys):   # configurations that differ from the baseline only in `keys`
         return all(r["env"][k] == base["env"][k] for k in env if k not in keys)
@@ -18,10 +18,5 @@ if base:
     for r in ok:
         if single(r, ("SE2GPU_ORB_ORIENT_BATCH",)) and r["per_kernel_ms"]["orb_orient_describe"] < best * 0.995:
             best = r["per_kernel_ms"]["orb_orient_describe"]; env["SE2GPU_ORB_ORIENT_BATCH"] = r["env"]["SE2GPU_ORB_ORIENT_BATCH"]
-    best = base["per_kernel_ms"]["pyramid"]
-    for r in ok:
-        if single(r, ("SE2GPU_ORB_RESIZE_TAB", "SE2GPU_ORB_RESIZE_OCC")) and r["per_kernel_ms"]["pyramid"] < best * 0.995:
-            best = r["per_kernel_ms"]["pyramid"]
-            env["SE2GPU_ORB_RESIZE_TAB"] = r["env"]["SE2GPU_ORB_RESIZE_TAB"]; env["SE2GPU_ORB_RESIZE_OCC"] = r["env"]["SE2GPU_ORB_RESIZE_OCC"]
 for k, v in env.items():
     print(f"export {k}={v}")

@@ -59,16 +59,11 @@ print(json.dumps({"ms_per_step": round(ms, 4), "mkps": round(total / NROT / ms /
 '''
 
 CONFIGS = [
-    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("fast tma (4 px)", {"SE2GPU_ORB_FAST_TMA": "1", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("fast tma8", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("orient batch", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
-    ("resize occ 5", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "0", "SE2GPU_ORB_RESIZE_OCC": "5", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("resize tab", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("resize tab occ 5", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "5", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("resize tab occ 6", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "6", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("all new (tma8, tab, occ 5, batch)", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "5", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
-    ("all new, occ 4", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_RESIZE_TAB": "1", "SE2GPU_ORB_RESIZE_OCC": "4", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
+    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("orient batch", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
+    ("fast tma (4 px)", {"SE2GPU_ORB_FAST_TMA": "1", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("fast tma8", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
+    ("fast tma8 + orient batch", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
 ]
 
 
