@@ -1429,7 +1429,8 @@ EncodeTiledFn tensor_map_encoder() {
 }
 
 constexpr bool ORIENT_BATCH_DEFAULT = true;    // measured: 0.0928 -> 0.0897 ms per 64 frames, bit-identical (profiles/r02b_orb_variants.jsonl)
-constexpr int FAST_TMA_DEFAULT = 0;   // flipped to 2 once the GPU parity run of the TMA kernels is on record (profiles/)
+constexpr int FAST_TMA_DEFAULT = 2;   // measured: orb_fast_cells 0.2976 -> 0.2543 ms per 64 frames, bit-identical (profiles/r02c_orb_variants.jsonl)
+constexpr int SUBMIT_CHUNKS_DEFAULT = 4;
 int fast_tma_variant() {   // SE2GPU_ORB_FAST_TMA = 0: LDG/STS staging (orb_fast_cells), 1: orb_fast_cells_tma, 2: orb_fast_cells_tma8
     static const int v = [] { const char* e = getenv("SE2GPU_ORB_FAST_TMA"); const int x = e ? atoi(e) : FAST_TMA_DEFAULT; return x < 0 || x > 2 ? FAST_TMA_DEFAULT : x; }();
     return v;
@@ -1782,7 +1783,7 @@ int se2gpu_orb_extract_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w
 
 // enqueue one host-buffer batch on this context (copies in, kernels, copies out); nothing is waited for
 static int orb_enqueue(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt, int stride, size_t frame_stride,
-                       se2gpu_keypoint* kps, uint8_t* desc, int* counts) {
+                       se2gpu_keypoint* kps, uint8_t* desc, int* counts, bool submit_mode = false) {
     SE2_NVTX("se2gpu.orb.enqueue");
     if (!h) return fail(SE2GPU_ERR_INVALID, "null handle");
     if (h->pend.on) return fail(SE2GPU_ERR_INVALID, "a submitted batch is still pending on this context: call se2gpu_orb_wait first");
@@ -1803,10 +1804,13 @@ static int orb_enqueue(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
     int lanes = 0;
     while (lanes < ORB_LANES && h->pipe[lanes]) ++lanes;
     if (env_lanes > 0) lanes = std::min(lanes, env_lanes);
-    const int nchunks = env_chunks > 0 ? env_chunks : 4;
-    const bool pipelined = lanes >= 2 && !h->prof.on && n > 1 && nchunks > 1;
+    // se2gpu_orb_submit keeps two batches in flight on twin contexts, so the copies of one batch already overlap the kernels of
+    // the other: there the batch can go down in fewer, larger chunks (SE2GPU_ORB_SUBMIT_CHUNKS; 1 = the whole batch on one stream)
+    static const int env_submit_chunks = [] { const char* e = getenv("SE2GPU_ORB_SUBMIT_CHUNKS"); return e ? atoi(e) : 0; }();
+    const int nchunks = submit_mode ? (env_submit_chunks > 0 ? env_submit_chunks : SUBMIT_CHUNKS_DEFAULT) : (env_chunks > 0 ? env_chunks : 4);
+    const bool pipelined = lanes >= 2 && !h->prof.on && n > 1 && (nchunks > 1 || submit_mode);
     const int chunk = pipelined ? std::max(1, (n + nchunks - 1) / nchunks) : n;
-    const int first = pipelined ? std::max(1, std::min(n, chunk * (env_first > 0 ? env_first : 50) / 100)) : n;
+    const int first = (pipelined && nchunks > 1) ? std::max(1, std::min(n, chunk * (env_first > 0 ? env_first : 50) / 100)) : n;
     auto is_pinned = [](const void* p) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1833,7 +1837,8 @@ static int orb_enqueue(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt
         else
             for (int i = f0; i < f0 + m; ++i)
                 SE2_CUDA(cudaMemcpy2DAsync(h->d_in + (size_t)i * w * hgt, w, imgs + i * frame_stride, stride, w, hgt, cudaMemcpyHostToDevice, s));
-        rc = run_device(h, h->d_in, m, w, hgt, w, (size_t)w * hgt, h->d_kps, h->d_desc, h->d_counts, s, f0, pipelined ? lane : -1);
+        // a single chunk keeps the blur on the context's side stream (like the device-resident entry); several chunks overlap each other
+        rc = run_device(h, h->d_in, m, w, hgt, w, (size_t)w * hgt, h->d_kps, h->d_desc, h->d_counts, s, f0, (pipelined && nchunks > 1) ? lane : -1);
         if (rc != SE2GPU_OK) return rc;
         SE2_CUDA(cudaMemcpyAsync(out_counts + f0, h->d_counts + f0, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
         SE2_CUDA(cudaMemcpyAsync(out_kps + (size_t)f0 * h->nfeatures, h->d_kps + (size_t)f0 * h->nfeatures, sizeof(se2gpu_keypoint) * (size_t)m * h->nfeatures, cudaMemcpyDeviceToHost, s));
@@ -1889,7 +1894,7 @@ int se2gpu_orb_submit(se2gpu_orb* h, const uint8_t* imgs, int n, int w, int hgt,
         if (h->und_on && se2gpu_orb_set_undistort(h->twin, h->und_K, h->und_nd ? h->und_D : nullptr, h->und_nd) != SE2GPU_OK) return SE2GPU_ERR_CUDA;
     }
     se2gpu_orb* ctx = (h->submit_next & 1) ? h->twin : h;
-    int rc = orb_enqueue(ctx, imgs, n, w, hgt, stride, frame_stride, kps, desc, counts);
+    int rc = orb_enqueue(ctx, imgs, n, w, hgt, stride, frame_stride, kps, desc, counts, true);
     if (rc != SE2GPU_OK) return rc;
     if (!ctx->pend.on) {          // empty image / n == 0: finished synchronously (outputs as se2gpu_orb_extract leaves them)
         return SE2GPU_OK;
