@@ -302,6 +302,163 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
     }
 }
 
+// orb_resize with a shared-memory diet (the resize is bound by shared-memory wavefronts: 0.62 per cycle and SM at level 1, 38 % of
+// them bank-conflict replays of the byte gathers, profiles/r02c_ncu_orb.md): the horizontal pass reads a 12-byte window per row and
+// thread (3 word loads instead of 8 byte loads; PRMT picks the byte pair, IDP.2A does src[sx]*a0 + src[sx+1]*a1) and its results are
+// kept as 16-bit values (<= 32 640), which halves the wavefronts of the store and of the two loads per output row of the vertical pass.
+// The arithmetic is that of orb_resize term by term; the planes are bit-identical. Values that do not fit the window form (scale
+// factors above ~2.6, negative coefficients) take the byte path inside the same kernel.
+__global__ void __launch_bounds__(256) orb_resize_w(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
+    extern __shared__ __align__(16) uint8_t rs_smem[];
+    __shared__ ResizeRow rowinfo[RESIZE_TR];
+    __shared__ __align__(16) ResizeCol colinfo[128];
+    __shared__ int s_lo[2], s_hi[2];     // [1] source rows
+    __shared__ int s_cmin[4], s_cmax[4]; // source column range per column warp
+    uint16_t* hbuf = reinterpret_cast<uint16_t*>(rs_smem);                  // [max_rows][128], 16 bit: (255 * 2048) >> 4 = 32 640
+    uint8_t* raw = rs_smem + (size_t)max_rows * 128 * sizeof(uint16_t);     // [max_rows][raw_pitch] (+16 B of slack behind the last row)
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x4 = blockIdx.x * 128 + tx * 4, y0 = blockIdx.y * RESIZE_TR;
+    const int f = blockIdx.z + d.frame0;
+    const int W = L.w + 2 * EDGE, H = L.h + 2 * EDGE;
+    const int* xofs = d.itab + L.tab_off;
+    const int* yofs = xofs + L.w;
+    const short2* ialpha = reinterpret_cast<const short2*>(d.stab + 2 * (size_t)L.tab_off);
+    const short2* ibeta = ialpha + L.w;
+    // column terms of the tile's 128 output columns: warps 0..3, one column per thread (the 8 thread rows share them through
+    // shared memory instead of each recomputing its 4 columns); row terms: warp 4
+    if (tid < 128) {
+        const int x = blockIdx.x * 128 + tid;
+        ResizeCol c{0, 0, 0, 0, 0};
+        int cmin = 0x7fffffff, cmax = -1;
+        if (x < W) {
+            const int dx = reflect101(x - EDGE, L.w);
+            c.sx0 = __ldg(xofs + dx);
+            c.sx1 = min(c.sx0 + 1, S.w - 1);
+            const short2 aa = __ldg(ialpha + dx);
+            c.a0 = aa.x; c.a1 = aa.y; c.valid = 1;
+            cmin = c.sx0; cmax = c.sx1;
+        }
+        colinfo[tid] = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o)); }
+        if (tx == 0) { s_cmin[ty] = cmin; s_cmax[ty] = cmax; }
+    } else if (ty == 4) {   // row terms of the tile's RESIZE_TR output rows and their source row range
+        const int y = y0 + tx;
+        int rmin = 0x7fffffff, rmax = -1;
+        if (y < H) {
+            const int dy = reflect101(y - EDGE, L.h);
+            const int sy = __ldg(yofs + dy);
+            const short2 bb = __ldg(ibeta + dy);
+            ResizeRow r{min(max(sy, 0), S.h - 1), min(max(sy + 1, 0), S.h - 1), bb.x, bb.y};
+            rowinfo[tx] = r;
+            rmin = r.s0; rmax = r.s1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o)); rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o)); }
+        if (tx == 0) { s_lo[1] = rmin; s_hi[1] = rmax; }
+    }
+    __syncthreads();
+    const int c_min = min(min(s_cmin[0], s_cmin[1]), min(s_cmin[2], s_cmin[3])), c_max = max(max(s_cmax[0], s_cmax[1]), max(s_cmax[2], s_cmax[3]));
+    const int c_lo = c_min & ~15, nvec = c_max < 0 ? 0 : (c_max - c_lo) / 16 + 1;
+    const int r_lo = s_lo[1], nsr = s_hi[1] - r_lo + 1;
+    if (nsr > max_rows || nvec * 16 > raw_pitch) { if (tid == 0) *d.err = 3; return; }   // sized on the host from the scale factor
+    const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
+    // stage 0: 16 vectors per source row and pass (a 128-column tile at scale <= 1.9 spans <= 16 vectors), no division
+    if (nvec <= 16) {
+        const int v = tid & 15;
+        if (v < nvec)
+            for (int r = tid >> 4; r < nsr; r += 16)
+                *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+    } else {
+        for (int i = tid; i < nsr * nvec; i += 256) {
+            const int r = i / nvec, v = i - r * nvec;
+            *reinterpret_cast<uint4*>(raw + r * raw_pitch + 16 * v) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(r_lo + r) * S.pitch + c_lo) + v);
+        }
+    }
+    // this thread's 4 columns
+    int sx0[4], sx1[4], a0[4], a1[4];
+    unsigned vmask = 0;                       // byte mask of the valid columns
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const ResizeCol c = colinfo[4 * tx + q];
+        sx0[q] = c.valid ? c.sx0 - c_lo : 0; sx1[q] = c.valid ? c.sx1 - c_lo : 0;
+        a0[q] = c.a0; a1[q] = c.a1;
+        vmask |= c.valid ? (0xFFu << (8 * q)) : 0u;
+    }
+    __syncthreads();
+    // the 4 columns' source bytes sx0, sx0+1 lie in one 12-byte window of the staged row (3 aligned words from word w0 on) as long
+    // as the scale factor is below ~2.6; byte pairs come out of the window with one PRMT (selector fixed per column), and
+    // src[sx0]*a0 + src[sx0+1]*a1 is one IDP.2A. Where cv::resize clamps sx1 to sx0 (right edge) a1 is 0, so the byte behind sx0
+    // may be anything. Three 32-bit loads per row instead of eight byte loads: the kernel is bound by shared-memory wavefronts.
+    unsigned wq[4], selq[4];
+    bool pairq[4];
+    int w0 = 0;
+    bool window_ok = true;
+    {
+        int mn = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if ((vmask >> (8 * q)) & 1u) mn = min(mn, sx0[q]);
+        if (mn == 0x7fffffff) mn = 0;
+        w0 = mn >> 2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool valid = (vmask >> (8 * q)) & 1u;
+            const int o = valid ? sx0[q] - 4 * w0 : 0;
+            if (valid && (o + 1 > 11 || (sx1[q] != sx0[q] + 1 && a1[q] != 0))) window_ok = false;
+            pairq[q] = o >= 7;
+            const int o2 = o - (pairq[q] ? 4 : 0);
+            selq[q] = (unsigned)o2 | ((unsigned)(o2 + 1) << 4);
+            wq[q] = ((unsigned)a0[q] & 0xFFFFu) | ((unsigned)a1[q] << 16);
+            if (a0[q] < 0 || a1[q] < 0) window_ok = false;     // cv's coefficients are in [0, 2048]; anything else takes the byte path
+        }
+    }
+    // stage 1: horizontal pass, stored pre-shifted (the vertical pass uses S >> 4 only)
+    if (x4 < W) {
+        if (window_ok) {
+            for (int r = ty; r < nsr; r += 8) {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + r * raw_pitch) + w0;
+                const uint32_t W0 = rw[0], W1 = rw[1], W2 = rw[2];
+                unsigned hq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned bytes = __byte_perm(pairq[q] ? W1 : W0, pairq[q] ? W2 : W1, selq[q]);
+                    hq[q] = __dp2a_lo(wq[q], bytes, 0u) >> 4;
+                }
+                *reinterpret_cast<uint2*>(hbuf + r * 128 + 4 * tx) = make_uint2(hq[0] | (hq[1] << 16), hq[2] | (hq[3] << 16));
+            }
+        } else {
+            for (int r = ty; r < nsr; r += 8) {
+                const uint8_t* rp = raw + r * raw_pitch;
+                const unsigned h0 = (unsigned)((rp[sx0[0]] * a0[0] + rp[sx1[0]] * a1[0]) >> 4), h1 = (unsigned)((rp[sx0[1]] * a0[1] + rp[sx1[1]] * a1[1]) >> 4);
+                const unsigned h2 = (unsigned)((rp[sx0[2]] * a0[2] + rp[sx1[2]] * a1[2]) >> 4), h3 = (unsigned)((rp[sx0[3]] * a0[3] + rp[sx1[3]] * a1[3]) >> 4);
+                *reinterpret_cast<uint2*>(hbuf + r * 128 + 4 * tx) = make_uint2((h0 & 0xFFFFu) | (h1 << 16), (h2 & 0xFFFFu) | (h3 << 16));
+            }
+        }
+    }
+    __syncthreads();
+    // stage 2: vertical pass. With coefficients in [0, 2048] (pairs summing to 2048 +- 1) and 8-bit pixels the result is in
+    // [0, 255] by construction ((2049 * (255 * 2049 >> 4) >> 16) + 2 >> 2 = 255): cv's saturate_cast never fires, no clamp here.
+    if (x4 >= L.pitch) return;
+    uint8_t* plane = d.plain + f * d.frame_plane_bytes + L.plane_off;
+#pragma unroll
+    for (int k = 0; k < RESIZE_TR / 8; ++k) {
+        const int r = ty + 8 * k, y = y0 + r;
+        if (y >= H) break;
+        uint32_t word = 0;
+        if (x4 < W) {
+            const ResizeRow ri = rowinfo[r];
+            const uint2 A = *reinterpret_cast<const uint2*>(hbuf + (ri.s0 - r_lo) * 128 + 4 * tx);
+            const uint2 B = *reinterpret_cast<const uint2*>(hbuf + (ri.s1 - r_lo) * 128 + 4 * tx);
+            const unsigned v0 = (unsigned)((((ri.b0 * (int)(A.x & 0xFFFFu)) >> 16) + ((ri.b1 * (int)(B.x & 0xFFFFu)) >> 16) + 2) >> 2);
+            const unsigned v1 = (unsigned)((((ri.b0 * (int)(A.x >> 16)) >> 16) + ((ri.b1 * (int)(B.x >> 16)) >> 16) + 2) >> 2);
+            const unsigned v2 = (unsigned)((((ri.b0 * (int)(A.y & 0xFFFFu)) >> 16) + ((ri.b1 * (int)(B.y & 0xFFFFu)) >> 16) + 2) >> 2);
+            const unsigned v3 = (unsigned)((((ri.b0 * (int)(A.y >> 16)) >> 16) + ((ri.b1 * (int)(B.y >> 16)) >> 16) + 2) >> 2);
+            word = (v0 | (v1 << 8) | (v2 << 16) | (v3 << 24)) & vmask;
+        }
+        *reinterpret_cast<uint32_t*>(plane + (size_t)y * L.pitch + x4) = word;
+    }
+}
+
 // FAST-9-16 on packed ring differences. For centre v and ring pixel p the s16x2 word
 //   q = (256 + v - p) | (256 + p - v) << 16  =  p * 0xFFFF + ((256 + v) | (256 - v) << 16)      (one IMAD; both halves in [1,511])
 // carries the "darker" and the "brighter" test side by side, so Blackwell's packed 3-input min/max (VIMNMX3.S16x2)
@@ -1271,7 +1428,7 @@ struct se2gpu_orb {
     std::vector<LevelGeo> levels;
     std::vector<CellGeo> cells;
     std::vector<TileGeo> tiles;
-    size_t fast_smem = 0, select_smem = 0, resize_smem = 0;
+    size_t fast_smem = 0, select_smem = 0, resize_smem = 0, resize_w_smem = 0;
     int resize_rows = 0, resize_raw_pitch = 0;   // shared-memory box of orb_resize, sized from the scale factor
     bool fast_big = false;       // cells too large for the compacting FAST kernel: use orb_fast_cells_big
     int fast_tma = 0;            // cells staged by the TMA unit: 0 off, 1 orb_fast_cells_tma, 2 orb_fast_cells_tma8 (SE2GPU_ORB_FAST_TMA)
@@ -1430,6 +1587,9 @@ EncodeTiledFn tensor_map_encoder() {
 
 constexpr bool ORIENT_BATCH_DEFAULT = true;    // measured: 0.0928 -> 0.0897 ms per 64 frames, bit-identical (profiles/r02b_orb_variants.jsonl)
 constexpr int FAST_TMA_DEFAULT = 2;   // measured: orb_fast_cells 0.2976 -> 0.2543 ms per 64 frames, bit-identical (profiles/r02c_orb_variants.jsonl)
+constexpr bool RESIZE_W_DEFAULT = false;
+constexpr int BLUR_SPLIT_DEFAULT = 2;             // levels 0-1 behind the pyramid tail (round 1)
+constexpr bool BLUR_B_AFTER_FAST_DEFAULT = false;
 constexpr int SUBMIT_CHUNKS_DEFAULT = 1;   // measured: 0.637 ms per 64-frame batch against 1.005 (4 chunks) / 0.857 (2) (profiles/r02d_orb_e2e_submit.jsonl)
 int fast_tma_variant() {   // SE2GPU_ORB_FAST_TMA = 0: LDG/STS staging (orb_fast_cells), 1: orb_fast_cells_tma, 2: orb_fast_cells_tma8
     static const int v = [] { const char* e = getenv("SE2GPU_ORB_FAST_TMA"); const int x = e ? atoi(e) : FAST_TMA_DEFAULT; return x < 0 || x > 2 ? FAST_TMA_DEFAULT : x; }();
@@ -1508,6 +1668,8 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
         h->resize_smem = (size_t)h->resize_rows * (128 * sizeof(int) + h->resize_raw_pitch);
         if (h->resize_smem > 200 * 1024) return fail(SE2GPU_ERR_CAPACITY, "scale factor %.3f needs %zu B of shared memory in orb_resize", ratio, h->resize_smem);
         SE2_CUDA(cudaFuncSetAttribute(orb_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
+        h->resize_w_smem = (size_t)h->resize_rows * (128 * sizeof(uint16_t) + h->resize_raw_pitch) + 16;   // 16-bit row-pass results, 16 B of slack behind the last staged row
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_w_smem));
     }
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
@@ -1626,13 +1788,21 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
             SE2_LAUNCH(orb_pyr0, grid, dim3(64, 4), 0, s, d, g, d_imgs, stride, frame_stride, nvec);
         }
     }
+    // blur schedule on the side stream: group A = levels [0, splitA) starts as soon as level splitA-1 exists; group B = the rest starts
+    // when the pyramid is complete (round-1 form) or, with SE2GPU_ORB_BLUR_B_AFTER_FAST=1, when FAST has been launched, i.e. it runs
+    // next to the selection kernel, whose level-0 CTAs leave most SMs idle, instead of competing with the issue-bound FAST kernel
+    static const int env_split = [] { const char* e = getenv("SE2GPU_ORB_BLUR_SPLIT"); return e ? atoi(e) : BLUR_SPLIT_DEFAULT; }();
+    static const bool b_after_fast = [] { const char* e = getenv("SE2GPU_ORB_BLUR_B_AFTER_FAST"); return e ? atoi(e) != 0 : BLUR_B_AFTER_FAST_DEFAULT; }();
+    const int splitA = std::min(std::max(env_split, 1), h->nlevels);
     for (int l = 1; l < h->nlevels; ++l) {
         const LevelGeo& g = h->levels[l];
         dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
-        SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
-        if (l == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
+        static const bool resize_w = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_W"); return e ? atoi(e) != 0 : RESIZE_W_DEFAULT; }();
+        if (resize_w) SE2_LAUNCH(orb_resize_w, grid, dim3(32, 8), h->resize_w_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
+        else SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
+        if (l == splitA - 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     }
-    if (h->nlevels == 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
+    if (splitA - 1 <= 0 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));   // level 0 alone is group A (or there is only one level)
     pr.end(s);
     nvtxRangePop();
     // The blur of a level only needs that level's plane: on the side stream the blur of levels 0-1 (55 % of the pixels,
@@ -1644,14 +1814,16 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     auto launch_blur = [&](cudaStream_t st, int t0, int t1) {
         if (t1 > t0) SE2_LAUNCH(orb_blur, dim3((t1 - t0 + 7) / 8, n), 256, 0, st, d, t0, t1);
     };
+    const int tilesA = splitA < h->nlevels ? h->levels[splitA].tile_base : d.n_tiles;
     if (overlap) {
-        const int tilesA = h->nlevels > 2 ? h->levels[2].tile_base : d.n_tiles;
         SE2_CUDA(cudaStreamWaitEvent(side, h->ev_l1, 0));
         launch_blur(side, 0, tilesA);
-        SE2_CUDA(cudaEventRecord(ev_pyr, s));
-        SE2_CUDA(cudaStreamWaitEvent(side, ev_pyr, 0));
-        launch_blur(side, tilesA, d.n_tiles);
-        SE2_CUDA(cudaEventRecord(ev_blur, side));
+        if (!b_after_fast) {
+            SE2_CUDA(cudaEventRecord(ev_pyr, s));
+            SE2_CUDA(cudaStreamWaitEvent(side, ev_pyr, 0));
+            launch_blur(side, tilesA, d.n_tiles);
+            SE2_CUDA(cudaEventRecord(ev_blur, side));
+        }
     }
     SE2_NVTX("se2gpu.orb.fast_select_blur_describe");
     pr.begin(1, s);
@@ -1660,6 +1832,12 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     else if (h->fast_tma == 1) SE2_LAUNCH(orb_fast_cells_tma, dim3(d.n_cells, n), FAST_THREADS, h->fast_tma_smem, s, d, h->fast_maps);
     else SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     pr.end(s);
+    if (overlap && b_after_fast) {      // group B behind FAST in stream order, concurrent with the selection
+        SE2_CUDA(cudaEventRecord(ev_pyr, s));
+        SE2_CUDA(cudaStreamWaitEvent(side, ev_pyr, 0));
+        launch_blur(side, tilesA, d.n_tiles);
+        SE2_CUDA(cudaEventRecord(ev_blur, side));
+    }
     pr.begin(2, s);
     SE2_LAUNCH(orb_select, dim3(h->nlevels, n), SEL_THREADS, h->select_smem, s, d);
     pr.end(s);

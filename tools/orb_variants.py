@@ -1,8 +1,8 @@
 """A/B of the ORB kernel variants the library selects through environment variables (read once per process, so every
 configuration runs in a child process). For each configuration: the device-resident 64-frame benchmark step (CUDA events, 8 rotating
 input batches = 157 MB > L2, like bench.py), the per-kernel times of an event-instrumented pass, and a SHA-256 over the keypoints,
-descriptors and counts of all 8 batches — every variant must reproduce the checksum of the round-1 kernels bit for bit (the first
-configuration), which tests/test_orb_gpu.py pins against the CPU oracle.
+descriptors and counts of all 8 batches — every variant must reproduce the checksum of the round-1 kernels bit for bit (ROUND1_SHA,
+recorded with SE2GPU_ORB_FAST_TMA=0 SE2GPU_ORB_ORIENT_BATCH=0), which tests/test_orb_gpu.py pins against the CPU oracle.
 
     python tools/orb_variants.py [--steps 20] [--out gpurun_out/orb_variants.jsonl]
 """
@@ -58,12 +58,20 @@ print(json.dumps({"ms_per_step": round(ms, 4), "mkps": round(total / NROT / ms /
                   "per_kernel_ms": {g: round(v[0] / max(v[1], 1), 4) for g, v in prof.items()}}))
 '''
 
+# SHA-256 (first 16 hex digits) of the round-1 kernels' output on this workload (profiles/r02c_orb_variants.jsonl)
+ROUND1_SHA = "49cd1e2540cf0775"
+
 CONFIGS = [
-    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("orient batch", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
-    ("fast tma (4 px)", {"SE2GPU_ORB_FAST_TMA": "1", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("fast tma8", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_ORIENT_BATCH": "0"}),
-    ("fast tma8 + orient batch", {"SE2GPU_ORB_FAST_TMA": "2", "SE2GPU_ORB_ORIENT_BATCH": "1"}),
+    ("defaults (tma8, orient batch, blur B with FAST)", {"SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("blur B after FAST", {"SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
+    ("blur A = levels 0-2, B after FAST", {"SE2GPU_ORB_BLUR_SPLIT": "3", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
+    ("blur A = levels 0-3, B after FAST", {"SE2GPU_ORB_BLUR_SPLIT": "4", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
+    ("blur A = levels 0-2, B with FAST", {"SE2GPU_ORB_BLUR_SPLIT": "3", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("all blur behind the pyramid tail (A = all levels)", {"SE2GPU_ORB_BLUR_SPLIT": "8", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("resize: window loads + IDP.2A + 16-bit rows", {"SE2GPU_ORB_RESIZE_W": "1", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("resize_w + blur B after FAST", {"SE2GPU_ORB_RESIZE_W": "1", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
+    ("resize_w + blur A = levels 0-2, B after FAST", {"SE2GPU_ORB_RESIZE_W": "1", "SE2GPU_ORB_BLUR_SPLIT": "3", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
+    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
 ]
 
 
@@ -74,7 +82,6 @@ def main():
     ap.add_argument("--timeout", type=int, default=120, help="seconds per configuration (a hung kernel must not eat the GPU call)")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    ref = None
     with open(args.out, "w") as out:
         for name, env in CONFIGS:
             rec = {"config": name, "env": env}
@@ -84,9 +91,7 @@ def main():
                 line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
                 if r.returncode == 0 and line.startswith("{"):
                     rec.update(json.loads(line))
-                    if ref is None:
-                        ref = rec["sha256"]
-                    rec["bit_identical_to_round1"] = rec["sha256"] == ref
+                    rec["bit_identical_to_round1"] = rec["sha256"] == ROUND1_SHA
                 else:
                     rec["error"] = (r.stderr or r.stdout)[-600:]
             except subprocess.TimeoutExpired:
