@@ -308,7 +308,14 @@ __global__ void __launch_bounds__(256) orb_resize(OrbDev d, LevelGeo L, LevelGeo
 // kept as 16-bit values (<= 32 640), which halves the wavefronts of the store and of the two loads per output row of the vertical pass.
 // The arithmetic is that of orb_resize term by term; the planes are bit-identical. Values that do not fit the window form (scale
 // factors above ~2.6, negative coefficients) take the byte path inside the same kernel.
+// PDL: launched with programmatic stream serialisation (cudaLaunchAttributeProgrammaticStreamSerialization). Every CTA releases its
+// dependents at once (griddepcontrol.launch_dependents), so the CTAs of the NEXT level's launch are scheduled into the SM slots
+// the last wave of this launch frees and run their table set-up there; they read this level's plane only behind
+// griddepcontrol.wait, which returns when this whole grid has completed and its writes are visible. The pyramid is a chain of seven
+// dependent, short launches: this overlaps each launch's ramp-up with its predecessor's tail.
+template <bool PDL>
 __global__ void __launch_bounds__(256) orb_resize_w(OrbDev d, LevelGeo L, LevelGeo S, int max_rows, int raw_pitch) {
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(16) uint8_t rs_smem[];
     __shared__ ResizeRow rowinfo[RESIZE_TR];
     __shared__ __align__(16) ResizeCol colinfo[128];
@@ -363,6 +370,7 @@ __global__ void __launch_bounds__(256) orb_resize_w(OrbDev d, LevelGeo L, LevelG
     const int r_lo = s_lo[1], nsr = s_hi[1] - r_lo + 1;
     if (nsr > max_rows || nvec * 16 > raw_pitch) { if (tid == 0) *d.err = 3; return; }   // sized on the host from the scale factor
     const uint8_t* src = d.plain + f * d.frame_plane_bytes + S.plane_off + (size_t)EDGE * S.pitch + EDGE;
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // the source level is complete and visible from here on
     // stage 0: 16 vectors per source row and pass (a 128-column tile at scale <= 1.9 spans <= 16 vectors), no division
     if (nvec <= 16) {
         const int v = tid & 15;
@@ -1587,7 +1595,8 @@ EncodeTiledFn tensor_map_encoder() {
 
 constexpr bool ORIENT_BATCH_DEFAULT = true;    // measured: 0.0928 -> 0.0897 ms per 64 frames, bit-identical (profiles/r02b_orb_variants.jsonl)
 constexpr int FAST_TMA_DEFAULT = 2;   // measured: orb_fast_cells 0.2976 -> 0.2543 ms per 64 frames, bit-identical (profiles/r02c_orb_variants.jsonl)
-constexpr bool RESIZE_W_DEFAULT = false;
+constexpr bool RESIZE_W_DEFAULT = true;     // measured: pyramid 0.1622 -> 0.155 ms per 64 frames, bit-identical (profiles/r02e_orb_variants.jsonl)
+constexpr bool PDL_DEFAULT = false;
 constexpr int BLUR_SPLIT_DEFAULT = 2;             // levels 0-1 behind the pyramid tail (round 1)
 constexpr bool BLUR_B_AFTER_FAST_DEFAULT = false;
 constexpr int SUBMIT_CHUNKS_DEFAULT = 1;   // measured: 0.637 ms per 64-frame batch against 1.005 (4 chunks) / 0.857 (2) (profiles/r02d_orb_e2e_submit.jsonl)
@@ -1669,7 +1678,8 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
         if (h->resize_smem > 200 * 1024) return fail(SE2GPU_ERR_CAPACITY, "scale factor %.3f needs %zu B of shared memory in orb_resize", ratio, h->resize_smem);
         SE2_CUDA(cudaFuncSetAttribute(orb_resize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_smem));
         h->resize_w_smem = (size_t)h->resize_rows * (128 * sizeof(uint16_t) + h->resize_raw_pitch) + 16;   // 16-bit row-pass results, 16 B of slack behind the last staged row
-        SE2_CUDA(cudaFuncSetAttribute(orb_resize_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_w_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize_w<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_w_smem));
+        SE2_CUDA(cudaFuncSetAttribute(orb_resize_w<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->resize_w_smem));
     }
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
     SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm, 1024)));
@@ -1798,7 +1808,17 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         const LevelGeo& g = h->levels[l];
         dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
         static const bool resize_w = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_W"); return e ? atoi(e) != 0 : RESIZE_W_DEFAULT; }();
-        if (resize_w) SE2_LAUNCH(orb_resize_w, grid, dim3(32, 8), h->resize_w_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
+        static const bool pdl = [] { const char* e = getenv("SE2GPU_ORB_PDL"); return e ? atoi(e) != 0 : PDL_DEFAULT; }();
+        if (resize_w && pdl) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(32, 8); cfg.dynamicSmemBytes = h->resize_w_smem; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            SE2_CUDA(cudaLaunchKernelEx(&cfg, orb_resize_w<true>, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch));
+            ::se2gpu::g_launches.fetch_add(1, std::memory_order_relaxed);
+        } else if (resize_w) SE2_LAUNCH(orb_resize_w<false>, grid, dim3(32, 8), h->resize_w_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
         else SE2_LAUNCH(orb_resize, grid, dim3(32, 8), h->resize_smem, s, d, g, h->levels[l - 1], h->resize_rows, h->resize_raw_pitch);
         if (l == splitA - 1 && side && !pr.on) SE2_CUDA(cudaEventRecord(h->ev_l1, s));
     }

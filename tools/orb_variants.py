@@ -62,16 +62,9 @@ print(json.dumps({"ms_per_step": round(ms, 4), "mkps": round(total / NROT / ms /
 ROUND1_SHA = "49cd1e2540cf0775"
 
 CONFIGS = [
-    ("defaults (tma8, orient batch, blur B with FAST)", {"SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
-    ("blur B after FAST", {"SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
-    ("blur A = levels 0-2, B after FAST", {"SE2GPU_ORB_BLUR_SPLIT": "3", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
-    ("blur A = levels 0-3, B after FAST", {"SE2GPU_ORB_BLUR_SPLIT": "4", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
-    ("blur A = levels 0-2, B with FAST", {"SE2GPU_ORB_BLUR_SPLIT": "3", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
-    ("all blur behind the pyramid tail (A = all levels)", {"SE2GPU_ORB_BLUR_SPLIT": "8", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
-    ("resize: window loads + IDP.2A + 16-bit rows", {"SE2GPU_ORB_RESIZE_W": "1", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
-    ("resize_w + blur B after FAST", {"SE2GPU_ORB_RESIZE_W": "1", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
-    ("resize_w + blur A = levels 0-2, B after FAST", {"SE2GPU_ORB_RESIZE_W": "1", "SE2GPU_ORB_BLUR_SPLIT": "3", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
-    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_BLUR_SPLIT": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("defaults (tma8, orient batch, resize_w)", {"SE2GPU_ORB_PDL": "0"}),
+    ("+ programmatic dependent launch on the resize chain", {"SE2GPU_ORB_PDL": "1"}),
+    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_PDL": "0"}),
 ]
 
 
