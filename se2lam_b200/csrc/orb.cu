@@ -828,6 +828,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma(OrbDev d, con
 //     shared atomic per 128 pixels and its vote/election code are gone; passes B and C walk the warp's own segment (the 32-item
 //     chunks are dealt round-robin over the warps, so the segments are balanced). The list order never reaches the output:
 //     keypoints are emitted in raster order from the bitmap (pass E), so the result is bit-identical to orb_fast_cells.
+template <bool PDL>   // PDL: dependent launch behind the last resize (see orb_resize_w): cell geometry, barrier set-up and the smem pointers run in its tail
 __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma8(OrbDev d, const __grid_constant__ FastMaps maps) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ int s_total;
@@ -855,6 +856,7 @@ __global__ void __launch_bounds__(FAST_THREADS) orb_fast_cells_tma8(OrbDev d, co
     uint16_t* list = reinterpret_cast<uint16_t*>(woff + nwords);                          // [8 * nitems] entries y*pw + x, one segment per warp
     if (threadIdx.x == 0) orb_mbar_init(&s_bar, 1);
     __syncthreads();
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");     // the pyramid is complete and visible from here on
     if (threadIdx.x == 0) orb_tma_box3(patch, &maps.m[c.level], ax0, c.y0 - 3 + EDGE, f, (unsigned)(pw * bh), &s_bar);
     constexpr int NW = FAST_THREADS / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1596,7 +1598,7 @@ EncodeTiledFn tensor_map_encoder() {
 constexpr bool ORIENT_BATCH_DEFAULT = true;    // measured: 0.0928 -> 0.0897 ms per 64 frames, bit-identical (profiles/r02b_orb_variants.jsonl)
 constexpr int FAST_TMA_DEFAULT = 2;   // measured: orb_fast_cells 0.2976 -> 0.2543 ms per 64 frames, bit-identical (profiles/r02c_orb_variants.jsonl)
 constexpr bool RESIZE_W_DEFAULT = true;     // measured: pyramid 0.1622 -> 0.155 ms per 64 frames, bit-identical (profiles/r02e_orb_variants.jsonl)
-constexpr bool PDL_DEFAULT = false;
+constexpr int PDL_DEFAULT = 0;
 constexpr int BLUR_SPLIT_DEFAULT = 2;             // levels 0-1 behind the pyramid tail (round 1)
 constexpr bool BLUR_B_AFTER_FAST_DEFAULT = false;
 constexpr int SUBMIT_CHUNKS_DEFAULT = 1;   // measured: 0.637 ms per 64-frame batch against 1.005 (4 chunks) / 0.857 (2) (profiles/r02d_orb_e2e_submit.jsonl)
@@ -1687,7 +1689,10 @@ int set_geometry(se2gpu_orb* h, int w, int hgt, cudaStream_t s) {
     h->fast_tma = (fast_tma_variant() && fsm_tma > 0 && encode_fast_maps(h, pb)) ? fast_tma_variant() : 0;
     h->fast_tma_smem = fsm_tma;
     if (h->fast_tma == 1) SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm_tma, 1024)));
-    if (h->fast_tma == 2) SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_tma8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm_tma, 1024)));
+    if (h->fast_tma == 2) {
+        SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_tma8<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm_tma, 1024)));
+        SE2_CUDA(cudaFuncSetAttribute(orb_fast_cells_tma8<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fsm_tma, 1024)));
+    }
     SE2_CUDA(cudaFuncSetAttribute(orb_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(ssm, 1024)));
     OrbDev& d = h->d;
     d.n_cells = (int)h->cells.size(); d.n_tiles = (int)h->tiles.size();
@@ -1801,6 +1806,8 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     // blur schedule on the side stream: group A = levels [0, splitA) starts as soon as level splitA-1 exists; group B = the rest starts
     // when the pyramid is complete (round-1 form) or, with SE2GPU_ORB_BLUR_B_AFTER_FAST=1, when FAST has been launched, i.e. it runs
     // next to the selection kernel, whose level-0 CTAs leave most SMs idle, instead of competing with the issue-bound FAST kernel
+    // SE2GPU_ORB_PDL: 0 plain launches, 1 programmatic dependent launch along the resize chain, 2 also the FAST kernel behind the last resize
+    static const int pdl_mode = [] { const char* e = getenv("SE2GPU_ORB_PDL"); const int v = e ? atoi(e) : PDL_DEFAULT; return v < 0 || v > 2 ? 0 : v; }();
     static const int env_split = [] { const char* e = getenv("SE2GPU_ORB_BLUR_SPLIT"); return e ? atoi(e) : BLUR_SPLIT_DEFAULT; }();
     static const bool b_after_fast = [] { const char* e = getenv("SE2GPU_ORB_BLUR_B_AFTER_FAST"); return e ? atoi(e) != 0 : BLUR_B_AFTER_FAST_DEFAULT; }();
     const int splitA = std::min(std::max(env_split, 1), h->nlevels);
@@ -1808,8 +1815,7 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
         const LevelGeo& g = h->levels[l];
         dim3 grid((g.pitch + 127) / 128, (g.h + 2 * EDGE + RESIZE_TR - 1) / RESIZE_TR, n);
         static const bool resize_w = [] { const char* e = getenv("SE2GPU_ORB_RESIZE_W"); return e ? atoi(e) != 0 : RESIZE_W_DEFAULT; }();
-        static const bool pdl = [] { const char* e = getenv("SE2GPU_ORB_PDL"); return e ? atoi(e) != 0 : PDL_DEFAULT; }();
-        if (resize_w && pdl) {
+        if (resize_w && pdl_mode >= 1) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = grid; cfg.blockDim = dim3(32, 8); cfg.dynamicSmemBytes = h->resize_w_smem; cfg.stream = s;
             cudaLaunchAttribute at[1];
@@ -1848,7 +1854,17 @@ int run_device(se2gpu_orb* h, const uint8_t* d_imgs, int n, int w, int hgt, int 
     SE2_NVTX("se2gpu.orb.fast_select_blur_describe");
     pr.begin(1, s);
     if (h->fast_big) SE2_LAUNCH(orb_fast_cells_big, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
-    else if (h->fast_tma == 2) SE2_LAUNCH(orb_fast_cells_tma8, dim3(d.n_cells, n), FAST_THREADS, h->fast_tma_smem, s, d, h->fast_maps);
+    else if (h->fast_tma == 2 && pdl_mode == 2 && !pr.on) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(d.n_cells, n); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = h->fast_tma_smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SE2_CUDA(cudaLaunchKernelEx(&cfg, orb_fast_cells_tma8<true>, d, h->fast_maps));
+        ::se2gpu::g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    else if (h->fast_tma == 2) SE2_LAUNCH(orb_fast_cells_tma8<false>, dim3(d.n_cells, n), FAST_THREADS, h->fast_tma_smem, s, d, h->fast_maps);
     else if (h->fast_tma == 1) SE2_LAUNCH(orb_fast_cells_tma, dim3(d.n_cells, n), FAST_THREADS, h->fast_tma_smem, s, d, h->fast_maps);
     else SE2_LAUNCH(orb_fast_cells, dim3(d.n_cells, n), FAST_THREADS, h->fast_smem, s, d);
     pr.end(s);

@@ -62,9 +62,10 @@ print(json.dumps({"ms_per_step": round(ms, 4), "mkps": round(total / NROT / ms /
 ROUND1_SHA = "49cd1e2540cf0775"
 
 CONFIGS = [
-    ("defaults (tma8, orient batch, resize_w)", {"SE2GPU_ORB_PDL": "0"}),
-    ("+ programmatic dependent launch on the resize chain", {"SE2GPU_ORB_PDL": "1"}),
-    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_PDL": "0"}),
+    ("defaults (tma8, orient batch, resize_w)", {"SE2GPU_ORB_PDL": "0", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("+ programmatic dependent launch on the resize chain", {"SE2GPU_ORB_PDL": "1", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
+    ("+ PDL on the resize chain and FAST (blur B behind FAST)", {"SE2GPU_ORB_PDL": "2", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "1"}),
+    ("round-1 kernels", {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_PDL": "0", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"}),
 ]
 
 
