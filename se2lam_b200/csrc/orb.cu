@@ -1598,9 +1598,9 @@ EncodeTiledFn tensor_map_encoder() {
 constexpr bool ORIENT_BATCH_DEFAULT = true;    // measured: 0.0928 -> 0.0897 ms per 64 frames, bit-identical (profiles/r02b_orb_variants.jsonl)
 constexpr int FAST_TMA_DEFAULT = 2;   // measured: orb_fast_cells 0.2976 -> 0.2543 ms per 64 frames, bit-identical (profiles/r02c_orb_variants.jsonl)
 constexpr bool RESIZE_W_DEFAULT = true;     // measured: pyramid 0.1622 -> 0.155 ms per 64 frames, bit-identical (profiles/r02e_orb_variants.jsonl)
-constexpr int PDL_DEFAULT = 0;
+constexpr int PDL_DEFAULT = 2;               // measured: pyramid 0.154 -> 0.1346 ms, step 0.618 -> 0.597 ms per 64 frames, bit-identical (profiles/r02f_orb_variants.jsonl)
 constexpr int BLUR_SPLIT_DEFAULT = 2;             // levels 0-1 behind the pyramid tail (round 1)
-constexpr bool BLUR_B_AFTER_FAST_DEFAULT = false;
+constexpr bool BLUR_B_AFTER_FAST_DEFAULT = true;   // no event between the last resize and FAST, so that FAST can be its programmatic dependent
 constexpr int SUBMIT_CHUNKS_DEFAULT = 1;   // measured: 0.637 ms per 64-frame batch against 1.005 (4 chunks) / 0.857 (2) (profiles/r02d_orb_e2e_submit.jsonl)
 int fast_tma_variant() {   // SE2GPU_ORB_FAST_TMA = 0: LDG/STS staging (orb_fast_cells), 1: orb_fast_cells_tma, 2: orb_fast_cells_tma8
     static const int v = [] { const char* e = getenv("SE2GPU_ORB_FAST_TMA"); const int x = e ? atoi(e) : FAST_TMA_DEFAULT; return x < 0 || x > 2 ? FAST_TMA_DEFAULT : x; }();
