@@ -10,13 +10,13 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-VARIANTS = [
+VARIANTS = [   # combinations that tools/orb_variants.py has run on a B200 (profiles/r02c / r02e / r02f _orb_variants.jsonl)
     {"SE2GPU_ORB_FAST_TMA": "0", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_PDL": "0", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"},
-    {"SE2GPU_ORB_FAST_TMA": "1"},
+    {"SE2GPU_ORB_FAST_TMA": "1", "SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_PDL": "0", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"},
     {"SE2GPU_ORB_PDL": "0"},
     {"SE2GPU_ORB_PDL": "1", "SE2GPU_ORB_BLUR_B_AFTER_FAST": "0"},
-    {"SE2GPU_ORB_RESIZE_W": "0"},
-    {"SE2GPU_ORB_ORIENT_BATCH": "0", "SE2GPU_ORB_BLUR_SPLIT": "3"},
+    {"SE2GPU_ORB_RESIZE_W": "0", "SE2GPU_ORB_PDL": "0"},
+    {"SE2GPU_ORB_ORIENT_BATCH": "0"},
 ]
 
 
